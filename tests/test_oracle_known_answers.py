@@ -1,0 +1,108 @@
+"""Pins the ORACLE (CPU restatement) against the reference's own known-answer tests.
+
+Every expectation below is restated from a test in /root/reference/src/Infidex.Tests (file:line cited);
+none comes from the oracle itself. The reference is C#/.NET and cannot run in this image, so these
+known answers (exact result lists on the 10-doc corpus, top-1 / ordering relations on movies.csv) are
+the strongest pin available; complete ranked lists and Score constants remain "parity unpinned" (SURVEY 8c).
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+# ReferenceMatchingTests.cs:40-98
+@pytest.mark.parametrize("query,expected,exact", [
+    ("batman", [6], False), ("qick fux", [5, 1], True), ("battamam", [6], True), ("new york", [8], True), ("speeding", [7], True)])
+def test_reference_matching(oracle_ref10, query, expected, exact):
+    r = oracle_ref10.search(query, 10)
+    assert r["status"] == 0
+    if exact:
+        assert r["keys"] == expected
+    else:
+        assert r["keys"][: len(expected)] == expected
+
+
+# README 3-doc example (BASELINE.json configs[0]; SURVEY 8c C1 hand trace: exactly one record, DocumentId 1)
+def test_readme_quik_fox():
+    e = O.OracleEngine()
+    e.index_texts(["The quick brown fox jumps over the lazy dog", "A journey of a thousand miles begins with a single step",
+                   "To be or not to be, that is the question"], keys=np.arange(1, 4))
+    r = e.search("quik fox", 10)
+    assert r["keys"] == [1]
+
+
+# FuzzyRegressionTests.cs:20-52
+def test_fuzzy_regression_matrix_above_mat():
+    e = O.OracleEngine()
+    e.index_texts(["The Mat", "The Matrix", "The Matriarx", "The Match", "The Meatrix"], keys=np.arange(1, 6))
+    r = e.search("the matrx", 10)
+    s = dict(zip(r["keys"], r["scores"]))
+    assert 2 in s and (1 not in s or s[2] > s[1])
+
+
+# LevenshteinDistanceTests.cs:11-79
+@pytest.mark.parametrize("a,b,d", [("hello", "hello", 0), ("hello", "hallo", 1), ("bat", "brat", 1), ("batman", "batma", 1), ("", "", 0),
+                                   ("hello", "", 5), ("", "hello", 5), ("kitten", "sitting", 3), ("saturday", "sunday", 3)])
+def test_levenshtein(a, b, d):
+    assert O.levenshtein(a, b) == d
+
+
+def test_levenshtein_within():
+    assert O.levenshtein("batman", "batmam", 1) <= 1
+    assert O.levenshtein("batman", "ratmin", 1) > 1
+
+
+# CoverageEngineTests.cs:19-75 (engine without corpus statistics: IDF falls back to log2(len+1))
+def test_coverage_engine_known_answers():
+    e = O.OracleEngine()
+    c = e.coverage("hello world", "this is hello world text")
+    assert c["coverage"] > 200 and c["word_hits"] == 2
+    assert e.coverage("xyz abc", "hello world test")["coverage"] < 100
+    c = e.coverage("hello world test", "hello world")
+    assert c["coverage"] > 100 and c["word_hits"] == 2
+    c = e.coverage("batmam", "batman is a superhero")
+    assert c["coverage"] > 150 and c["word_hits"] > 0
+
+
+# MovieSearchParityTests.cs (33 tests; the n-gram-path ones are restated in movie_known_answers.json)
+def _cases():
+    return json.load(open(os.path.join(HERE, "golden", "movie_known_answers.json")))["cases"]
+
+
+@pytest.mark.parametrize("case", _cases(), ids=lambda c: c["query"])
+def test_movie_known_answers(oracle_movies, movie_titles, case):
+    r = oracle_movies.search(case["query"], case["max"])
+    assert r["status"] == 0
+    check_movie_case(case, r["keys"], r["scores"], movie_titles)
+
+
+def check_movie_case(c, keys, scores, titles_all):
+    titles = [titles_all[k] for k in keys]
+    if "top1" in c:
+        assert titles and titles[0] == c["top1"]
+    if "top1_contains" in c:
+        assert titles and c["top1_contains"].lower() in titles[0].lower()
+    if c.get("strict_gt_second"):
+        assert len(titles) >= 2 and scores[0] > scores[1]
+    if "min_results" in c:
+        assert len(titles) >= c["min_results"]
+    if "a_before_b_score" in c:
+        a, b = c["a_before_b_score"]
+        assert a in titles and b in titles and scores[titles.index(a)] > scores[titles.index(b)]
+    if "a_before_b_rank" in c:
+        a, b = c["a_before_b_rank"]
+        assert a in titles and b in titles and titles.index(a) < titles.index(b)
+    if "title_within_top" in c:
+        a, k = c["title_within_top"]
+        assert a in titles and titles.index(a) < k
+
+
+def test_short_query_path_is_flagged_not_faked(oracle_movies):
+    # queries with no word >= 3 chars take ShortQueryProcessor (SURVEY 8f "next"): status 1, never a silent answer
+    assert oracle_movies.search("as am", 20)["status"] == 1
