@@ -1,0 +1,32 @@
+/* infidex_host.h -- host-side index builder of infidex_b200 (libinfidex_host.so, no CUDA dependency).
+ *
+ * Stands in for the C# host's indexing half (SearchEngine.IndexDocuments, src/Infidex/SearchEngine.cs:96-192):
+ * documents in, the flattened immutable index (ifx_index_image, see infidex_gpu.h) out. With the real C# host the
+ * image is marshalled from its own in-memory structures instead; the search path is identical.
+ */
+#ifndef INFIDEX_HOST_H
+#define INFIDEX_HOST_H
+#include "infidex_gpu.h"
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum { IFX_FIELD_INDEXABLE = 1, IFX_FIELD_FILTERABLE = 2, IFX_FIELD_FACETABLE = 4 };   /* Field.Indexable / Filterable / Facetable */
+
+typedef struct ifx_builder ifx_builder;
+
+/* schema = DocumentFields of the documents (Api/DocumentFields.cs); weight: 0 High, 1 Med, 2 Low (Api/Weight.cs) */
+ifx_builder* ifx_builder_create(int nfields, const uint16_t* names, const int32_t* name_off, const int32_t* weight, const int32_t* flags);
+void ifx_builder_destroy(ifx_builder* b);
+/* columnar documents; kinds[f]: 0 null, 1 string (cols[f] = UTF-16 blob, offs[f] = int64[n+1]), 2 int64[n], 3 double[n] */
+int ifx_builder_add_docs(ifx_builder* b, int n, const int64_t* keys, const int32_t* kinds, const void* const* cols, const long long* const* offs);
+int ifx_builder_finish(ifx_builder* b, int threads);
+const ifx_index_image* ifx_builder_image(ifx_builder* b);   /* valid until ifx_builder_destroy */
+
+/* SearchEngine.Search step 1 (src/Infidex/SearchEngine.cs:264-274): Trim + TextNormalizer.Normalize + ToLowerInvariant. Returns the output length. */
+int ifx_host_prepare_query(const uint16_t* in, int n, uint16_t* out, int cap);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,217 @@
+// infidex_b200 -- implementation of the C-ABI (include/infidex_gpu.h).
+// Included by ifx_api.cu (CUDA product) and by tests/emu/emu_api.cpp (IFX_EMU host emulation of the kernels, tests only).
+#include "../../include/infidex_gpu.h"
+#include "ifx_stage1.h"
+#include "ifx_stage2.h"
+#include <vector>
+#include <string>
+#include <algorithm>
+#include <numeric>
+#include <cstring>
+#include <cstdio>
+#include <cmath>
+#include <mutex>
+
+namespace {
+#include "chartables.inc"
+}
+
+using namespace ifx;
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string& m) { g_err = m; return code; }
+
+// ---- device memory / launch shims ---------------------------------------------------------------------------------
+#ifdef IFX_EMU
+static bool dev_ok() { return true; }
+static void* dev_alloc(size_t n) { return calloc(n ? n : 1, 1); }
+static void dev_free(void* p) { free(p); }
+static void h2d(void* d, const void* s, size_t n) { if (n) memcpy(d, s, n); }
+static void d2h(void* d, const void* s, size_t n) { if (n) memcpy(d, s, n); }
+static void dev_zero(void* d, size_t n) { if (n) memset(d, 0, n); }
+struct Timer { void start() {} float stop() { return 0.f; } };
+static const int kS1Threads = 1;
+#else
+#define CUDA_TRY(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) throw std::string(#x ": ") + cudaGetErrorString(e_); } while (0)
+static bool dev_ok() { int n = 0; return cudaGetDeviceCount(&n) == cudaSuccess && n > 0; }
+static void* dev_alloc(size_t n) { void* p = nullptr; CUDA_TRY(cudaMalloc(&p, n ? n : 1)); return p; }
+static void dev_free(void* p) { if (p) cudaFree(p); }
+static void h2d(void* d, const void* s, size_t n) { if (n) CUDA_TRY(cudaMemcpy(d, s, n, cudaMemcpyHostToDevice)); }
+static void d2h(void* d, const void* s, size_t n) { if (n) CUDA_TRY(cudaMemcpy(d, s, n, cudaMemcpyDeviceToHost)); }
+static void dev_zero(void* d, size_t n) { if (n) CUDA_TRY(cudaMemset(d, 0, n)); }
+struct Timer { cudaEvent_t a = nullptr, b = nullptr; cudaStream_t s = 0;
+    void start() { if (!a) { cudaEventCreate(&a); cudaEventCreate(&b); } cudaEventRecord(a, s); }
+    float stop() { cudaEventRecord(b, s); cudaEventSynchronize(b); float ms = 0; cudaEventElapsedTime(&ms, a, b); return ms; } };
+static const int kS1Threads = 256;
+#endif
+
+// ---- host-side handle ----------------------------------------------------------------------------------------------
+struct FilterDev { std::vector<uint8_t> blob; FilterProg prog; void* d_consts = nullptr; void* d_code = nullptr; void* d_chars = nullptr; void* d_arr = nullptr; };
+
+struct ifx_index {
+    DevIndex v{};                       // device pointers
+    std::vector<void*> allocs;
+    uint8_t* d_sorted_len = nullptr;
+    int n_ctas = 1;
+    std::vector<S1Workspace> ws; S1Workspace* d_ws = nullptr;
+    int32_t* d_pool = nullptr; unsigned long long pool_cap = 0;
+    int max_batch = 16384;
+    int device = 0;
+    std::vector<FilterDev> filters; FilterProg* d_filters = nullptr; int d_filters_n = 0;
+    std::vector<Column> h_columns; std::vector<std::u16string> column_names;
+    std::mutex mu;
+    ~ifx_index() { for (void* p : allocs) dev_free(p); }
+    template <class T> T* up(const T* src, size_t n) { T* d = (T*)dev_alloc(n * sizeof(T)); allocs.push_back(d); if (src && n) h2d(d, src, n * sizeof(T)); return d; }
+    template <class T> T* alloc(size_t n) { T* d = (T*)dev_alloc(n * sizeof(T)); allocs.push_back(d); return d; }
+};
+
+struct ifx_batch {
+    ifx_index* idx = nullptr; int nq = 0; int depth_max = 0; int cap_max = 0;
+    std::vector<void*> allocs;
+    uint16_t* d_text = nullptr; int64_t* d_off = nullptr; int32_t* d_par = nullptr;   // par: [nq][5] max_results, depth, enable_cov, filter_id, enable_facets
+    QueryPlan* d_plans = nullptr; FuzzyItem* d_items = nullptr; BatchCounters* d_bc = nullptr; int* d_work = nullptr;
+    int64_t* d_s1_key = nullptr; int32_t* d_s1_doc = nullptr; float* d_s1_score = nullptr; int32_t* d_s1_n = nullptr;
+    Stage2Buffers s2{};                 // WordMatcher + coverage outputs
+    FinalOut fin{}; int fcap = 0;
+    bool ran = false;
+    ~ifx_batch() { for (void* p : allocs) dev_free(p); }
+    template <class T> T* alloc(size_t n) { T* d = (T*)dev_alloc(n * sizeof(T)); allocs.push_back(d); return d; }
+};
+
+static uint64_t hash_host(const uint16_t* s, int n) {
+    uint64_t h = 0xcbf29ce484222325ULL ^ (uint64_t)n;
+    for (int i = 0; i < n; i++) { h ^= s[i]; h *= 0x100000001b3ULL; }
+    h ^= h >> 29; h *= 0xbf58476d1ce4e5b9ULL; h ^= h >> 32;
+    return h | 1ULL;
+}
+
+static StrDict upload_dict(ifx_index* ix, const ifx_strings& s) {
+    StrDict d{}; d.n = s.n;
+    size_t nchars = s.n ? s.off[s.n] : 0;
+    d.chars = ix->up(s.chars, nchars ? nchars : 1); d.off = ix->up(s.off, (size_t)s.n + 1);
+    uint32_t cap = 8; while (cap < (uint32_t)s.n * 2u + 2u) cap <<= 1;
+    std::vector<uint64_t> hk(cap, 0); std::vector<int32_t> hv(cap, -1);
+    for (int i = 0; i < s.n; i++) {
+        uint64_t h = hash_host(s.chars + s.off[i], (int)(s.off[i + 1] - s.off[i])); uint32_t slot = (uint32_t)(h >> 7) & (cap - 1);
+        while (hk[slot] != 0) slot = (slot + 1) & (cap - 1);
+        hk[slot] = h; hv[slot] = i;
+    }
+    d.hkeys = ix->up(hk.data(), cap); d.hvals = ix->up(hv.data(), cap); d.hmask = cap - 1;
+    return d;
+}
+static DocsetDict upload_docset(ifx_index* ix, const ifx_docset_dict& s) {
+    DocsetDict d{}; d.keys = upload_dict(ix, s.keys);
+    size_t np = s.keys.n ? (size_t)s.row_ptr[s.keys.n] : 0;
+    static const int64_t zero = 0;
+    d.row_ptr = ix->up(s.keys.n ? s.row_ptr : &zero, (size_t)s.keys.n + 1); d.doc_id = ix->up(s.doc_id, np ? np : 1);
+    return d;
+}
+
+static bool host_try_parse_double(const uint16_t* s, int n, double& out);   // defined with the filter code below
+
+extern "C" void ifx_params_default(ifx_params* p) { p->stop_term_limit = 1250000; p->device = 0; p->max_batch = 16384; p->reserved = 0; }
+extern "C" const char* ifx_last_error(void) { return g_err.c_str(); }
+extern "C" int ifx_device_count(void) {
+#ifdef IFX_EMU
+    return 1;
+#else
+    int n = 0; if (cudaGetDeviceCount(&n) != cudaSuccess) return 0; return n;
+#endif
+}
+
+extern "C" int ifx_index_create(const ifx_index_image* img, const ifx_params* pp, ifx_index** out) {
+    if (!img || !out) return fail(IFX_ERR_INVALID, "null argument");
+    if (!dev_ok()) return fail(IFX_ERR_NO_DEVICE, "no CUDA device available (infidex_b200 has no CPU fallback)");
+    ifx_params P; if (pp) P = *pp; else ifx_params_default(&P);
+    if (img->n_docs < 0 || ((int64_t)img->n_docs + 65535) / 65536 > MAX_CONTAINERS) return fail(IFX_ERR_INVALID, "n_docs out of range");
+    ifx_index* ix = new ifx_index();
+    try {
+#ifndef IFX_EMU
+        CUDA_TRY(cudaSetDevice(P.device)); ix->device = P.device;
+#endif
+        DevIndex& v = ix->v; const int N = img->n_docs;
+        v.n_docs = N; v.n_live = img->n_live; v.avgdl = img->avgdl; v.stop_term_limit = P.stop_term_limit;
+        v.doc_key = ix->up(img->doc_key, N); v.deleted = ix->up(img->deleted, N); v.doc_len = ix->up(img->doc_len, N);
+        size_t ntext = N ? (size_t)img->text_off[N] : 0;
+        v.text = ix->up(img->text_chars, ntext ? ntext : 1); v.text_off = ix->up(img->text_off, (size_t)N + 1);
+        v.first_token = upload_dict(ix, img->first_token); v.token_count = ix->up(img->token_count, N);
+        v.terms = upload_dict(ix, img->terms); const int T = img->terms.n;
+        v.df = ix->up(img->df, T); v.row_ptr = ix->up(img->row_ptr, (size_t)T + 1);
+        size_t P_ = T ? (size_t)img->row_ptr[T] : 0;
+        v.post_doc = ix->up(img->post_doc, P_ ? P_ : 1); v.post_tf = ix->up(img->post_tf, P_ ? P_ : 1);
+        // trie DFS order == ordinal-lexicographic order of the term texts (FstBuilder.CompactTrie sorts arcs by label)
+        std::vector<int32_t> order(T); std::iota(order.begin(), order.end(), 0);
+        auto term_sv = [&](int i) { return std::u16string_view((const char16_t*)img->terms.chars + img->terms.off[i], img->terms.off[i + 1] - img->terms.off[i]); };
+        std::sort(order.begin(), order.end(), [&](int a, int b) { return term_sv(a) < term_sv(b); });
+        std::vector<uint8_t> slen(T); for (int i = 0; i < T; i++) { size_t l = term_sv(order[i]).size(); slen[i] = (uint8_t)(l > 255 ? 255 : l); }
+        v.term_sorted = ix->up(order.data(), T ? T : 1); ix->d_sorted_len = ix->up(slen.data(), T ? T : 1);
+        v.words = upload_dict(ix, img->words); v.word_idf = ix->up(img->word_idf, img->words.n ? img->words.n : 1);
+        v.prefix = upload_docset(ix, img->prefix); v.wm_exact = upload_docset(ix, img->wm_exact); v.wm_ld1 = upload_docset(ix, img->wm_ld1);
+        {   // affix words: forward (prefix) order and reverse-string (suffix) order, each with the doc its trie output resolves to
+            const int A = img->affix_words.n;
+            auto aw = [&](int i) { return std::u16string_view((const char16_t*)img->affix_words.chars + img->affix_words.off[i], img->affix_words.off[i + 1] - img->affix_words.off[i]); };
+            std::vector<int32_t> fo(A); std::iota(fo.begin(), fo.end(), 0); std::sort(fo.begin(), fo.end(), [&](int a, int b) { return aw(a) < aw(b); });
+            std::vector<uint16_t> chars; std::vector<uint32_t> off(A + 1, 0); std::vector<int32_t> fdoc(A);
+            for (int i = 0; i < A; i++) { auto s = aw(fo[i]); chars.insert(chars.end(), s.begin(), s.end()); off[i + 1] = (uint32_t)chars.size(); fdoc[i] = img->affix_last_doc[fo[i]]; }
+            ifx_strings ss{chars.data(), off.data(), A}; if (chars.empty()) chars.push_back(0); ss.chars = chars.data();
+            v.affix = upload_dict(ix, ss); v.affix_fwd_doc = ix->up(fdoc.data(), A ? A : 1);
+            auto rev_less = [&](int a, int b) { auto x = std::u16string_view((const char16_t*)chars.data() + off[a], off[a + 1] - off[a]), y = std::u16string_view((const char16_t*)chars.data() + off[b], off[b + 1] - off[b]);
+                size_t n = std::min(x.size(), y.size()); for (size_t k = 0; k < n; k++) { char16_t p = x[x.size() - 1 - k], q = y[y.size() - 1 - k]; if (p != q) return p < q; } return x.size() < y.size(); };
+            std::vector<int32_t> ro(A); std::iota(ro.begin(), ro.end(), 0); std::sort(ro.begin(), ro.end(), rev_less);
+            std::vector<int32_t> rdoc(A); for (int i = 0; i < A; i++) rdoc[i] = fdoc[ro[i]];
+            v.affix_rev = ix->up(ro.data(), A ? A : 1); v.affix_rev_doc = ix->up(rdoc.data(), A ? A : 1);
+        }
+        {   // character tables (tools/gen_chartables.py) + host-evaluated MathF.Log2(len + 1)
+            std::vector<uint16_t> lo(65536), upv(65536); std::vector<uint8_t> fl(65536, 0);
+            for (int i = 0; i < 65536; i++) lo[i] = upv[i] = (uint16_t)i;
+            for (int i = 0; i < IFX_LOWER_PAIRS_N; i++) lo[IFX_LOWER_PAIRS[i][0]] = IFX_LOWER_PAIRS[i][1];
+            for (int i = 0; i < IFX_UPPER_PAIRS_N; i++) upv[IFX_UPPER_PAIRS[i][0]] = IFX_UPPER_PAIRS[i][1];
+            for (int i = 0; i < IFX_LETTER_RANGES_N; i++) for (int c = IFX_LETTER_RANGES[i][0]; c <= IFX_LETTER_RANGES[i][1]; c++) fl[c] |= 1;
+            for (int i = 0; i < IFX_SPACE_LIST_N; i++) fl[IFX_SPACE_LIST[i]] |= 2;
+            const uint16_t dl[] = {' ', '-', '/', '.', ',', ':', ';', '\'', '`', 0x2013, 0x2014, '*', '&', '\\', '_', '(', ')', '{', '}', '[', ']', '\t'};
+            for (uint16_t c : dl) fl[c] |= 4;
+            v.lower = ix->up(lo.data(), 65536); v.upper = ix->up(upv.data(), 65536); v.cflags = ix->up(fl.data(), 65536);
+            std::vector<float> l2(1024); for (int i = 0; i < 1024; i++) l2[i] = std::log2((float)(i + 1));
+            v.log2_len = ix->up(l2.data(), 1024);
+        }
+        {   // filter / facet columns: ToString() dictionary + parsed numeric view of every dictionary entry
+            ix->h_columns.resize(img->n_columns);
+            for (int c = 0; c < img->n_columns; c++) {
+                const ifx_column& ic = img->columns[c]; Column& col = ix->h_columns[c];
+                col.value_id = ix->up(ic.value_id, N); col.dict = upload_dict(ix, ic.dict); col.flags = ic.flags;
+                std::vector<double> num(std::max(ic.dict.n, 1), 0.0); std::vector<uint8_t> isn(std::max(ic.dict.n, 1), 0);
+                for (int i = 0; i < ic.dict.n; i++) { double d; if (host_try_parse_double(ic.dict.chars + ic.dict.off[i], (int)(ic.dict.off[i + 1] - ic.dict.off[i]), d)) { num[i] = d; isn[i] = 1; } }
+                col.dict_num = ix->up(num.data(), num.size()); col.dict_is_num = ix->up(isn.data(), isn.size());
+                col.name_const_hash_lo = (int32_t)hash_host(ic.name, ic.name_len);
+            }
+            v.n_columns = img->n_columns; v.columns = ix->up(ix->h_columns.data(), std::max(img->n_columns, 1));
+            for (int c = 0; c < img->n_columns; c++) ix->column_names.emplace_back((const char16_t*)img->columns[c].name, (size_t)img->columns[c].name_len);
+        }
+        // persistent-CTA workspaces
+        int64_t max_list = 1; for (int t = 0; t < T; t++) max_list = std::max<int64_t>(max_list, img->row_ptr[t + 1] - img->row_ptr[t]);
+        for (int k = 0; k < img->prefix.keys.n; k++) (void)k;
+        max_list = std::max<int64_t>(max_list, std::min<int64_t>(N, P.stop_term_limit));
+        int64_t nwords = ((int64_t)N + 31) / 32 + 2048;
+        size_t per_cta = (size_t)nwords * 4 + (size_t)(N + 1) * 4 + 2 * (size_t)max_list * 4;
+#ifdef IFX_EMU
+        ix->n_ctas = 1;
+#else
+        { cudaDeviceProp prop; CUDA_TRY(cudaGetDeviceProperties(&prop, P.device));
+          size_t free_b = 0, total_b = 0; CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
+          int want = prop.multiProcessorCount * 3; size_t budget = free_b / 3;
+          ix->n_ctas = (int)std::max<size_t>(1, std::min<size_t>((size_t)want, budget / std::max<size_t>(per_cta, 1))); }
+#endif
+        ix->ws.resize(ix->n_ctas);
+        for (auto& w : ix->ws) { w.bits = ix->alloc<unsigned>(nwords); dev_zero(w.bits, (size_t)nwords * 4); w.cand = ix->alloc<int32_t>((size_t)N + 1); w.cand_cap = N; w.buf_a = ix->alloc<int32_t>(max_list); w.buf_b = ix->alloc<int32_t>(max_list); w.buf_cap = max_list; }
+        ix->d_ws = ix->up(ix->ws.data(), ix->ws.size());
+        ix->pool_cap = (unsigned long long)std::max<int64_t>(1 << 20, std::min<int64_t>((int64_t)N * 64, (int64_t)1 << 31));
+        ix->d_pool = ix->alloc<int32_t>(ix->pool_cap);
+        ix->max_batch = P.max_batch > 0 ? P.max_batch : 16384;
+    } catch (const std::string& e) { delete ix; return fail(IFX_ERR_CUDA, e); }
+    catch (const std::bad_alloc&) { delete ix; return fail(IFX_ERR_OOM, "host allocation failed"); }
+    *out = ix; return IFX_OK;
+}
+
+extern "C" void ifx_index_destroy(ifx_index* idx) { delete idx; }
+
+#include "ifx_launch.inl"

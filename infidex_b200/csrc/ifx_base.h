@@ -1,0 +1,161 @@
+// infidex_b200 -- shared POD layout + execution-context abstraction.
+//
+// The search kernels are written once against `Ctx` (a cooperative group of threads):
+//   * CUDA build (nvcc, sm_100a): Ctx == one CTA; sync() is __syncthreads, ballot() is __ballot_sync, atomics are
+//     the hardware ones. This is the product.
+//   * IFX_EMU build (g++, tests only): Ctx == one host thread (group size 1, warp size 1). Used by the CPU test
+//     suite to check the kernel *logic* against the oracle without a GPU. It is never loaded by the product.
+#pragma once
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef IFX_EMU
+#include <cstring>
+#include <cmath>
+#include <algorithm>
+#define IFX_FN inline
+#define IFX_KERNEL_ATTR
+#else
+#include <cuda_runtime.h>
+#define IFX_FN __device__ __forceinline__
+#endif
+
+namespace ifx {
+
+constexpr int MAX_QLEN = 256;        // UTF-16 units of a (normalised) query; longer -> IFX_Q_OVERFLOW
+constexpr int MAX_RAW_TOKENS = 128;  // VectorModel.cs:381 (ArrayPool rent of 128 RawToken)
+constexpr int MAX_TERMS = 128;
+constexpr int MAX_FUZZY = 16;        // unknown words (len >= 4) expanded per query
+constexpr int LD1_CAP = 1024;        // VectorModel.cs:662 stackalloc int[1024]
+constexpr int CHUNK = 4096;          // Bm25Scorer.cs:209 blockSize
+constexpr int MAX_K = 1024;          // coverage depth supported by the on-chip heap
+constexpr int AFFIX_CAP = 4096;      // WordMatcher.cs:41 MaxFstAffixTermsPerQuery
+constexpr int MAX_QTOK = 64;         // coverage query tokens (len >= 2, deduped)
+constexpr int MAX_WM_WORDS = 32;     // query words (len >= 2) looked up in the WordMatcher
+constexpr int MAX_CONTAINERS = 8192; // 65536-doc containers per shard (N <= 536M)
+constexpr char16_t PAD = 0xFFFF;
+
+struct StrDict {                     // n strings + open-addressing hash (key = hash64 of the UTF-16 units)
+    const uint16_t* chars; const uint32_t* off; int32_t n;
+    const uint64_t* hkeys; const int32_t* hvals; uint32_t hmask;
+};
+
+struct DocsetDict { StrDict keys; const int64_t* row_ptr; const int32_t* doc_id; };
+
+struct Column { const int32_t* value_id; StrDict dict; const double* dict_num; const uint8_t* dict_is_num; int32_t flags; int32_t name_const_hash_lo; };
+
+struct DevIndex {
+    int32_t n_docs, n_live; float avgdl; int32_t stop_term_limit;
+    const int64_t* doc_key; const uint8_t* deleted; const float* doc_len;
+    const uint16_t* text; const int64_t* text_off;
+    StrDict first_token; const uint16_t* token_count;
+    StrDict terms; const int32_t* df; const int64_t* row_ptr; const int32_t* post_doc; const uint8_t* post_tf;
+    const int32_t* term_sorted;      // term ordinals in ordinal-lexicographic order (trie DFS order)
+    StrDict words; const float* word_idf;
+    DocsetDict prefix, wm_exact, wm_ld1;
+    StrDict affix;                   // affix words in ordinal-lexicographic order
+    const int32_t* affix_fwd_doc;    // last doc per affix word (forward order)
+    const int32_t* affix_rev;        // indices into `affix`, ordered by the reversed string
+    const int32_t* affix_rev_doc;    // last doc, in reverse-trie order
+    const uint16_t* lower; const uint16_t* upper; const uint8_t* cflags;   // 65536-entry tables
+    const float* log2_len;           // MathF.Log2(len + 1) for len < 1024 (host glibc)
+    int32_t n_columns; const Column* columns;
+};
+
+IFX_FN uint64_t hash64(const uint16_t* s, int n) {
+    uint64_t h = 0xcbf29ce484222325ULL ^ (uint64_t)n;
+    for (int i = 0; i < n; i++) { h ^= s[i]; h *= 0x100000001b3ULL; }
+    h ^= h >> 29; h *= 0xbf58476d1ce4e5b9ULL; h ^= h >> 32;
+    return h | 1ULL;                 // 0 marks an empty slot
+}
+
+IFX_FN int dict_lookup(const StrDict& d, const uint16_t* s, int n) {
+    if (d.n == 0) return -1;
+    uint64_t h = hash64(s, n); uint32_t slot = (uint32_t)(h >> 7) & d.hmask;
+    for (;;) {
+        uint64_t k = d.hkeys[slot];
+        if (k == 0) return -1;
+        if (k == h) {
+            int idx = d.hvals[slot]; uint32_t b = d.off[idx], e = d.off[idx + 1];
+            if ((int)(e - b) == n) { bool eq = true; for (int i = 0; i < n; i++) if (d.chars[b + i] != s[i]) { eq = false; break; } if (eq) return idx; }
+        }
+        slot = (slot + 1) & d.hmask;
+    }
+}
+
+// ---- execution context ------------------------------------------------------------------------------------------
+#ifdef IFX_EMU
+struct Ctx {
+    static constexpr int WS = 1;
+    int tid() const { return 0; } int nthreads() const { return 1; } int lane() const { return 0; } int warp() const { return 0; } int nwarps() const { return 1; }
+    void sync() const {}
+    unsigned ballot(bool p) const { return p ? 1u : 0u; }
+    unsigned lanemask_lt() const { return 0u; }
+    template <class T> T shfl(T v, int) const { return v; }
+};
+inline unsigned atomic_or(unsigned* p, unsigned v) { unsigned o = *p; *p = o | v; return o; }
+inline int atomic_add(int* p, int v) { int o = *p; *p = o + v; return o; }
+inline unsigned long long atomic_add64(unsigned long long* p, unsigned long long v) { unsigned long long o = *p; *p = o + v; return o; }
+inline int popc(unsigned v) { return __builtin_popcount(v); }
+inline int ffs32(unsigned v) { return __builtin_ffs((int)v); }
+inline float dev_logf_exact(float x) { return std::log(x); }
+#else
+struct Ctx {
+    static constexpr int WS = 32;
+    __device__ int tid() const { return threadIdx.x; } __device__ int nthreads() const { return blockDim.x; }
+    __device__ int lane() const { return threadIdx.x & 31; } __device__ int warp() const { return threadIdx.x >> 5; } __device__ int nwarps() const { return blockDim.x >> 5; }
+    __device__ void sync() const { __syncthreads(); }
+    __device__ unsigned ballot(bool p) const { return __ballot_sync(0xffffffffu, p); }
+    __device__ unsigned lanemask_lt() const { return (1u << (threadIdx.x & 31)) - 1u; }
+    template <class T> __device__ T shfl(T v, int src) const { return __shfl_sync(0xffffffffu, v, src); }
+};
+__device__ __forceinline__ unsigned atomic_or(unsigned* p, unsigned v) { return atomicOr(p, v); }
+__device__ __forceinline__ int atomic_add(int* p, int v) { return atomicAdd(p, v); }
+__device__ __forceinline__ unsigned long long atomic_add64(unsigned long long* p, unsigned long long v) { return atomicAdd(p, v); }
+__device__ __forceinline__ int popc(unsigned v) { return __popc(v); }
+__device__ __forceinline__ int ffs32(unsigned v) { return __ffs((int)v); }
+// MathF.Log on the reference host is glibc logf (<1 ulp, effectively correctly rounded); evaluate in fp64 and round once.
+__device__ __forceinline__ float dev_logf_exact(float x) { return (float)log((double)x); }
+#endif
+
+// Bm25Scorer.ComputeIdf (src/Infidex/Indexing/Bm25Scorer.cs:686-695)
+IFX_FN float compute_idf(int total, int df) {
+    if (df <= 0 || total <= 0) return 0.f;
+    float d = (float)df, N = (float)total;
+    float ratio = (N - d + 0.5f) / (d + 0.5f);
+    return ratio <= 0.f ? 0.f : dev_logf_exact(ratio + 1.f);
+}
+
+// ---- per-query plan written by k_prepare, completed by k_expand, consumed by k_stage1 / k_wm / k_stage2 -----------
+struct QTerm {
+    int64_t list_off;     // offset into post_doc/post_tf (known term) or into the fuzzy pool (fuzzy term)
+    int32_t list_len;     // postings in the list (== df for live lists)
+    int32_t df;
+    int32_t term_id;      // >= 0 known term; -1 fuzzy union
+    float idf, max_score;
+};
+
+struct FuzzyReq { uint16_t off, len; int32_t term_slot; };
+
+struct CovToken { uint16_t off, len; };
+
+struct QueryPlan {
+    int32_t status;
+    int32_t qlen;                          // full normalised lower query (Stage 2 text)
+    int32_t tlen;                          // Stage-1 text (short words removed when mixed)
+    int32_t n_terms;                       // slots used in `terms` (reference order; df filter applied later)
+    int32_t n_fuzzy;
+    int32_t depth, max_results, enable_coverage, filter_id, enable_facets;
+    int32_t short_skip_coverage;           // SearchPipeline.cs:139-142 (3-char query whose prefix docset > 500)
+    int32_t is_short3;                     // SearchPipeline.cs:110-112
+    uint16_t qtext[MAX_QLEN];
+    uint16_t ttext[MAX_QLEN];
+    QTerm terms[MAX_TERMS];
+    FuzzyReq fuzzy[MAX_FUZZY];
+};
+
+struct BatchCounters { int32_t n_fuzzy_items; int32_t overflow; unsigned long long fuzzy_pool_used; unsigned long long algo_bytes; };
+
+struct FuzzyItem { int32_t query; int32_t slot; };
+
+}  // namespace ifx

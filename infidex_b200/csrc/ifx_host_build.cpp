@@ -1,0 +1,288 @@
+// infidex_b200 -- host-side index builder (libinfidex_host.so): documents -> ifx_index_image.
+//
+// This is the product's stand-in for the part of the C# host that runs *before* the search path
+// (SearchEngine.IndexDocuments, src/Infidex/SearchEngine.cs:96-192): it produces exactly the state the reference
+// holds after IndexDocumentsInternal, flattened into the image that ifx_index_create uploads. Bulk / sort-based and
+// multi-threaded (doc-range partitions, flat posting records, counting-sort into CSR), not a per-term dictionary of lists.
+//
+// Index-time semantics reproduced:
+//   DocumentFields.GetSearchableTexts ('§' join, High->Low)      Api/DocumentFields.cs:124-170
+//   Tokenizer.EnumerateTokensForIndexing (padded 3-grams + words) Tokenization/Tokenizer.cs:89-139
+//   Term.FirstCycleAdd / TermCollection.CountTermUsage            Core/Term.cs:71-121, Core/TermCollection.cs:75-138
+//   VectorModel.BuildInvertedLists / BuildWordIdfCache / metadata Indexing/VectorModel.cs:130-220,250-313,864-908
+//   PositionalPrefixIndex / WordMatcher.Load                      Indexing/ShortQuery/PositionalPrefixIndex.cs:55-119, WordMatcher/WordMatcher.cs:82-196
+#include "../../include/infidex_gpu.h"
+#include "../../include/infidex_host.h"
+#include <vector>
+#include <string>
+#include <string_view>
+#include <thread>
+#include <algorithm>
+#include <numeric>
+#include <cmath>
+#include <cstring>
+#include <charconv>
+#include <memory>
+
+namespace {
+#include "chartables.inc"
+
+using sv = std::u16string_view; using str = std::u16string;
+
+struct Tables {
+    std::vector<uint16_t> lower, norm; std::vector<uint8_t> flags;
+    Tables() : lower(65536), norm(65536), flags(65536, 0) {
+        for (int i = 0; i < 65536; i++) lower[i] = norm[i] = (uint16_t)i;
+        for (int i = 0; i < IFX_LOWER_PAIRS_N; i++) lower[IFX_LOWER_PAIRS[i][0]] = IFX_LOWER_PAIRS[i][1];
+        for (int i = 0; i < IFX_NORM_PAIRS_N; i++) norm[IFX_NORM_PAIRS[i][0]] = IFX_NORM_PAIRS[i][1];
+        const uint16_t d[] = {' ', '-', '/', '.', ',', ':', ';', '\'', '`', 0x2013, 0x2014, '*', '&', '\\', '_', '(', ')', '{', '}', '[', ']', '\t'};
+        for (uint16_t c : d) flags[c] |= 4;
+    }
+};
+const Tables& TB() { static Tables t; return t; }
+inline bool is_delim(char16_t c) { return TB().flags[c] & 4; }
+void normalize_into(sv in, str& out) {   // TextNormalizer.Normalize (default map + whitespace collapse)
+    out.clear(); bool prev = false;
+    for (char16_t c : in) { char16_t m = (c == u'\t' || c == u'\n' || c == u'\r') ? u' ' : (char16_t)TB().norm[c]; bool sp = m == u' '; if (sp && prev) continue; out.push_back(m); prev = sp; }
+}
+void lower_inplace(str& s) { for (auto& c : s) c = (char16_t)TB().lower[c]; }
+
+inline uint64_t hash64(const char16_t* s, size_t n) {
+    uint64_t h = 0xcbf29ce484222325ULL ^ (uint64_t)n;
+    for (size_t i = 0; i < n; i++) { h ^= s[i]; h *= 0x100000001b3ULL; }
+    h ^= h >> 29; h *= 0xbf58476d1ce4e5b9ULL; h ^= h >> 32; return h | 1ULL;
+}
+
+// string interner: open addressing over a char arena; ids in first-insertion order
+struct Interner {
+    std::vector<char16_t> arena; std::vector<uint32_t> off{0}; std::vector<uint64_t> hk; std::vector<int32_t> hv; size_t mask = 0;
+    Interner() { rehash(1024); }
+    int size() const { return (int)off.size() - 1; }
+    sv get(int id) const { return sv(arena.data() + off[id], off[id + 1] - off[id]); }
+    void rehash(size_t cap) { std::vector<uint64_t> k(cap, 0); std::vector<int32_t> v(cap, -1); for (size_t i = 0; i < hk.size(); i++) if (hk[i]) { size_t s = (hk[i] >> 7) & (cap - 1); while (k[s]) s = (s + 1) & (cap - 1); k[s] = hk[i]; v[s] = hv[i]; } hk.swap(k); hv.swap(v); mask = cap - 1; }
+    int find(sv s) const { uint64_t h = hash64(s.data(), s.size()); size_t slot = (h >> 7) & mask; for (;;) { if (!hk[slot]) return -1; if (hk[slot] == h && get(hv[slot]) == s) return hv[slot]; slot = (slot + 1) & mask; } }
+    int intern(sv s, bool* is_new = nullptr) {
+        uint64_t h = hash64(s.data(), s.size()); size_t slot = (h >> 7) & mask;
+        for (;;) { if (!hk[slot]) break; if (hk[slot] == h && get(hv[slot]) == s) { if (is_new) *is_new = false; return hv[slot]; } slot = (slot + 1) & mask; }
+        int id = size(); arena.insert(arena.end(), s.begin(), s.end()); off.push_back((uint32_t)arena.size());
+        hk[slot] = h; hv[slot] = id; if (is_new) *is_new = true;
+        if ((size_t)size() * 2 > mask) rehash((mask + 1) * 2);
+        return id;
+    }
+};
+
+// key -> ascending doc list with optional byte weight, as flat records (thread-local), merged into CSR later
+struct KeyedRecords {
+    Interner keys; std::vector<int32_t> rec_key, rec_doc; std::vector<uint8_t> rec_w; std::vector<int32_t> last_rec; std::vector<uint8_t> extra;   // extra: saturated repeats (df not decremented)
+    bool weighted;
+    explicit KeyedRecords(bool w) : weighted(w) {}
+    int key(sv s) { bool nw; int k = keys.intern(s, &nw); if (nw) { last_rec.push_back(-1); rec_rep_last.push_back(0); } return k; }
+    void add_doc(int k, int doc) { int lr = last_rec[k]; if (lr >= 0 && rec_doc[lr] == doc) return; last_rec[k] = (int)rec_doc.size(); rec_key.push_back(k); rec_doc.push_back(doc); }
+    int sat_count = 0; std::vector<int32_t> sat_keys;
+    void add_weighted(int k, int doc, float fw) {   // Term.FirstCycleAdd (Core/Term.cs:71-121) without the stop rule (applied globally)
+        int lr = last_rec[k];
+        if (lr >= 0 && rec_doc[lr] == doc) {
+            float nw = (float)rec_w[lr] + fw;
+            if (nw <= 255.f) rec_w[lr] = (uint8_t)std::nearbyint((double)nw); else sat_keys.push_back(k);
+            rec_rep_last[k] = 1;
+            return;
+        }
+        last_rec[k] = (int)rec_doc.size(); rec_key.push_back(k); rec_doc.push_back(doc);
+        rec_w.push_back((uint8_t)std::min(std::nearbyint((double)fw), 255.0));
+        rec_rep_last[k] = 0;
+    }
+    std::vector<uint8_t> rec_rep_last;   // did the key's latest posting see a repeat occurrence (stop-term edge rule)
+};
+
+struct Csr { std::vector<char16_t> chars; std::vector<uint32_t> off; std::vector<int64_t> row; std::vector<int32_t> docs; std::vector<uint8_t> w; std::vector<int32_t> extra; std::vector<uint8_t> rep_last; int n = 0; };
+
+// merge thread-local KeyedRecords (threads own ascending doc ranges) -> global keys in first-occurrence order + CSR
+void merge_records(std::vector<std::unique_ptr<KeyedRecords>>& parts, Csr& out, bool weighted) {
+    Interner g; std::vector<std::vector<int32_t>> l2g(parts.size());
+    for (size_t t = 0; t < parts.size(); t++) { auto& p = *parts[t]; l2g[t].resize(p.keys.size()); for (int k = 0; k < p.keys.size(); k++) l2g[t][k] = g.intern(p.keys.get(k)); }
+    int G = g.size(); out.n = G; out.chars.assign(g.arena.begin(), g.arena.end()); out.off = g.off; if (out.chars.empty()) out.chars.push_back(0);
+    out.row.assign((size_t)G + 1, 0);
+    for (size_t t = 0; t < parts.size(); t++) for (int32_t k : parts[t]->rec_key) out.row[l2g[t][k] + 1]++;
+    for (int i = 0; i < G; i++) out.row[i + 1] += out.row[i];
+    out.docs.resize((size_t)out.row[G] ? out.row[G] : 1); if (weighted) out.w.resize(out.docs.size());
+    std::vector<int64_t> pos(out.row.begin(), out.row.end() - 1);
+    for (size_t t = 0; t < parts.size(); t++) { auto& p = *parts[t]; for (size_t r = 0; r < p.rec_key.size(); r++) { int64_t o = pos[l2g[t][p.rec_key[r]]]++; out.docs[o] = p.rec_doc[r]; if (weighted) out.w[o] = p.rec_w[r]; } }
+    if (weighted) {
+        out.extra.assign(G, 0); out.rep_last.assign(G, 0);
+        for (size_t t = 0; t < parts.size(); t++) { auto& p = *parts[t]; for (int32_t k : p.sat_keys) out.extra[l2g[t][k]]++;
+            for (int k = 0; k < p.keys.size(); k++) if (p.last_rec[k] >= 0) out.rep_last[l2g[t][k]] = p.rec_rep_last[k]; }   // later threads overwrite: state of the globally last posting
+    }
+}
+
+struct FieldSpec { str name; int weight; int flags; };
+
+str value_to_string(int kind, const void* col, const long long* offs, int d) {
+    char buf[64];
+    if (kind == 1) { const char16_t* b = (const char16_t*)col; return str(b + offs[d], (size_t)(offs[d + 1] - offs[d])); }
+    if (kind == 2) { auto r = std::to_chars(buf, buf + 64, ((const long long*)col)[d]); return str(buf, r.ptr); }
+    if (kind == 3) { auto r = std::to_chars(buf, buf + 64, ((const double*)col)[d]); return str(buf, r.ptr); }
+    return str();
+}
+
+}  // namespace
+
+struct ifx_builder {
+    std::vector<FieldSpec> schema; float field_weights[3] = {1.5f, 1.25f, 1.0f}; int stop_term_limit = 1250000;
+    // documents (columnar, appended per add_docs call)
+    std::vector<int64_t> keys; std::vector<std::vector<str>> values;   // values[f][d] = ToString(), kind 0 -> null flag
+    std::vector<std::vector<uint8_t>> is_null;
+    // image storage
+    ifx_index_image img{}; bool finished = false;
+    std::vector<uint8_t> deleted; std::vector<float> doc_len; std::vector<char16_t> text; std::vector<int64_t> text_off;
+    std::vector<char16_t> ft_chars; std::vector<uint32_t> ft_off; std::vector<uint16_t> tok_count;
+    Csr terms, prefix, wm_exact, wm_ld1; std::vector<int32_t> df;
+    std::vector<char16_t> word_chars; std::vector<uint32_t> word_off; std::vector<float> word_idf;
+    std::vector<char16_t> affix_chars; std::vector<uint32_t> affix_off; std::vector<int32_t> affix_last;
+    std::vector<ifx_column> cols; std::vector<std::vector<int32_t>> col_ids; std::vector<std::vector<char16_t>> col_chars; std::vector<std::vector<uint32_t>> col_off; std::vector<str> col_names;
+};
+
+static float compute_idf_host(int total, int df) {   // Bm25Scorer.ComputeIdf
+    if (df <= 0 || total <= 0) return 0.f;
+    float d = (float)df, N = (float)total; float ratio = (N - d + 0.5f) / (d + 0.5f);
+    return ratio <= 0.f ? 0.f : std::log(ratio + 1.f);
+}
+
+extern "C" {
+
+ifx_builder* ifx_builder_create(int nfields, const uint16_t* names, const int32_t* name_off, const int32_t* weight, const int32_t* flags) {
+    ifx_builder* b = new ifx_builder();
+    for (int i = 0; i < nfields; i++) b->schema.push_back({str((const char16_t*)names + name_off[i], name_off[i + 1] - name_off[i]), weight[i], flags[i]});
+    b->values.resize(nfields); b->is_null.resize(nfields);
+    return b;
+}
+void ifx_builder_destroy(ifx_builder* b) { delete b; }
+
+int ifx_builder_add_docs(ifx_builder* b, int n, const int64_t* keys, const int32_t* kinds, const void* const* cols, const long long* const* offs) {
+    if (b->finished) return IFX_ERR_INVALID;
+    int F = (int)b->schema.size();
+    b->keys.insert(b->keys.end(), keys, keys + n);
+    for (int f = 0; f < F; f++) { auto& v = b->values[f]; auto& nl = b->is_null[f]; v.reserve(v.size() + n);
+        for (int d = 0; d < n; d++) { if (kinds[f] == 0) { v.emplace_back(); nl.push_back(1); } else { v.push_back(value_to_string(kinds[f], cols[f], offs ? offs[f] : nullptr, d)); nl.push_back(0); } } }
+    return IFX_OK;
+}
+
+int ifx_builder_finish(ifx_builder* b, int threads) {
+    if (b->finished) return IFX_OK;
+    const int N = (int)b->keys.size(); const int F = (int)b->schema.size();
+    if (threads < 1) threads = 1; if (threads > N) threads = std::max(1, N);
+    // indexable fields ordered by Weight (stable): GetSearchAbleFieldList
+    std::vector<int> order; for (int w = 0; w < 3; w++) for (int f = 0; f < F; f++) if ((b->schema[f].flags & IFX_FIELD_INDEXABLE) && b->schema[f].weight == w) order.push_back(f);
+    struct Part {
+        std::unique_ptr<KeyedRecords> terms, prefix, exact, ld1; Interner words; std::vector<int32_t> word_df; Interner affix; std::vector<int32_t> affix_last;
+        std::vector<char16_t> text; std::vector<int64_t> text_len; std::vector<char16_t> ft; std::vector<uint32_t> ft_len; std::vector<uint16_t> tokc;
+    };
+    std::vector<Part> parts(threads);
+    auto work = [&](int t) {
+        Part& P = parts[t]; P.terms.reset(new KeyedRecords(true)); P.prefix.reset(new KeyedRecords(false)); P.exact.reset(new KeyedRecords(false)); P.ld1.reset(new KeyedRecords(false));
+        int d0 = (int)((int64_t)N * t / threads), d1 = (int)((int64_t)N * (t + 1) / threads);
+        str raw, nrm, idx, padded, wm, tmp; std::vector<std::pair<int, int>> bounds; std::vector<int> seen_words;
+        for (int d = d0; d < d1; d++) {
+            raw.clear(); bounds.clear();
+            for (size_t k = 0; k < order.size(); k++) { bounds.emplace_back((int)(uint16_t)raw.size(), b->schema[order[k]].weight); raw += b->values[order[k]][d]; if (k + 1 < order.size()) raw.push_back(u'§'); }
+            normalize_into(raw, nrm);                       // normalize(IndexedText): coverage doc text
+            P.text.insert(P.text.end(), nrm.begin(), nrm.end()); P.text_len.push_back((int64_t)nrm.size());
+            idx = nrm; lower_inplace(idx);                  // VectorModel.IndexDocument: Normalize then ToLowerInvariant
+            // 3-grams of PAD PAD + text, then words (len >= 3)
+            padded.assign(2, (char16_t)0xFFFF); padded += idx;
+            auto fw_at = [&](int pos) { if (bounds.empty()) return 1.0f; int wi = 0; for (auto& bd : bounds) { if (bd.first <= pos) wi = bd.second; else break; } return wi < 3 ? b->field_weights[wi] : 1.0f; };
+            if (padded.size() >= 3) for (size_t i = 0; i + 3 <= padded.size(); i++) { sv g(padded.data() + i, 3); if (g[0] == 0xFFFF && g[1] == 0xFFFF && g[2] == 0xFFFF) continue; P.terms->add_weighted(P.terms->key(g), d, fw_at((int)i)); }
+            for (size_t i = 0; i < idx.size();) { while (i < idx.size() && is_delim(idx[i])) i++; if (i >= idx.size()) break; size_t s = i; while (i < idx.size() && !is_delim(idx[i])) i++;
+                if (i - s >= 3) P.terms->add_weighted(P.terms->key(sv(idx.data() + s, i - s)), d, fw_at(2 + (int)s)); }
+            // prefix docsets (PositionalPrefixIndex over the index text)
+            for (size_t i = 0; i < idx.size();) { while (i < idx.size() && is_delim(idx[i])) i++; if (i >= idx.size()) break; size_t s = i; while (i < idx.size() && !is_delim(idx[i])) i++;
+                size_t ml = std::min<size_t>(3, i - s); for (size_t l = 1; l <= ml; l++) P.prefix->add_doc(P.prefix->key(sv(idx.data() + s, l)), d); }
+            // WordMatcher.Load / word-idf / metadata work on normalize(lower(IndexedText))
+            tmp = raw; lower_inplace(tmp); normalize_into(tmp, wm);
+            int ntok = 0; bool first = true; seen_words.clear();
+            for (size_t i = 0; i < wm.size();) { while (i < wm.size() && is_delim(wm[i])) i++; if (i >= wm.size()) break; size_t s = i; while (i < wm.size() && !is_delim(wm[i])) i++;
+                sv w(wm.data() + s, i - s); int len = (int)w.size(); ntok++;
+                if (first) { P.ft.insert(P.ft.end(), w.begin(), w.end()); P.ft_len.push_back((uint32_t)len); first = false; }
+                if (len >= 2 && len <= 8) P.exact->add_doc(P.exact->key(w), d);
+                if (len >= 3 && len <= 8) for (int k = 0; k < len; k++) { tmp.assign(w); tmp.erase(k, 1); P.ld1->add_doc(P.ld1->key(tmp), d); }
+                if (len >= 3) { bool nw; int a = P.affix.intern(w, &nw); if (nw) P.affix_last.push_back(d); else P.affix_last[a] = d; }
+                bool nw2; int wid = P.words.intern(w, &nw2); if (nw2) P.word_df.push_back(0);
+                if (std::find(seen_words.begin(), seen_words.end(), wid) == seen_words.end()) { seen_words.push_back(wid); P.word_df[wid]++; }
+            }
+            if (first) P.ft_len.push_back(0);
+            P.tokc.push_back((uint16_t)std::min(ntok, 65535));
+        }
+    };
+    { std::vector<std::thread> ts; for (int t = 0; t < threads; t++) ts.emplace_back(work, t); for (auto& t : ts) t.join(); }
+    // ---- merge
+    b->deleted.assign(N, 0); b->text_off.assign(1, 0); b->ft_off.assign(1, 0);
+    for (auto& P : parts) { b->text.insert(b->text.end(), P.text.begin(), P.text.end()); for (auto l : P.text_len) b->text_off.push_back(b->text_off.back() + l);
+        b->ft_chars.insert(b->ft_chars.end(), P.ft.begin(), P.ft.end()); for (auto l : P.ft_len) b->ft_off.push_back(b->ft_off.back() + l); b->tok_count.insert(b->tok_count.end(), P.tokc.begin(), P.tokc.end()); }
+    if (b->text.empty()) b->text.push_back(0); if (b->ft_chars.empty()) b->ft_chars.push_back(0);
+    { std::vector<std::unique_ptr<KeyedRecords>> v; for (auto& P : parts) v.push_back(std::move(P.terms)); merge_records(v, b->terms, true); }
+    { std::vector<std::unique_ptr<KeyedRecords>> v; for (auto& P : parts) v.push_back(std::move(P.prefix)); merge_records(v, b->prefix, false); }
+    { std::vector<std::unique_ptr<KeyedRecords>> v; for (auto& P : parts) v.push_back(std::move(P.exact)); merge_records(v, b->wm_exact, false); }
+    { std::vector<std::unique_ptr<KeyedRecords>> v; for (auto& P : parts) v.push_back(std::move(P.ld1)); merge_records(v, b->wm_ld1, false); }
+    // stop terms + df (Term.IncrementTermUsageCounter / FirstCycleAdd): df = postings + saturated repeats; a term dies when df would exceed the limit
+    const int T = b->terms.n; b->df.assign(T, 0);
+    std::vector<int64_t> new_row((size_t)T + 1, 0); int64_t wpos = 0;
+    for (int t = 0; t < T; t++) {
+        int64_t r0 = b->terms.row[t], r1 = b->terms.row[t + 1]; int64_t cnt = r1 - r0; int64_t dfv = cnt + b->terms.extra[t];
+        bool stop = dfv > b->stop_term_limit || (cnt == b->stop_term_limit && b->terms.rep_last[t]);
+        new_row[t] = wpos;
+        if (stop) { b->df[t] = -1; continue; }
+        b->df[t] = (int32_t)dfv;
+        if (wpos != r0) { std::memmove(b->terms.docs.data() + wpos, b->terms.docs.data() + r0, (size_t)cnt * 4); std::memmove(b->terms.w.data() + wpos, b->terms.w.data() + r0, (size_t)cnt); }
+        wpos += cnt;
+    }
+    new_row[T] = wpos; b->terms.row.swap(new_row);
+    // doc lengths (integer sums) and avgdl (sequential float sum, VectorModel.cs:212-216)
+    std::vector<uint32_t> dl(N, 0);
+    for (int64_t i = 0; i < wpos; i++) dl[b->terms.docs[i]] += b->terms.w[i];
+    b->doc_len.resize(N); float total = 0.f; for (int d = 0; d < N; d++) { b->doc_len[d] = (float)dl[d]; total += b->doc_len[d]; }
+    float avgdl = N > 0 ? total / (float)N : 0.f;
+    // word idf
+    { Interner g; std::vector<int32_t> gdf; for (auto& P : parts) for (int k = 0; k < P.words.size(); k++) { bool nw; int id = g.intern(P.words.get(k), &nw); if (nw) gdf.push_back(0); gdf[id] += P.word_df[k]; }
+      b->word_chars.assign(g.arena.begin(), g.arena.end()); if (b->word_chars.empty()) b->word_chars.push_back(0); b->word_off = g.off; b->word_idf.resize(gdf.size());
+      for (size_t i = 0; i < gdf.size(); i++) b->word_idf[i] = (gdf[i] > 0 && gdf[i] <= N) ? compute_idf_host(N, gdf[i]) : 0.f; }
+    // affix words: last doc wins (WordMatcher.IndexWordInFst quirk Q4)
+    { Interner g; for (auto& P : parts) for (int k = 0; k < P.affix.size(); k++) { bool nw; int id = g.intern(P.affix.get(k), &nw); if (nw) b->affix_last.push_back(P.affix_last[k]); else b->affix_last[id] = P.affix_last[k]; }
+      b->affix_chars.assign(g.arena.begin(), g.arena.end()); if (b->affix_chars.empty()) b->affix_chars.push_back(0); b->affix_off = g.off; if (b->affix_last.empty()) b->affix_last.push_back(0); }
+    // filter / facet columns
+    for (int f = 0; f < F; f++) {
+        if (!(b->schema[f].flags & (IFX_FIELD_FILTERABLE | IFX_FIELD_FACETABLE))) continue;
+        Interner g; std::vector<int32_t> ids(N);
+        for (int d = 0; d < N; d++) ids[d] = b->is_null[f][d] ? -1 : g.intern(b->values[f][d]);
+        b->col_ids.push_back(std::move(ids)); b->col_chars.emplace_back(g.arena.begin(), g.arena.end()); if (b->col_chars.back().empty()) b->col_chars.back().push_back(0); b->col_off.push_back(g.off); b->col_names.push_back(b->schema[f].name);
+    }
+    b->cols.resize(b->col_ids.size());
+    { int ci = 0; for (int f = 0; f < F; f++) { if (!(b->schema[f].flags & (IFX_FIELD_FILTERABLE | IFX_FIELD_FACETABLE))) continue; ifx_column& c = b->cols[ci];
+        c.name = (const uint16_t*)b->col_names[ci].data(); c.name_len = (int)b->col_names[ci].size(); c.flags = ((b->schema[f].flags & IFX_FIELD_FILTERABLE) ? IFX_COL_FILTERABLE : 0) | ((b->schema[f].flags & IFX_FIELD_FACETABLE) ? IFX_COL_FACETABLE : 0);
+        c.value_id = b->col_ids[ci].data(); c.dict = {(const uint16_t*)b->col_chars[ci].data(), b->col_off[ci].data(), (int)b->col_off[ci].size() - 1}; ci++; } }
+    // ---- image
+    ifx_index_image& I = b->img; auto S = [](std::vector<char16_t>& c, std::vector<uint32_t>& o) { return ifx_strings{(const uint16_t*)c.data(), o.data(), (int)o.size() - 1}; };
+    I.n_docs = N; I.n_live = N; I.avgdl = avgdl; I.doc_key = b->keys.data(); I.deleted = b->deleted.data(); I.doc_len = b->doc_len.data();
+    I.text_chars = (const uint16_t*)b->text.data(); I.text_off = b->text_off.data(); I.first_token = S(b->ft_chars, b->ft_off); I.token_count = b->tok_count.data();
+    I.terms = S(b->terms.chars, b->terms.off); I.df = b->df.data(); I.row_ptr = b->terms.row.data(); I.post_doc = b->terms.docs.data(); I.post_tf = b->terms.w.data();
+    I.words = S(b->word_chars, b->word_off); I.word_idf = b->word_idf.data();
+    I.prefix = {S(b->prefix.chars, b->prefix.off), b->prefix.row.data(), b->prefix.docs.data()};
+    I.wm_exact = {S(b->wm_exact.chars, b->wm_exact.off), b->wm_exact.row.data(), b->wm_exact.docs.data()};
+    I.wm_ld1 = {S(b->wm_ld1.chars, b->wm_ld1.off), b->wm_ld1.row.data(), b->wm_ld1.docs.data()};
+    I.affix_words = S(b->affix_chars, b->affix_off); I.affix_last_doc = b->affix_last.data();
+    I.n_columns = (int)b->cols.size(); I.columns = b->cols.data();
+    // free the raw documents
+    b->values.clear(); b->values.shrink_to_fit(); b->is_null.clear();
+    b->finished = true; return IFX_OK;
+}
+
+const ifx_index_image* ifx_builder_image(ifx_builder* b) { return b->finished ? &b->img : nullptr; }
+
+}  // extern "C"
+
+// SearchEngine.Search step 1 (src/Infidex/SearchEngine.cs:264-274): Trim, TextNormalizer.Normalize, ToLowerInvariant.
+extern "C" int ifx_host_prepare_query(const uint16_t* in, int n, uint16_t* out, int cap) {
+    static std::vector<uint8_t> ws = [] { std::vector<uint8_t> w(65536, 0); for (int i = 0; i < IFX_SPACE_LIST_N; i++) w[IFX_SPACE_LIST[i]] = 1; return w; }();
+    int b = 0, e = n; while (b < e && ws[in[b]]) b++; while (e > b && ws[in[e - 1]]) e--;
+    str nrm; normalize_into(sv((const char16_t*)in + b, (size_t)(e - b)), nrm); lower_inplace(nrm);
+    int m = (int)std::min<size_t>(nrm.size(), (size_t)cap); std::memcpy(out, nrm.data(), (size_t)m * 2);
+    return (int)nrm.size();
+}

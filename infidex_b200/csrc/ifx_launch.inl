@@ -1,0 +1,111 @@
+// infidex_b200 -- kernels (thin wrappers over the Ctx-based routines) and the batch entry points.
+
+#ifndef IFX_EMU
+__global__ void k_prepare(DevIndex ix, const uint16_t* text, const int64_t* off, const int32_t* par, int nq, QueryPlan* plans,
+                          FuzzyItem* items, int items_cap, BatchCounters* bc) {
+    int q = blockIdx.x * blockDim.x + threadIdx.x; if (q >= nq) return;
+    prepare_query(ix, text + off[q], (int)(off[q + 1] - off[q]), par[q * 5 + 1], par[q * 5 + 0], par[q * 5 + 2], par[q * 5 + 3], par[q * 5 + 4], plans[q], items, items_cap, bc, q);
+}
+__global__ void __launch_bounds__(256) k_expand(DevIndex ix, QueryPlan* plans, const FuzzyItem* items, BatchCounters* bc, S1Workspace* wss,
+                                                int32_t* pool, unsigned long long pool_cap, const uint8_t* sorted_len, int* work) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    S1Shared& sh = *reinterpret_cast<S1Shared*>(smem_raw); Ctx c; S1Workspace ws = wss[blockIdx.x];
+    for (int i = threadIdx.x; i < MAX_CONTAINERS; i += blockDim.x) sh.dirty[i] = 0;
+    __syncthreads();
+    const int n_items = min(bc->n_fuzzy_items, (int)(gridDim.x * 0 + 0x7fffffff));
+    for (;;) {
+        if (threadIdx.x == 0) sh.bcast[7] = atomicAdd(work, 1);
+        __syncthreads();
+        int it = sh.bcast[7]; __syncthreads();
+        if (it >= n_items) break;
+        FuzzyItem fi = items[it];
+        expand_fuzzy(c, ix, plans[fi.query], fi.slot, ws, sh, pool, pool_cap, bc, sorted_len, sh.cand_s);
+    }
+}
+__global__ void __launch_bounds__(256) k_stage1(DevIndex ix, const QueryPlan* plans, int nq, const int32_t* pool, S1Workspace* wss, BatchCounters* bc,
+                                                int64_t* s1_key, int32_t* s1_doc, float* s1_score, int32_t* s1_n, int K, int* work) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    S1Shared& sh = *reinterpret_cast<S1Shared*>(smem_raw); Ctx c; S1Workspace ws = wss[blockIdx.x];
+    for (int i = threadIdx.x; i < MAX_CONTAINERS; i += blockDim.x) sh.dirty[i] = 0;
+    __syncthreads();
+    for (;;) {
+        if (threadIdx.x == 0) sh.bcast[7] = atomicAdd(work, 1);
+        __syncthreads();
+        int q = sh.bcast[7]; __syncthreads();
+        if (q >= nq) break;
+        Stage1Out o{s1_key + (size_t)q * K, s1_doc + (size_t)q * K, s1_score + (size_t)q * K, s1_n + q};
+        stage1_query(c, ix, plans[q], pool, ws, sh, o, bc);
+        __syncthreads();
+    }
+}
+#endif
+
+static void run_stage1_phase(ifx_batch* b, ifx_stats* st) {
+    ifx_index* ix = b->idx; const int nq = b->nq; const int K = b->depth_max;
+    BatchCounters zero{}; h2d(b->d_bc, &zero, sizeof(zero));
+    int items_cap = nq * 4 + 64;
+    Timer t;
+#ifdef IFX_EMU
+    std::vector<int64_t> off(nq + 1); d2h(off.data(), b->d_off, (nq + 1) * 8);
+    for (int q = 0; q < nq; q++) prepare_query(ix->v, b->d_text + off[q], (int)(off[q + 1] - off[q]), b->d_par[q * 5 + 1], b->d_par[q * 5 + 0], b->d_par[q * 5 + 2], b->d_par[q * 5 + 3], b->d_par[q * 5 + 4], b->d_plans[q], b->d_items, items_cap, b->d_bc, q);
+    static S1Shared* sh = new S1Shared(); memset(sh->dirty, 0, sizeof(sh->dirty));
+    Ctx c; int nit = std::min(b->d_bc->n_fuzzy_items, items_cap);
+    for (int i = 0; i < nit; i++) expand_fuzzy(c, ix->v, b->d_plans[b->d_items[i].query], b->d_items[i].slot, ix->ws[0], *sh, ix->d_pool, ix->pool_cap, b->d_bc, ix->d_sorted_len, sh->cand_s);
+    for (int q = 0; q < nq; q++) { Stage1Out o{b->d_s1_key + (size_t)q * K, b->d_s1_doc + (size_t)q * K, b->d_s1_score + (size_t)q * K, b->d_s1_n + q}; stage1_query(c, ix->v, b->d_plans[q], ix->d_pool, ix->ws[0], *sh, o, b->d_bc); }
+    (void)t;
+#else
+    size_t smem = sizeof(S1Shared);
+    static bool attr_set = false;
+    if (!attr_set) { CUDA_TRY(cudaFuncSetAttribute(k_expand, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); CUDA_TRY(cudaFuncSetAttribute(k_stage1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_set = true; }
+    t.start();
+    k_prepare<<<(nq + 127) / 128, 128>>>(ix->v, b->d_text, b->d_off, b->d_par, nq, b->d_plans, b->d_items, items_cap, b->d_bc);
+    float ms_prep = t.stop();
+    t.start();
+    CUDA_TRY(cudaMemsetAsync(b->d_work, 0, 2 * sizeof(int)));
+    k_expand<<<ix->n_ctas, kS1Threads, smem>>>(ix->v, b->d_plans, b->d_items, b->d_bc, ix->d_ws, ix->d_pool, ix->pool_cap, ix->d_sorted_len, b->d_work);
+    float ms_exp = t.stop();
+    t.start();
+    k_stage1<<<std::min(ix->n_ctas, nq), kS1Threads, smem>>>(ix->v, b->d_plans, nq, ix->d_pool, ix->d_ws, b->d_bc, b->d_s1_key, b->d_s1_doc, b->d_s1_score, b->d_s1_n, K, b->d_work + 1);
+    float ms_s1 = t.stop();
+    CUDA_TRY(cudaGetLastError());
+    if (st) { st->ms_prepare += ms_prep; st->ms_expand += ms_exp; st->ms_stage1 += ms_s1; st->kernel_launches += 3; }
+#endif
+    if (st) { BatchCounters bc; d2h(&bc, b->d_bc, sizeof(bc)); st->algo_bytes_stage1 += (int64_t)bc.algo_bytes; }
+}
+
+extern "C" int ifx_batch_upload(ifx_index* idx, const ifx_query* q, int nq, ifx_batch** out) {
+    if (!idx || !q || nq <= 0 || !out) return fail(IFX_ERR_INVALID, "bad batch arguments");
+    ifx_batch* b = new ifx_batch(); b->idx = idx; b->nq = nq;
+    try {
+        std::vector<int64_t> off(nq + 1, 0); std::vector<int32_t> par((size_t)nq * 5);
+        for (int i = 0; i < nq; i++) { off[i + 1] = off[i] + std::max(q[i].len, 0); par[i * 5 + 0] = q[i].max_results; par[i * 5 + 1] = q[i].coverage_depth; par[i * 5 + 2] = q[i].enable_coverage; par[i * 5 + 3] = q[i].filter_id; par[i * 5 + 4] = q[i].enable_facets;
+            b->depth_max = std::max(b->depth_max, q[i].coverage_depth); b->cap_max = std::max(b->cap_max, q[i].max_results); }
+        if (b->depth_max < 1 || b->depth_max > MAX_K) { delete b; return fail(IFX_ERR_INVALID, "coverage_depth must be in [1,1024]"); }
+        std::vector<uint16_t> text((size_t)off[nq] + 1);
+        for (int i = 0; i < nq; i++) if (q[i].len > 0) memcpy(text.data() + off[i], q[i].text, (size_t)q[i].len * 2);
+        b->d_text = b->alloc<uint16_t>(text.size()); h2d(b->d_text, text.data(), text.size() * 2);
+        b->d_off = b->alloc<int64_t>(nq + 1); h2d(b->d_off, off.data(), (nq + 1) * 8);
+        b->d_par = b->alloc<int32_t>(par.size()); h2d(b->d_par, par.data(), par.size() * 4);
+        b->d_plans = b->alloc<QueryPlan>(nq); b->d_items = b->alloc<FuzzyItem>((size_t)nq * 4 + 64); b->d_bc = b->alloc<BatchCounters>(1); b->d_work = b->alloc<int>(8);
+        size_t K = b->depth_max;
+        b->d_s1_key = b->alloc<int64_t>(nq * K); b->d_s1_doc = b->alloc<int32_t>(nq * K); b->d_s1_score = b->alloc<float>(nq * K); b->d_s1_n = b->alloc<int32_t>(nq);
+    } catch (const std::string& e) { delete b; return fail(IFX_ERR_CUDA, e); }
+    *out = b; return IFX_OK;
+}
+extern "C" void ifx_batch_free(ifx_batch* b) { delete b; }
+
+extern "C" int ifx_stage1_batch(ifx_index* idx, const ifx_query* q, int nq, int depth, int64_t* doc_key, float* score, int32_t* n, int32_t* status, ifx_stats* st) {
+    if (!dev_ok()) return fail(IFX_ERR_NO_DEVICE, "no CUDA device available (infidex_b200 has no CPU fallback)");
+    std::vector<ifx_query> qq(q, q + nq); for (auto& x : qq) x.coverage_depth = depth;
+    ifx_batch* b = nullptr; int rc = ifx_batch_upload(idx, qq.data(), nq, &b); if (rc) return rc;
+    if (st) memset(st, 0, sizeof(*st));
+    try {
+        std::lock_guard<std::mutex> lk(idx->mu);
+        run_stage1_phase(b, st);
+        d2h(doc_key, b->d_s1_key, (size_t)nq * depth * 8); d2h(score, b->d_s1_score, (size_t)nq * depth * 4); d2h(n, b->d_s1_n, (size_t)nq * 4);
+        if (status) { std::vector<QueryPlan> pl(nq); d2h(pl.data(), b->d_plans, sizeof(QueryPlan) * (size_t)nq); for (int i = 0; i < nq; i++) { status[i] = pl[i].status; if (n[i] < 0) { status[i] |= IFX_Q_OVERFLOW; n[i] = 0; } } }
+    } catch (const std::string& e) { delete b; return fail(IFX_ERR_CUDA, e); }
+    delete b; return IFX_OK;
+}
+
+#include "ifx_search.inl"

@@ -1,0 +1,567 @@
+// infidex_b200 -- Stage 1 on device: query term resolution, LD1 expansion, tiered candidate selection,
+// BM25+ with MaxScore over 4096-candidate chunks, exact emulation of the reference's pruning heap, top-K.
+//
+// What each routine replaces in the reference (src/Infidex/...):
+//   prepare_query   Scoring/QueryAnalyzer.cs:10-54, Tokenization/Tokenizer.cs:144-200, Indexing/VectorModel.cs:376-563
+//   expand_fuzzy    Indexing/Fst/FstIndex.cs:202-352 (MatchWithinEditDistance1), Indexing/VectorModel.cs:643-743
+//   stage1_query    Scoring/TieredCandidateSelector.cs:53-532, Indexing/Bm25Scorer.cs:56-445,654-670
+// Written against ifx::Ctx (one CTA on the GPU).
+#pragma once
+#include "ifx_base.h"
+
+namespace ifx {
+
+IFX_FN bool is_delim(const DevIndex& ix, uint16_t c) { return ix.cflags[c] & 4; }
+IFX_FN bool is_space(const DevIndex& ix, uint16_t c) { return ix.cflags[c] & 2; }
+
+IFX_FN int cmp_ordinal(const uint16_t* a, int na, const uint16_t* b, int nb) {   // string.CompareOrdinal
+    int n = na < nb ? na : nb;
+    for (int i = 0; i < n; i++) if (a[i] != b[i]) return a[i] < b[i] ? -1 : 1;
+    return na == nb ? 0 : (na < nb ? -1 : 1);
+}
+
+IFX_FN float max_term_score(float idf, float avgdl) {   // VectorModel.cs:523-531
+    const float maxTf = 255.f, k1 = 1.2f, b = 0.75f, delta = 1.0f;
+    float minDlNorm = 1.f - b + b * (1.f / avgdl);
+    float core = (maxTf * (k1 + 1.f)) / (maxTf + k1 * minDlNorm);
+    return idf * (core + delta);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// prepare_query: one thread per query.
+IFX_FN void prepare_query(const DevIndex& ix, const uint16_t* text, int len, int depth, int max_results, int enable_cov,
+                          int filter_id, int enable_facets, QueryPlan& p, FuzzyItem* items, int items_cap, BatchCounters* bc, int qi) {
+    p.status = 0; p.n_terms = 0; p.n_fuzzy = 0; p.qlen = 0; p.tlen = 0; p.depth = depth; p.max_results = max_results;
+    p.enable_coverage = enable_cov; p.filter_id = filter_id; p.enable_facets = enable_facets; p.short_skip_coverage = 0; p.is_short3 = 0;
+    if (len > MAX_QLEN || depth > MAX_K || depth < 1) { p.status = 4; return; }
+    bool blank = true;
+    for (int i = 0; i < len; i++) { p.qtext[i] = text[i]; if (!is_space(ix, text[i])) blank = false; }
+    p.qlen = len;
+    if (blank) { p.status = 8; return; }
+    // QueryAnalyzer.Analyze
+    int n_words = 0, n_long = 0, n_short = 0, tl = 0;
+    for (int i = 0; i < len;) {
+        while (i < len && is_delim(ix, text[i])) i++;
+        if (i >= len) break;
+        int b = i; while (i < len && !is_delim(ix, text[i])) i++;
+        n_words++;
+        if (i - b >= 3) { if (n_long > 0) p.ttext[tl++] = u' '; for (int k = b; k < i; k++) p.ttext[tl++] = text[k]; n_long++; } else n_short++;
+    }
+    bool can_ngrams = n_words == 0 ? len >= 3 : n_long > 0;
+    if (!can_ngrams) { p.status = 1; return; }
+    bool mixed = n_short > 0 && n_long > 0;
+    if (!mixed) { tl = len; for (int i = 0; i < len; i++) p.ttext[i] = text[i]; }
+    p.tlen = tl;
+    // SearchPipeline.cs:110-142 short (<= 3 chars, no delimiter) query rules
+    bool short3 = len <= 3; for (int i = 0; i < len; i++) if (is_delim(ix, text[i])) short3 = false;
+    p.is_short3 = short3;
+    if (short3) { int k = dict_lookup(ix.prefix.keys, text, len); if (k >= 0 && ix.prefix.row_ptr[k + 1] - ix.prefix.row_ptr[k] > 500) p.short_skip_coverage = 1; }
+    // tokens: words (len >= 3) then padded 3-grams (Tokenizer.EnumerateShinglesForSearch), first 128 kept
+    uint16_t padded[MAX_QLEN + 2]; padded[0] = PAD; padded[1] = PAD; for (int i = 0; i < tl; i++) padded[2 + i] = p.ttext[i];
+    struct Raw { int32_t id; uint16_t off, len; };
+    Raw raw[MAX_RAW_TOKENS]; int nr = 0;
+    for (int i = 0; i < tl && nr < MAX_RAW_TOKENS;) {
+        while (i < tl && is_delim(ix, p.ttext[i])) i++;
+        if (i >= tl) break;
+        int b = i; while (i < tl && !is_delim(ix, p.ttext[i])) i++;
+        if (i - b >= 3) { raw[nr].off = (uint16_t)(b + 2); raw[nr].len = (uint16_t)(i - b); nr++; }
+    }
+    for (int k = 0; k + 3 <= tl + 2 && nr < MAX_RAW_TOKENS; k++) {
+        if (padded[k] == PAD && padded[k + 1] == PAD && padded[k + 2] == PAD) continue;
+        raw[nr].off = (uint16_t)k; raw[nr].len = 3; nr++;
+    }
+    for (int i = 0; i < nr; i++) raw[i].id = dict_lookup(ix.terms, padded + raw[i].off, raw[i].len);
+    // RawToken.CompareTo: (TermId, ordinal text); equal elements are interchangeable so any sort gives the same sequence
+    for (int i = 1; i < nr; i++) {
+        Raw t = raw[i]; int j = i - 1;
+        while (j >= 0) {
+            int c = raw[j].id != t.id ? (raw[j].id < t.id ? -1 : 1) : (t.id >= 0 ? 0 : cmp_ordinal(padded + raw[j].off, raw[j].len, padded + t.off, t.len));
+            if (c <= 0) break;
+            raw[j + 1] = raw[j]; j--;
+        }
+        raw[j + 1] = t;
+    }
+    float avgdl = ix.avgdl > 0.f ? ix.avgdl : 1.f;
+    int nt = 0;
+    for (int i = 0; i < nr; i++) {
+        if (i > 0 && raw[i].id == raw[i - 1].id && (raw[i].id >= 0 || cmp_ordinal(padded + raw[i].off, raw[i].len, padded + raw[i - 1].off, raw[i - 1].len) == 0)) continue;
+        if (raw[i].id >= 0) {
+            int df = ix.df[raw[i].id];
+            if (df <= 0 || df > ix.stop_term_limit) continue;
+            QTerm& t = p.terms[nt++];
+            t.term_id = raw[i].id; t.df = df; t.list_off = ix.row_ptr[raw[i].id]; t.list_len = (int32_t)(ix.row_ptr[raw[i].id + 1] - ix.row_ptr[raw[i].id]);
+            t.idf = compute_idf(ix.n_live, df); t.max_score = max_term_score(t.idf, avgdl);
+        } else if (raw[i].len >= 4) {
+            if (p.n_fuzzy >= MAX_FUZZY || raw[i].len > 64) { p.status |= 4; continue; }
+            int slot = atomic_add(&bc->n_fuzzy_items, 1);
+            if (slot >= items_cap) { p.status |= 4; continue; }
+            QTerm& t = p.terms[nt]; t.term_id = -1; t.df = 0; t.list_off = 0; t.list_len = 0; t.idf = 0.f; t.max_score = 0.f;
+            FuzzyReq& f = p.fuzzy[p.n_fuzzy++]; f.off = (uint16_t)(raw[i].off - 2); f.len = raw[i].len; f.term_slot = nt;
+            items[slot].query = qi; items[slot].slot = p.n_fuzzy - 1;
+            nt++;
+        }
+    }
+    p.n_terms = nt;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// block primitives
+struct ScanTmp { int w[33]; };
+
+IFX_FN int block_excl_scan(const Ctx& c, int v, ScanTmp& tmp, int& total) {
+#ifdef IFX_EMU
+    (void)c; (void)tmp; total = v; return 0;
+#else
+    int incl = v;
+    for (int d = 1; d < 32; d <<= 1) { int o = __shfl_up_sync(0xffffffffu, incl, d); if (c.lane() >= d) incl += o; }
+    if (c.lane() == 31) tmp.w[c.warp()] = incl;
+    c.sync();
+    int base = 0, tot = 0, nw = c.nwarps();
+    for (int i = 0; i < nw; i++) { int x = tmp.w[i]; if (i < c.warp()) base += x; tot += x; }
+    total = tot;
+    c.sync();
+    return base + incl - v;
+#endif
+}
+IFX_FN int block_sum(const Ctx& c, int v, ScanTmp& tmp) { int t; block_excl_scan(c, v, tmp, t); return t; }
+
+IFX_FN int64_t lower_bound_i32(const int32_t* a, int64_t lo, int64_t hi, int32_t target) {   // first index in [lo,hi) with a[i] >= target
+    while (lo < hi) { int64_t mid = lo + ((hi - lo) >> 1); if (a[mid] < target) lo = mid + 1; else hi = mid; }
+    return lo;
+}
+IFX_FN int64_t gallop_lower_bound(const int32_t* a, int64_t from, int64_t n, int32_t target) {
+    if (from >= n || a[from] >= target) return from;
+    int64_t step = 1, lo = from, hi = from + 1;
+    while (hi < n && a[hi] < target) { lo = hi; step <<= 1; hi = lo + step; }
+    if (hi > n) hi = n;
+    return lower_bound_i32(a, lo + 1, hi, target);
+}
+
+// per-CTA global workspace
+struct S1Workspace {
+    unsigned* bits;        // candidate bitset over the shard's docs (all zero between uses)
+    int32_t* cand;         // sorted candidate ids
+    int32_t* buf_a; int32_t* buf_b;   // AND-tier ping-pong arrays
+    int64_t cand_cap, buf_cap;
+};
+
+struct TermS {             // term as seen by the scorer
+    const int32_t* docs; const uint8_t* tf; int32_t len; int32_t df; float idf, max_score, suffix_after; int64_t cursor, s0, s1;
+};
+
+struct S1Shared {
+    TermS terms[MAX_TERMS];
+    int order[MAX_TERMS];
+    int n_terms;
+    float score[CHUNK];
+    uint8_t tfbuf[2][CHUNK];
+    int32_t cand_s[CHUNK];
+    unsigned ballots[CHUNK / Ctx::WS + 8]; int bprefix[CHUNK / Ctx::WS + 8];
+    int heap_doc[MAX_K]; float heap_score[MAX_K]; int heap_size; float thr;
+    uint8_t dirty[MAX_CONTAINERS];
+    ScanTmp scan;
+    int bcast[8]; long long bcast64[4];
+    unsigned long long streamed_mask[2];   // terms whose list the selector streamed in full (roofline accounting)
+};
+
+// OR a sorted id list into the CTA's bitset; returns the number of newly set docs (block-wide).
+IFX_FN int or_list_into_bits(const Ctx& c, const int32_t* list, int64_t n, S1Workspace& ws, S1Shared& sh) {
+    int fresh = 0;
+    for (int64_t i = c.tid(); i < n; i += c.nthreads()) {
+        int d = list[i]; unsigned bit = 1u << (d & 31);
+        unsigned old = atomic_or(&ws.bits[d >> 5], bit);
+        if (!(old & bit)) fresh++;
+        sh.dirty[d >> 16] = 1;
+    }
+    c.sync();
+    return block_sum(c, fresh, sh.scan);
+}
+
+// Expand the dirty containers of the bitset into ws.cand (ascending) and clear them. Returns the count.
+IFX_FN int64_t compact_bits(const Ctx& c, const DevIndex& ix, S1Workspace& ws, S1Shared& sh, int32_t* out, int64_t out_cap, bool& overflow) {
+    int ncont = (ix.n_docs + 65535) >> 16; int64_t total = 0; int64_t nwords = ((int64_t)ix.n_docs + 31) >> 5;
+    overflow = false;
+    for (int k = 0; k < ncont; k++) {
+        if (!sh.dirty[k]) continue;                    // uniform across the CTA (shared flag, synced by callers)
+        int64_t w0 = (int64_t)k * 2048, w1 = w0 + 2048; if (w1 > nwords) w1 = nwords;
+        int per = (int)((w1 - w0 + c.nthreads() - 1) / c.nthreads());
+        int64_t my0 = w0 + (int64_t)c.tid() * per, my1 = my0 + per; if (my1 > w1) my1 = w1;
+        int cnt = 0; for (int64_t w = my0; w < my1; w++) cnt += popc(ws.bits[w]);
+        int tot; int off = block_excl_scan(c, cnt, sh.scan, tot);
+        if (total + tot > out_cap) { overflow = true; }
+        else { int64_t o = total + off;
+            for (int64_t w = my0; w < my1; w++) { unsigned v = ws.bits[w]; while (v) { int b = ffs32(v) - 1; out[o++] = (int32_t)((w << 5) | b); v &= v - 1; } } }
+        for (int64_t w = my0; w < my1; w++) ws.bits[w] = 0;
+        total += tot;
+        c.sync();
+        if (c.tid() == 0) sh.dirty[k] = 0;
+    }
+    c.sync();
+    return total;
+}
+
+// dst <- elements of src[0..n) that occur in list[0..len) (both ascending). Ordered. Returns count.
+IFX_FN int64_t filter_members(const Ctx& c, const int32_t* src, int64_t n, const int32_t* list, int64_t len, int32_t* dst, S1Shared& sh) {
+    const int E = 8; int64_t total = 0;
+    for (int64_t base = 0; base < n; base += (int64_t)c.nthreads() * E) {
+        int64_t b = base + (int64_t)c.tid() * E, e = b + E; if (e > n) e = n;
+        int32_t keep[E]; int cnt = 0; int64_t lo = 0;
+        for (int64_t i = b; i < e; i++) {
+            int32_t d = src[i];
+            lo = (i == b) ? lower_bound_i32(list, 0, len, d) : gallop_lower_bound(list, lo, len, d);
+            if (lo < len && list[lo] == d) keep[cnt++] = d;
+        }
+        int tot; int off = block_excl_scan(c, cnt, sh.scan, tot);
+        for (int k = 0; k < cnt; k++) dst[total + off + k] = keep[k];
+        total += tot;
+    }
+    c.sync();
+    return total;
+}
+
+// .NET ArraySortHelper<T>.IntrospectiveSort with comparison (b.Idf.CompareTo(a.Idf)) over term indices -- unstable,
+// reproduced exactly because idf ties decide which lists the selector unions (TieredCandidateSelector.cs:128,253).
+struct IdfSorter {
+    const TermS* t;
+    IFX_FN int cmp(int a, int b) const { float x = t[b].idf, y = t[a].idf; return x < y ? -1 : (x > y ? 1 : 0); }
+    IFX_FN void swap_if_greater(int* k, int i, int j) const { if (cmp(k[i], k[j]) > 0) { int x = k[i]; k[i] = k[j]; k[j] = x; } }
+    IFX_FN void insertion(int* k, int n) const { for (int i = 0; i < n - 1; i++) { int t2 = k[i + 1]; int j = i; while (j >= 0 && cmp(t2, k[j]) < 0) { k[j + 1] = k[j]; j--; } k[j + 1] = t2; } }
+    IFX_FN void down_heap(int* k, int i, int n) const { int d = k[i - 1]; while (i <= n / 2) { int ch = 2 * i; if (ch < n && cmp(k[ch - 1], k[ch]) < 0) ch++; if (!(cmp(d, k[ch - 1]) < 0)) break; k[i - 1] = k[ch - 1]; i = ch; } k[i - 1] = d; }
+    IFX_FN void heap_sort(int* k, int n) const { for (int i = n >> 1; i >= 1; i--) down_heap(k, i, n); for (int i = n; i > 1; i--) { int x = k[0]; k[0] = k[i - 1]; k[i - 1] = x; down_heap(k, 1, i - 1); } }
+    IFX_FN int partition(int* k, int n) const {
+        int hi = n - 1, mid = hi >> 1;
+        swap_if_greater(k, 0, mid); swap_if_greater(k, 0, hi); swap_if_greater(k, mid, hi);
+        int pivot = k[mid]; { int x = k[mid]; k[mid] = k[hi - 1]; k[hi - 1] = x; }
+        int left = 0, right = hi - 1;
+        while (left < right) {
+            while (cmp(k[++left], pivot) < 0) {}
+            while (cmp(pivot, k[--right]) < 0) {}
+            if (left >= right) break;
+            int x = k[left]; k[left] = k[right]; k[right] = x;
+        }
+        if (left != hi - 1) { int x = k[left]; k[left] = k[hi - 1]; k[hi - 1] = x; }
+        return left;
+    }
+    IFX_FN void sort(int* keys, int n) const {
+        if (n < 2) return;
+        int lg = 0; for (unsigned v = (unsigned)n; v >>= 1;) lg++;
+        // explicit stack instead of recursion: (start, length, depth)
+        int st_s[64], st_n[64], st_d[64]; int sp = 0; st_s[0] = 0; st_n[0] = n; st_d[0] = 2 * (lg + 1); sp = 1;
+        while (sp > 0) {
+            sp--; int* k = keys + st_s[sp]; int len = st_n[sp], depth = st_d[sp]; int s0 = st_s[sp];
+            while (len > 1) {
+                if (len <= 16) { if (len == 2) swap_if_greater(k, 0, 1); else if (len == 3) { swap_if_greater(k, 0, 1); swap_if_greater(k, 0, 2); swap_if_greater(k, 1, 2); } else insertion(k, len); break; }
+                if (depth == 0) { heap_sort(k, len); break; }
+                depth--;
+                int p = partition(k, len);
+                // reference recurses into the right part first, then loops on the left part; the two parts are disjoint so order is irrelevant
+                st_s[sp] = s0 + p + 1; st_n[sp] = len - (p + 1); st_d[sp] = depth; sp++;
+                len = p;
+            }
+        }
+    }
+};
+
+// .NET PriorityQueue<int,float> (4-ary min-heap) on shared arrays -- Bm25Scorer.UpdateTopK (Bm25Scorer.cs:654-670)
+IFX_FN void heap_move_up(S1Shared& sh, int doc, float pr, int idx) {
+    while (idx > 0) { int parent = (idx - 1) >> 2; if (pr < sh.heap_score[parent]) { sh.heap_doc[idx] = sh.heap_doc[parent]; sh.heap_score[idx] = sh.heap_score[parent]; idx = parent; } else break; }
+    sh.heap_doc[idx] = doc; sh.heap_score[idx] = pr;
+}
+IFX_FN void heap_move_down(S1Shared& sh, int doc, float pr, int idx) {
+    int sz = sh.heap_size, i;
+    while ((i = 4 * idx + 1) < sz) {
+        int mi = i; float mp = sh.heap_score[i]; int upper = i + 4 < sz ? i + 4 : sz;
+        while (++i < upper) { float x = sh.heap_score[i]; if (x < mp) { mp = x; mi = i; } }
+        if (!(mp < pr)) break;
+        sh.heap_doc[idx] = sh.heap_doc[mi]; sh.heap_score[idx] = mp; idx = mi;
+    }
+    sh.heap_doc[idx] = doc; sh.heap_score[idx] = pr;
+}
+IFX_FN void update_topk(S1Shared& sh, int doc, float s, int K) {
+    if (sh.heap_size < K) { int i = sh.heap_size++; heap_move_up(sh, doc, s, i); if (sh.heap_size == K) sh.thr = sh.heap_score[0]; }
+    else if (s > sh.thr) { heap_move_down(sh, doc, s, 0); sh.thr = sh.heap_score[0]; }
+}
+
+// Bm25Scorer.cs:395-433 (Vector256 lanes) and :643-652 (scalar remainder); must not be contracted into FMAs.
+IFX_FN float bm25_vector(float tf, float dl, float avgdl, float idf) {
+    const float K1 = 1.2f, B = 0.75f, Delta = 1.0f;
+    float bdiv = B / avgdl; float norm = K1 * ((1.f - B) + bdiv * dl); float denom = tf + norm;
+    float core = (tf * (K1 + 1.0f)) / denom; return idf * (core + Delta);
+}
+IFX_FN float bm25_scalar(float tf, float dl, float avgdl, float idf) {
+    const float K1 = 1.2f, B = 0.75f, Delta = 1.0f;
+    if (dl <= 0.f) dl = 1.f;
+    float norm = K1 * (1.f - B + B * (dl / avgdl)); float denom = tf + norm;
+    if (denom <= 0.f) return 0.f;
+    float core = (tf * (K1 + 1.f)) / denom; return idf * (core + Delta);
+}
+
+struct Stage1Out { int64_t* key; int32_t* doc; float* score; int32_t* n; };   // row pointers for this query (cap = depth)
+
+// ---------------------------------------------------------------------------------------------------------------
+// LD1 expansion of one unknown word: first 1024 trie-order matches (Myers bit-vector, search variant), union of
+// their posting lists -> ascending unique doc list appended to the fuzzy pool.
+IFX_FN void expand_fuzzy(const Ctx& c, const DevIndex& ix, QueryPlan& p, int fslot, S1Workspace& ws, S1Shared& sh,
+                         int32_t* pool, unsigned long long pool_cap, BatchCounters* bc, const uint8_t* sorted_len, int32_t* matches /* [LD1_CAP] global or shared */) {
+    const FuzzyReq fr = p.fuzzy[fslot];
+    const uint16_t* q = p.ttext + fr.off; const int m = fr.len;
+    const uint64_t maskM = 1ULL << (m - 1);
+    int64_t T = ix.terms.n; int total = 0;
+    for (int64_t base = 0; base < T && total < LD1_CAP; base += c.nthreads()) {
+        int64_t i = base + c.tid(); bool hit = false; int ord = -1;
+        if (i < T) {
+            int L = sorted_len[i];
+            if (L >= m - 1 && L <= m + 1 && L < 255) {
+                ord = ix.term_sorted[i]; const uint16_t* s = ix.terms.chars + ix.terms.off[ord];
+                uint64_t vp = ~0ULL, vn = 0ULL; int score = m;
+                for (int k = 0; k < L; k++) {
+                    uint16_t ch = s[k]; uint64_t pm = 0; for (int j = 0; j < m; j++) if (q[j] == ch) pm |= 1ULL << j;
+                    uint64_t x = pm | vn; uint64_t d0 = ((vp + (x & vp)) ^ vp) | x; uint64_t hn = vp & d0; uint64_t hp = vn | ~(vp | d0);
+                    uint64_t nvp = (hn << 1) | ~(d0 | (hp << 1)); uint64_t nvn = d0 & (hp << 1);
+                    if (hp & maskM) score++; if (hn & maskM) score--;
+                    vp = nvp; vn = nvn;
+                }
+                hit = score <= 1;
+            }
+        }
+        int tot; int off = block_excl_scan(c, hit ? 1 : 0, sh.scan, tot);
+        if (hit && total + off < LD1_CAP) matches[total + off] = ord;
+        total += tot;
+    }
+    c.sync();
+    int nm = total < LD1_CAP ? total : LD1_CAP;
+    int df = 0;
+    for (int k = 0; k < nm; k++) {
+        int ord = matches[k]; if (ix.df[ord] <= 0) continue;
+        int64_t r0 = ix.row_ptr[ord], r1 = ix.row_ptr[ord + 1];
+        df += or_list_into_bits(c, ix.post_doc + r0, r1 - r0, ws, sh);
+    }
+    c.sync();
+    QTerm& t = p.terms[fr.term_slot];
+    if (df == 0) { if (c.tid() == 0) { t.df = 0; t.list_len = 0; } c.sync(); return; }
+    if (c.tid() == 0) { unsigned long long b = atomic_add64(&bc->fuzzy_pool_used, (unsigned long long)df); sh.bcast64[0] = (long long)b; }
+    c.sync();
+    unsigned long long b = (unsigned long long)sh.bcast64[0]; bool ovf = false;
+    int64_t cap = b + (unsigned long long)df <= pool_cap ? df : 0;
+    int64_t n = compact_bits(c, ix, ws, sh, pool + b, cap, ovf);
+    if (c.tid() == 0) {
+        if (ovf || n != df) { p.status |= 4; atomic_add(&bc->overflow, 1); t.df = 0; t.list_len = 0; }
+        else { float avgdl = ix.avgdl > 0.f ? ix.avgdl : 1.f; t.df = df; t.list_len = df; t.list_off = (int64_t)b; t.idf = compute_idf(ix.n_live, df); t.max_score = max_term_score(t.idf, avgdl); }
+    }
+    c.sync();
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+IFX_FN void stage1_query(const Ctx& c, const DevIndex& ix, const QueryPlan& p, const int32_t* pool, S1Workspace& ws, S1Shared& sh,
+                         Stage1Out out, BatchCounters* bc) {
+    const int K = p.depth; const int NT = c.nthreads();
+    if (c.tid() == 0) {
+        int n = 0;
+        for (int i = 0; i < p.n_terms; i++) {
+            const QTerm& q = p.terms[i];
+            if (q.df <= 0 || q.df > ix.stop_term_limit) continue;      // VectorModel.cs:521
+            TermS& t = sh.terms[n]; t.len = q.list_len; t.df = q.df; t.idf = q.idf; t.max_score = q.max_score; t.cursor = 0;
+            if (q.term_id >= 0) { t.docs = ix.post_doc + q.list_off; t.tf = ix.post_tf + q.list_off; } else { t.docs = pool + q.list_off; t.tf = nullptr; }
+            n++;
+        }
+        float suf = 0.f; for (int i = n - 1; i >= 0; i--) { sh.terms[i].suffix_after = suf; suf = suf + sh.terms[i].max_score; }   // ComputeSuffixSums
+        sh.n_terms = n; sh.heap_size = 0; sh.thr = 0.f; sh.streamed_mask[0] = sh.streamed_mask[1] = 0;
+        out.n[0] = 0;
+    }
+    c.sync();
+    const int T = sh.n_terms;
+    if (T == 0 || ix.n_live == 0 || p.status != 0) return;
+    const float avgdl = ix.avgdl > 0.f ? ix.avgdl : 1.f;
+
+    // ---- candidate selection (TieredCandidateSelector.SelectCandidates)
+    const int32_t* cand = nullptr; int64_t n_cand = 0;
+    if (c.tid() == 0) {   // prefix precedence (TrySelectPrefixCandidates)
+        sh.bcast64[0] = -1; sh.bcast64[1] = 0;
+        int maxl = p.tlen < 3 ? p.tlen : 3;
+        for (int len = maxl; len >= 1; len--) {
+            int k = dict_lookup(ix.prefix.keys, p.ttext, len); if (k < 0) continue;
+            int64_t r0 = ix.prefix.row_ptr[k], pop = ix.prefix.row_ptr[k + 1] - r0;
+            if (pop == 0) continue;
+            if (pop > (int64_t)K * 20) continue;
+            if (pop <= (int64_t)K * 10) { int lim = K * 2 < 100 ? K * 2 : 100; if (pop >= lim) { sh.bcast64[0] = r0; sh.bcast64[1] = pop; } break; }
+        }
+    }
+    c.sync();
+    unsigned long long algo = 0;
+    if (sh.bcast64[0] >= 0) { cand = ix.prefix.doc_id + sh.bcast64[0]; n_cand = sh.bcast64[1]; algo += 4ULL * (unsigned long long)n_cand; }
+    else {
+        if (c.tid() == 0) {
+            bool typo = false; float max_idf = 0.f;
+            for (int i = 0; i < T; i++) { if (sh.terms[i].df < 10) typo = true; if (sh.terms[i].idf > max_idf) max_idf = sh.terms[i].idf; sh.order[i] = i; }
+            IdfSorter srt{sh.terms}; srt.sort(sh.order, T);
+            sh.bcast[0] = (typo || T == 1) ? 1 : 0; ((float*)sh.bcast)[1] = max_idf;
+        }
+        c.sync();
+        const bool disjunctive = sh.bcast[0] != 0; const float max_idf = ((float*)sh.bcast)[1];
+        int64_t g = 0;
+        if (disjunctive) {   // SelectCandidatesDisjunctive
+            bool selective = false;
+            for (int oi = 0; oi < T; oi++) {
+                const TermS& t = sh.terms[sh.order[oi]];
+                bool lowq = t.idf < (max_idf * 0.2f);
+                if (T > 1 && lowq && selective) continue;
+                g += or_list_into_bits(c, t.docs, t.len, ws, sh);
+                if (c.tid() == 0) sh.streamed_mask[sh.order[oi] >> 6] |= 1ULL << (sh.order[oi] & 63);
+                if (!lowq && g > 0) selective = true;
+                if (g >= (int64_t)K * 100) break;
+            }
+        } else {
+            // IntersectTerms over `cnt` leading terms of the idf order, smallest list drives
+            auto intersect = [&](int cnt, int32_t*& res) -> int64_t {
+                int by_len[MAX_TERMS];
+                for (int i = 0; i < cnt; i++) by_len[i] = sh.order[i];
+                for (int i = 1; i < cnt; i++) { int x = by_len[i]; int j = i - 1; while (j >= 0 && sh.terms[by_len[j]].len > sh.terms[x].len) { by_len[j + 1] = by_len[j]; j--; } by_len[j + 1] = x; }
+                const int32_t* cur = sh.terms[by_len[0]].docs; int64_t n = sh.terms[by_len[0]].len; int32_t* dst = ws.buf_a; res = nullptr;
+                if (n > ws.buf_cap) return -1;
+                if (cnt == 1) { for (int64_t i = c.tid(); i < n; i += NT) ws.buf_a[i] = cur[i]; c.sync(); res = ws.buf_a; return n; }
+                for (int i = 1; i < cnt && n > 0; i++) {
+                    const TermS& t = sh.terms[by_len[i]];
+                    n = filter_members(c, cur, n, t.docs, t.len, dst, sh);
+                    cur = dst; res = dst; dst = (dst == ws.buf_a) ? ws.buf_b : ws.buf_a;
+                }
+                if (n == 0) res = ws.buf_a;
+                return n;
+            };
+            if (c.tid() == 0) for (int i = 0; i < T; i++) sh.streamed_mask[i >> 6] |= 1ULL << (i & 63);   // every list of the AND tier
+            int32_t* r0 = nullptr; int64_t n0 = intersect(T, r0);
+            if (n0 < 0) { if (c.tid() == 0) out.n[0] = -1; return; }
+            g += or_list_into_bits(c, r0, n0, ws, sh);
+            if (g < (int64_t)K * 2) {
+                if (T >= 3 && g < (int64_t)K * 3) { int32_t* r1 = nullptr; int64_t n1 = intersect(T - 1, r1); if (n1 > 0) g += or_list_into_bits(c, r1, n1, ws, sh); }
+                if (g < (int64_t)K * 5) {
+                    int sel[2]; int ns = 0; float cutoff = max_idf * 0.3f; int capn = T < 2 ? T : 2;
+                    for (int oi = 0; oi < T && ns < capn; oi++) { const TermS& t = sh.terms[sh.order[oi]]; if (t.idf <= 0.f) continue; if (t.idf < cutoff) continue; sel[ns++] = sh.order[oi]; }
+                    for (int si = 0; si < ns; si++) { const TermS& t = sh.terms[sel[si]]; g += or_list_into_bits(c, t.docs, t.len, ws, sh); if (g >= (int64_t)K * 10) break; }
+                }
+            }
+        }
+        bool ovf = false;
+        n_cand = compact_bits(c, ix, ws, sh, ws.cand, ws.cand_cap, ovf);
+        if (ovf) { if (c.tid() == 0) out.n[0] = -1; return; }
+        cand = ws.cand;
+        algo += 2ULL * (unsigned long long)((ix.n_docs + 7) / 8);
+    }
+    // ---- roofline accounting: full-stream lists 5 B/posting, probe-only lists min(5 df, 32 |C|), 4 B doc_len per candidate
+    if (c.tid() == 0) {
+        for (int i = 0; i < T; i++) {
+            unsigned long long full = (sh.terms[i].tf ? 5ULL : 4ULL) * (unsigned long long)sh.terms[i].len;
+            bool streamed = (sh.streamed_mask[i >> 6] >> (i & 63)) & 1ULL;
+            unsigned long long probe = 32ULL * (unsigned long long)n_cand;
+            algo += streamed ? full : (full < probe ? full : probe);
+        }
+        algo += 4ULL * (unsigned long long)n_cand;
+        atomic_add64(&bc->algo_bytes, algo);
+    }
+
+    // ---- BM25 scoring over chunks (ProcessBlockedCandidates / ProcessChunk / ScoreBlockStruct)
+    const int NW = c.nwarps();
+    for (int64_t pos = 0; pos < n_cand;) {
+        // container run: candidates sharing id >> 16, cut into sub-chunks of 4096
+        if (c.tid() == 0) {
+            int hb = cand[pos] >> 16; int64_t lim = ((int64_t)hb + 1) << 16;
+            int64_t ce = lim > 0x7fffffffLL ? n_cand : lower_bound_i32(cand, pos, n_cand, (int32_t)lim);
+            int64_t cnt = ce - pos; if (cnt > CHUNK) cnt = CHUNK; sh.bcast[2] = (int)cnt;
+        }
+        c.sync();
+        const int cnt = sh.bcast[2];
+        for (int j = c.tid(); j < cnt; j += NT) { sh.cand_s[j] = cand[pos + j]; sh.score[j] = 0.f; sh.tfbuf[0][j] = 0; sh.tfbuf[1][j] = 0; }
+        c.sync();
+        const int32_t first = sh.cand_s[0], last = sh.cand_s[cnt - 1];
+        for (int t = c.tid(); t < T; t += NT) {      // posting sub-range of every term for this chunk (monotone cursors)
+            TermS& tm = sh.terms[t];
+            int64_t s0 = gallop_lower_bound(tm.docs, tm.cursor, tm.len, first);
+            int64_t s1 = last == 0x7fffffff ? tm.len : gallop_lower_bound(tm.docs, s0, tm.len, last + 1);
+            tm.s0 = s0; tm.s1 = s1; tm.cursor = s1;
+        }
+        c.sync();
+        const float thr = sh.thr; const int rounds = (cnt + NT - 1) / NT;
+        for (int t = 0; t < T; t++) {
+            const TermS& tm = sh.terms[t];
+            if (tm.idf <= 0.f) continue;
+            const int64_t sublen = tm.s1 - tm.s0; if (sublen == 0) continue;   // uniform: no candidate of this chunk can match
+            uint8_t* tfb = sh.tfbuf[t & 1];
+            const float bound = tm.max_score + tm.suffix_after;
+            if (sublen <= 8LL * cnt) {           // stream the posting sub-range, look each posting up among the chunk's candidates
+                for (int64_t i = tm.s0 + c.tid(); i < tm.s1; i += NT) {
+                    int32_t d = tm.docs[i]; int lo = 0, hi = cnt;
+                    while (lo < hi) { int mid = (lo + hi) >> 1; if (sh.cand_s[mid] < d) lo = mid + 1; else hi = mid; }
+                    if (lo < cnt && sh.cand_s[lo] == d) tfb[lo] = tm.tf ? tm.tf[i] : (uint8_t)1;
+                }
+            } else {                             // sparse candidates: probe the sub-range per candidate
+                for (int j = c.tid(); j < cnt; j += NT) {
+                    int32_t d = sh.cand_s[j]; int64_t i = lower_bound_i32(tm.docs, tm.s0, tm.s1, d);
+                    if (i < tm.s1 && tm.docs[i] == d) tfb[j] = tm.tf ? tm.tf[i] : (uint8_t)1;
+                }
+            }
+            c.sync();
+            // match flags in candidate order; MaxScore skip (Bm25Scorer.cs:354) removes pairs before ranks are taken
+            for (int r = 0; r < rounds; r++) {
+                int j = r * NT + c.tid();
+                bool f = j < cnt && tfb[j] != 0 && !(sh.score[j] + tm.max_score + tm.suffix_after <= thr);
+                unsigned b = c.ballot(f);
+                if (c.lane() == 0) sh.ballots[r * NW + c.warp()] = b;
+            }
+            (void)bound;
+            c.sync();
+            if (c.warp() == 0) {                 // exclusive prefix of popcounts over (round, warp) slots
+                int slots = rounds * NW; int run = 0;
+#ifdef IFX_EMU
+                for (int s = 0; s < slots; s++) { sh.bprefix[s] = run; run += popc(sh.ballots[s]); }
+#else
+                for (int s0 = 0; s0 < slots; s0 += 32) {
+                    int s = s0 + c.lane(); int v = s < slots ? popc(sh.ballots[s]) : 0; int incl = v;
+                    for (int d = 1; d < 32; d <<= 1) { int o = __shfl_up_sync(0xffffffffu, incl, d); if (c.lane() >= d) incl += o; }
+                    if (s < slots) sh.bprefix[s] = run + incl - v;
+                    run += __shfl_sync(0xffffffffu, incl, 31);
+                }
+#endif
+                if (c.lane() == 0) sh.bcast[3] = run;
+            }
+            c.sync();
+            const int m = sh.bcast[3]; const int vec_end = m - (m & 7);
+            for (int r = 0; r < rounds; r++) {
+                int j = r * NT + c.tid();
+                if (j < cnt) {
+                    if (tfb[j] != 0 && !(sh.score[j] + tm.max_score + tm.suffix_after <= thr)) {   // same predicate as above (score[j] untouched since)
+                        int slot = r * NW + c.warp(); int rank = sh.bprefix[slot] + popc(sh.ballots[slot] & c.lanemask_lt());
+                        float tf = (float)tfb[j]; float dl = ix.doc_len[sh.cand_s[j]];
+                        float s = rank < vec_end ? bm25_vector(tf, dl, avgdl, tm.idf) : bm25_scalar(tf, dl, avgdl, tm.idf);
+                        sh.score[j] += s;
+                    }
+                    tfb[j] = 0;
+                }
+            }
+            // no barrier needed here: the next term writes the other tf buffer, and three barriers separate reuse of this one
+        }
+        c.sync();
+        if (c.tid() == 0) {   // flush (Bm25Scorer.cs:316-329) -- sequential by construction (exact heap emulation)
+            for (int j = 0; j < cnt; j++) { float s = sh.score[j]; if (s > 0.f) { int d = sh.cand_s[j]; if (!ix.deleted[d]) { if (sh.heap_size < K || s > sh.thr) update_topk(sh, d, s, K); } } }
+        }
+        c.sync();
+        pos += cnt;
+    }
+    // ---- PopulateResultHeapFromPruning + TopKHeap.GetTopK + ConsolidateSegments: order by (score desc, key asc)
+    const int n = sh.heap_size; int n2 = 1; while (n2 < n) n2 <<= 1;
+    float* ks = sh.score; int32_t* kd = sh.cand_s;            // reuse chunk arrays (CHUNK >= MAX_K)
+    for (int i = c.tid(); i < n2; i += NT) { if (i < n) { ks[i] = sh.heap_score[i]; kd[i] = sh.heap_doc[i]; } else { ks[i] = -1.f; kd[i] = 0x7fffffff; } }
+    c.sync();
+    auto before = [&](int a, int b) -> bool {   // a ranks before b
+        if (ks[a] != ks[b]) return ks[a] > ks[b];
+        if (kd[a] == 0x7fffffff || kd[b] == 0x7fffffff) return kd[a] < kd[b];
+        return ix.doc_key[kd[a]] < ix.doc_key[kd[b]];
+    };
+    for (int k = 2; k <= n2; k <<= 1) for (int j = k >> 1; j > 0; j >>= 1) {
+        for (int i = c.tid(); i < n2; i += NT) { int l = i ^ j; if (l > i) { bool up = (i & k) == 0; bool sw = up ? before(l, i) : before(i, l); if (sw) { float x = ks[i]; ks[i] = ks[l]; ks[l] = x; int y = kd[i]; kd[i] = kd[l]; kd[l] = y; } } }
+        c.sync();
+    }
+    for (int i = c.tid(); i < n; i += NT) { out.doc[i] = kd[i]; out.score[i] = ks[i]; out.key[i] = ix.doc_key[kd[i]]; }
+    if (c.tid() == 0) out.n[0] = n;
+    c.sync();
+}
+
+}  // namespace ifx

@@ -88,6 +88,8 @@ class OracleEngine:
                 a = np.ascontiguousarray(col, np.int64); kinds[i] = 2; cols[i] = a.ctypes.data; keep.append(a)
             elif isinstance(col, np.ndarray) and col.dtype.kind == "f":
                 a = np.ascontiguousarray(col, np.float64); kinds[i] = 3; cols[i] = a.ctypes.data; keep.append(a)
+            elif isinstance(col, tuple):
+                blob, o = col; kinds[i] = 1; cols[i] = blob.ctypes.data; offs[i] = o.ctypes.data; keep += [blob, o]
             else:
                 blob, o = pack_strings(col); kinds[i] = 1; cols[i] = blob.ctypes.data; offs[i] = o.ctypes.data; keep += [blob, o]
         lib().ifxo_add_docs(self.h, n, _p(keys), _p(kinds), cols, offs)
