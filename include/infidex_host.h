@@ -26,6 +26,12 @@ const ifx_index_image* ifx_builder_image(ifx_builder* b);   /* valid until ifx_b
 /* SearchEngine.Search step 1 (src/Infidex/SearchEngine.cs:264-274): Trim + TextNormalizer.Normalize + ToLowerInvariant. Returns the output length. */
 int ifx_host_prepare_query(const uint16_t* in, int n, uint16_t* out, int cap);
 
+/* filter / facet columns of the finished image (index = ifx_batch_result.facet_column) */
+int ifx_builder_num_columns(ifx_builder* b);
+int ifx_builder_column_name(ifx_builder* b, int c, uint16_t* buf, int cap);
+int ifx_builder_column_dict_size(ifx_builder* b, int c);
+int ifx_builder_column_value(ifx_builder* b, int c, int id, uint16_t* buf, int cap);
+
 #ifdef __cplusplus
 }
 #endif

@@ -46,7 +46,6 @@ static const int kS1Threads = 256;
 #endif
 
 // ---- host-side handle ----------------------------------------------------------------------------------------------
-struct FilterDev { std::vector<uint8_t> blob; FilterProg prog; void* d_consts = nullptr; void* d_code = nullptr; void* d_chars = nullptr; void* d_arr = nullptr; };
 
 struct ifx_index {
     DevIndex v{};                       // device pointers
@@ -57,7 +56,7 @@ struct ifx_index {
     int32_t* d_pool = nullptr; unsigned long long pool_cap = 0;
     int max_batch = 16384;
     int device = 0;
-    std::vector<FilterDev> filters; FilterProg* d_filters = nullptr; int d_filters_n = 0;
+    std::vector<FilterProg> h_filters; FilterProg* d_filters = nullptr;
     std::vector<Column> h_columns; std::vector<std::u16string> column_names;
     std::mutex mu;
     ~ifx_index() { for (void* p : allocs) dev_free(p); }

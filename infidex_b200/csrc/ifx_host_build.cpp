@@ -286,3 +286,11 @@ extern "C" int ifx_host_prepare_query(const uint16_t* in, int n, uint16_t* out, 
     int m = (int)std::min<size_t>(nrm.size(), (size_t)cap); std::memcpy(out, nrm.data(), (size_t)m * 2);
     return (int)nrm.size();
 }
+
+// accessors used by the host mirror to turn facet (column, value id) pairs back into strings
+extern "C" int ifx_builder_num_columns(ifx_builder* b) { return (int)b->cols.size(); }
+extern "C" int ifx_builder_column_name(ifx_builder* b, int c, uint16_t* buf, int cap) { const str& s = b->col_names[c]; int n = (int)std::min<size_t>(s.size(), (size_t)cap); std::memcpy(buf, s.data(), (size_t)n * 2); return (int)s.size(); }
+extern "C" int ifx_builder_column_dict_size(ifx_builder* b, int c) { return (int)b->col_off[c].size() - 1; }
+extern "C" int ifx_builder_column_value(ifx_builder* b, int c, int id, uint16_t* buf, int cap) {
+    uint32_t o = b->col_off[c][id], e = b->col_off[c][id + 1]; int n = (int)std::min<size_t>(e - o, (size_t)cap); std::memcpy(buf, b->col_chars[c].data() + o, (size_t)n * 2); return (int)(e - o);
+}

@@ -86,7 +86,7 @@ extern "C" int ifx_batch_upload(ifx_index* idx, const ifx_query* q, int nq, ifx_
         b->d_text = b->alloc<uint16_t>(text.size()); h2d(b->d_text, text.data(), text.size() * 2);
         b->d_off = b->alloc<int64_t>(nq + 1); h2d(b->d_off, off.data(), (nq + 1) * 8);
         b->d_par = b->alloc<int32_t>(par.size()); h2d(b->d_par, par.data(), par.size() * 4);
-        b->d_plans = b->alloc<QueryPlan>(nq); b->d_items = b->alloc<FuzzyItem>((size_t)nq * 4 + 64); b->d_bc = b->alloc<BatchCounters>(1); b->d_work = b->alloc<int>(8);
+        b->d_plans = b->alloc<QueryPlan>(nq); b->d_items = b->alloc<FuzzyItem>((size_t)nq * 4 + 64); b->d_bc = b->alloc<BatchCounters>(1); b->d_work = b->alloc<int>(8); dev_zero(b->d_work, 8 * sizeof(int));
         size_t K = b->depth_max;
         b->d_s1_key = b->alloc<int64_t>(nq * K); b->d_s1_doc = b->alloc<int32_t>(nq * K); b->d_s1_score = b->alloc<float>(nq * K); b->d_s1_n = b->alloc<int32_t>(nq);
     } catch (const std::string& e) { delete b; return fail(IFX_ERR_CUDA, e); }

@@ -1,5 +1,6 @@
-// infidex_b200 -- full search (Stage 2 + filter + facets) entry points. (Filled in by the Stage-2 milestone.)
-static bool host_try_parse_double(const uint16_t* s, int n, double& out) {
+// infidex_b200 -- full search entry points: Stage 2 launches, Infiscript registration, batch run / download.
+
+static bool host_try_parse_double(const uint16_t* s, int n, double& out) {   // double.TryParse (Float | AllowThousands, invariant)
     int b = 0, e = n; while (b < e && (s[b] == ' ' || (s[b] >= 9 && s[b] <= 13))) b++; while (e > b && (s[e - 1] == ' ' || (s[e - 1] >= 9 && s[e - 1] <= 13))) e--;
     if (b >= e) return false;
     std::string a; bool digits = false; int i = b;
@@ -11,7 +12,181 @@ static bool host_try_parse_double(const uint16_t* s, int n, double& out) {
     if (i != e) return false;
     out = strtod(a.c_str(), nullptr); return true;
 }
-extern "C" int ifx_filter_register(ifx_index*, const uint8_t*, size_t, int*) { return fail(IFX_ERR_UNSUPPORTED, "filter VM not built yet"); }
-extern "C" int ifx_batch_run(ifx_batch*, ifx_stats*) { return fail(IFX_ERR_UNSUPPORTED, "stage 2 not built yet"); }
-extern "C" int ifx_batch_download(ifx_batch*, ifx_batch_result*) { return fail(IFX_ERR_UNSUPPORTED, "stage 2 not built yet"); }
-extern "C" int ifx_search_batch(ifx_index*, const ifx_query*, int, ifx_batch_result*, ifx_stats*) { return fail(IFX_ERR_UNSUPPORTED, "stage 2 not built yet"); }
+
+// ---- INFISCRIPT-V1 (src/Infidex/Filtering/BytecodeSerializer.cs:16-117, ConstantPool.cs:75-163) -> device program ------------
+static bool op_has_operand(uint8_t op) { return op == 0x01 || op == 0x02 || op == 0x60 || op == 0x61 || op == 0x62; }
+static bool op_valid(uint8_t op) {
+    switch (op) { case 0x01: case 0x02: case 0x03: case 0x04: case 0x10: case 0x11: case 0x12: case 0x13: case 0x14: case 0x15: case 0x20: case 0x21: case 0x22: case 0x30: case 0x31: case 0x32:
+        case 0x33: case 0x34: case 0x40: case 0x41: case 0x50: case 0x51: case 0x60: case 0x61: case 0x62: case 0xFF: return true; default: return false; }
+}
+static std::u16string utf8_to_u16(const uint8_t* p, size_t n) {
+    std::u16string r; size_t i = 0;
+    while (i < n) { uint32_t c = p[i]; int extra = 0; if (c < 0x80) extra = 0; else if ((c >> 5) == 6) { c &= 0x1F; extra = 1; } else if ((c >> 4) == 14) { c &= 0x0F; extra = 2; } else { c &= 0x07; extra = 3; }
+        i++; for (int k = 0; k < extra && i < n; k++, i++) c = (c << 6) | (p[i] & 0x3F);
+        if (c >= 0x10000) { c -= 0x10000; r.push_back((char16_t)(0xD800 + (c >> 10))); r.push_back((char16_t)(0xDC00 + (c & 0x3FF))); } else r.push_back((char16_t)c); }
+    return r;
+}
+
+extern "C" int ifx_filter_register(ifx_index* idx, const uint8_t* data, size_t len, int* out_id) {
+    if (!idx || !data || !out_id) return fail(IFX_ERR_INVALID, "null argument");
+    size_t p = 0; auto need = [&](size_t n) { return p + n <= len; };
+    auto rd_i32 = [&]() { int32_t v; memcpy(&v, data + p, 4); p += 4; return v; };
+    auto rd_str = [&]() { uint32_t n = 0; int sh = 0; while (p < len) { uint8_t b = data[p++]; n |= (uint32_t)(b & 0x7F) << sh; if (!(b & 0x80)) break; sh += 7; } std::u16string s = utf8_to_u16(data + p, std::min<size_t>(n, len - p)); p += n; return s; };
+    if (len < 23 || memcmp(data, "INFISCRIPT-V1", 13) != 0) return fail(IFX_ERR_INVALID, "bad INFISCRIPT magic");
+    p = 13; uint16_t ver; memcpy(&ver, data + p, 2); p += 2; if (ver != 1) return fail(IFX_ERR_INVALID, "unsupported INFISCRIPT version");
+    int pool_size = rd_i32(); size_t pool_end = p + (size_t)pool_size; if (pool_end > len) return fail(IFX_ERR_INVALID, "truncated constant pool");
+    int cnt = rd_i32();
+    std::vector<FConst> consts(cnt); std::vector<uint16_t> chars; std::vector<FConst> extra;
+    std::vector<std::vector<std::u16string>> arrays(cnt);
+    auto add_str = [&](FConst& k, const std::u16string& s) { k.kind = 1; k.off = (int32_t)chars.size(); k.len = (int32_t)s.size(); chars.insert(chars.end(), s.begin(), s.end()); double d = 0; k.is_num = host_try_parse_double((const uint16_t*)s.data(), (int)s.size(), d) ? 1 : 0; k.num = d; k.col = -1; k.arr_start = k.arr_len = 0;
+        for (size_t c = 0; c < idx->column_names.size(); c++) if (idx->column_names[c] == s) { k.col = (int32_t)c; break; } };
+    for (int i = 0; i < cnt; i++) {
+        if (!need(1)) return fail(IFX_ERR_INVALID, "truncated constant"); int kind = data[p++]; FConst& k = consts[i]; memset(&k, 0, sizeof(k)); k.col = -1;
+        if (kind == 1) add_str(k, rd_str());
+        else if (kind == 2) { k.kind = 2; memcpy(&k.num, data + p, 8); p += 8; k.is_num = 1; }
+        else if (kind == 3) { k.kind = 3; int n = rd_i32(); for (int j = 0; j < n; j++) arrays[i].push_back(rd_str()); }
+        else return fail(IFX_ERR_INVALID, "unknown constant type");
+    }
+    for (int i = 0; i < cnt; i++) if (consts[i].kind == 3) { consts[i].arr_start = cnt + (int)extra.size(); consts[i].arr_len = (int)arrays[i].size(); for (auto& s : arrays[i]) { FConst e; memset(&e, 0, sizeof(e)); add_str(e, s); extra.push_back(e); } }
+    consts.insert(consts.end(), extra.begin(), extra.end());
+    p = pool_end; if (!need(4)) return fail(IFX_ERR_INVALID, "truncated code"); int ic = rd_i32();
+    std::vector<FInstr> code;
+    for (int i = 0; i < ic; i++) { if (!need(1)) return fail(IFX_ERR_INVALID, "truncated code"); FInstr in; in.op = data[p++]; in.a = 0;
+        if (!op_valid((uint8_t)in.op)) return fail(IFX_ERR_INVALID, "unknown opcode");
+        if (op_has_operand((uint8_t)in.op)) { if (!need(4)) return fail(IFX_ERR_INVALID, "truncated operand"); in.a = rd_i32(); if (p < len && !op_valid(data[p]) && need(4)) rd_i32(); }
+        if ((in.op == 0x01 || in.op == 0x02) && (in.a < 0 || in.a >= cnt)) return fail(IFX_ERR_INVALID, "constant index out of range");
+        if (in.op == 0x01 && consts[in.a].kind != 1) return fail(IFX_ERR_INVALID, "PUSH_FIELD operand is not a string");
+        if ((in.op == 0x60 || in.op == 0x61 || in.op == 0x62) && (in.a < 0 || in.a > ic)) return fail(IFX_ERR_INVALID, "jump target out of range");
+        code.push_back(in); }
+    try {
+        std::lock_guard<std::mutex> lk(idx->mu);
+        FilterProg fp{}; if (chars.empty()) chars.push_back(0);
+        fp.consts = idx->up(consts.data(), std::max<size_t>(consts.size(), 1)); fp.code = idx->up(code.data(), std::max<size_t>(code.size(), 1)); fp.chars = idx->up(chars.data(), chars.size());
+        fp.n_consts = (int)consts.size(); fp.n_code = (int)code.size();
+        idx->h_filters.push_back(fp);
+        idx->d_filters = idx->up(idx->h_filters.data(), idx->h_filters.size());   // small; previous copies are released with the index
+        *out_id = (int)idx->h_filters.size() - 1;
+    } catch (const std::string& e) { return fail(IFX_ERR_CUDA, e); }
+    return IFX_OK;
+}
+
+// ---- kernels ---------------------------------------------------------------------------------------------------------------
+#ifndef IFX_EMU
+__global__ void __launch_bounds__(256) k_wm(DevIndex ix, const QueryPlan* plans, int nq, const int32_t* s1_doc, const float* s1_score, const int32_t* s1_n, int K,
+                                            S1Workspace* wss, Stage2Buffers B, int* work) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    WmShared& sh = *reinterpret_cast<WmShared*>(smem_raw); Ctx c; S1Workspace ws = wss[blockIdx.x];
+    for (int i = threadIdx.x; i < MAX_CONTAINERS; i += blockDim.x) sh.dirty[i] = 0;
+    __syncthreads();
+    for (;;) {
+        if (threadIdx.x == 0) sh.bcast[7] = atomicAdd(work, 1);
+        __syncthreads();
+        int q = sh.bcast[7]; __syncthreads();
+        if (q >= nq) break;
+        wm_query(c, ix, plans[q], s1_doc + (size_t)q * K, s1_score + (size_t)q * K, s1_n[q], ws, sh, B, q);
+        __syncthreads();
+    }
+}
+__global__ void k_cov_prepare(DevIndex ix, const QueryPlan* plans, int nq, Stage2Buffers B) {
+    int q = blockIdx.x * blockDim.x + threadIdx.x; if (q >= nq) return;
+    if (B.mode[q] == 0) prepare_cov_query(ix, plans[q].qtext, plans[q].qlen, B.covq[q]);
+}
+__global__ void __launch_bounds__(128) k_cov_eval(DevIndex ix, const QueryPlan* plans, int nq, Stage2Buffers B) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; int q = (int)(i / B.ent_cap), e = (int)(i % B.ent_cap);
+    if (q >= nq || B.mode[q] != 0 || e >= B.ent_n[q]) return;
+    cov_eval_entry(ix, plans[q], B, q, e);
+}
+__global__ void __launch_bounds__(256) k_finalize(DevIndex ix, const QueryPlan* plans, int nq, const int32_t* s1_doc, const float* s1_score, const int32_t* s1_n, int K,
+                                                  Stage2Buffers B, const FilterProg* filters, int n_filters, FinalOut O) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    FinShared& sh = *reinterpret_cast<FinShared*>(smem_raw); Ctx c; int q = blockIdx.x;
+    finalize_query(c, ix, plans[q], s1_doc + (size_t)q * K, s1_score + (size_t)q * K, s1_n[q], B, filters, n_filters, sh, O, q);
+}
+#endif
+
+static void run_stage2_phase(ifx_batch* b, ifx_stats* st) {
+    ifx_index* ix = b->idx; const int nq = b->nq; const int K = b->depth_max;
+    Timer t;
+#ifdef IFX_EMU
+    static WmShared* wsh = new WmShared(); static FinShared* fsh = new FinShared(); memset(wsh->dirty, 0, sizeof(wsh->dirty));
+    Ctx c;
+    for (int q = 0; q < nq; q++) wm_query(c, ix->v, b->d_plans[q], b->d_s1_doc + (size_t)q * K, b->d_s1_score + (size_t)q * K, b->d_s1_n[q], ix->ws[0], *wsh, b->s2, q);
+    for (int q = 0; q < nq; q++) if (b->s2.mode[q] == 0) { prepare_cov_query(ix->v, b->d_plans[q].qtext, b->d_plans[q].qlen, b->s2.covq[q]); for (int e = 0; e < b->s2.ent_n[q]; e++) cov_eval_entry(ix->v, b->d_plans[q], b->s2, q, e); }
+    for (int q = 0; q < nq; q++) finalize_query(c, ix->v, b->d_plans[q], b->d_s1_doc + (size_t)q * K, b->d_s1_score + (size_t)q * K, b->d_s1_n[q], b->s2, ix->d_filters, (int)ix->h_filters.size(), *fsh, b->fin, q);
+    (void)t; (void)st;
+#else
+    static bool attr_set = false;
+    if (!attr_set) { CUDA_TRY(cudaFuncSetAttribute(k_wm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WmShared))); CUDA_TRY(cudaFuncSetAttribute(k_finalize, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FinShared))); attr_set = true; }
+    t.start();
+    CUDA_TRY(cudaMemsetAsync(b->d_work + 2, 0, sizeof(int)));
+    k_wm<<<std::min(ix->n_ctas, nq), 256, sizeof(WmShared)>>>(ix->v, b->d_plans, nq, b->d_s1_doc, b->d_s1_score, b->d_s1_n, K, ix->d_ws, b->s2, b->d_work + 2);
+    float ms_wm = t.stop();
+    t.start();
+    k_cov_prepare<<<(nq + 63) / 64, 64>>>(ix->v, b->d_plans, nq, b->s2);
+    long long total = (long long)nq * b->s2.ent_cap;
+    k_cov_eval<<<(unsigned)((total + 127) / 128), 128>>>(ix->v, b->d_plans, nq, b->s2);
+    float ms_cov = t.stop();
+    t.start();
+    k_finalize<<<nq, 256, sizeof(FinShared)>>>(ix->v, b->d_plans, nq, b->d_s1_doc, b->d_s1_score, b->d_s1_n, K, b->s2, ix->d_filters, (int)ix->h_filters.size(), b->fin);
+    float ms_fin = t.stop();
+    CUDA_TRY(cudaGetLastError());
+    if (st) { st->ms_wordmatch += ms_wm; st->ms_stage2 += ms_cov; st->ms_final += ms_fin; st->kernel_launches += 4; }
+#endif
+}
+
+static int alloc_stage2(ifx_batch* b, int cap, int fcap) {
+    const size_t nq = b->nq; const size_t ec = 2 * (size_t)b->depth_max;
+    Stage2Buffers& S = b->s2; S.ent_cap = (int)ec;
+    S.ent_doc = b->alloc<int32_t>(nq * ec); S.ent_base = b->alloc<float>(nq * ec); S.ent_twin = b->alloc<int32_t>(nq * ec); S.ent_n = b->alloc<int32_t>(nq);
+    S.ent_score = b->alloc<float>(nq * ec); S.ent_tie = b->alloc<uint8_t>(nq * ec); S.ent_hits = b->alloc<int32_t>(nq * ec); S.ent_lcs = b->alloc<uint8_t>(nq * ec);
+    S.di_doc = b->alloc<int32_t>(nq * 2); S.wm_any = b->alloc<int32_t>(nq); S.mode = b->alloc<int32_t>(nq); S.covq = b->alloc<CovQuery>(nq);
+    FinalOut& O = b->fin; O.cap = cap; O.fcap = fcap; size_t fc = std::max(fcap, 1);
+    O.key = b->alloc<int64_t>(nq * cap); O.score = b->alloc<float>(nq * cap); O.tie = b->alloc<uint8_t>(nq * cap); O.n = b->alloc<int32_t>(nq); O.total = b->alloc<int32_t>(nq); O.status = b->alloc<int32_t>(nq);
+    O.facet_col = b->alloc<int32_t>(nq * fc); O.facet_val = b->alloc<int32_t>(nq * fc); O.facet_cnt = b->alloc<int32_t>(nq * fc); O.n_facets = b->alloc<int32_t>(nq);
+    return IFX_OK;
+}
+
+extern "C" int ifx_batch_run(ifx_batch* b, ifx_stats* st) {
+    if (!b) return fail(IFX_ERR_INVALID, "null batch");
+    if (!dev_ok()) return fail(IFX_ERR_NO_DEVICE, "no CUDA device available (infidex_b200 has no CPU fallback)");
+    if (st) { int64_t h = st->h2d_bytes, d = st->d2h_bytes; memset(st, 0, sizeof(*st)); st->h2d_bytes = h; st->d2h_bytes = d; }
+    try {
+        std::lock_guard<std::mutex> lk(b->idx->mu);
+        if (!b->s2.ent_doc) alloc_stage2(b, std::max(b->cap_max, 1), b->fcap);
+        Timer tt; tt.start();
+        run_stage1_phase(b, st);
+        run_stage2_phase(b, st);
+        float ms = tt.stop(); if (st) st->ms_total = ms;
+        b->ran = true;
+    } catch (const std::string& e) { return fail(IFX_ERR_CUDA, e); }
+    return IFX_OK;
+}
+
+extern "C" int ifx_batch_download(ifx_batch* b, ifx_batch_result* out) {
+    if (!b || !out || !b->ran) return fail(IFX_ERR_INVALID, "batch has not been run");
+    if (out->cap < b->fin.cap) return fail(IFX_ERR_INVALID, "result capacity smaller than the batch's max_results");
+    const size_t nq = b->nq; const int cap = b->fin.cap;
+    try {
+        if (out->cap == cap) { d2h(out->doc_key, b->fin.key, nq * cap * 8); d2h(out->score, b->fin.score, nq * cap * 4); d2h(out->tie, b->fin.tie, nq * cap); }
+        else { std::vector<int64_t> k(nq * cap); std::vector<float> s(nq * cap); std::vector<uint8_t> t(nq * cap); d2h(k.data(), b->fin.key, nq * cap * 8); d2h(s.data(), b->fin.score, nq * cap * 4); d2h(t.data(), b->fin.tie, nq * cap);
+            for (size_t q = 0; q < nq; q++) { memcpy(out->doc_key + q * out->cap, k.data() + q * cap, cap * 8); memcpy(out->score + q * out->cap, s.data() + q * cap, cap * 4); memcpy(out->tie + q * out->cap, t.data() + q * cap, cap); } }
+        d2h(out->n, b->fin.n, nq * 4); d2h(out->total_candidates, b->fin.total, nq * 4); d2h(out->status, b->fin.status, nq * 4);
+        if (out->n_facets) { d2h(out->n_facets, b->fin.n_facets, nq * 4);
+            if (out->facet_cap > 0 && b->fin.fcap > 0 && out->facet_column) {
+                if (out->facet_cap == b->fin.fcap) { size_t n = nq * b->fin.fcap * 4; d2h(out->facet_column, b->fin.facet_col, n); d2h(out->facet_value, b->fin.facet_val, n); d2h(out->facet_count, b->fin.facet_cnt, n); }
+                else return fail(IFX_ERR_INVALID, "facet_cap mismatch"); } }
+    } catch (const std::string& e) { return fail(IFX_ERR_CUDA, e); }
+    return IFX_OK;
+}
+
+extern "C" int ifx_search_batch(ifx_index* idx, const ifx_query* q, int nq, ifx_batch_result* out, ifx_stats* st) {
+    if (!out) return fail(IFX_ERR_INVALID, "null result");
+    if (!dev_ok()) return fail(IFX_ERR_NO_DEVICE, "no CUDA device available (infidex_b200 has no CPU fallback)");
+    ifx_batch* b = nullptr; int rc = ifx_batch_upload(idx, q, nq, &b); if (rc) return rc;
+    b->fcap = out->facet_cap; b->cap_max = std::max(b->cap_max, std::min(out->cap, b->cap_max));
+    if (st) { memset(st, 0, sizeof(*st)); int64_t h = 0; for (int i = 0; i < nq; i++) h += 2LL * q[i].len + 20; st->h2d_bytes = h; }
+    rc = ifx_batch_run(b, st);
+    if (!rc) rc = ifx_batch_download(b, out);
+    if (!rc && st) st->d2h_bytes = (int64_t)nq * ((int64_t)b->fin.cap * 13 + 12 + (out->facet_cap > 0 ? 12LL * out->facet_cap + 4 : 0));
+    delete b; return rc;
+}

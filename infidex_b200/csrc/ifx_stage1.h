@@ -539,8 +539,21 @@ IFX_FN void stage1_query(const Ctx& c, const DevIndex& ix, const QueryPlan& p, c
             // no barrier needed here: the next term writes the other tf buffer, and three barriers separate reuse of this one
         }
         c.sync();
-        if (c.tid() == 0) {   // flush (Bm25Scorer.cs:316-329) -- sequential by construction (exact heap emulation)
-            for (int j = 0; j < cnt; j++) { float s = sh.score[j]; if (s > 0.f) { int d = sh.cand_s[j]; if (!ix.deleted[d]) { if (sh.heap_size < K || s > sh.thr) update_topk(sh, d, s, K); } } }
+        {   // flush (Bm25Scorer.cs:316-329): eligibility in parallel (the threshold only rises during a flush, so anything not above the
+            // chunk-start threshold can never enter), then the exact sequential heap emulation over the survivors in candidate order
+            const bool full = sh.heap_size >= K;
+            for (int r = 0; r < rounds; r++) {
+                int j = r * NT + c.tid();
+                bool e = j < cnt && sh.score[j] > 0.f && (!full || sh.score[j] > thr) && !ix.deleted[sh.cand_s[j]];
+                unsigned b = c.ballot(e);
+                if (c.lane() == 0) sh.ballots[r * NW + c.warp()] = b;
+            }
+            c.sync();
+            if (c.tid() == 0) {
+                const int slots = rounds * NW;
+                for (int sl = 0; sl < slots; sl++) { unsigned mk = sh.ballots[sl]; int jb = (sl / NW) * NT + (sl % NW) * Ctx::WS;
+                    while (mk) { int l = ffs32(mk) - 1; mk &= mk - 1; int j = jb + l; float s = sh.score[j]; if (sh.heap_size < K || s > sh.thr) update_topk(sh, sh.cand_s[j], s, K); } }
+            }
         }
         c.sync();
         pos += cnt;

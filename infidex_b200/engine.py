@@ -220,6 +220,10 @@ class SearchEngine:
         self._host.ifx_builder_finish(C.c_void_p(self._builder), threads or max(1, min(os.cpu_count() or 1, 16)))
         img = self._host.ifx_builder_image(C.c_void_p(self._builder))
         self._schema = list(schema)
+        self._columns = []
+        buf = np.zeros(4096, np.uint16); b = C.c_void_p(self._builder)
+        for c in range(self._host.ifx_builder_num_columns(b)):
+            n = self._host.ifx_builder_column_name(b, c, _p(buf), len(buf)); self._columns.append(buf[:n].tobytes().decode("utf-16-le"))
         self._upload(img)
 
     def image_ptr(self):
@@ -283,9 +287,14 @@ class SearchEngine:
             if queries[i].EnableFacets:
                 facets = {}
                 for k in range(nf[i]):
-                    facets.setdefault(int(fcol[i, k]), []).append((int(fval[i, k]), int(fcnt[i, k])))
+                    facets.setdefault(self._columns[int(fcol[i, k])], []).append((self._facet_value(int(fcol[i, k]), int(fval[i, k])), int(fcnt[i, k])))
             res.append(Result(recs, facets, int(total[i]), int(status[i])))
         return res
+
+    def _facet_value(self, col, vid):
+        buf = np.zeros(1024, np.uint16)
+        n = self._host.ifx_builder_column_value(C.c_void_p(self._builder), col, vid, _p(buf), len(buf))
+        return buf[:n].tobytes().decode("utf-16-le", "surrogatepass")
 
     def Search(self, query):
         if isinstance(query, str):
