@@ -172,6 +172,9 @@ extern "C" int ifx_index_create(const ifx_index_image* img, const ifx_params* pp
             v.lower = ix->up(lo.data(), 65536); v.upper = ix->up(upv.data(), 65536); v.cflags = ix->up(fl.data(), 65536);
             std::vector<float> l2(1024); for (int i = 0; i < 1024; i++) l2[i] = std::log2((float)(i + 1));
             v.log2_len = ix->up(l2.data(), 1024);
+            int tn = std::max(1, std::min(img->n_live, P.stop_term_limit)) + 1; std::vector<float> idf(tn, 0.f);
+            for (int df = 1; df < tn; df++) { float d = (float)df, Nf = (float)img->n_live; float ratio = (Nf - d + 0.5f) / (d + 0.5f); idf[df] = ratio <= 0.f ? 0.f : std::log(ratio + 1.f); }
+            v.idf_table = ix->up(idf.data(), tn); v.idf_table_n = tn;
         }
         {   // filter / facet columns: ToString() dictionary + parsed numeric view of every dictionary entry
             ix->h_columns.resize(img->n_columns);

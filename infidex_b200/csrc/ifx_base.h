@@ -59,6 +59,8 @@ struct DevIndex {
     const int32_t* affix_rev_doc;    // last doc, in reverse-trie order
     const uint16_t* lower; const uint16_t* upper; const uint8_t* cflags;   // 65536-entry tables
     const float* log2_len;           // MathF.Log2(len + 1) for len < 1024 (host glibc)
+    const float* idf_table;          // Bm25Scorer.ComputeIdf(n_live, df) for df in [0, idf_table_n): evaluated on the host with the
+    int32_t idf_table_n;             // C runtime's logf (what MathF.Log calls), so device scores cannot drift from the reference by an ulp
     int32_t n_columns; const Column* columns;
 };
 
@@ -118,10 +120,11 @@ __device__ __forceinline__ int ffs32(unsigned v) { return __ffs((int)v); }
 __device__ __forceinline__ float dev_logf_exact(float x) { return (float)log((double)x); }
 #endif
 
-// Bm25Scorer.ComputeIdf (src/Infidex/Indexing/Bm25Scorer.cs:686-695)
-IFX_FN float compute_idf(int total, int df) {
-    if (df <= 0 || total <= 0) return 0.f;
-    float d = (float)df, N = (float)total;
+// Bm25Scorer.ComputeIdf (src/Infidex/Indexing/Bm25Scorer.cs:686-695) -- table lookup, see DevIndex::idf_table
+IFX_FN float compute_idf(const DevIndex& ix, int df) {
+    if (df <= 0 || ix.n_live <= 0) return 0.f;
+    if (df < ix.idf_table_n) return ix.idf_table[df];
+    float d = (float)df, N = (float)ix.n_live;          // df > stop-term limit: the term is dropped by the caller anyway
     float ratio = (N - d + 0.5f) / (d + 0.5f);
     return ratio <= 0.f ? 0.f : dev_logf_exact(ratio + 1.f);
 }

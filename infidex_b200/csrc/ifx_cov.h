@@ -127,7 +127,7 @@ IFX_FN void prepare_cov_query(const DevIndex& ix, const uint16_t* q, int qlen, C
     c.n_tok = nu;
     for (int i = 0; i < nu; i++) {   // ComputeTermIdf: mean idf of the token's unpadded 3-grams with df > 0, else log2(len + 1)
         Str t = sub(qs, c.tok[i].off, c.tok[i].len); float sum = 0.f; int cnt = 0;
-        if (ix.n_live > 0) for (int k = 0; k + 3 <= t.n; k++) { int id = dict_lookup(ix.terms, t.p + k, 3); if (id >= 0 && ix.df[id] > 0) { sum += compute_idf(ix.n_live, ix.df[id]); cnt++; } }
+        if (ix.n_live > 0) for (int k = 0; k + 3 <= t.n; k++) { int id = dict_lookup(ix.terms, t.p + k, 3); if (id >= 0 && ix.df[id] > 0) { sum += compute_idf(ix, ix.df[id]); cnt++; } }
         c.term_idf[i] = cnt > 0 ? sum / (float)cnt : ix.log2_len[t.n < 1023 ? t.n : 1023];
         int w = dict_lookup(ix.words, t.p, t.n);        // query is lower case == cache key case
         c.word_idf[i] = w >= 0 ? ix.word_idf[w] : 0.f;

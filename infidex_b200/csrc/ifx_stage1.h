@@ -90,7 +90,7 @@ IFX_FN void prepare_query(const DevIndex& ix, const uint16_t* text, int len, int
             if (df <= 0 || df > ix.stop_term_limit) continue;
             QTerm& t = p.terms[nt++];
             t.term_id = raw[i].id; t.df = df; t.list_off = ix.row_ptr[raw[i].id]; t.list_len = (int32_t)(ix.row_ptr[raw[i].id + 1] - ix.row_ptr[raw[i].id]);
-            t.idf = compute_idf(ix.n_live, df); t.max_score = max_term_score(t.idf, avgdl);
+            t.idf = compute_idf(ix, df); t.max_score = max_term_score(t.idf, avgdl);
         } else if (raw[i].len >= 4) {
             if (p.n_fuzzy >= MAX_FUZZY || raw[i].len > 64) { p.status |= 4; continue; }
             int slot = atomic_add(&bc->n_fuzzy_items, 1);
@@ -346,7 +346,7 @@ IFX_FN void expand_fuzzy(const Ctx& c, const DevIndex& ix, QueryPlan& p, int fsl
     int64_t n = compact_bits(c, ix, ws, sh, pool + b, cap, ovf);
     if (c.tid() == 0) {
         if (ovf || n != df) { p.status |= 4; atomic_add(&bc->overflow, 1); t.df = 0; t.list_len = 0; }
-        else { float avgdl = ix.avgdl > 0.f ? ix.avgdl : 1.f; t.df = df; t.list_len = df; t.list_off = (int64_t)b; t.idf = compute_idf(ix.n_live, df); t.max_score = max_term_score(t.idf, avgdl); }
+        else { float avgdl = ix.avgdl > 0.f ? ix.avgdl : 1.f; t.df = df; t.list_len = df; t.list_off = (int64_t)b; t.idf = compute_idf(ix, df); t.max_score = max_term_score(t.idf, avgdl); }
     }
     c.sync();
 }

@@ -13,3 +13,7 @@ t0 = time.time(); e = ib.SearchEngine.CreateDefault(); e.IndexColumns(docs["keys
 for r in range(reps):
     st = ib.Stats(); t0 = time.time(); k, s, n, status = e.Stage1Batch(qs, 500, st); dt = time.time() - t0
     print("rep", r, "wall %.1f ms" % (dt * 1e3), {k2: round(v, 3) if isinstance(v, float) else v for k2, v in st.as_dict().items()}, "mean n", n.mean(), "bad status", int((status != 0).sum()), flush=True)
+queries = [ib.Query(q, 10) for q in qs]
+for r in range(reps):
+    st = ib.Stats(); t0 = time.time(); res = e.SearchBatch(queries, st); dt = time.time() - t0
+    print("search rep", r, "wall %.1f ms" % (dt * 1e3), {k2: round(v, 3) if isinstance(v, float) else v for k2, v in st.as_dict().items()}, "bad status", sum(1 for x in res if x.Status & ~8), flush=True)
