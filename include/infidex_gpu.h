@@ -153,6 +153,9 @@ void ifx_batch_free(ifx_batch* b);
 int  ifx_stage1_batch(ifx_index* idx, const ifx_query* q, int nq, int depth, int64_t* doc_key, float* score, int32_t* n,
                       int32_t* status, ifx_stats* st);
 
+/* benchmark hygiene: overwrite a 256 MiB scratch buffer so the next run starts with a cold L2 */
+int  ifx_flush_l2(ifx_index* idx);
+
 const char* ifx_last_error(void);     /* thread-local description of the last failure */
 int  ifx_device_count(void);
 

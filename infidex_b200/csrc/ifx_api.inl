@@ -55,17 +55,17 @@ struct ifx_index {
     std::vector<S1Workspace> ws; S1Workspace* d_ws = nullptr;
     int32_t* d_pool = nullptr; unsigned long long pool_cap = 0;
     int max_batch = 16384;
-    int device = 0;
+    int device = 0; uint8_t* d_flush = nullptr;
     std::vector<FilterProg> h_filters; FilterProg* d_filters = nullptr;
     std::vector<Column> h_columns; std::vector<std::u16string> column_names;
-    std::mutex mu;
-    ~ifx_index() { for (void* p : allocs) dev_free(p); }
+    std::mutex mu; std::mutex call_mu; struct ifx_batch* cached = nullptr;   // batch workspace reused by ifx_search_batch
+    ~ifx_index();
     template <class T> T* up(const T* src, size_t n) { T* d = (T*)dev_alloc(n * sizeof(T)); allocs.push_back(d); if (src && n) h2d(d, src, n * sizeof(T)); return d; }
     template <class T> T* alloc(size_t n) { T* d = (T*)dev_alloc(n * sizeof(T)); allocs.push_back(d); return d; }
 };
 
 struct ifx_batch {
-    ifx_index* idx = nullptr; int nq = 0; int depth_max = 0; int cap_max = 0;
+    ifx_index* idx = nullptr; int nq = 0; int depth_max = 0; int cap_max = 0; size_t text_cap = 0;
     std::vector<void*> allocs;
     uint16_t* d_text = nullptr; int64_t* d_off = nullptr; int32_t* d_par = nullptr;   // par: [nq][5] max_results, depth, enable_cov, filter_id, enable_facets
     QueryPlan* d_plans = nullptr; FuzzyItem* d_items = nullptr; BatchCounters* d_bc = nullptr; int* d_work = nullptr;
@@ -76,6 +76,8 @@ struct ifx_batch {
     ~ifx_batch() { for (void* p : allocs) dev_free(p); }
     template <class T> T* alloc(size_t n) { T* d = (T*)dev_alloc(n * sizeof(T)); allocs.push_back(d); return d; }
 };
+
+ifx_index::~ifx_index() { delete cached; for (void* p : allocs) dev_free(p); }
 
 static uint64_t hash_host(const uint16_t* s, int n) {
     uint64_t h = 0xcbf29ce484222325ULL ^ (uint64_t)n;
@@ -138,6 +140,15 @@ extern "C" int ifx_index_create(const ifx_index_image* img, const ifx_params* pp
         v.df = ix->up(img->df, T); v.row_ptr = ix->up(img->row_ptr, (size_t)T + 1);
         size_t P_ = T ? (size_t)img->row_ptr[T] : 0;
         v.post_doc = ix->up(img->post_doc, P_ ? P_ : 1); v.post_tf = ix->up(img->post_tf, P_ ? P_ : 1);
+        {   // container skip table for long posting lists: turns the per-chunk sub-range search of the scorer into a lookup
+            const int ncont = (N + 65535) >> 16; const int64_t SKIP_MIN = 512; v.n_cont = ncont;
+            std::vector<int32_t> sid(std::max(T, 1), -1); std::vector<int32_t> sp; int ns = 0;
+            for (int t = 0; t < T; t++) { int64_t r0 = img->row_ptr[t], len = img->row_ptr[t + 1] - r0; if (len < SKIP_MIN) continue;
+                sid[t] = ns++; size_t base = sp.size(); sp.resize(base + ncont + 1); int64_t i = 0;
+                for (int c = 0; c <= ncont; c++) { int64_t lim = (int64_t)c << 16; while (i < len && img->post_doc[r0 + i] < lim) i++; sp[base + c] = (int32_t)i; } }
+            if (sp.empty()) sp.push_back(0);
+            v.skip_id = ix->up(sid.data(), sid.size()); v.skip_ptr = ix->up(sp.data(), sp.size());
+        }
         // trie DFS order == ordinal-lexicographic order of the term texts (FstBuilder.CompactTrie sorts arcs by label)
         std::vector<int32_t> order(T); std::iota(order.begin(), order.end(), 0);
         auto term_sv = [&](int i) { return std::u16string_view((const char16_t*)img->terms.chars + img->terms.off[i], img->terms.off[i + 1] - img->terms.off[i]); };

@@ -51,6 +51,9 @@ struct DevIndex {
     StrDict first_token; const uint16_t* token_count;
     StrDict terms; const int32_t* df; const int64_t* row_ptr; const int32_t* post_doc; const uint8_t* post_tf;
     const int32_t* term_sorted;      // term ordinals in ordinal-lexicographic order (trie DFS order)
+    const int32_t* skip_id;          // per term: row of the container skip table, or -1 (short lists)
+    const int32_t* skip_ptr;         // [n_skip][n_cont + 1] offset (relative to the row start) of the first posting with doc >= c << 16
+    int32_t n_cont;                  // 65536-doc containers in this shard
     StrDict words; const float* word_idf;
     DocsetDict prefix, wm_exact, wm_ld1;
     StrDict affix;                   // affix words in ordinal-lexicographic order

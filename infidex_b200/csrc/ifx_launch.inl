@@ -73,23 +73,34 @@ static void run_stage1_phase(ifx_batch* b, ifx_stats* st) {
     if (st) { BatchCounters bc; d2h(&bc, b->d_bc, sizeof(bc)); st->algo_bytes_stage1 += (int64_t)bc.algo_bytes; }
 }
 
-extern "C" int ifx_batch_upload(ifx_index* idx, const ifx_query* q, int nq, ifx_batch** out) {
-    if (!idx || !q || nq <= 0 || !out) return fail(IFX_ERR_INVALID, "bad batch arguments");
-    ifx_batch* b = new ifx_batch(); b->idx = idx; b->nq = nq;
-    try {
-        std::vector<int64_t> off(nq + 1, 0); std::vector<int32_t> par((size_t)nq * 5);
-        for (int i = 0; i < nq; i++) { off[i + 1] = off[i] + std::max(q[i].len, 0); par[i * 5 + 0] = q[i].max_results; par[i * 5 + 1] = q[i].coverage_depth; par[i * 5 + 2] = q[i].enable_coverage; par[i * 5 + 3] = q[i].filter_id; par[i * 5 + 4] = q[i].enable_facets;
-            b->depth_max = std::max(b->depth_max, q[i].coverage_depth); b->cap_max = std::max(b->cap_max, q[i].max_results); }
-        if (b->depth_max < 1 || b->depth_max > MAX_K) { delete b; return fail(IFX_ERR_INVALID, "coverage_depth must be in [1,1024]"); }
-        std::vector<uint16_t> text((size_t)off[nq] + 1);
-        for (int i = 0; i < nq; i++) if (q[i].len > 0) memcpy(text.data() + off[i], q[i].text, (size_t)q[i].len * 2);
-        b->d_text = b->alloc<uint16_t>(text.size()); h2d(b->d_text, text.data(), text.size() * 2);
-        b->d_off = b->alloc<int64_t>(nq + 1); h2d(b->d_off, off.data(), (nq + 1) * 8);
-        b->d_par = b->alloc<int32_t>(par.size()); h2d(b->d_par, par.data(), par.size() * 4);
+// (re)fill the per-batch inputs; allocates on first use or when the batch outgrows its buffers
+static int fill_batch(ifx_batch* b, const ifx_query* q, int nq) {
+    std::vector<int64_t> off(nq + 1, 0); std::vector<int32_t> par((size_t)nq * 5);
+    int depth_max = 0, cap_max = 0;
+    for (int i = 0; i < nq; i++) { off[i + 1] = off[i] + std::max(q[i].len, 0); par[i * 5 + 0] = q[i].max_results; par[i * 5 + 1] = q[i].coverage_depth; par[i * 5 + 2] = q[i].enable_coverage; par[i * 5 + 3] = q[i].filter_id; par[i * 5 + 4] = q[i].enable_facets;
+        depth_max = std::max(depth_max, q[i].coverage_depth); cap_max = std::max(cap_max, q[i].max_results); }
+    if (depth_max < 1 || depth_max > MAX_K) return fail(IFX_ERR_INVALID, "coverage_depth must be in [1,1024]");
+    std::vector<uint16_t> text((size_t)off[nq] + 1);
+    for (int i = 0; i < nq; i++) if (q[i].len > 0) memcpy(text.data() + off[i], q[i].text, (size_t)q[i].len * 2);
+    const bool fresh = b->d_plans == nullptr;
+    if (!fresh && (nq != b->nq || depth_max != b->depth_max || cap_max > b->cap_max)) return fail(IFX_ERR_INVALID, "batch shape changed");
+    if (fresh) {
+        b->nq = nq; b->depth_max = depth_max; b->cap_max = cap_max; b->text_cap = std::max<size_t>(text.size(), (size_t)nq * 64);
+        b->d_text = b->alloc<uint16_t>(b->text_cap); b->d_off = b->alloc<int64_t>(nq + 1); b->d_par = b->alloc<int32_t>(par.size());
         b->d_plans = b->alloc<QueryPlan>(nq); b->d_items = b->alloc<FuzzyItem>((size_t)nq * 4 + 64); b->d_bc = b->alloc<BatchCounters>(1); b->d_work = b->alloc<int>(8); dev_zero(b->d_work, 8 * sizeof(int));
         size_t K = b->depth_max;
         b->d_s1_key = b->alloc<int64_t>(nq * K); b->d_s1_doc = b->alloc<int32_t>(nq * K); b->d_s1_score = b->alloc<float>(nq * K); b->d_s1_n = b->alloc<int32_t>(nq);
-    } catch (const std::string& e) { delete b; return fail(IFX_ERR_CUDA, e); }
+    } else if (text.size() > b->text_cap) return fail(IFX_ERR_INVALID, "batch text outgrew its buffer");
+    h2d(b->d_text, text.data(), text.size() * 2); h2d(b->d_off, off.data(), (nq + 1) * 8); h2d(b->d_par, par.data(), par.size() * 4);
+    b->ran = false;
+    return IFX_OK;
+}
+
+extern "C" int ifx_batch_upload(ifx_index* idx, const ifx_query* q, int nq, ifx_batch** out) {
+    if (!idx || !q || nq <= 0 || !out) return fail(IFX_ERR_INVALID, "bad batch arguments");
+    ifx_batch* b = new ifx_batch(); b->idx = idx;
+    try { int rc = fill_batch(b, q, nq); if (rc) { delete b; return rc; } }
+    catch (const std::string& e) { delete b; return fail(IFX_ERR_CUDA, e); }
     *out = b; return IFX_OK;
 }
 extern "C" void ifx_batch_free(ifx_batch* b) { delete b; }

@@ -180,13 +180,29 @@ extern "C" int ifx_batch_download(ifx_batch* b, ifx_batch_result* out) {
 }
 
 extern "C" int ifx_search_batch(ifx_index* idx, const ifx_query* q, int nq, ifx_batch_result* out, ifx_stats* st) {
-    if (!out) return fail(IFX_ERR_INVALID, "null result");
+    if (!idx || !q || nq <= 0 || !out) return fail(IFX_ERR_INVALID, "bad arguments");
     if (!dev_ok()) return fail(IFX_ERR_NO_DEVICE, "no CUDA device available (infidex_b200 has no CPU fallback)");
-    ifx_batch* b = nullptr; int rc = ifx_batch_upload(idx, q, nq, &b); if (rc) return rc;
-    b->fcap = out->facet_cap; b->cap_max = std::max(b->cap_max, std::min(out->cap, b->cap_max));
-    if (st) { memset(st, 0, sizeof(*st)); int64_t h = 0; for (int i = 0; i < nq; i++) h += 2LL * q[i].len + 20; st->h2d_bytes = h; }
-    rc = ifx_batch_run(b, st);
-    if (!rc) rc = ifx_batch_download(b, out);
-    if (!rc && st) st->d2h_bytes = (int64_t)nq * ((int64_t)b->fin.cap * 13 + 12 + (out->facet_cap > 0 ? 12LL * out->facet_cap + 4 : 0));
-    delete b; return rc;
+    std::lock_guard<std::mutex> call_lock(idx->call_mu);      // one batch in flight per index (callers queue, like writers on the C# RW lock)
+    int rc = IFX_OK;
+    try {
+        ifx_batch* b = idx->cached;
+        if (b) { rc = fill_batch(b, q, nq); if (rc || b->fcap != out->facet_cap) { delete b; b = nullptr; idx->cached = nullptr; } }
+        if (!b) { b = new ifx_batch(); b->idx = idx; b->fcap = out->facet_cap; rc = fill_batch(b, q, nq); if (rc) { delete b; return rc; } idx->cached = b; }
+        if (st) { memset(st, 0, sizeof(*st)); int64_t h = 0; for (int i = 0; i < nq; i++) h += 2LL * q[i].len; st->h2d_bytes = h + (int64_t)nq * 28 + 8; }
+        rc = ifx_batch_run(b, st);
+        if (!rc) rc = ifx_batch_download(b, out);
+        if (!rc && st) st->d2h_bytes = (int64_t)nq * ((int64_t)b->fin.cap * 13 + 12 + (out->facet_cap > 0 ? 12LL * out->facet_cap + 4 : 0));
+    } catch (const std::string& e) { return fail(IFX_ERR_CUDA, e); }
+    return rc;
+}
+
+// Benchmark hygiene helper: evict the L2 (126 MB on B200) by overwriting a 256 MiB scratch buffer.
+extern "C" int ifx_flush_l2(ifx_index* idx) {
+    if (!idx) return fail(IFX_ERR_INVALID, "null index");
+    try { if (!idx->d_flush) idx->d_flush = idx->alloc<uint8_t>((size_t)256 << 20); dev_zero(idx->d_flush, (size_t)256 << 20);
+#ifndef IFX_EMU
+        CUDA_TRY(cudaDeviceSynchronize());
+#endif
+    } catch (const std::string& e) { return fail(IFX_ERR_CUDA, e); }
+    return IFX_OK;
 }

@@ -137,6 +137,27 @@ IFX_FN int64_t gallop_lower_bound(const int32_t* a, int64_t from, int64_t n, int
     return lower_bound_i32(a, lo + 1, hi, target);
 }
 
+// lower bound executed by one full warp: 32-way splits instead of binary halving (log32 n dependent loads).
+// Every lane of the calling warp must participate; the result is uniform across the warp.
+IFX_FN int64_t warp_lower_bound(const Ctx& c, const int32_t* a, int64_t lo, int64_t hi, int32_t target) {
+#ifdef IFX_EMU
+    (void)c; return lower_bound_i32(a, lo, hi, target);
+#else
+    while (hi - lo > 32) {   // invariant: a[x] < target for x < lo, a[x] >= target for x >= hi
+        int64_t step = (hi - lo + 31) / 32; int64_t p = lo + (int64_t)(c.lane() + 1) * step - 1; if (p > hi - 1) p = hi - 1;
+        unsigned m = __ballot_sync(0xffffffffu, a[p] < target); int k = __popc(m);          // probes are monotone: lanes [0,k) see "less"
+        int64_t pk = lo + (int64_t)(k + 1) * step - 1; if (pk > hi - 1) pk = hi - 1;          // first probe that is >= target (k < 32)
+        int64_t pk1 = lo + (int64_t)k * step - 1; if (pk1 > hi - 1) pk1 = hi - 1;            // last probe that is < target (k > 0)
+        if (k == 32) { lo = hi; break; }
+        if (k > 0) lo = pk1 + 1;
+        hi = pk;
+    }
+    int64_t i = lo + c.lane(); bool less = i < hi && a[i] < target;
+    unsigned m = __ballot_sync(0xffffffffu, less);
+    return lo + __popc(m);
+#endif
+}
+
 // per-CTA global workspace
 struct S1Workspace {
     unsigned* bits;        // candidate bitset over the shard's docs (all zero between uses)
@@ -146,7 +167,7 @@ struct S1Workspace {
 };
 
 struct TermS {             // term as seen by the scorer
-    const int32_t* docs; const uint8_t* tf; int32_t len; int32_t df; float idf, max_score, suffix_after; int64_t cursor, s0, s1;
+    const int32_t* docs; const uint8_t* tf; const int32_t* skip; int32_t len; int32_t df; float idf, max_score, suffix_after; int64_t cursor, s0, s1;
 };
 
 struct S1Shared {
@@ -162,6 +183,7 @@ struct S1Shared {
     ScanTmp scan;
     int bcast[8]; long long bcast64[4];
     unsigned long long streamed_mask[2];   // terms whose list the selector streamed in full (roofline accounting)
+    unsigned long long peq[128];           // Myers pattern masks of the word being expanded (ASCII fast path)
 };
 
 // OR a sorted id list into the CTA's bitset; returns the number of newly set docs (block-wide).
@@ -307,26 +329,42 @@ IFX_FN void expand_fuzzy(const Ctx& c, const DevIndex& ix, QueryPlan& p, int fsl
     const uint16_t* q = p.ttext + fr.off; const int m = fr.len;
     const uint64_t maskM = 1ULL << (m - 1);
     int64_t T = ix.terms.n; int total = 0;
-    for (int64_t base = 0; base < T && total < LD1_CAP; base += c.nthreads()) {
-        int64_t i = base + c.tid(); bool hit = false; int ord = -1;
-        if (i < T) {
-            int L = sorted_len[i];
-            if (L >= m - 1 && L <= m + 1 && L < 255) {
-                ord = ix.term_sorted[i]; const uint16_t* s = ix.terms.chars + ix.terms.off[ord];
-                uint64_t vp = ~0ULL, vn = 0ULL; int score = m;
-                for (int k = 0; k < L; k++) {
-                    uint16_t ch = s[k]; uint64_t pm = 0; for (int j = 0; j < m; j++) if (q[j] == ch) pm |= 1ULL << j;
-                    uint64_t x = pm | vn; uint64_t d0 = ((vp + (x & vp)) ^ vp) | x; uint64_t hn = vp & d0; uint64_t hp = vn | ~(vp | d0);
-                    uint64_t nvp = (hn << 1) | ~(d0 | (hp << 1)); uint64_t nvn = d0 & (hp << 1);
-                    if (hp & maskM) score++; if (hn & maskM) score--;
-                    vp = nvp; vn = nvn;
-                }
-                hit = score <= 1;
+    for (int ch = c.tid(); ch < 128; ch += c.nthreads()) { unsigned long long pm = 0; for (int j = 0; j < m; j++) if (q[j] == ch) pm |= 1ULL << j; sh.peq[ch] = pm; }
+    c.sync();
+    // Myers bit-vector (search variant, FstIndex.cs:316-335) along one dictionary term
+    auto myers_hit = [&](int64_t i, int L) -> bool {
+        int ord = ix.term_sorted[i]; const uint16_t* s = ix.terms.chars + ix.terms.off[ord];
+        uint64_t vp = ~0ULL, vn = 0ULL; int score = m;
+        for (int k = 0; k < L; k++) {
+            uint16_t ch = s[k]; uint64_t pm;
+            if (ch < 128) pm = sh.peq[ch]; else { pm = 0; for (int j = 0; j < m; j++) if (q[j] == ch) pm |= 1ULL << j; }
+            uint64_t x = pm | vn; uint64_t d0 = ((vp + (x & vp)) ^ vp) | x; uint64_t hn = vp & d0; uint64_t hp = vn | ~(vp | d0);
+            uint64_t nvp = (hn << 1) | ~(d0 | (hp << 1)); uint64_t nvn = d0 & (hp << 1);
+            if (hp & maskM) score++; if (hn & maskM) score--;
+            vp = nvp; vn = nvn;
+        }
+        return score <= 1;
+    };
+    {   // fast path: every thread scans one contiguous strip of the sorted dictionary (trie DFS order), one block scan at the end
+        const int HB = 8; int64_t hits[HB]; int cnt = 0;
+        int64_t per = (T + c.nthreads() - 1) / c.nthreads(); per = (per + 15) & ~15LL;
+        int64_t b = (int64_t)c.tid() * per, e = b + per; if (e > T) e = T;
+        for (int64_t i = b; i < e; i++) { int L = sorted_len[i]; if (L >= m - 1 && L <= m + 1 && L < 255 && myers_hit(i, L)) { if (cnt < HB) hits[cnt] = i; cnt++; } }
+        int tot; int off = block_excl_scan(c, cnt, sh.scan, tot);
+        int over = block_sum(c, cnt > HB ? 1 : 0, sh.scan);
+        if (over == 0) {
+            for (int k = 0; k < cnt; k++) if (off + k < LD1_CAP) matches[off + k] = ix.term_sorted[hits[k]];
+            total = tot;
+        } else {
+            // dense-match fallback: ordered compaction round by round, stop after LD1_CAP matches
+            for (int64_t base = 0; base < T && total < LD1_CAP; base += c.nthreads()) {
+                int64_t i = base + c.tid(); bool hit = false;
+                if (i < T) { int L = sorted_len[i]; hit = L >= m - 1 && L <= m + 1 && L < 255 && myers_hit(i, L); }
+                int t2; int o2 = block_excl_scan(c, hit ? 1 : 0, sh.scan, t2);
+                if (hit && total + o2 < LD1_CAP) matches[total + o2] = ix.term_sorted[i];
+                total += t2;
             }
         }
-        int tot; int off = block_excl_scan(c, hit ? 1 : 0, sh.scan, tot);
-        if (hit && total + off < LD1_CAP) matches[total + off] = ord;
-        total += tot;
     }
     c.sync();
     int nm = total < LD1_CAP ? total : LD1_CAP;
@@ -361,7 +399,8 @@ IFX_FN void stage1_query(const Ctx& c, const DevIndex& ix, const QueryPlan& p, c
             const QTerm& q = p.terms[i];
             if (q.df <= 0 || q.df > ix.stop_term_limit) continue;      // VectorModel.cs:521
             TermS& t = sh.terms[n]; t.len = q.list_len; t.df = q.df; t.idf = q.idf; t.max_score = q.max_score; t.cursor = 0;
-            if (q.term_id >= 0) { t.docs = ix.post_doc + q.list_off; t.tf = ix.post_tf + q.list_off; } else { t.docs = pool + q.list_off; t.tf = nullptr; }
+            if (q.term_id >= 0) { t.docs = ix.post_doc + q.list_off; t.tf = ix.post_tf + q.list_off; int sk = ix.skip_id[q.term_id]; t.skip = sk >= 0 ? ix.skip_ptr + (size_t)sk * (ix.n_cont + 1) : nullptr; }
+            else { t.docs = pool + q.list_off; t.tf = nullptr; t.skip = nullptr; }
             n++;
         }
         float suf = 0.f; for (int i = n - 1; i >= 0; i--) { sh.terms[i].suffix_after = suf; suf = suf + sh.terms[i].max_score; }   // ComputeSuffixSums
@@ -462,20 +501,27 @@ IFX_FN void stage1_query(const Ctx& c, const DevIndex& ix, const QueryPlan& p, c
     const int NW = c.nwarps();
     for (int64_t pos = 0; pos < n_cand;) {
         // container run: candidates sharing id >> 16, cut into sub-chunks of 4096
-        if (c.tid() == 0) {
+        if (c.warp() == 0) {
             int hb = cand[pos] >> 16; int64_t lim = ((int64_t)hb + 1) << 16;
-            int64_t ce = lim > 0x7fffffffLL ? n_cand : lower_bound_i32(cand, pos, n_cand, (int32_t)lim);
-            int64_t cnt = ce - pos; if (cnt > CHUNK) cnt = CHUNK; sh.bcast[2] = (int)cnt;
+            int64_t ce = lim > 0x7fffffffLL ? n_cand : warp_lower_bound(c, cand, pos, n_cand, (int32_t)lim);
+            if (c.lane() == 0) {
+            int64_t cnt = ce - pos; sh.bcast[4] = (cnt <= CHUNK && (pos == 0 || (cand[pos - 1] >> 16) != hb)) ? 1 : 0;   // chunk == all candidates of the container
+            if (cnt > CHUNK) cnt = CHUNK; sh.bcast[2] = (int)cnt;
+            }
         }
         c.sync();
-        const int cnt = sh.bcast[2];
+        const int cnt = sh.bcast[2]; const bool whole_container = sh.bcast[4] != 0;
         for (int j = c.tid(); j < cnt; j += NT) { sh.cand_s[j] = cand[pos + j]; sh.score[j] = 0.f; sh.tfbuf[0][j] = 0; sh.tfbuf[1][j] = 0; }
         c.sync();
         const int32_t first = sh.cand_s[0], last = sh.cand_s[cnt - 1];
         for (int t = c.tid(); t < T; t += NT) {      // posting sub-range of every term for this chunk (monotone cursors)
             TermS& tm = sh.terms[t];
-            int64_t s0 = gallop_lower_bound(tm.docs, tm.cursor, tm.len, first);
-            int64_t s1 = last == 0x7fffffff ? tm.len : gallop_lower_bound(tm.docs, s0, tm.len, last + 1);
+            int64_t lo = tm.cursor, hi = tm.len;
+            if (tm.skip) { int cc = first >> 16; int64_t b0 = tm.skip[cc], b1 = tm.skip[cc + 1]; if (b0 > lo) lo = b0; hi = b1; if (lo > hi) lo = hi; }   // window = this container's postings
+            int64_t s0, s1;
+            if (tm.skip && whole_container) { s0 = lo; s1 = hi; }
+            else if (tm.skip || tm.len < 1024) { s0 = lower_bound_i32(tm.docs, lo, hi, first); s1 = last == 0x7fffffff ? hi : lower_bound_i32(tm.docs, s0, hi, last + 1); }
+            else { s0 = gallop_lower_bound(tm.docs, lo, hi, first); s1 = last == 0x7fffffff ? hi : gallop_lower_bound(tm.docs, s0, hi, last + 1); }
             tm.s0 = s0; tm.s1 = s1; tm.cursor = s1;
         }
         c.sync();

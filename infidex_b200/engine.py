@@ -263,6 +263,26 @@ class SearchEngine:
             arr[i].enable_coverage = int(q.EnableCoverage); arr[i].filter_id = self._filter_id(q.Filter); arr[i].enable_facets = int(q.EnableFacets)
         return arr, texts
 
+    def PackBatch(self, queries, facet_cap=0):
+        """Host-side marshalling of a batch (what the C# shim does with `fixed` pointers): returns a reusable call object."""
+        nq = len(queries)
+        arr, keep = self._pack_queries(queries)
+        cap = max(1, max(q.MaxNumberOfRecordsToReturn for q in queries))
+        fc = facet_cap or (256 if any(q.EnableFacets for q in queries) else 0)
+        out = _BatchResult(); out.cap = cap; out.facet_cap = fc
+        bufs = dict(keys=np.zeros((nq, cap), np.int64), scores=np.zeros((nq, cap), np.float32), ties=np.zeros((nq, cap), np.uint8),
+                    n=np.zeros(nq, np.int32), total=np.zeros(nq, np.int32), status=np.zeros(nq, np.int32),
+                    fcol=np.zeros((nq, max(fc, 1)), np.int32), fval=np.zeros((nq, max(fc, 1)), np.int32), fcnt=np.zeros((nq, max(fc, 1)), np.int32), nf=np.zeros(nq, np.int32))
+        out.doc_key, out.score, out.tie, out.n, out.total_candidates, out.status = _p(bufs["keys"]), _p(bufs["scores"]), _p(bufs["ties"]), _p(bufs["n"]), _p(bufs["total"]), _p(bufs["status"])
+        out.facet_column, out.facet_value, out.facet_count, out.n_facets = _p(bufs["fcol"]), _p(bufs["fval"]), _p(bufs["fcnt"]), _p(bufs["nf"])
+        return {"arr": arr, "keep": keep, "nq": nq, "out": out, "bufs": bufs}
+
+    def SearchPacked(self, packed, stats=None):
+        """The bare C-ABI call ifx_search_batch on pre-marshalled host buffers (host -> device -> host)."""
+        st = stats if stats is not None else Stats()
+        self._check(self._gpu.ifx_search_batch(self._index, packed["arr"], packed["nq"], C.byref(packed["out"]), C.byref(st)), "ifx_search_batch")
+        return st
+
     def SearchBatch(self, queries, stats=None, facet_cap=0):
         """Batch form of Search: one C-ABI call for all queries (host buffers in, host buffers out)."""
         if not self._is_indexed:
@@ -300,6 +320,24 @@ class SearchEngine:
         if isinstance(query, str):
             query = Query(query)
         return self.SearchBatch([query])[0]
+
+    # ---- device-resident batches (bench `value`: inputs already in HBM when the timed region starts) -----------------
+    def UploadBatch(self, queries):
+        arr, keep = self._pack_queries(queries)
+        h = C.c_void_p()
+        self._check(self._gpu.ifx_batch_upload(self._index, arr, len(queries), C.byref(h)), "ifx_batch_upload")
+        return h
+
+    def RunBatch(self, handle, stats=None):
+        st = stats if stats is not None else Stats()
+        self._check(self._gpu.ifx_batch_run(handle, C.byref(st)), "ifx_batch_run")
+        return st
+
+    def FreeBatch(self, handle):
+        self._gpu.ifx_batch_free(handle)
+
+    def FlushL2(self):
+        self._check(self._gpu.ifx_flush_l2(self._index), "ifx_flush_l2")
 
     def Stage1Batch(self, texts, depth=500, stats=None):
         """Stage-1 (BM25 backbone) lists for a batch: (keys[nq,depth], scores[nq,depth], n[nq], status[nq])."""

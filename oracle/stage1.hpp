@@ -179,16 +179,19 @@ struct Stage1 {
             if (st) st->path = 2;
             dotnet_sort(terms, idf_desc);
             bool selective = false; long long local = 0;
-            std::vector<uint8_t> seen(ix.docs.size(), 0); std::vector<int> result;
+            // per-thread reusable membership array (the reference rents its float[N] upperBounds from ArrayPool the same way)
+            static thread_local std::vector<uint8_t> seen; if (seen.size() < ix.docs.size()) seen.assign(ix.docs.size(), 0);
+            std::vector<int> result;
             for (auto t : terms) {
                 bool lowq = t->idf < (max_idf * 0.2f);
                 if (terms.size() > 1 && lowq && selective) continue;
-                for (int d : *t->docs) if (!seen[d]) { seen[d] = 1; local++; }
+                for (int d : *t->docs) if (!seen[d]) { seen[d] = 1; local++; result.push_back(d); }
                 if (st) st->streamed_postings += (long long)t->docs->size();
-                result = set_union(result, *t->docs);
                 if (!lowq && local > 0) selective = true;
                 if (local >= (long long)K * 100) break;
             }
+            for (int d : result) seen[d] = 0;
+            std::sort(result.begin(), result.end());
             return result;
         }
         if (st) st->path = 3;

@@ -574,9 +574,9 @@ struct Pipeline {
         std::vector<uint8_t> lcs_row(2, 0), hits_row(2, 0);   // Span2D height-2 quirk (Q3): only docIndex < 2 are stored
         TopKHeap final_scores(depth); int max_hits = 0;
         QueryCtx ctx = cov.prepare(search);
-        std::vector<char> in_top(ix.docs.size(), 0);
-        for (auto& e : top) { int id = ix.doc_by_key(e.key); if (id >= 0) in_top[id] = 1; }
-        std::vector<int> overlap, uniq; for (int id : wm) (in_top[id] ? overlap : uniq).push_back(id);
+        std::vector<int> top_ids; for (auto& e : top) { int id = ix.doc_by_key(e.key); if (id >= 0) top_ids.push_back(id); }
+        std::sort(top_ids.begin(), top_ids.end());
+        std::vector<int> overlap, uniq; for (int id : wm) (std::binary_search(top_ids.begin(), top_ids.end(), id) ? overlap : uniq).push_back(id);
         int wm_limit = std::max(0, depth - (int)overlap.size());
         auto process = [&](int id, float base) {
             const Doc& d = ix.docs[id]; if (d.deleted) return;

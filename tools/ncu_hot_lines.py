@@ -2,7 +2,11 @@
 """Map the warp-stall samples of an ncu report (source page, SASS) to CUDA source lines using nvdisasm -g line markers.
 usage: ncu_hot_lines.py <sass_source_page.csv> <all.sass from nvdisasm -g -c> <kernel name substring> [top]"""
 import csv, re, sys, linecache
-rows = list(csv.reader(open(sys.argv[1]))); hdr = rows[1]; data = rows[2:]
+allrows = list(csv.reader(open(sys.argv[1])))
+# the export holds one section per kernel: ['Kernel Name', name], header row, instruction rows
+secs = [i for i, r in enumerate(allrows) if r and r[0] == 'Kernel Name'] + [len(allrows)]
+pick = [k for k in range(len(secs) - 1) if sys.argv[3] in allrows[secs[k]][1]][0]
+rows = allrows[secs[pick]:secs[pick + 1]]; hdr = rows[1]; data = [r for r in rows[2:] if len(r) == len(hdr)]
 sc = hdr.index('# Samples')
 def f(x):
     try: return float(x)
