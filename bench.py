@@ -141,7 +141,7 @@ def main():
     stop = threading.Event(); clk = []
     th = threading.Thread(target=clocks_sampler, args=(stop, clk, local), daemon=True)
     agg = {k: 0.0 for k in ("ms_total", "ms_prepare", "ms_expand", "ms_stage1", "ms_wordmatch", "ms_stage2", "ms_final")}
-    algo = 0; launches = 0
+    algo = 0; launches = 0; q_max = 0.0; q_sum = 0.0
     for s in range(n_total):
         if s == args.warmup:
             barrier(); th.start()
@@ -150,7 +150,7 @@ def main():
         if s >= args.warmup:
             for k in agg:
                 agg[k] += getattr(st, k)
-            algo += st.algo_bytes_stage1; launches += st.kernel_launches
+            algo += st.algo_bytes_stage1; launches += st.kernel_launches; q_max = max(q_max, st.s1_query_ms_max); q_sum += st.s1_query_ms_sum
     barrier()
     # ---- e2e: host buffers in / out through the C-ABI call ifx_search_batch (query upload + result download inside the region) --
     packed = [eng.PackBatch(b) for b in batches]
@@ -200,7 +200,8 @@ def main():
                        "setup_s": round(t_setup, 1), "bad_status": bad},
             "phases_ms_per_step": {k: round(v / args.steps, 3) for k, v in agg.items()},
             "roofline": {"bound": "hbm", "kernel": "k_stage1", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                         "algo_bytes_per_launch": s1_bytes, "ms_per_launch": s1_ms, "peak_source": peak_src},
+                         "algo_bytes_per_launch": s1_bytes, "ms_per_launch": s1_ms, "peak_source": peak_src,
+                         "longest_query_ms": q_max, "sum_query_ms_per_launch": q_sum / args.steps},
             "e2e": {"value": e2e, "unit": "queries/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
             "gpu_launches": int(launches), "clocks": clocks}
     if not args.no_cpu_baseline and world == 1:

@@ -129,6 +129,8 @@ typedef struct ifx_stats {            /* filled by ifx_search_batch / ifx_batch_
     int64_t algo_bytes_stage1;        /* algorithmic bytes (SURVEY 8d B_q terms 1-3) summed over the batch */
     int64_t kernel_launches;
     int64_t h2d_bytes, d2h_bytes;
+    float s1_query_ms_max;            /* longest single query inside k_stage1 (device globaltimer) */
+    float s1_query_ms_sum;            /* sum over queries of their time inside k_stage1 */
 } ifx_stats;
 
 typedef struct ifx_index ifx_index;   /* opaque: device-resident index + workspaces */

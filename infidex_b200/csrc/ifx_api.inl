@@ -43,6 +43,9 @@ struct Timer { cudaEvent_t a = nullptr, b = nullptr; cudaStream_t s = 0;
     void start() { if (!a) { cudaEventCreate(&a); cudaEventCreate(&b); } cudaEventRecord(a, s); }
     float stop() { cudaEventRecord(b, s); cudaEventSynchronize(b); float ms = 0; cudaEventElapsedTime(&ms, a, b); return ms; } };
 static const int kS1Threads = 256;
+#ifndef IFX_S1_THREADS
+#define IFX_S1_THREADS 512
+#endif
 #endif
 
 // ---- host-side handle ----------------------------------------------------------------------------------------------
@@ -69,6 +72,7 @@ struct ifx_batch {
     std::vector<void*> allocs;
     uint16_t* d_text = nullptr; int64_t* d_off = nullptr; int32_t* d_par = nullptr;   // par: [nq][5] max_results, depth, enable_cov, filter_id, enable_facets
     QueryPlan* d_plans = nullptr; FuzzyItem* d_items = nullptr; BatchCounters* d_bc = nullptr; int* d_work = nullptr;
+    int* d_order = nullptr; long long* d_qdbg = nullptr;
     int64_t* d_s1_key = nullptr; int32_t* d_s1_doc = nullptr; float* d_s1_score = nullptr; int32_t* d_s1_n = nullptr;
     Stage2Buffers s2{};                 // WordMatcher + coverage outputs
     FinalOut fin{}; int fcap = 0;
@@ -149,6 +153,16 @@ extern "C" int ifx_index_create(const ifx_index_image* img, const ifx_params* pp
             if (sp.empty()) sp.push_back(0);
             v.skip_id = ix->up(sid.data(), sid.size()); v.skip_ptr = ix->up(sp.data(), sp.size());
         }
+        {   // dense terms additionally get a membership bitmap + rank directory: O(1) probes (doc -> posting index -> tf) in the scorer
+            const int bw = (N + 31) / 32; v.bm_words = bw; const int64_t dense = std::max<int64_t>(1024, N / 32);
+            std::vector<int32_t> bid(std::max(T, 1), -1); int nb = 0;
+            for (int t = 0; t < T; t++) if (img->row_ptr[t + 1] - img->row_ptr[t] >= dense) bid[t] = nb++;
+            std::vector<unsigned> bits((size_t)std::max(nb, 1) * std::max(bw, 1), 0u); std::vector<int32_t> rank((size_t)std::max(nb, 1) * std::max(bw, 1), 0);
+            for (int t = 0; t < T; t++) { if (bid[t] < 0) continue; unsigned* b = bits.data() + (size_t)bid[t] * bw; int32_t* r = rank.data() + (size_t)bid[t] * bw;
+                for (int64_t i = img->row_ptr[t]; i < img->row_ptr[t + 1]; i++) { int d = img->post_doc[i]; b[d >> 5] |= 1u << (d & 31); }
+                int run = 0; for (int w = 0; w < bw; w++) { r[w] = run; run += __builtin_popcount(b[w]); } }
+            v.bm_id = ix->up(bid.data(), bid.size()); v.bm_bits = ix->up(bits.data(), bits.size()); v.bm_rank = ix->up(rank.data(), rank.size());
+        }
         // trie DFS order == ordinal-lexicographic order of the term texts (FstBuilder.CompactTrie sorts arcs by label)
         std::vector<int32_t> order(T); std::iota(order.begin(), order.end(), 0);
         auto term_sv = [&](int i) { return std::u16string_view((const char16_t*)img->terms.chars + img->terms.off[i], img->terms.off[i + 1] - img->terms.off[i]); };
@@ -205,7 +219,7 @@ extern "C" int ifx_index_create(const ifx_index_image* img, const ifx_params* pp
         for (int k = 0; k < img->prefix.keys.n; k++) (void)k;
         max_list = std::max<int64_t>(max_list, std::min<int64_t>(N, P.stop_term_limit));
         int64_t nwords = ((int64_t)N + 31) / 32 + 2048;
-        size_t per_cta = (size_t)nwords * 4 + (size_t)(N + 1) * 4 + 2 * (size_t)max_list * 4;
+        size_t per_cta = (size_t)nwords * 8 + (size_t)(N + 1) * 4 + 2 * (size_t)max_list * 4;
 #ifdef IFX_EMU
         ix->n_ctas = 1;
 #else
@@ -215,7 +229,7 @@ extern "C" int ifx_index_create(const ifx_index_image* img, const ifx_params* pp
           ix->n_ctas = (int)std::max<size_t>(1, std::min<size_t>((size_t)want, budget / std::max<size_t>(per_cta, 1))); }
 #endif
         ix->ws.resize(ix->n_ctas);
-        for (auto& w : ix->ws) { w.bits = ix->alloc<unsigned>(nwords); dev_zero(w.bits, (size_t)nwords * 4); w.cand = ix->alloc<int32_t>((size_t)N + 1); w.cand_cap = N; w.buf_a = ix->alloc<int32_t>(max_list); w.buf_b = ix->alloc<int32_t>(max_list); w.buf_cap = max_list; }
+        for (auto& w : ix->ws) { w.bits = ix->alloc<unsigned>(nwords); dev_zero(w.bits, (size_t)nwords * 4); w.bits2 = ix->alloc<unsigned>(nwords); dev_zero(w.bits2, (size_t)nwords * 4); w.cand = ix->alloc<int32_t>((size_t)N + 1); w.cand_cap = N; w.buf_a = ix->alloc<int32_t>(max_list); w.buf_b = ix->alloc<int32_t>(max_list); w.buf_cap = max_list; }
         ix->d_ws = ix->up(ix->ws.data(), ix->ws.size());
         ix->pool_cap = (unsigned long long)std::max<int64_t>(1 << 20, std::min<int64_t>((int64_t)N * 64, (int64_t)1 << 31));
         ix->d_pool = ix->alloc<int32_t>(ix->pool_cap);

@@ -54,6 +54,10 @@ struct DevIndex {
     const int32_t* skip_id;          // per term: row of the container skip table, or -1 (short lists)
     const int32_t* skip_ptr;         // [n_skip][n_cont + 1] offset (relative to the row start) of the first posting with doc >= c << 16
     int32_t n_cont;                  // 65536-doc containers in this shard
+    const int32_t* bm_id;            // per term: row of the dense-term bitmap table, or -1
+    const unsigned* bm_bits;         // [n_bm][bm_words] membership bitmap of the posting list (dense terms: df >= n_docs / 32)
+    const int32_t* bm_rank;          // [n_bm][bm_words] postings before doc (w << 5): posting index = rank[w] + popc(bits[w] & (bit - 1))
+    int32_t bm_words;
     StrDict words; const float* word_idf;
     DocsetDict prefix, wm_exact, wm_ld1;
     StrDict affix;                   // affix words in ordinal-lexicographic order
@@ -100,6 +104,7 @@ struct Ctx {
 };
 inline unsigned atomic_or(unsigned* p, unsigned v) { unsigned o = *p; *p = o | v; return o; }
 inline int atomic_add(int* p, int v) { int o = *p; *p = o + v; return o; }
+inline unsigned atomic_and(unsigned* p, unsigned v) { unsigned o = *p; *p = o & v; return o; }
 inline unsigned long long atomic_add64(unsigned long long* p, unsigned long long v) { unsigned long long o = *p; *p = o + v; return o; }
 inline int popc(unsigned v) { return __builtin_popcount(v); }
 inline int ffs32(unsigned v) { return __builtin_ffs((int)v); }
@@ -116,6 +121,7 @@ struct Ctx {
 };
 __device__ __forceinline__ unsigned atomic_or(unsigned* p, unsigned v) { return atomicOr(p, v); }
 __device__ __forceinline__ int atomic_add(int* p, int v) { return atomicAdd(p, v); }
+__device__ __forceinline__ unsigned atomic_and(unsigned* p, unsigned v) { return atomicAnd(p, v); }
 __device__ __forceinline__ unsigned long long atomic_add64(unsigned long long* p, unsigned long long v) { return atomicAdd(p, v); }
 __device__ __forceinline__ int popc(unsigned v) { return __popc(v); }
 __device__ __forceinline__ int ffs32(unsigned v) { return __ffs((int)v); }
@@ -160,7 +166,7 @@ struct QueryPlan {
     FuzzyReq fuzzy[MAX_FUZZY];
 };
 
-struct BatchCounters { int32_t n_fuzzy_items; int32_t overflow; unsigned long long fuzzy_pool_used; unsigned long long algo_bytes; };
+struct BatchCounters { int32_t n_fuzzy_items; int32_t overflow; unsigned long long fuzzy_pool_used; unsigned long long algo_bytes; unsigned long long s1_ns_sum; unsigned long long s1_ns_max; unsigned long long s1_cand_sum; };
 
 struct FuzzyItem { int32_t query; int32_t slot; };
 

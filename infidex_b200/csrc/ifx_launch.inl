@@ -6,6 +6,19 @@ __global__ void k_prepare(DevIndex ix, const uint16_t* text, const int64_t* off,
     int q = blockIdx.x * blockDim.x + threadIdx.x; if (q >= nq) return;
     prepare_query(ix, text + off[q], (int)(off[q + 1] - off[q]), par[q * 5 + 1], par[q * 5 + 0], par[q * 5 + 2], par[q * 5 + 3], par[q * 5 + 4], plans[q], items, items_cap, bc, q);
 }
+// Longest-processing-time-first order: queries bucketed by log2 of their posting volume, heaviest bucket first, so the
+// long sequential chunk chains of heavy queries start at once instead of forming the tail of the launch.
+__global__ void k_order(const QueryPlan* plans, int nq, int* order) {
+    __shared__ int cnt[64]; __shared__ int base[64];
+    if (threadIdx.x < 64) cnt[threadIdx.x] = 0;
+    __syncthreads();
+    auto bucket = [&](int q) { const QueryPlan& p = plans[q]; long long c = 1; for (int i = 0; i < p.n_terms; i++) c += p.terms[i].list_len; return 63 - __clzll(c); };
+    for (int q = threadIdx.x; q < nq; q += blockDim.x) atomicAdd(&cnt[bucket(q)], 1);
+    __syncthreads();
+    if (threadIdx.x == 0) { int run = 0; for (int b = 63; b >= 0; b--) { base[b] = run; run += cnt[b]; } }
+    __syncthreads();
+    for (int q = threadIdx.x; q < nq; q += blockDim.x) { int pos = atomicAdd(&base[bucket(q)], 1); order[pos] = q; }
+}
 __global__ void __launch_bounds__(256) k_expand(DevIndex ix, QueryPlan* plans, const FuzzyItem* items, BatchCounters* bc, S1Workspace* wss,
                                                 int32_t* pool, unsigned long long pool_cap, const uint8_t* sorted_len, int* work) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -22,20 +35,24 @@ __global__ void __launch_bounds__(256) k_expand(DevIndex ix, QueryPlan* plans, c
         expand_fuzzy(c, ix, plans[fi.query], fi.slot, ws, sh, pool, pool_cap, bc, sorted_len, sh.cand_s);
     }
 }
-__global__ void __launch_bounds__(256) k_stage1(DevIndex ix, const QueryPlan* plans, int nq, const int32_t* pool, S1Workspace* wss, BatchCounters* bc,
-                                                int64_t* s1_key, int32_t* s1_doc, float* s1_score, int32_t* s1_n, int K, int* work) {
+__global__ void __launch_bounds__(IFX_S1_THREADS, 2) k_stage1(DevIndex ix, const QueryPlan* plans, int nq, const int32_t* pool, S1Workspace* wss, BatchCounters* bc,
+                                                int64_t* s1_key, int32_t* s1_doc, float* s1_score, int32_t* s1_n, int K, int* work, const int* order, long long* qdbg) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     S1Shared& sh = *reinterpret_cast<S1Shared*>(smem_raw); Ctx c; S1Workspace ws = wss[blockIdx.x];
     for (int i = threadIdx.x; i < MAX_CONTAINERS; i += blockDim.x) sh.dirty[i] = 0;
+    for (int i = threadIdx.x; i < S1_TILE * CHUNK; i += blockDim.x) (&sh.tfm[0][0])[i] = 0;
     __syncthreads();
     for (;;) {
         if (threadIdx.x == 0) sh.bcast[7] = atomicAdd(work, 1);
         __syncthreads();
-        int q = sh.bcast[7]; __syncthreads();
-        if (q >= nq) break;
-        Stage1Out o{s1_key + (size_t)q * K, s1_doc + (size_t)q * K, s1_score + (size_t)q * K, s1_n + q};
+        int qi = sh.bcast[7]; __syncthreads();
+        if (qi >= nq) break;
+        const int q = order[qi];
+        Stage1Out o{s1_key + (size_t)q * K, s1_doc + (size_t)q * K, s1_score + (size_t)q * K, s1_n + q, qdbg + (size_t)q * 12};
+        unsigned long long t0 = 0; if (threadIdx.x == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
         stage1_query(c, ix, plans[q], pool, ws, sh, o, bc);
         __syncthreads();
+        if (threadIdx.x == 0) { unsigned long long t1; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1)); atomicAdd(&bc->s1_ns_sum, t1 - t0); atomicMax(&bc->s1_ns_max, t1 - t0); qdbg[(size_t)q * 12 + 4] = (long long)(t1 - t0); qdbg[(size_t)q * 12 + 2] -= (long long)t0; qdbg[(size_t)q * 12 + 5] = blockIdx.x; }
     }
 }
 #endif
@@ -51,7 +68,7 @@ static void run_stage1_phase(ifx_batch* b, ifx_stats* st) {
     static S1Shared* sh = new S1Shared(); memset(sh->dirty, 0, sizeof(sh->dirty));
     Ctx c; int nit = std::min(b->d_bc->n_fuzzy_items, items_cap);
     for (int i = 0; i < nit; i++) expand_fuzzy(c, ix->v, b->d_plans[b->d_items[i].query], b->d_items[i].slot, ix->ws[0], *sh, ix->d_pool, ix->pool_cap, b->d_bc, ix->d_sorted_len, sh->cand_s);
-    for (int q = 0; q < nq; q++) { Stage1Out o{b->d_s1_key + (size_t)q * K, b->d_s1_doc + (size_t)q * K, b->d_s1_score + (size_t)q * K, b->d_s1_n + q}; stage1_query(c, ix->v, b->d_plans[q], ix->d_pool, ix->ws[0], *sh, o, b->d_bc); }
+    for (int q = 0; q < nq; q++) { Stage1Out o{b->d_s1_key + (size_t)q * K, b->d_s1_doc + (size_t)q * K, b->d_s1_score + (size_t)q * K, b->d_s1_n + q, nullptr}; stage1_query(c, ix->v, b->d_plans[q], ix->d_pool, ix->ws[0], *sh, o, b->d_bc); }
     (void)t;
 #else
     size_t smem = sizeof(S1Shared);
@@ -65,12 +82,13 @@ static void run_stage1_phase(ifx_batch* b, ifx_stats* st) {
     k_expand<<<ix->n_ctas, kS1Threads, smem>>>(ix->v, b->d_plans, b->d_items, b->d_bc, ix->d_ws, ix->d_pool, ix->pool_cap, ix->d_sorted_len, b->d_work);
     float ms_exp = t.stop();
     t.start();
-    k_stage1<<<std::min(ix->n_ctas, nq), kS1Threads, smem>>>(ix->v, b->d_plans, nq, ix->d_pool, ix->d_ws, b->d_bc, b->d_s1_key, b->d_s1_doc, b->d_s1_score, b->d_s1_n, K, b->d_work + 1);
+    k_order<<<1, 1024>>>(b->d_plans, nq, b->d_order);
+    k_stage1<<<std::min(ix->n_ctas, nq), IFX_S1_THREADS, smem>>>(ix->v, b->d_plans, nq, ix->d_pool, ix->d_ws, b->d_bc, b->d_s1_key, b->d_s1_doc, b->d_s1_score, b->d_s1_n, K, b->d_work + 1, b->d_order, b->d_qdbg);
     float ms_s1 = t.stop();
     CUDA_TRY(cudaGetLastError());
-    if (st) { st->ms_prepare += ms_prep; st->ms_expand += ms_exp; st->ms_stage1 += ms_s1; st->kernel_launches += 3; }
+    if (st) { st->ms_prepare += ms_prep; st->ms_expand += ms_exp; st->ms_stage1 += ms_s1; st->kernel_launches += 4; }
 #endif
-    if (st) { BatchCounters bc; d2h(&bc, b->d_bc, sizeof(bc)); st->algo_bytes_stage1 += (int64_t)bc.algo_bytes; }
+    if (st) { BatchCounters bc; d2h(&bc, b->d_bc, sizeof(bc)); st->algo_bytes_stage1 += (int64_t)bc.algo_bytes; st->s1_query_ms_max = (float)(bc.s1_ns_max * 1e-6); st->s1_query_ms_sum = (float)(bc.s1_ns_sum * 1e-6); }
 }
 
 // (re)fill the per-batch inputs; allocates on first use or when the batch outgrows its buffers
@@ -83,13 +101,13 @@ static int fill_batch(ifx_batch* b, const ifx_query* q, int nq) {
     std::vector<uint16_t> text((size_t)off[nq] + 1);
     for (int i = 0; i < nq; i++) if (q[i].len > 0) memcpy(text.data() + off[i], q[i].text, (size_t)q[i].len * 2);
     const bool fresh = b->d_plans == nullptr;
-    if (!fresh && (nq != b->nq || depth_max != b->depth_max || cap_max > b->cap_max)) return fail(IFX_ERR_INVALID, "batch shape changed");
+    if (!fresh && (nq != b->nq || depth_max != b->depth_max || cap_max != b->cap_max)) return fail(IFX_ERR_INVALID, "batch shape changed");
     if (fresh) {
         b->nq = nq; b->depth_max = depth_max; b->cap_max = cap_max; b->text_cap = std::max<size_t>(text.size(), (size_t)nq * 64);
         b->d_text = b->alloc<uint16_t>(b->text_cap); b->d_off = b->alloc<int64_t>(nq + 1); b->d_par = b->alloc<int32_t>(par.size());
         b->d_plans = b->alloc<QueryPlan>(nq); b->d_items = b->alloc<FuzzyItem>((size_t)nq * 4 + 64); b->d_bc = b->alloc<BatchCounters>(1); b->d_work = b->alloc<int>(8); dev_zero(b->d_work, 8 * sizeof(int));
         size_t K = b->depth_max;
-        b->d_s1_key = b->alloc<int64_t>(nq * K); b->d_s1_doc = b->alloc<int32_t>(nq * K); b->d_s1_score = b->alloc<float>(nq * K); b->d_s1_n = b->alloc<int32_t>(nq);
+        b->d_s1_key = b->alloc<int64_t>(nq * K); b->d_s1_doc = b->alloc<int32_t>(nq * K); b->d_s1_score = b->alloc<float>(nq * K); b->d_s1_n = b->alloc<int32_t>(nq); b->d_order = b->alloc<int>(nq); b->d_qdbg = b->alloc<long long>((size_t)nq * 12); dev_zero(b->d_qdbg, (size_t)nq * 96);
     } else if (text.size() > b->text_cap) return fail(IFX_ERR_INVALID, "batch text outgrew its buffer");
     h2d(b->d_text, text.data(), text.size() * 2); h2d(b->d_off, off.data(), (nq + 1) * 8); h2d(b->d_par, par.data(), par.size() * 4);
     b->ran = false;
@@ -120,3 +138,6 @@ extern "C" int ifx_stage1_batch(ifx_index* idx, const ifx_query* q, int nq, int 
 }
 
 #include "ifx_search.inl"
+
+// debugging aid: per-query [n_cand, n_terms, selection_ns, path, total_ns, cta] of the last run's k_stage1
+extern "C" int ifx_debug_stage1_queries(ifx_batch* b, long long* out) { try { d2h(out, b->d_qdbg, (size_t)b->nq * 96); } catch (const std::string& e) { return fail(IFX_ERR_CUDA, e); } return IFX_OK; }

@@ -123,6 +123,21 @@ IFX_FN int block_excl_scan(const Ctx& c, int v, ScanTmp& tmp, int& total) {
     return base + incl - v;
 #endif
 }
+// single-barrier variant: callers alternate between two ScanTmp buffers (the barrier of the next call protects reuse)
+IFX_FN int block_excl_scan_1b(const Ctx& c, int v, ScanTmp& tmp, int& total) {
+#ifdef IFX_EMU
+    (void)c; (void)tmp; total = v; return 0;
+#else
+    int incl = v;
+    for (int d = 1; d < 32; d <<= 1) { int o = __shfl_up_sync(0xffffffffu, incl, d); if (c.lane() >= d) incl += o; }
+    if (c.lane() == 31) tmp.w[c.warp()] = incl;
+    c.sync();
+    int base = 0, tot = 0, nw = c.nwarps();
+    for (int i = 0; i < nw; i++) { int x = tmp.w[i]; if (i < c.warp()) base += x; tot += x; }
+    total = tot;
+    return base + incl - v;
+#endif
+}
 IFX_FN int block_sum(const Ctx& c, int v, ScanTmp& tmp) { int t; block_excl_scan(c, v, tmp, t); return t; }
 
 IFX_FN int64_t lower_bound_i32(const int32_t* a, int64_t lo, int64_t hi, int32_t target) {   // first index in [lo,hi) with a[i] >= target
@@ -161,26 +176,36 @@ IFX_FN int64_t warp_lower_bound(const Ctx& c, const int32_t* a, int64_t lo, int6
 // per-CTA global workspace
 struct S1Workspace {
     unsigned* bits;        // candidate bitset over the shard's docs (all zero between uses)
+    unsigned* bits2;       // membership bitset of the running AND-tier intersection (all zero between uses)
     int32_t* cand;         // sorted candidate ids
     int32_t* buf_a; int32_t* buf_b;   // AND-tier ping-pong arrays
     int64_t cand_cap, buf_cap;
 };
 
 struct TermS {             // term as seen by the scorer
-    const int32_t* docs; const uint8_t* tf; const int32_t* skip; int32_t len; int32_t df; float idf, max_score, suffix_after; int64_t cursor, s0, s1;
+    const int32_t* docs; const uint8_t* tf; const int32_t* skip; const unsigned* bm; const int32_t* bmr; int32_t len; int32_t df; float idf, max_score, suffix_after; int64_t cursor, s0, s1;
 };
+
+constexpr int S1_TILE = 6;
 
 struct S1Shared {
     TermS terms[MAX_TERMS];
     int order[MAX_TERMS];
     int n_terms;
-    float score[CHUNK];
-    uint8_t tfbuf[2][CHUNK];
-    int32_t cand_s[CHUNK];
-    unsigned ballots[CHUNK / Ctx::WS + 8]; int bprefix[CHUNK / Ctx::WS + 8];
-    int heap_doc[MAX_K]; float heap_score[MAX_K]; int heap_size; float thr;
-    uint8_t dirty[MAX_CONTAINERS];
-    ScanTmp scan;
+    alignas(16) float score[CHUNK];
+    alignas(16) uint8_t tfm[S1_TILE][CHUNK];   // per-tile tf of (term, candidate slot); 0 = no match
+    int32_t cand_s[CHUNK]; alignas(16) float nv_s[CHUNK];   // per-slot length norm of the vector form (the scalar form is needed for < 8 matches per term and chunk: recomputed)
+    uint16_t cpref[2048];                // rank directory of `cbits`
+    unsigned ballots[2][CHUNK / Ctx::WS + 8]; int bprefix[CHUNK / Ctx::WS + 8];
+    int heap_size; float thr;
+    // .NET PriorityQueue nodes packed as (doc << 32 | float bits of the priority), stored with a +3 shift so the four children of
+    // node i (4i+1..4i+4) form one aligned 32-byte group; slots beyond the current size hold +huge sentinels
+    alignas(32) unsigned long long heap_kv[MAX_K + 8];
+    union {                               // never live at the same time: selection/compaction vs. chunk scoring
+        uint8_t dirty[MAX_CONTAINERS];    // containers of the global bitset touched by the current set operation (all zero between uses)
+        unsigned cbits[2048];             // container-local bitmap of the current chunk's candidates (stream mode)
+    };
+    ScanTmp scan; ScanTmp scan2[2];
     int bcast[8]; long long bcast64[4];
     unsigned long long streamed_mask[2];   // terms whose list the selector streamed in full (roofline accounting)
     unsigned long long peq[128];           // Myers pattern masks of the word being expanded (ASCII fast path)
@@ -188,15 +213,82 @@ struct S1Shared {
 
 // OR a sorted id list into the CTA's bitset; returns the number of newly set docs (block-wide).
 IFX_FN int or_list_into_bits(const Ctx& c, const int32_t* list, int64_t n, S1Workspace& ws, S1Shared& sh) {
-    int fresh = 0;
-    for (int64_t i = c.tid(); i < n; i += c.nthreads()) {
-        int d = list[i]; unsigned bit = 1u << (d & 31);
-        unsigned old = atomic_or(&ws.bits[d >> 5], bit);
-        if (!(old & bit)) fresh++;
-        sh.dirty[d >> 16] = 1;
+    int fresh = 0; const int64_t NT4 = 4LL * c.nthreads();
+    for (int64_t i0 = c.tid(); i0 < n; i0 += NT4) {      // four independent loads in flight per thread
+        int dd[4];
+        for (int u = 0; u < 4; u++) { int64_t i = i0 + (int64_t)u * c.nthreads(); dd[u] = i < n ? list[i] : -1; }
+        for (int u = 0; u < 4; u++) if (dd[u] >= 0) {
+            int d = dd[u]; unsigned bit = 1u << (d & 31);
+            unsigned old = atomic_or(&ws.bits[d >> 5], bit);
+            if (!(old & bit)) fresh++;
+            sh.dirty[d >> 16] = 1;
+        }
     }
     c.sync();
     return block_sum(c, fresh, sh.scan);
+}
+
+// Warp-aggregated unordered append (all lanes of the warp must call it together).
+IFX_FN void warp_append(const Ctx& c, bool pred, int32_t value, int32_t* arr, int* counter) {
+    unsigned m = c.ballot(pred); if (m == 0) return;
+    int leader = ffs32(m) - 1; int base = 0;
+    if (c.lane() == leader) base = atomic_add(counter, popc(m));
+    base = c.shfl(base, leader);
+    if (pred) arr[base + popc(m & c.lanemask_lt())] = value;
+}
+
+// AND of the first `cnt` terms of sh.order (TieredCandidateSelector.IntersectTerms). The running intersection lives both as an
+// unordered id array (ping-pong ws.buf_a / ws.buf_b) and as the membership bitset ws.bits2. Each further list either streams
+// past the bitset (coalesced, when it is not much longer than the running set) or is probed per surviving id (binary search).
+// Returns the size (-1: buffer overflow); `res` points at the surviving ids; ws.bits2 is left all-zero.
+IFX_FN int64_t intersect_terms(const Ctx& c, S1Workspace& ws, S1Shared& sh, int cnt, const int32_t*& res) {
+    const int NT = c.nthreads();
+    int by_len[MAX_TERMS];
+    for (int i = 0; i < cnt; i++) by_len[i] = sh.order[i];
+    for (int i = 1; i < cnt; i++) { int x = by_len[i]; int j = i - 1; while (j >= 0 && sh.terms[by_len[j]].len > sh.terms[x].len) { by_len[j + 1] = by_len[j]; j--; } by_len[j + 1] = x; }
+    const TermS& t0 = sh.terms[by_len[0]];
+    int64_t n = t0.len; if (n > ws.buf_cap) return -1;
+    int32_t* cur = ws.buf_a; int32_t* nxt = ws.buf_b;
+    for (int64_t i = c.tid(); i < n; i += NT) { int d = t0.docs[i]; cur[i] = d; if (cnt > 1) atomic_or(&ws.bits2[d >> 5], 1u << (d & 31)); }
+    c.sync();
+    for (int li = 1; li < cnt && n > 0; li++) {
+        const TermS& t = sh.terms[by_len[li]];
+        if (c.tid() == 0) sh.bcast[6] = 0;
+        c.sync();
+        if (!t.bm && (int64_t)t.len <= 32 * n) {             // stream the list past the membership bitset (dense terms are probed through their bitmap instead)
+            const int64_t rounds = ((int64_t)t.len + NT - 1) / NT;
+            for (int64_t r = 0; r < rounds; r += 4) {         // four independent loads in flight per thread
+                int64_t i0 = r * NT + c.tid(); int32_t d[4]; bool in[4];
+                for (int u = 0; u < 4; u++) { int64_t i = i0 + (int64_t)u * NT; d[u] = (r + u < rounds && i < t.len) ? t.docs[i] : -1; }
+                for (int u = 0; u < 4; u++) in[u] = d[u] >= 0 && ((ws.bits2[d[u] >> 5] >> (d[u] & 31)) & 1u);
+                for (int u = 0; u < 4; u++) warp_append(c, in[u], d[u], nxt, &sh.bcast[6]);
+            }
+            c.sync();
+            for (int64_t i = c.tid(); i < n; i += NT) { int d = cur[i]; atomic_and(&ws.bits2[d >> 5], ~(1u << (d & 31))); }   // drop the old set ...
+            c.sync();
+            const int64_t nn = sh.bcast[6];
+            if (li + 1 < cnt) for (int64_t i = c.tid(); i < nn; i += NT) { int d = nxt[i]; atomic_or(&ws.bits2[d >> 5], 1u << (d & 31)); }   // ... keep the survivors
+            n = nn;
+        } else {                                              // probe the (much longer) list once per surviving id
+            const int64_t rounds = (n + NT - 1) / NT;
+            for (int64_t r = 0; r < rounds; r += 4) {        // four independent probes in flight per thread
+                int dd[4]; bool found[4]; unsigned wv[4];
+                for (int u = 0; u < 4; u++) { int64_t i = (r + u) * NT + c.tid(); dd[u] = (r + u < rounds && i < n) ? cur[i] : -1; }
+                if (t.bm) { for (int u = 0; u < 4; u++) wv[u] = dd[u] >= 0 ? t.bm[dd[u] >> 5] : 0u; for (int u = 0; u < 4; u++) found[u] = dd[u] >= 0 && ((wv[u] >> (dd[u] & 31)) & 1u); }
+                else for (int u = 0; u < 4; u++) { found[u] = false; if (dd[u] >= 0) { int d = dd[u]; int64_t lo = 0, hi = t.len; if (t.skip) { lo = t.skip[d >> 16]; hi = t.skip[(d >> 16) + 1]; } int64_t p = lower_bound_i32(t.docs, lo, hi, d); found[u] = p < hi && t.docs[p] == d; } }
+                for (int u = 0; u < 4; u++) { if (dd[u] >= 0 && !found[u]) atomic_and(&ws.bits2[dd[u] >> 5], ~(1u << (dd[u] & 31))); if (r + u < rounds) warp_append(c, found[u], dd[u], nxt, &sh.bcast[6]); }
+            }
+            c.sync();
+            n = sh.bcast[6];
+            if (li + 1 == cnt) { for (int64_t i = c.tid(); i < n; i += NT) { int d = nxt[i]; atomic_and(&ws.bits2[d >> 5], ~(1u << (d & 31))); } }
+        }
+        c.sync();
+        int32_t* tmp = cur; cur = nxt; nxt = tmp;
+    }
+    if (cnt > 1 && n == 0) { /* bitset already empty: every id was cleared when it dropped out */ }
+    res = cur;
+    c.sync();
+    return n;
 }
 
 // Expand the dirty containers of the bitset into ws.cand (ascending) and clear them. Returns the count.
@@ -285,26 +377,56 @@ struct IdfSorter {
 };
 
 // .NET PriorityQueue<int,float> (4-ary min-heap) on shared arrays -- Bm25Scorer.UpdateTopK (Bm25Scorer.cs:654-670)
+IFX_FN float kv_score(unsigned long long kv) {
+#ifdef IFX_EMU
+    unsigned u = (unsigned)kv; float f; memcpy(&f, &u, 4); return f;
+#else
+    return __uint_as_float((unsigned)kv);
+#endif
+}
+IFX_FN unsigned long long kv_pack(int doc, float pr) {
+#ifdef IFX_EMU
+    unsigned u; memcpy(&u, &pr, 4); return ((unsigned long long)(unsigned)doc << 32) | u;
+#else
+    return ((unsigned long long)(unsigned)doc << 32) | __float_as_uint(pr);
+#endif
+}
+#define IFX_KV(i) heap_kv[(i) + 3]
 IFX_FN void heap_move_up(S1Shared& sh, int doc, float pr, int idx) {
-    while (idx > 0) { int parent = (idx - 1) >> 2; if (pr < sh.heap_score[parent]) { sh.heap_doc[idx] = sh.heap_doc[parent]; sh.heap_score[idx] = sh.heap_score[parent]; idx = parent; } else break; }
-    sh.heap_doc[idx] = doc; sh.heap_score[idx] = pr;
+    while (idx > 0) { int parent = (idx - 1) >> 2; unsigned long long pk = sh.IFX_KV(parent); if (pr < kv_score(pk)) { sh.IFX_KV(idx) = pk; idx = parent; } else break; }
+    sh.IFX_KV(idx) = kv_pack(doc, pr);
 }
 IFX_FN void heap_move_down(S1Shared& sh, int doc, float pr, int idx) {
-    int sz = sh.heap_size, i;
+    const int sz = sh.heap_size; int i;
     while ((i = 4 * idx + 1) < sz) {
-        int mi = i; float mp = sh.heap_score[i]; int upper = i + 4 < sz ? i + 4 : sz;
-        while (++i < upper) { float x = sh.heap_score[i]; if (x < mp) { mp = x; mi = i; } }
+        // first strictly-smallest of the (up to) four children, exactly as PriorityQueue.MoveDown scans them
+#ifdef IFX_EMU
+        unsigned long long k0 = sh.IFX_KV(i), k1 = sh.IFX_KV(i + 1), k2 = sh.IFX_KV(i + 2), k3 = sh.IFX_KV(i + 3);
+#else
+        const ulonglong2 va = *reinterpret_cast<const ulonglong2*>(&sh.heap_kv[i + 3]); const ulonglong2 vb = *reinterpret_cast<const ulonglong2*>(&sh.heap_kv[i + 5]);
+        unsigned long long k0 = va.x, k1 = va.y, k2 = vb.x, k3 = vb.y;
+#endif
+        unsigned long long mk = k0; float mp = kv_score(k0); int mi = i;
+        { float x = kv_score(k1); if (x < mp) { mp = x; mk = k1; mi = i + 1; } }
+        { float x = kv_score(k2); if (x < mp) { mp = x; mk = k2; mi = i + 2; } }
+        { float x = kv_score(k3); if (x < mp) { mp = x; mk = k3; mi = i + 3; } }
         if (!(mp < pr)) break;
-        sh.heap_doc[idx] = sh.heap_doc[mi]; sh.heap_score[idx] = mp; idx = mi;
+        sh.IFX_KV(idx) = mk; idx = mi;
     }
-    sh.heap_doc[idx] = doc; sh.heap_score[idx] = pr;
+    sh.IFX_KV(idx) = kv_pack(doc, pr);
 }
 IFX_FN void update_topk(S1Shared& sh, int doc, float s, int K) {
-    if (sh.heap_size < K) { int i = sh.heap_size++; heap_move_up(sh, doc, s, i); if (sh.heap_size == K) sh.thr = sh.heap_score[0]; }
-    else if (s > sh.thr) { heap_move_down(sh, doc, s, 0); sh.thr = sh.heap_score[0]; }
+    if (sh.heap_size < K) { int i = sh.heap_size++; heap_move_up(sh, doc, s, i); if (sh.heap_size == K) sh.thr = kv_score(sh.IFX_KV(0)); }
+    else if (s > sh.thr) { heap_move_down(sh, doc, s, 0); sh.thr = kv_score(sh.IFX_KV(0)); }
 }
 
 // Bm25Scorer.cs:395-433 (Vector256 lanes) and :643-652 (scalar remainder); must not be contracted into FMAs.
+// The document-length part of both forms depends only on the candidate, so it is evaluated once per chunk and slot:
+//   vector form  norm = K1 * ((1 - B) + (B / avgdl) * dl)        scalar form  norm = K1 * (1 - B + B * (dl / avgdl)), dl <= 0 -> 1
+IFX_FN float bm25_norm_vector(float dl, float avgdl) { const float K1 = 1.2f, B = 0.75f; float bdiv = B / avgdl; return K1 * ((1.f - B) + bdiv * dl); }
+IFX_FN float bm25_norm_scalar(float dl, float avgdl) { const float K1 = 1.2f, B = 0.75f; if (dl <= 0.f) dl = 1.f; return K1 * (1.f - B + B * (dl / avgdl)); }
+IFX_FN float bm25_from_norm_vector(float tf, float norm, float idf) { const float K1 = 1.2f, Delta = 1.0f; float denom = tf + norm; float core = (tf * (K1 + 1.0f)) / denom; return idf * (core + Delta); }
+IFX_FN float bm25_from_norm_scalar(float tf, float norm, float idf) { const float K1 = 1.2f, Delta = 1.0f; float denom = tf + norm; if (denom <= 0.f) return 0.f; float core = (tf * (K1 + 1.f)) / denom; return idf * (core + Delta); }
 IFX_FN float bm25_vector(float tf, float dl, float avgdl, float idf) {
     const float K1 = 1.2f, B = 0.75f, Delta = 1.0f;
     float bdiv = B / avgdl; float norm = K1 * ((1.f - B) + bdiv * dl); float denom = tf + norm;
@@ -318,7 +440,7 @@ IFX_FN float bm25_scalar(float tf, float dl, float avgdl, float idf) {
     float core = (tf * (K1 + 1.f)) / denom; return idf * (core + Delta);
 }
 
-struct Stage1Out { int64_t* key; int32_t* doc; float* score; int32_t* n; };   // row pointers for this query (cap = depth)
+struct Stage1Out { int64_t* key; int32_t* doc; float* score; int32_t* n; long long* dbg; };   // dbg: [n_cand, n_terms, selection ns, path] or null   // row pointers for this query (cap = depth)
 
 // ---------------------------------------------------------------------------------------------------------------
 // LD1 expansion of one unknown word: first 1024 trie-order matches (Myers bit-vector, search variant), union of
@@ -399,12 +521,14 @@ IFX_FN void stage1_query(const Ctx& c, const DevIndex& ix, const QueryPlan& p, c
             const QTerm& q = p.terms[i];
             if (q.df <= 0 || q.df > ix.stop_term_limit) continue;      // VectorModel.cs:521
             TermS& t = sh.terms[n]; t.len = q.list_len; t.df = q.df; t.idf = q.idf; t.max_score = q.max_score; t.cursor = 0;
-            if (q.term_id >= 0) { t.docs = ix.post_doc + q.list_off; t.tf = ix.post_tf + q.list_off; int sk = ix.skip_id[q.term_id]; t.skip = sk >= 0 ? ix.skip_ptr + (size_t)sk * (ix.n_cont + 1) : nullptr; }
-            else { t.docs = pool + q.list_off; t.tf = nullptr; t.skip = nullptr; }
+            if (q.term_id >= 0) { t.docs = ix.post_doc + q.list_off; t.tf = ix.post_tf + q.list_off; int sk = ix.skip_id[q.term_id]; t.skip = sk >= 0 ? ix.skip_ptr + (size_t)sk * (ix.n_cont + 1) : nullptr;
+                int bi = ix.bm_id[q.term_id]; t.bm = bi >= 0 ? ix.bm_bits + (size_t)bi * ix.bm_words : nullptr; t.bmr = bi >= 0 ? ix.bm_rank + (size_t)bi * ix.bm_words : nullptr; }
+            else { t.docs = pool + q.list_off; t.tf = nullptr; t.skip = nullptr; t.bm = nullptr; t.bmr = nullptr; }
             n++;
         }
         float suf = 0.f; for (int i = n - 1; i >= 0; i--) { sh.terms[i].suffix_after = suf; suf = suf + sh.terms[i].max_score; }   // ComputeSuffixSums
         sh.n_terms = n; sh.heap_size = 0; sh.thr = 0.f; sh.streamed_mask[0] = sh.streamed_mask[1] = 0;
+        for (int i = 0; i < MAX_K + 8; i++) sh.heap_kv[i] = kv_pack(0, 3.0e38f);    // sentinels (any real BM25 score is far smaller)
         out.n[0] = 0;
     }
     c.sync();
@@ -450,28 +574,12 @@ IFX_FN void stage1_query(const Ctx& c, const DevIndex& ix, const QueryPlan& p, c
                 if (g >= (int64_t)K * 100) break;
             }
         } else {
-            // IntersectTerms over `cnt` leading terms of the idf order, smallest list drives
-            auto intersect = [&](int cnt, int32_t*& res) -> int64_t {
-                int by_len[MAX_TERMS];
-                for (int i = 0; i < cnt; i++) by_len[i] = sh.order[i];
-                for (int i = 1; i < cnt; i++) { int x = by_len[i]; int j = i - 1; while (j >= 0 && sh.terms[by_len[j]].len > sh.terms[x].len) { by_len[j + 1] = by_len[j]; j--; } by_len[j + 1] = x; }
-                const int32_t* cur = sh.terms[by_len[0]].docs; int64_t n = sh.terms[by_len[0]].len; int32_t* dst = ws.buf_a; res = nullptr;
-                if (n > ws.buf_cap) return -1;
-                if (cnt == 1) { for (int64_t i = c.tid(); i < n; i += NT) ws.buf_a[i] = cur[i]; c.sync(); res = ws.buf_a; return n; }
-                for (int i = 1; i < cnt && n > 0; i++) {
-                    const TermS& t = sh.terms[by_len[i]];
-                    n = filter_members(c, cur, n, t.docs, t.len, dst, sh);
-                    cur = dst; res = dst; dst = (dst == ws.buf_a) ? ws.buf_b : ws.buf_a;
-                }
-                if (n == 0) res = ws.buf_a;
-                return n;
-            };
             if (c.tid() == 0) for (int i = 0; i < T; i++) sh.streamed_mask[i >> 6] |= 1ULL << (i & 63);   // every list of the AND tier
-            int32_t* r0 = nullptr; int64_t n0 = intersect(T, r0);
+            const int32_t* r0 = nullptr; int64_t n0 = intersect_terms(c, ws, sh, T, r0);
             if (n0 < 0) { if (c.tid() == 0) out.n[0] = -1; return; }
             g += or_list_into_bits(c, r0, n0, ws, sh);
             if (g < (int64_t)K * 2) {
-                if (T >= 3 && g < (int64_t)K * 3) { int32_t* r1 = nullptr; int64_t n1 = intersect(T - 1, r1); if (n1 > 0) g += or_list_into_bits(c, r1, n1, ws, sh); }
+                if (T >= 3 && g < (int64_t)K * 3) { const int32_t* r1 = nullptr; int64_t n1 = intersect_terms(c, ws, sh, T - 1, r1); if (n1 > 0) g += or_list_into_bits(c, r1, n1, ws, sh); }
                 if (g < (int64_t)K * 5) {
                     int sel[2]; int ns = 0; float cutoff = max_idf * 0.3f; int capn = T < 2 ? T : 2;
                     for (int oi = 0; oi < T && ns < capn; oi++) { const TermS& t = sh.terms[sh.order[oi]]; if (t.idf <= 0.f) continue; if (t.idf < cutoff) continue; sel[ns++] = sh.order[oi]; }
@@ -484,6 +592,11 @@ IFX_FN void stage1_query(const Ctx& c, const DevIndex& ix, const QueryPlan& p, c
         if (ovf) { if (c.tid() == 0) out.n[0] = -1; return; }
         cand = ws.cand;
         algo += 2ULL * (unsigned long long)((ix.n_docs + 7) / 8);
+    }
+    if (c.tid() == 0 && out.dbg) { out.dbg[0] = n_cand; out.dbg[1] = T; out.dbg[3] = sh.bcast64[0] >= 0 ? 1 : (sh.bcast[0] ? 2 : 3);
+#ifndef IFX_EMU
+        unsigned long long tn; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tn)); out.dbg[2] = (long long)tn;
+#endif
     }
     // ---- roofline accounting: full-stream lists 5 B/posting, probe-only lists min(5 df, 32 |C|), 4 B doc_len per candidate
     if (c.tid() == 0) {
@@ -499,6 +612,13 @@ IFX_FN void stage1_query(const Ctx& c, const DevIndex& ix, const QueryPlan& p, c
 
     // ---- BM25 scoring over chunks (ProcessBlockedCandidates / ProcessChunk / ScoreBlockStruct)
     const int NW = c.nwarps();
+    long long tph[6] = {0, 0, 0, 0, 0, 0}; long long tmark = 0;
+#ifndef IFX_EMU
+#define IFX_TICK(k) do { if (c.tid() == 0) { long long now_ = clock64(); tph[k] += now_ - tmark; tmark = now_; } } while (0)
+    if (c.tid() == 0) tmark = clock64();
+#else
+#define IFX_TICK(k) do { } while (0)
+#endif
     for (int64_t pos = 0; pos < n_cand;) {
         // container run: candidates sharing id >> 16, cut into sub-chunks of 4096
         if (c.warp() == 0) {
@@ -511,7 +631,8 @@ IFX_FN void stage1_query(const Ctx& c, const DevIndex& ix, const QueryPlan& p, c
         }
         c.sync();
         const int cnt = sh.bcast[2]; const bool whole_container = sh.bcast[4] != 0;
-        for (int j = c.tid(); j < cnt; j += NT) { sh.cand_s[j] = cand[pos + j]; sh.score[j] = 0.f; sh.tfbuf[0][j] = 0; sh.tfbuf[1][j] = 0; }
+        for (int j = c.tid(); j < cnt; j += NT) { int d = cand[pos + j]; sh.cand_s[j] = d; float dl = ix.doc_len[d]; sh.nv_s[j] = bm25_norm_vector(dl, avgdl); sh.score[j] = 0.f; }
+        if (c.tid() == 0) sh.bcast[5] = 0;
         c.sync();
         const int32_t first = sh.cand_s[0], last = sh.cand_s[cnt - 1];
         for (int t = c.tid(); t < T; t += NT) {      // posting sub-range of every term for this chunk (monotone cursors)
@@ -523,91 +644,159 @@ IFX_FN void stage1_query(const Ctx& c, const DevIndex& ix, const QueryPlan& p, c
             else if (tm.skip || tm.len < 1024) { s0 = lower_bound_i32(tm.docs, lo, hi, first); s1 = last == 0x7fffffff ? hi : lower_bound_i32(tm.docs, s0, hi, last + 1); }
             else { s0 = gallop_lower_bound(tm.docs, lo, hi, first); s1 = last == 0x7fffffff ? hi : gallop_lower_bound(tm.docs, s0, hi, last + 1); }
             tm.s0 = s0; tm.s1 = s1; tm.cursor = s1;
+            if (s1 > s0 && s1 - s0 <= 16LL * cnt) sh.bcast[5] = 1;     // benign race: every writer stores 1
         }
         c.sync();
+        IFX_TICK(0);   // chunk setup + sub-range bounds
         const float thr = sh.thr; const int rounds = (cnt + NT - 1) / NT;
-        for (int t = 0; t < T; t++) {
-            const TermS& tm = sh.terms[t];
-            if (tm.idf <= 0.f) continue;
-            const int64_t sublen = tm.s1 - tm.s0; if (sublen == 0) continue;   // uniform: no candidate of this chunk can match
-            uint8_t* tfb = sh.tfbuf[t & 1];
-            const float bound = tm.max_score + tm.suffix_after;
-            if (sublen <= 8LL * cnt) {           // stream the posting sub-range, look each posting up among the chunk's candidates
-                for (int64_t i = tm.s0 + c.tid(); i < tm.s1; i += NT) {
-                    int32_t d = tm.docs[i]; int lo = 0, hi = cnt;
-                    while (lo < hi) { int mid = (lo + hi) >> 1; if (sh.cand_s[mid] < d) lo = mid + 1; else hi = mid; }
-                    if (lo < cnt && sh.cand_s[lo] == d) tfb[lo] = tm.tf ? tm.tf[i] : (uint8_t)1;
-                }
-            } else {                             // sparse candidates: probe the sub-range per candidate
-                for (int j = c.tid(); j < cnt; j += NT) {
-                    int32_t d = sh.cand_s[j]; int64_t i = lower_bound_i32(tm.docs, tm.s0, tm.s1, d);
-                    if (i < tm.s1 && tm.docs[i] == d) tfb[j] = tm.tf ? tm.tf[i] : (uint8_t)1;
-                }
-            }
+        const int per_thread = (CHUNK + NT - 1) / NT; const int j0 = c.tid() * per_thread < cnt ? c.tid() * per_thread : cnt; const int j1 = j0 + per_thread < cnt ? j0 + per_thread : cnt;
+        // Container-local bitmap of the chunk's candidates + per-word rank directory: posting -> candidate slot in O(1)
+        // (all candidates of a chunk share id >> 16). Built only when some term streams its posting sub-range.
+        const bool use_bitmap = sh.bcast[5] != 0;
+        if (use_bitmap) {
+            for (int w = c.tid(); w < 2048; w += NT) sh.cbits[w] = 0;
             c.sync();
-            // match flags in candidate order; MaxScore skip (Bm25Scorer.cs:354) removes pairs before ranks are taken
-            for (int r = 0; r < rounds; r++) {
-                int j = r * NT + c.tid();
-                bool f = j < cnt && tfb[j] != 0 && !(sh.score[j] + tm.max_score + tm.suffix_after <= thr);
-                unsigned b = c.ballot(f);
-                if (c.lane() == 0) sh.ballots[r * NW + c.warp()] = b;
-            }
-            (void)bound;
+            for (int j = c.tid(); j < cnt; j += NT) { int d = sh.cand_s[j] & 0xFFFF; atomic_or(&sh.cbits[d >> 5], 1u << (d & 31)); }
             c.sync();
-            if (c.warp() == 0) {                 // exclusive prefix of popcounts over (round, warp) slots
-                int slots = rounds * NW; int run = 0;
-#ifdef IFX_EMU
-                for (int s = 0; s < slots; s++) { sh.bprefix[s] = run; run += popc(sh.ballots[s]); }
-#else
-                for (int s0 = 0; s0 < slots; s0 += 32) {
-                    int s = s0 + c.lane(); int v = s < slots ? popc(sh.ballots[s]) : 0; int incl = v;
-                    for (int d = 1; d < 32; d <<= 1) { int o = __shfl_up_sync(0xffffffffu, incl, d); if (c.lane() >= d) incl += o; }
-                    if (s < slots) sh.bprefix[s] = run + incl - v;
-                    run += __shfl_sync(0xffffffffu, incl, 31);
-                }
-#endif
-                if (c.lane() == 0) sh.bcast[3] = run;
-            }
+            int per = (2048 + NT - 1) / NT; int w0 = c.tid() * per, w1 = w0 + per < 2048 ? w0 + per : 2048; int mine = 0;
+            for (int w = w0; w < w1; w++) mine += popc(sh.cbits[w]);
+            int tot; int run = block_excl_scan(c, mine, sh.scan, tot);
+            for (int w = w0; w < w1; w++) { sh.cpref[w] = (uint16_t)run; run += popc(sh.cbits[w]); }
             c.sync();
-            const int m = sh.bcast[3]; const int vec_end = m - (m & 7);
-            for (int r = 0; r < rounds; r++) {
-                int j = r * NT + c.tid();
-                if (j < cnt) {
-                    if (tfb[j] != 0 && !(sh.score[j] + tm.max_score + tm.suffix_after <= thr)) {   // same predicate as above (score[j] untouched since)
-                        int slot = r * NW + c.warp(); int rank = sh.bprefix[slot] + popc(sh.ballots[slot] & c.lanemask_lt());
-                        float tf = (float)tfb[j]; float dl = ix.doc_len[sh.cand_s[j]];
-                        float s = rank < vec_end ? bm25_vector(tf, dl, avgdl, tm.idf) : bm25_scalar(tf, dl, avgdl, tm.idf);
-                        sh.score[j] += s;
+        }
+        // Terms are processed in tiles: the membership (tf) lookups of a whole tile are issued back to back with no barrier in
+        // between (independent of the scores), then the order-dependent part -- MaxScore skip, rank within the chunk, formula
+        // choice, accumulation -- runs term by term with a single barrier each.
+        IFX_TICK(1);   // candidate bitmap
+        for (int t0 = 0; t0 < T; t0 += S1_TILE) {
+            const int tile = T - t0 < S1_TILE ? T - t0 : S1_TILE;
+            for (int tt = 0; tt < tile; tt++) {
+                const TermS& tm = sh.terms[t0 + tt];
+                const int64_t sublen = tm.s1 - tm.s0; if (tm.idf <= 0.f || sublen == 0) continue;   // uniform
+                uint8_t* tfb = sh.tfm[tt];
+                if (tm.bm && sublen > 2LL * cnt) {          // dense term, sparse chunk: O(1) bitmap probe per candidate (doc -> posting index -> tf)
+                    for (int jb = c.tid(); jb < cnt; jb += 4 * NT) {
+                        unsigned wv[4]; int rk[4]; int dd[4];
+                        for (int u = 0; u < 4; u++) { int j = jb + u * NT; dd[u] = j < cnt ? sh.cand_s[j] : -1; if (dd[u] >= 0) { wv[u] = tm.bm[dd[u] >> 5]; rk[u] = tm.bmr[dd[u] >> 5]; } }
+                        for (int u = 0; u < 4; u++) if (dd[u] >= 0) { unsigned bit = 1u << (dd[u] & 31); if (wv[u] & bit) tfb[jb + u * NT] = tm.tf[rk[u] + popc(wv[u] & (bit - 1))]; }
                     }
-                    tfb[j] = 0;
+                } else if (use_bitmap && sublen <= 16LL * cnt) {   // stream the posting sub-range (coalesced), O(1) slot lookup per posting
+                    for (int64_t i0 = tm.s0 + c.tid(); i0 < tm.s1; i0 += 4LL * NT) {      // four independent loads in flight per thread
+                        int dd[4];
+                        for (int u = 0; u < 4; u++) { int64_t i = i0 + (int64_t)u * NT; dd[u] = i < tm.s1 ? tm.docs[i] : -1; }
+                        for (int u = 0; u < 4; u++) if (dd[u] >= 0) {
+                            int d = dd[u] & 0xFFFF; unsigned wv = sh.cbits[d >> 5], bit = 1u << (d & 31);
+                            if (wv & bit) tfb[sh.cpref[d >> 5] + popc(wv & (bit - 1))] = tm.tf ? tm.tf[i0 + (int64_t)u * NT] : (uint8_t)1;
+                        }
+                    }
+                } else {                                    // sparse candidates: level-synchronous binary searches, four per thread at a time
+                    for (int jb = c.tid(); jb < cnt; jb += 4 * NT) {
+                        int64_t lo[4], hi[4]; int32_t d[4];
+                        for (int u = 0; u < 4; u++) { int j = jb + u * NT; d[u] = j < cnt ? sh.cand_s[j] : 0x7fffffff; lo[u] = tm.s0; hi[u] = j < cnt ? tm.s1 : tm.s0; }
+                        for (int64_t span = sublen; span > 0; span >>= 1) {
+                            int32_t v[4]; int64_t mid[4];
+                            for (int u = 0; u < 4; u++) { mid[u] = lo[u] + ((hi[u] - lo[u]) >> 1); v[u] = lo[u] < hi[u] ? tm.docs[mid[u]] : 0; }
+                            for (int u = 0; u < 4; u++) if (lo[u] < hi[u]) { if (v[u] < d[u]) lo[u] = mid[u] + 1; else hi[u] = mid[u]; }
+                        }
+                        for (int u = 0; u < 4; u++) { int j = jb + u * NT; if (j < cnt && lo[u] < tm.s1 && tm.docs[lo[u]] == d[u]) tfb[j] = tm.tf ? tm.tf[lo[u]] : (uint8_t)1; }
+                    }
                 }
             }
-            // no barrier needed here: the next term writes the other tf buffer, and three barriers separate reuse of this one
+            c.sync();
+            IFX_TICK(2);   // phase A (tf lookups)
+            for (int tt = 0; tt < tile; tt++) {
+                const TermS& tm = sh.terms[t0 + tt];
+                if (tm.idf <= 0.f || tm.s1 == tm.s0) continue;
+                uint8_t* tfb = sh.tfm[tt];
+                // Each thread owns the consecutive candidate slots [j0, j1). A (candidate, term) pair counts as a match only if the
+                // MaxScore test keeps it (Bm25Scorer.cs:354); its rank among the chunk's matches of this term selects the formula
+                // (first 8*floor(m/8) matches: Vector256 form, the rest: scalar form; Bm25Scorer.cs:395-444).
+                int mine = 0; const float tbound = tm.max_score; const float tsuffix = tm.suffix_after;
+                // NOTE: the block scan below contains a barrier and full-mask shuffles, so it sits at ONE convergent call site;
+                // only the per-thread counting / accumulation around it may diverge.
+#ifndef IFX_EMU
+                const bool fast = per_thread == 8 && j1 - j0 == 8;      // the 8 owned slots live in registers for the whole term
+                unsigned long long tf8 = 0ULL; unsigned alive = 0; float sc8[8];
+                if (fast) {
+                    tf8 = *reinterpret_cast<const unsigned long long*>(tfb + j0);
+                    if (tf8 != 0ULL) {
+                        float4 sa = *reinterpret_cast<const float4*>(&sh.score[j0]), sb = *reinterpret_cast<const float4*>(&sh.score[j0 + 4]);
+                        sc8[0] = sa.x; sc8[1] = sa.y; sc8[2] = sa.z; sc8[3] = sa.w; sc8[4] = sb.x; sc8[5] = sb.y; sc8[6] = sb.z; sc8[7] = sb.w;
+#pragma unroll
+                        for (int k = 0; k < 8; k++) { unsigned tfv = (unsigned)(tf8 >> (8 * k)) & 0xFFu; if (tfv != 0 && !(sc8[k] + tbound + tsuffix <= thr)) alive |= 1u << k; }
+                        mine = __popc(alive);
+                    }
+                } else
+#else
+                const bool fast = false;
+#endif
+                { for (int j = j0; j < j1; j++) if (tfb[j] != 0 && !(sh.score[j] + tbound + tsuffix <= thr)) mine++; }
+                int m; int rank = block_excl_scan_1b(c, mine, sh.scan2[tt & 1], m);
+                const int vec_end = m - (m & 7);
+#ifndef IFX_EMU
+                if (fast) {
+                    if (alive) {
+                        float4 da = *reinterpret_cast<const float4*>(&sh.nv_s[j0]), db = *reinterpret_cast<const float4*>(&sh.nv_s[j0 + 4]);
+                        float nv8[8] = {da.x, da.y, da.z, da.w, db.x, db.y, db.z, db.w};
+#pragma unroll
+                        for (int k = 0; k < 8; k++) if (alive & (1u << k)) {
+                            float tf = (float)((unsigned)(tf8 >> (8 * k)) & 0xFFu);
+                            float add = rank < vec_end ? bm25_from_norm_vector(tf, nv8[k], tm.idf) : bm25_scalar(tf, ix.doc_len[sh.cand_s[j0 + k]], avgdl, tm.idf);
+                            sc8[k] += add; rank++;
+                        }
+                        *reinterpret_cast<float4*>(&sh.score[j0]) = make_float4(sc8[0], sc8[1], sc8[2], sc8[3]);
+                        *reinterpret_cast<float4*>(&sh.score[j0 + 4]) = make_float4(sc8[4], sc8[5], sc8[6], sc8[7]);
+                    }
+                    if (tf8 != 0ULL) *reinterpret_cast<unsigned long long*>(tfb + j0) = 0ULL;
+                } else
+#endif
+                for (int j = j0; j < j1; j++) {
+                    const uint8_t tfv = tfb[j];
+                    if (tfv != 0) {
+                        if (!(sh.score[j] + tbound + tsuffix <= thr)) {
+                            float tf = (float)tfv;
+                            float sc = rank < vec_end ? bm25_from_norm_vector(tf, sh.nv_s[j], tm.idf) : bm25_scalar(tf, ix.doc_len[sh.cand_s[j]], avgdl, tm.idf);
+                            sh.score[j] += sc; rank++;
+                        }
+                        tfb[j] = 0;
+                    }
+                }
+                // no further barrier: score[j] / tfm[.][j] of these slots are private to this thread throughout the tile
+            }
+            c.sync();                                    // tile buffers are rewritten by arbitrary threads in the next tile
+            IFX_TICK(3);   // phase B (ranks + accumulation)
         }
         c.sync();
         {   // flush (Bm25Scorer.cs:316-329): eligibility in parallel (the threshold only rises during a flush, so anything not above the
-            // chunk-start threshold can never enter), then the exact sequential heap emulation over the survivors in candidate order
+            // chunk-start threshold can never enter), then the exact sequential emulation of .NET's 4-ary PriorityQueue over the
+            // survivors in candidate order. (A set-based top-K was tried: it is only equivalent when no documents tied at the final
+            // threshold straddle the cut, and on real corpora such ties are the norm -- identical tf pattern and length -- so the
+            // heap layout, which decides which of them survive, has to be reproduced.)
             const bool full = sh.heap_size >= K;
             for (int r = 0; r < rounds; r++) {
                 int j = r * NT + c.tid();
                 bool e = j < cnt && sh.score[j] > 0.f && (!full || sh.score[j] > thr) && !ix.deleted[sh.cand_s[j]];
                 unsigned b = c.ballot(e);
-                if (c.lane() == 0) sh.ballots[r * NW + c.warp()] = b;
+                if (c.lane() == 0) sh.ballots[0][r * NW + c.warp()] = b;
             }
             c.sync();
             if (c.tid() == 0) {
                 const int slots = rounds * NW;
-                for (int sl = 0; sl < slots; sl++) { unsigned mk = sh.ballots[sl]; int jb = (sl / NW) * NT + (sl % NW) * Ctx::WS;
-                    while (mk) { int l = ffs32(mk) - 1; mk &= mk - 1; int j = jb + l; float s = sh.score[j]; if (sh.heap_size < K || s > sh.thr) update_topk(sh, sh.cand_s[j], s, K); } }
+                for (int sl = 0; sl < slots; sl++) { unsigned mk = sh.ballots[0][sl]; int jb = (sl / NW) * NT + (sl % NW) * Ctx::WS;
+                    while (mk) { int l = ffs32(mk) - 1; mk &= mk - 1; int j = jb + l; float s = sh.score[j]; tph[5] += 1; if (sh.heap_size < K || s > sh.thr) { update_topk(sh, sh.cand_s[j], s, K); tph[5] += 1 << 20; } } }
             }
         }
         c.sync();
+        IFX_TICK(4);   // flush
         pos += cnt;
     }
+    if (c.tid() == 0 && out.dbg) for (int k = 0; k < 6; k++) out.dbg[6 + k] = tph[k];
+    for (int i = c.tid(); i < MAX_CONTAINERS; i += NT) sh.dirty[i] = 0;   // `cbits` aliased the dirty flags during scoring
+    c.sync();
     // ---- PopulateResultHeapFromPruning + TopKHeap.GetTopK + ConsolidateSegments: order by (score desc, key asc)
     const int n = sh.heap_size; int n2 = 1; while (n2 < n) n2 <<= 1;
     float* ks = sh.score; int32_t* kd = sh.cand_s;            // reuse chunk arrays (CHUNK >= MAX_K)
-    for (int i = c.tid(); i < n2; i += NT) { if (i < n) { ks[i] = sh.heap_score[i]; kd[i] = sh.heap_doc[i]; } else { ks[i] = -1.f; kd[i] = 0x7fffffff; } }
+    for (int i = c.tid(); i < n2; i += NT) { if (i < n) { ks[i] = kv_score(sh.IFX_KV(i)); kd[i] = (int)(sh.IFX_KV(i) >> 32); } else { ks[i] = -1.f; kd[i] = 0x7fffffff; } }
     c.sync();
     auto before = [&](int a, int b) -> bool {   // a ranks before b
         if (ks[a] != ks[b]) return ks[a] > ks[b];
