@@ -51,6 +51,7 @@ struct DevIndex {
     StrDict first_token; const uint16_t* token_count;
     StrDict terms; const int32_t* df; const int64_t* row_ptr; const int32_t* post_doc; const uint8_t* post_tf;
     const int32_t* term_sorted;      // term ordinals in ordinal-lexicographic order (trie DFS order)
+    const unsigned long long* term_sig;   // per sorted position: 64-bit character-set signature (LD1 pre-filter)
     const int32_t* skip_id;          // per term: row of the container skip table, or -1 (short lists)
     const int32_t* skip_ptr;         // [n_skip][n_cont + 1] offset (relative to the row start) of the first posting with doc >= c << 16
     int32_t n_cont;                  // 65536-doc containers in this shard
@@ -76,6 +77,10 @@ IFX_FN uint64_t hash64(const uint16_t* s, int n) {
     for (int i = 0; i < n; i++) { h ^= s[i]; h *= 0x100000001b3ULL; }
     h ^= h >> 29; h *= 0xbf58476d1ce4e5b9ULL; h ^= h >> 32;
     return h | 1ULL;                 // 0 marks an empty slot
+}
+
+IFX_FN unsigned long long char_sig(const uint16_t* s, int n) {   // one bit per (hashed) character present
+    unsigned long long g = 0; for (int i = 0; i < n; i++) g |= 1ULL << ((s[i] * 0x9E37u >> 4) & 63); return g;
 }
 
 IFX_FN int dict_lookup(const StrDict& d, const uint16_t* s, int n) {
@@ -108,6 +113,7 @@ inline unsigned atomic_and(unsigned* p, unsigned v) { unsigned o = *p; *p = o & 
 inline unsigned long long atomic_add64(unsigned long long* p, unsigned long long v) { unsigned long long o = *p; *p = o + v; return o; }
 inline int popc(unsigned v) { return __builtin_popcount(v); }
 inline int ffs32(unsigned v) { return __builtin_ffs((int)v); }
+inline int popc64(unsigned long long v) { return __builtin_popcountll(v); }
 inline float dev_logf_exact(float x) { return std::log(x); }
 #else
 struct Ctx {
@@ -125,6 +131,7 @@ __device__ __forceinline__ unsigned atomic_and(unsigned* p, unsigned v) { return
 __device__ __forceinline__ unsigned long long atomic_add64(unsigned long long* p, unsigned long long v) { return atomicAdd(p, v); }
 __device__ __forceinline__ int popc(unsigned v) { return __popc(v); }
 __device__ __forceinline__ int ffs32(unsigned v) { return __ffs((int)v); }
+__device__ __forceinline__ int popc64(unsigned long long v) { return __popcll(v); }
 // MathF.Log on the reference host is glibc logf (<1 ulp, effectively correctly rounded); evaluate in fp64 and round once.
 __device__ __forceinline__ float dev_logf_exact(float x) { return (float)log((double)x); }
 #endif

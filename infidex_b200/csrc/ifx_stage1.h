@@ -451,6 +451,8 @@ IFX_FN void expand_fuzzy(const Ctx& c, const DevIndex& ix, QueryPlan& p, int fsl
     const uint16_t* q = p.ttext + fr.off; const int m = fr.len;
     const uint64_t maskM = 1ULL << (m - 1);
     int64_t T = ix.terms.n; int total = 0;
+    // a term within (search-variant) edit distance 1 of the word lacks at most one of the word's distinct characters
+    const unsigned long long qsig = char_sig(q, m);
     for (int ch = c.tid(); ch < 128; ch += c.nthreads()) { unsigned long long pm = 0; for (int j = 0; j < m; j++) if (q[j] == ch) pm |= 1ULL << j; sh.peq[ch] = pm; }
     c.sync();
     // Myers bit-vector (search variant, FstIndex.cs:316-335) along one dictionary term
@@ -471,7 +473,7 @@ IFX_FN void expand_fuzzy(const Ctx& c, const DevIndex& ix, QueryPlan& p, int fsl
         const int HB = 8; int64_t hits[HB]; int cnt = 0;
         int64_t per = (T + c.nthreads() - 1) / c.nthreads(); per = (per + 15) & ~15LL;
         int64_t b = (int64_t)c.tid() * per, e = b + per; if (e > T) e = T;
-        for (int64_t i = b; i < e; i++) { int L = sorted_len[i]; if (L >= m - 1 && L <= m + 1 && L < 255 && myers_hit(i, L)) { if (cnt < HB) hits[cnt] = i; cnt++; } }
+        for (int64_t i = b; i < e; i++) { int L = sorted_len[i]; if (L >= m - 1 && L <= m + 1 && L < 255 && popc64(qsig & ~ix.term_sig[i]) <= 1 && myers_hit(i, L)) { if (cnt < HB) hits[cnt] = i; cnt++; } }
         int tot; int off = block_excl_scan(c, cnt, sh.scan, tot);
         int over = block_sum(c, cnt > HB ? 1 : 0, sh.scan);
         if (over == 0) {
@@ -481,7 +483,7 @@ IFX_FN void expand_fuzzy(const Ctx& c, const DevIndex& ix, QueryPlan& p, int fsl
             // dense-match fallback: ordered compaction round by round, stop after LD1_CAP matches
             for (int64_t base = 0; base < T && total < LD1_CAP; base += c.nthreads()) {
                 int64_t i = base + c.tid(); bool hit = false;
-                if (i < T) { int L = sorted_len[i]; hit = L >= m - 1 && L <= m + 1 && L < 255 && myers_hit(i, L); }
+                if (i < T) { int L = sorted_len[i]; hit = L >= m - 1 && L <= m + 1 && L < 255 && popc64(qsig & ~ix.term_sig[i]) <= 1 && myers_hit(i, L); }
                 int t2; int o2 = block_excl_scan(c, hit ? 1 : 0, sh.scan, t2);
                 if (hit && total + o2 < LD1_CAP) matches[total + o2] = ix.term_sorted[i];
                 total += t2;
