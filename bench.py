@@ -110,6 +110,7 @@ def main():
         return run_reference(args, wl, rank, world)
 
     import infidex_b200 as ib
+    from infidex_b200 import dist as ifxd
     from infidex_b200 import synth
     dist = None
     if world > 1:
@@ -125,7 +126,7 @@ def main():
     n_total = args.warmup + args.steps
     batches = []
     for s in range(n_total):   # a distinct batch per step and per rank
-        qs = synth.gen_queries(wl["nq"], docs, vocab, seed=synth.SEED + s + 1000 * rank)
+        qs = synth.gen_queries(wl["nq"], docs, vocab, seed=ifxd.rank_batch_seed(synth.SEED, s, rank))
         qq = []
         for t in qs:
             x = ib.Query(t, 10); x.Filter = flt; x.EnableFacets = bool(flt); qq.append(x)
@@ -166,11 +167,8 @@ def main():
     dev_ms = agg["ms_total"]; step_ms = dev_ms / args.steps
     if dist is not None:
         import torch
-        t = torch.tensor([dev_ms, e2e_t], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX); dev_ms, e2e_t = float(t[0]), float(t[1]); step_ms = dev_ms / args.steps
-        payload = torch.from_numpy(np.ascontiguousarray(packed[-1]["bufs"]["keys"])).cuda()      # per-batch result exchange: all-gather to every rank
-        outl = [torch.empty_like(payload) for _ in range(world)]
-        dist.all_gather(outl, payload)
+        dev_ms, e2e_t = ifxd.max_over_ranks(dist, [dev_ms, e2e_t], device="cuda"); step_ms = dev_ms / args.steps
+        gathered = ifxd.gather_results(dist, packed[-1]["bufs"]["keys"], device="cuda")      # per-batch result exchange over NCCL
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
