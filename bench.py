@@ -119,9 +119,16 @@ def main():
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     t_setup = time.time()
-    vocab, docs, schema, cols = make_corpus(wl)
     eng = ib.SearchEngine.CreateDefault(device=local)
-    eng.IndexColumns(docs["keys"], schema, cols)
+    if wl["n_docs"] > 2_000_000:          # large corpora are generated and indexed chunk by chunk
+        vocab = synth.make_vocab(wl["vocab"])
+        cc = synth.ChunkedCorpus(wl["n_docs"], vocab, wl["multi"], chunk=250_000)
+        eng.IndexChunks(cc.schema, cc.chunks())     # numpy generation is fastest single-threaded (measured)
+        docs = cc.docs_for_queries(); schema = cc.schema; cols = None; text_mb = cc.text_chars * 2 / 1e6
+    else:
+        vocab, docs, schema, cols = make_corpus(wl)
+        eng.IndexColumns(docs["keys"], schema, cols); text_mb = docs["title"][1][-1] * 2 / 1e6
+    t_index = time.time() - t_setup
     flt = ib.Filter.Parse("year >= 2000 AND rating > 7.0") if args.filter else None
     n_total = args.warmup + args.steps
     batches = []
@@ -194,7 +201,7 @@ def main():
     line = {"metric": "queries/sec", "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": wl["label"], "batch_per_gpu": wl["nq"], "filter": bool(flt), "parallelism": "replica x%d (query-parallel)" % world,
-                       "l2": "256 MiB L2 flush before every timed step; index (%.0f MB postings+text) also exceeds L2" % (docs["title"][1][-1] * 2 / 1e6 + 125),
+                       "l2": "256 MiB L2 flush before every timed step; the index (text alone %.0f MB) also exceeds the 126 MB L2" % text_mb, "index_build_s": round(t_index, 1),
                        "setup_s": round(t_setup, 1), "bad_status": bad},
             "phases_ms_per_step": {k: round(v / args.steps, 3) for k, v in agg.items()},
             "roofline": {"bound": "hbm", "kernel": "k_stage1", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
@@ -202,7 +209,7 @@ def main():
                          "longest_query_ms": q_max, "sum_query_ms_per_launch": q_sum / args.steps},
             "e2e": {"value": e2e, "unit": "queries/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
             "gpu_launches": int(launches), "clocks": clocks}
-    if not args.no_cpu_baseline and world == 1:
+    if not args.no_cpu_baseline and world == 1 and cols is not None:
         line["cpu_baseline"] = cpu_baseline(wl, vocab, docs, schema, cols, flt, args)
     print(json.dumps(line), flush=True)
     if dist is not None:

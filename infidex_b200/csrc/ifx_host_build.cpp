@@ -101,12 +101,20 @@ void merge_records(std::vector<std::unique_ptr<KeyedRecords>>& parts, Csr& out, 
     Interner g; std::vector<std::vector<int32_t>> l2g(parts.size());
     for (size_t t = 0; t < parts.size(); t++) { auto& p = *parts[t]; l2g[t].resize(p.keys.size()); for (int k = 0; k < p.keys.size(); k++) l2g[t][k] = g.intern(p.keys.get(k)); }
     int G = g.size(); out.n = G; out.chars.assign(g.arena.begin(), g.arena.end()); out.off = g.off; if (out.chars.empty()) out.chars.push_back(0);
+    // per-part per-key counts -> row pointers -> every part scatters its records in parallel (parts own ascending doc ranges,
+    // so placing part t's records after those of parts < t keeps every row ascending)
+    const size_t NP = parts.size();
+    std::vector<std::vector<int32_t>> cnt(NP);
+    { std::vector<std::thread> ts; for (size_t t = 0; t < NP; t++) ts.emplace_back([&, t] { cnt[t].assign(G, 0); for (int32_t k : parts[t]->rec_key) cnt[t][l2g[t][k]]++; }); for (auto& th : ts) th.join(); }
     out.row.assign((size_t)G + 1, 0);
-    for (size_t t = 0; t < parts.size(); t++) for (int32_t k : parts[t]->rec_key) out.row[l2g[t][k] + 1]++;
-    for (int i = 0; i < G; i++) out.row[i + 1] += out.row[i];
+    for (int g2 = 0; g2 < G; g2++) { int64_t c = 0; for (size_t t = 0; t < NP; t++) c += cnt[t][g2]; out.row[g2 + 1] = out.row[g2] + c; }
     out.docs.resize((size_t)out.row[G] ? out.row[G] : 1); if (weighted) out.w.resize(out.docs.size());
-    std::vector<int64_t> pos(out.row.begin(), out.row.end() - 1);
-    for (size_t t = 0; t < parts.size(); t++) { auto& p = *parts[t]; for (size_t r = 0; r < p.rec_key.size(); r++) { int64_t o = pos[l2g[t][p.rec_key[r]]]++; out.docs[o] = p.rec_doc[r]; if (weighted) out.w[o] = p.rec_w[r]; } }
+    std::vector<std::vector<int64_t>> start(NP);
+    for (size_t t = 0; t < NP; t++) start[t].resize(G);
+    for (int g2 = 0; g2 < G; g2++) { int64_t o = out.row[g2]; for (size_t t = 0; t < NP; t++) { start[t][g2] = o; o += cnt[t][g2]; } }
+    { std::vector<std::thread> ts; for (size_t t = 0; t < NP; t++) ts.emplace_back([&, t] { auto& p = *parts[t]; auto& pos = start[t];
+          for (size_t r = 0; r < p.rec_key.size(); r++) { int64_t o = pos[l2g[t][p.rec_key[r]]]++; out.docs[o] = p.rec_doc[r]; if (weighted) out.w[o] = p.rec_w[r]; } });
+      for (auto& th : ts) th.join(); }
     if (weighted) {
         out.extra.assign(G, 0); out.rep_last.assign(G, 0);
         for (size_t t = 0; t < parts.size(); t++) { auto& p = *parts[t]; for (int32_t k : p.sat_keys) out.extra[l2g[t][k]]++;
@@ -218,10 +226,12 @@ int ifx_builder_finish(ifx_builder* b, int threads) {
     for (auto& P : parts) { b->text.insert(b->text.end(), P.text.begin(), P.text.end()); for (auto l : P.text_len) b->text_off.push_back(b->text_off.back() + l);
         b->ft_chars.insert(b->ft_chars.end(), P.ft.begin(), P.ft.end()); for (auto l : P.ft_len) b->ft_off.push_back(b->ft_off.back() + l); b->tok_count.insert(b->tok_count.end(), P.tokc.begin(), P.tokc.end()); }
     if (b->text.empty()) b->text.push_back(0); if (b->ft_chars.empty()) b->ft_chars.push_back(0);
-    { std::vector<std::unique_ptr<KeyedRecords>> v; for (auto& P : parts) v.push_back(std::move(P.terms)); merge_records(v, b->terms, true); }
-    { std::vector<std::unique_ptr<KeyedRecords>> v; for (auto& P : parts) v.push_back(std::move(P.prefix)); merge_records(v, b->prefix, false); }
-    { std::vector<std::unique_ptr<KeyedRecords>> v; for (auto& P : parts) v.push_back(std::move(P.exact)); merge_records(v, b->wm_exact, false); }
-    { std::vector<std::unique_ptr<KeyedRecords>> v; for (auto& P : parts) v.push_back(std::move(P.ld1)); merge_records(v, b->wm_ld1, false); }
+    {   // the four keyed-record sets merge independently
+        std::vector<std::unique_ptr<KeyedRecords>> v0, v1, v2, v3;
+        for (auto& P : parts) { v0.push_back(std::move(P.terms)); v1.push_back(std::move(P.prefix)); v2.push_back(std::move(P.exact)); v3.push_back(std::move(P.ld1)); }
+        std::thread t0([&] { merge_records(v0, b->terms, true); }), t1([&] { merge_records(v1, b->prefix, false); }), t2([&] { merge_records(v2, b->wm_exact, false); }), t3([&] { merge_records(v3, b->wm_ld1, false); });
+        t0.join(); t1.join(); t2.join(); t3.join();
+    }
     // stop terms + df (Term.IncrementTermUsageCounter / FirstCycleAdd): df = postings + saturated repeats; a term dies when df would exceed the limit
     const int T = b->terms.n; b->df.assign(T, 0);
     std::vector<int64_t> new_row((size_t)T + 1, 0); int64_t wpos = 0;

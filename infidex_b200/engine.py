@@ -203,6 +203,11 @@ class SearchEngine:
         w = np.array([f.Weight for f in schema], np.int32)
         fl = np.array([(1 if f.Indexable else 0) | (2 if f.Filterable else 0) | (4 if f.Facetable else 0) for f in schema], np.int32)
         self._builder = self._host.ifx_builder_create(len(schema), _p(nb), _p(no.astype(np.int32)), _p(w), _p(fl))
+        self._add_columns(keys, columns)
+        self._finish(schema, threads)
+
+    def _add_columns(self, keys, columns):
+        n = len(keys)
         kinds = np.zeros(len(columns), np.int32)
         keep, cptr, optr = [], (C.c_void_p * len(columns))(), (C.c_void_p * len(columns))()
         for i, col in enumerate(columns):
@@ -217,7 +222,9 @@ class SearchEngine:
         rc = self._host.ifx_builder_add_docs(C.c_void_p(self._builder), n, _p(keys), _p(kinds), cptr, optr)
         if rc:
             raise NativeError("ifx_builder_add_docs failed")
-        self._host.ifx_builder_finish(C.c_void_p(self._builder), threads or max(1, min(os.cpu_count() or 1, 16)))
+
+    def _finish(self, schema, threads=None):
+        self._host.ifx_builder_finish(C.c_void_p(self._builder), threads or max(1, min(os.cpu_count() or 1, 32)))
         img = self._host.ifx_builder_image(C.c_void_p(self._builder))
         self._schema = list(schema)
         self._columns = []
@@ -225,6 +232,17 @@ class SearchEngine:
         for c in range(self._host.ifx_builder_num_columns(b)):
             n = self._host.ifx_builder_column_name(b, c, _p(buf), len(buf)); self._columns.append(buf[:n].tobytes().decode("utf-16-le"))
         self._upload(img)
+
+    def IndexChunks(self, schema, chunks, threads=None):
+        """Streaming form of IndexColumns for corpora that do not fit one numpy batch: `chunks` yields (keys, columns)."""
+        self.Dispose()
+        nb, no = pack_strings([f.Name for f in schema])
+        w = np.array([f.Weight for f in schema], np.int32)
+        fl = np.array([(1 if f.Indexable else 0) | (2 if f.Filterable else 0) | (4 if f.Facetable else 0) for f in schema], np.int32)
+        self._builder = self._host.ifx_builder_create(len(schema), _p(nb), _p(no.astype(np.int32)), _p(w), _p(fl))
+        for keys, columns in chunks:
+            self._add_columns(np.ascontiguousarray(keys, np.int64), columns)
+        self._finish(schema, threads)
 
     def image_ptr(self):
         return self._host.ifx_builder_image(C.c_void_p(self._builder))

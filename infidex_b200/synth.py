@@ -123,3 +123,31 @@ def schema_and_columns(docs, multi_field):
               Field("rating", None, Weight.Med, indexable=False, filterable=True),
               Field("genre", None, Weight.Med, indexable=False, filterable=True, facetable=True)]
     return schema, [docs["title"], docs["description"], docs["year"], docs["rating"], genre]
+
+
+class ChunkedCorpus:
+    """Streams a large synthetic corpus chunk by chunk (deterministic per chunk) and keeps only what query sampling needs."""
+
+    def __init__(self, n_docs, vocab, multi_field, chunk=500_000, seed=SEED):
+        self.n, self.vocab, self.multi, self.chunk, self.seed = n_docs, vocab, multi_field, chunk, seed
+        self.title_ids, self.title_off = [], [np.zeros(1, np.int64)]
+        self.schema = schema_and_columns({"title": None, "description": None, "year": None, "rating": None, "genre_id": np.zeros(0, np.int64)}, multi_field)[0]
+        self.text_chars = 0
+
+    def chunks(self, workers=1):
+        """Yields (keys, columns) in document order; chunk generation (numpy, releases the GIL) runs `workers` chunks ahead."""
+        from concurrent.futures import ThreadPoolExecutor
+        starts = list(range(0, self.n, self.chunk))
+        gen = lambda st: gen_docs(min(self.chunk, self.n - st), self.vocab, seed=self.seed, with_description=self.multi, start=st)
+        with ThreadPoolExecutor(max_workers=max(1, workers)) as ex:
+            pending = [ex.submit(gen, st) for st in starts[:workers]]; nxt = workers
+            for _ in starts:
+                d = pending.pop(0).result()
+                if nxt < len(starts):
+                    pending.append(ex.submit(gen, starts[nxt])); nxt += 1
+                self.title_ids.append(d["title_ids"].astype(np.int32)); self.title_off.append(d["title_off"][1:] + self.title_off[-1][-1])
+                self.text_chars += int(d["title"][1][-1]) + (int(d["description"][1][-1]) if self.multi else 0)
+                yield d["keys"], schema_and_columns(d, self.multi)[1]
+
+    def docs_for_queries(self):
+        return {"n": self.n, "title_ids": np.concatenate(self.title_ids), "title_off": np.concatenate(self.title_off)}
