@@ -169,7 +169,12 @@ extern "C" int ifx_index_create(const ifx_index_image* img, const ifx_params* pp
         std::sort(order.begin(), order.end(), [&](int a, int b) { return term_sv(a) < term_sv(b); });
         std::vector<uint8_t> slen(T); for (int i = 0; i < T; i++) { size_t l = term_sv(order[i]).size(); slen[i] = (uint8_t)(l > 255 ? 255 : l); }
         v.term_sorted = ix->up(order.data(), T ? T : 1); ix->d_sorted_len = ix->up(slen.data(), T ? T : 1);
-        { std::vector<unsigned long long> sig(std::max(T, 1), 0ULL); for (int i = 0; i < T; i++) { auto sv = term_sv(order[i]); unsigned long long g = 0; for (char16_t ch : sv) g |= 1ULL << (((uint16_t)ch * 0x9E37u >> 4) & 63); sig[i] = g; } v.term_sig = ix->up(sig.data(), sig.size()); }
+        {   std::vector<unsigned long long> sig(std::max(T, 1), 0ULL); for (int i = 0; i < T; i++) { auto sv = term_sv(order[i]); unsigned long long g = 0; for (char16_t ch : sv) g |= 1ULL << (((uint16_t)ch * 0x9E37u >> 4) & 63); sig[i] = g; } v.term_sig = ix->up(sig.data(), sig.size());
+            // counting sort of the sorted positions by length
+            std::vector<int32_t> lp(257, 0); for (int i = 0; i < T; i++) lp[slen[i] + 1]++; for (int l = 0; l < 256; l++) lp[l + 1] += lp[l];
+            std::vector<int32_t> cur(lp.begin(), lp.end() - 1), lord(std::max(T, 1), 0); std::vector<unsigned long long> lsig(std::max(T, 1), 0ULL);
+            for (int i = 0; i < T; i++) { int at = cur[slen[i]]++; lord[at] = order[i]; lsig[at] = sig[i]; }
+            v.len_ptr = ix->up(lp.data(), lp.size()); v.len_sig = ix->up(lsig.data(), lsig.size()); v.len_ord = ix->up(lord.data(), lord.size()); }
         v.words = upload_dict(ix, img->words); v.word_idf = ix->up(img->word_idf, img->words.n ? img->words.n : 1);
         v.prefix = upload_docset(ix, img->prefix); v.wm_exact = upload_docset(ix, img->wm_exact); v.wm_ld1 = upload_docset(ix, img->wm_ld1);
         {   // affix words: forward (prefix) order and reverse-string (suffix) order, each with the doc its trie output resolves to

@@ -14,10 +14,18 @@
 #include <cmath>
 #include <algorithm>
 #define IFX_FN inline
+#define IFX_FN_OUTLINED inline
 #define IFX_KERNEL_ATTR
 #else
 #include <cuda_runtime.h>
 #define IFX_FN __device__ __forceinline__
+// large helpers with several call sites inside one kernel: one shared body keeps the instruction footprint (and the i-cache
+// miss rate of divergent warps) down
+#ifdef IFX_COV_INLINE_ALL
+#define IFX_FN_OUTLINED __device__ __forceinline__
+#else
+#define IFX_FN_OUTLINED __device__ __noinline__
+#endif
 #endif
 
 namespace ifx {
@@ -26,6 +34,7 @@ constexpr int MAX_QLEN = 256;        // UTF-16 units of a (normalised) query; lo
 constexpr int MAX_RAW_TOKENS = 128;  // VectorModel.cs:381 (ArrayPool rent of 128 RawToken)
 constexpr int MAX_TERMS = 128;
 constexpr int MAX_FUZZY = 16;        // unknown words (len >= 4) expanded per query
+#define IFX_QDBG 24                   // int64 slots of the per-query Stage-1 debug record (ifx_debug_stage1_queries)
 constexpr int LD1_CAP = 1024;        // VectorModel.cs:662 stackalloc int[1024]
 constexpr int CHUNK = 4096;          // Bm25Scorer.cs:209 blockSize
 constexpr int MAX_K = 1024;          // coverage depth supported by the on-chip heap
@@ -52,6 +61,10 @@ struct DevIndex {
     StrDict terms; const int32_t* df; const int64_t* row_ptr; const int32_t* post_doc; const uint8_t* post_tf;
     const int32_t* term_sorted;      // term ordinals in ordinal-lexicographic order (trie DFS order)
     const unsigned long long* term_sig;   // per sorted position: 64-bit character-set signature (LD1 pre-filter)
+    // the same dictionary grouped by term length (stable, so lexicographic inside a group): LD1 scans touch lengths m-1..m+1 only
+    const int32_t* len_ptr;          // [257] group start per length (255 = 255 or longer), [256] = n terms
+    const unsigned long long* len_sig;   // signature per grouped position
+    const int32_t* len_ord;          // term ordinal per grouped position
     const int32_t* skip_id;          // per term: row of the container skip table, or -1 (short lists)
     const int32_t* skip_ptr;         // [n_skip][n_cont + 1] offset (relative to the row start) of the first posting with doc >= c << 16
     int32_t n_cont;                  // 65536-doc containers in this shard
@@ -103,6 +116,7 @@ struct Ctx {
     static constexpr int WS = 1;
     int tid() const { return 0; } int nthreads() const { return 1; } int lane() const { return 0; } int warp() const { return 0; } int nwarps() const { return 1; }
     void sync() const {}
+    void sync_workers(int) const {}
     unsigned ballot(bool p) const { return p ? 1u : 0u; }
     unsigned lanemask_lt() const { return 0u; }
     template <class T> T shfl(T v, int) const { return v; }
@@ -121,6 +135,8 @@ struct Ctx {
     __device__ int tid() const { return threadIdx.x; } __device__ int nthreads() const { return blockDim.x; }
     __device__ int lane() const { return threadIdx.x & 31; } __device__ int warp() const { return threadIdx.x >> 5; } __device__ int nwarps() const { return blockDim.x >> 5; }
     __device__ void sync() const { __syncthreads(); }
+    // named barrier 1 over the `n` worker threads of a warp-specialised region (n: multiple of 32; every worker warp calls it)
+    __device__ void sync_workers(int n) const { asm volatile("bar.sync 1, %0;" :: "r"(n) : "memory"); }
     __device__ unsigned ballot(bool p) const { return __ballot_sync(0xffffffffu, p); }
     __device__ unsigned lanemask_lt() const { return (1u << (threadIdx.x & 31)) - 1u; }
     template <class T> __device__ T shfl(T v, int src) const { return __shfl_sync(0xffffffffu, v, src); }

@@ -56,7 +56,7 @@ IFX_FN int lev(const DevIndex& ix, Str pattern, Str text, int max_errors, bool i
     return costs[m];
 }
 // LevenshteinDistance.CalculateDamerau
-IFX_FN int damerau(const DevIndex& ix, Str s, Str t, int maxd, bool ic) {
+IFX_FN_OUTLINED int damerau(const DevIndex& ix, Str s, Str t, int maxd, bool ic) {
     int ld = s.n - t.n; if (ld < 0) ld = -ld;
     if (ld > maxd) return maxd + 1;
     int dist = lev(ix, s, t, maxd + 1, ic);

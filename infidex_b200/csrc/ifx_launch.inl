@@ -48,11 +48,11 @@ __global__ void __launch_bounds__(IFX_S1_THREADS, 2) k_stage1(DevIndex ix, const
         int qi = sh.bcast[7]; __syncthreads();
         if (qi >= nq) break;
         const int q = order[qi];
-        Stage1Out o{s1_key + (size_t)q * K, s1_doc + (size_t)q * K, s1_score + (size_t)q * K, s1_n + q, qdbg + (size_t)q * 12};
+        Stage1Out o{s1_key + (size_t)q * K, s1_doc + (size_t)q * K, s1_score + (size_t)q * K, s1_n + q, qdbg + (size_t)q * IFX_QDBG};
         unsigned long long t0 = 0; if (threadIdx.x == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
         stage1_query(c, ix, plans[q], pool, ws, sh, o, bc);
         __syncthreads();
-        if (threadIdx.x == 0) { unsigned long long t1; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1)); atomicAdd(&bc->s1_ns_sum, t1 - t0); atomicMax(&bc->s1_ns_max, t1 - t0); qdbg[(size_t)q * 12 + 4] = (long long)(t1 - t0); qdbg[(size_t)q * 12 + 2] -= (long long)t0; qdbg[(size_t)q * 12 + 5] = blockIdx.x; }
+        if (threadIdx.x == 0) { unsigned long long t1; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1)); atomicAdd(&bc->s1_ns_sum, t1 - t0); atomicMax(&bc->s1_ns_max, t1 - t0); qdbg[(size_t)q * IFX_QDBG + 4] = (long long)(t1 - t0); qdbg[(size_t)q * IFX_QDBG + 2] -= (long long)t0; qdbg[(size_t)q * IFX_QDBG + 5] = blockIdx.x; }
     }
 }
 #endif
@@ -107,7 +107,7 @@ static int fill_batch(ifx_batch* b, const ifx_query* q, int nq) {
         b->d_text = b->alloc<uint16_t>(b->text_cap); b->d_off = b->alloc<int64_t>(nq + 1); b->d_par = b->alloc<int32_t>(par.size());
         b->d_plans = b->alloc<QueryPlan>(nq); b->d_items = b->alloc<FuzzyItem>((size_t)nq * 4 + 64); b->d_bc = b->alloc<BatchCounters>(1); b->d_work = b->alloc<int>(8); dev_zero(b->d_work, 8 * sizeof(int));
         size_t K = b->depth_max;
-        b->d_s1_key = b->alloc<int64_t>(nq * K); b->d_s1_doc = b->alloc<int32_t>(nq * K); b->d_s1_score = b->alloc<float>(nq * K); b->d_s1_n = b->alloc<int32_t>(nq); b->d_order = b->alloc<int>(nq); b->d_qdbg = b->alloc<long long>((size_t)nq * 12); dev_zero(b->d_qdbg, (size_t)nq * 96);
+        b->d_s1_key = b->alloc<int64_t>(nq * K); b->d_s1_doc = b->alloc<int32_t>(nq * K); b->d_s1_score = b->alloc<float>(nq * K); b->d_s1_n = b->alloc<int32_t>(nq); b->d_order = b->alloc<int>(nq); b->d_qdbg = b->alloc<long long>((size_t)nq * IFX_QDBG); dev_zero(b->d_qdbg, (size_t)nq * IFX_QDBG * 8);
     } else if (text.size() > b->text_cap) return fail(IFX_ERR_INVALID, "batch text outgrew its buffer");
     h2d(b->d_text, text.data(), text.size() * 2); h2d(b->d_off, off.data(), (nq + 1) * 8); h2d(b->d_par, par.data(), par.size() * 4);
     b->ran = false;
@@ -140,4 +140,4 @@ extern "C" int ifx_stage1_batch(ifx_index* idx, const ifx_query* q, int nq, int 
 #include "ifx_search.inl"
 
 // debugging aid: per-query [n_cand, n_terms, selection_ns, path, total_ns, cta] of the last run's k_stage1
-extern "C" int ifx_debug_stage1_queries(ifx_batch* b, long long* out) { try { d2h(out, b->d_qdbg, (size_t)b->nq * 96); } catch (const std::string& e) { return fail(IFX_ERR_CUDA, e); } return IFX_OK; }
+extern "C" int ifx_debug_stage1_queries(ifx_batch* b, long long* out) { try { d2h(out, b->d_qdbg, (size_t)b->nq * IFX_QDBG * 8); } catch (const std::string& e) { return fail(IFX_ERR_CUDA, e); } return IFX_OK; }

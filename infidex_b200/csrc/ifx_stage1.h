@@ -188,6 +188,7 @@ struct TermS {             // term as seen by the scorer
 
 constexpr int S1_TILE = 6;
 
+constexpr int SURV_CAP = 512;
 struct S1Shared {
     TermS terms[MAX_TERMS];
     int order[MAX_TERMS];
@@ -201,6 +202,7 @@ struct S1Shared {
     // .NET PriorityQueue nodes packed as (doc << 32 | float bits of the priority), stored with a +3 shift so the four children of
     // node i (4i+1..4i+4) form one aligned 32-byte group; slots beyond the current size hold +huge sentinels
     alignas(32) unsigned long long heap_kv[MAX_K + 8];
+    unsigned long long surv[SURV_CAP];     // (doc, score) of the last chunk's flush survivors, drained into the heap while the next chunk is staged
     union {                               // never live at the same time: selection/compaction vs. chunk scoring
         uint8_t dirty[MAX_CONTAINERS];    // containers of the global bitset touched by the current set operation (all zero between uses)
         unsigned cbits[2048];             // container-local bitmap of the current chunk's candidates (stream mode)
@@ -420,6 +422,61 @@ IFX_FN void update_topk(S1Shared& sh, int doc, float s, int K) {
     else if (s > sh.thr) { heap_move_down(sh, doc, s, 0); sh.thr = kv_score(sh.IFX_KV(0)); }
 }
 
+// Exclusive scan over the worker threads [hw, nthreads) only (named barrier 1); every worker must call it.
+IFX_FN int worker_excl_scan(const Ctx& c, int v, ScanTmp& tmp, int hw, int ntw) {
+#ifdef IFX_EMU
+    (void)c; (void)v; (void)tmp; (void)hw; (void)ntw; return 0;
+#else
+    int incl = v;
+    for (int d = 1; d < 32; d <<= 1) { int o = __shfl_up_sync(0xffffffffu, incl, d); if (c.lane() >= d) incl += o; }
+    if (c.lane() == 31) tmp.w[c.warp()] = incl;
+    c.sync_workers(ntw);
+    int base = 0; const int w0 = hw >> 5;
+    for (int i = w0; i < c.warp(); i++) base += tmp.w[i];
+    c.sync_workers(ntw);
+    return base + incl - v;
+#endif
+}
+
+// Phase A of one term tile: tf of every (term, candidate slot) pair of the chunk into sh.tfm (0 = no match). Independent of the
+// scores and of the threshold, so it runs on the worker threads (wt of ntw) while the heap warp is still draining the last chunk.
+IFX_FN void stage1_phase_a(const Ctx& c, S1Shared& sh, int t0, int T, int cnt, int wt, int ntw) {
+    (void)c;
+    const int tile = T - t0 < S1_TILE ? T - t0 : S1_TILE; const bool use_bitmap = sh.bcast[5] != 0;
+    for (int tt = 0; tt < tile; tt++) {
+        const TermS& tm = sh.terms[t0 + tt];
+        const int64_t sublen = tm.s1 - tm.s0; if (tm.idf <= 0.f || sublen == 0) continue;   // uniform
+        uint8_t* tfb = sh.tfm[tt];
+        if (tm.bm && sublen > 2LL * cnt) {          // dense term, sparse chunk: O(1) bitmap probe per candidate (doc -> posting index -> tf)
+            for (int jb = wt; jb < cnt; jb += 4 * ntw) {
+                unsigned wv[4]; int rk[4]; int dd[4];
+                for (int u = 0; u < 4; u++) { int j = jb + u * ntw; dd[u] = j < cnt ? sh.cand_s[j] : -1; if (dd[u] >= 0) { wv[u] = tm.bm[dd[u] >> 5]; rk[u] = tm.bmr[dd[u] >> 5]; } }
+                for (int u = 0; u < 4; u++) if (dd[u] >= 0) { unsigned bit = 1u << (dd[u] & 31); if (wv[u] & bit) tfb[jb + u * ntw] = tm.tf[rk[u] + popc(wv[u] & (bit - 1))]; }
+            }
+        } else if (use_bitmap && sublen <= 16LL * cnt) {   // stream the posting sub-range (coalesced), O(1) slot lookup per posting
+            for (int64_t i0 = tm.s0 + wt; i0 < tm.s1; i0 += 4LL * ntw) {      // four independent loads in flight per thread
+                int dd[4];
+                for (int u = 0; u < 4; u++) { int64_t i = i0 + (int64_t)u * ntw; dd[u] = i < tm.s1 ? tm.docs[i] : -1; }
+                for (int u = 0; u < 4; u++) if (dd[u] >= 0) {
+                    int d = dd[u] & 0xFFFF; unsigned wv = sh.cbits[d >> 5], bit = 1u << (d & 31);
+                    if (wv & bit) tfb[sh.cpref[d >> 5] + popc(wv & (bit - 1))] = tm.tf ? tm.tf[i0 + (int64_t)u * ntw] : (uint8_t)1;
+                }
+            }
+        } else {                                    // sparse candidates: level-synchronous binary searches, four per thread at a time
+            for (int jb = wt; jb < cnt; jb += 4 * ntw) {
+                int64_t lo[4], hi[4]; int32_t d[4];
+                for (int u = 0; u < 4; u++) { int j = jb + u * ntw; d[u] = j < cnt ? sh.cand_s[j] : 0x7fffffff; lo[u] = tm.s0; hi[u] = j < cnt ? tm.s1 : tm.s0; }
+                for (int64_t span = sublen; span > 0; span >>= 1) {
+                    int32_t v[4]; int64_t mid[4];
+                    for (int u = 0; u < 4; u++) { mid[u] = lo[u] + ((hi[u] - lo[u]) >> 1); v[u] = lo[u] < hi[u] ? tm.docs[mid[u]] : 0; }
+                    for (int u = 0; u < 4; u++) if (lo[u] < hi[u]) { if (v[u] < d[u]) lo[u] = mid[u] + 1; else hi[u] = mid[u]; }
+                }
+                for (int u = 0; u < 4; u++) { int j = jb + u * ntw; if (j < cnt && lo[u] < tm.s1 && tm.docs[lo[u]] == d[u]) tfb[j] = tm.tf ? tm.tf[lo[u]] : (uint8_t)1; }
+            }
+        }
+    }
+}
+
 // Bm25Scorer.cs:395-433 (Vector256 lanes) and :643-652 (scalar remainder); must not be contracted into FMAs.
 // The document-length part of both forms depends only on the candidate, so it is evaluated once per chunk and slot:
 //   vector form  norm = K1 * ((1 - B) + (B / avgdl) * dl)        scalar form  norm = K1 * (1 - B + B * (dl / avgdl)), dl <= 0 -> 1
@@ -455,9 +512,9 @@ IFX_FN void expand_fuzzy(const Ctx& c, const DevIndex& ix, QueryPlan& p, int fsl
     const unsigned long long qsig = char_sig(q, m);
     for (int ch = c.tid(); ch < 128; ch += c.nthreads()) { unsigned long long pm = 0; for (int j = 0; j < m; j++) if (q[j] == ch) pm |= 1ULL << j; sh.peq[ch] = pm; }
     c.sync();
-    // Myers bit-vector (search variant, FstIndex.cs:316-335) along one dictionary term
-    auto myers_hit = [&](int64_t i, int L) -> bool {
-        int ord = ix.term_sorted[i]; const uint16_t* s = ix.terms.chars + ix.terms.off[ord];
+    // Myers bit-vector (search variant, FstIndex.cs:316-335) along one dictionary term (ordinal `ord`, length L)
+    auto myers_hit = [&](int ord, int L) -> bool {
+        const uint16_t* s = ix.terms.chars + ix.terms.off[ord];
         uint64_t vp = ~0ULL, vn = 0ULL; int score = m;
         for (int k = 0; k < L; k++) {
             uint16_t ch = s[k]; uint64_t pm;
@@ -469,21 +526,35 @@ IFX_FN void expand_fuzzy(const Ctx& c, const DevIndex& ix, QueryPlan& p, int fsl
         }
         return score <= 1;
     };
-    {   // fast path: every thread scans one contiguous strip of the sorted dictionary (trie DFS order), one block scan at the end
-        const int HB = 8; int64_t hits[HB]; int cnt = 0;
-        int64_t per = (T + c.nthreads() - 1) / c.nthreads(); per = (per + 15) & ~15LL;
-        int64_t b = (int64_t)c.tid() * per, e = b + per; if (e > T) e = T;
-        for (int64_t i = b; i < e; i++) { int L = sorted_len[i]; if (L >= m - 1 && L <= m + 1 && L < 255 && popc64(qsig & ~ix.term_sig[i]) <= 1 && myers_hit(i, L)) { if (cnt < HB) hits[cnt] = i; cnt++; } }
-        int tot; int off = block_excl_scan(c, cnt, sh.scan, tot);
-        int over = block_sum(c, cnt > HB ? 1 : 0, sh.scan);
-        if (over == 0) {
-            for (int k = 0; k < cnt; k++) if (off + k < LD1_CAP) matches[off + k] = ix.term_sorted[hits[k]];
-            total = tot;
-        } else {
-            // dense-match fallback: ordered compaction round by round, stop after LD1_CAP matches
+    {   // Fast path: only dictionary terms of length m-1..m+1 can match, and the dictionary is also stored grouped by length
+        // (ix.len_ptr / len_sig / len_ord), so the scan is a coalesced stream over those three groups. Matches are appended in
+        // arbitrary order: the union below is order-free as long as all of them fit (<= LD1_CAP, the usual case).
+        if (c.tid() == 0) sh.bcast[6] = 0;
+        c.sync();
+        const int l0 = m - 1 < 0 ? 0 : m - 1, l1 = m + 1 > 254 ? 254 : m + 1;
+        const int64_t gb = ix.len_ptr[l0], ge = l1 >= l0 ? ix.len_ptr[l1 + 1] : gb; const int64_t g1 = ix.len_ptr[l0 + 1], g2 = l0 + 2 <= 255 ? ix.len_ptr[l0 + 2] : ge;
+        const int64_t NT4 = 4LL * c.nthreads();
+        for (int64_t base0 = gb; base0 < ge; base0 += NT4) {       // uniform trip count (warp votes inside); four signature loads in flight per thread
+            const int64_t i0 = base0 + c.tid(); unsigned long long sg[4];
+            for (int u = 0; u < 4; u++) { int64_t i = i0 + (int64_t)u * c.nthreads(); sg[u] = i < ge ? ix.len_sig[i] : ~0ULL; }
+            for (int u = 0; u < 4; u++) {
+                int64_t i = i0 + (int64_t)u * c.nthreads(); bool hit = false; int ord = 0;
+                if (i < ge && popc64(qsig & ~sg[u]) <= 1) { ord = ix.len_ord[i]; int L = l0 + (i >= g1 ? 1 : 0) + (i >= g2 ? 1 : 0); hit = myers_hit(ord, L); }
+                unsigned bm = c.ballot(hit);
+                if (bm) { int leader = ffs32(bm) - 1; int base = 0; if (c.lane() == leader) base = atomic_add(&sh.bcast[6], popc(bm)); base = c.shfl(base, leader);
+                          int at = base + popc(bm & c.lanemask_lt()); if (hit && at < LD1_CAP) matches[at] = ord; }
+            }
+        }
+        c.sync();
+        total = sh.bcast[6];
+        c.sync();
+        if (total > LD1_CAP) {
+            // more matches than VectorModel.cs:662 keeps: the reference takes the first LD1_CAP in trie DFS order, so redo the scan
+            // over the lexicographically sorted dictionary with an ordered compaction and stop there
+            total = 0;
             for (int64_t base = 0; base < T && total < LD1_CAP; base += c.nthreads()) {
                 int64_t i = base + c.tid(); bool hit = false;
-                if (i < T) { int L = sorted_len[i]; hit = L >= m - 1 && L <= m + 1 && L < 255 && popc64(qsig & ~ix.term_sig[i]) <= 1 && myers_hit(i, L); }
+                if (i < T) { int L = sorted_len[i]; hit = L >= m - 1 && L <= m + 1 && L < 255 && popc64(qsig & ~ix.term_sig[i]) <= 1 && myers_hit(ix.term_sorted[i], L); }
                 int t2; int o2 = block_excl_scan(c, hit ? 1 : 0, sh.scan, t2);
                 if (hit && total + o2 < LD1_CAP) matches[total + o2] = ix.term_sorted[i];
                 total += t2;
@@ -491,13 +562,27 @@ IFX_FN void expand_fuzzy(const Ctx& c, const DevIndex& ix, QueryPlan& p, int fsl
         }
     }
     c.sync();
-    int nm = total < LD1_CAP ? total : LD1_CAP;
-    int df = 0;
-    for (int k = 0; k < nm; k++) {
+    const int nm = total < LD1_CAP ? total : LD1_CAP;
+    // Union of the matches' posting lists into the CTA's bitset: short lists one warp each (no block barrier per list), long
+    // lists block-wide afterwards.
+    const int BIG = 4096, BIGQ = 128; int fresh = 0;
+    if (c.tid() == 0) sh.bcast[5] = 0;
+    c.sync();
+    for (int k = c.warp(); k < nm; k += c.nwarps()) {
         int ord = matches[k]; if (ix.df[ord] <= 0) continue;
         int64_t r0 = ix.row_ptr[ord], r1 = ix.row_ptr[ord + 1];
-        df += or_list_into_bits(c, ix.post_doc + r0, r1 - r0, ws, sh);
+        if (r1 - r0 >= BIG) { int slot = BIGQ; if (c.lane() == 0) slot = atomic_add(&sh.bcast[5], 1); slot = c.shfl(slot, 0); if (slot < BIGQ) { if (c.lane() == 0) sh.bprefix[slot] = ord; continue; } }
+        for (int64_t i = r0 + c.lane(); i < r1; i += Ctx::WS) {
+            int d = ix.post_doc[i]; unsigned bit = 1u << (d & 31);
+            unsigned old = atomic_or(&ws.bits[d >> 5], bit);
+            if (!(old & bit)) fresh++;
+            sh.dirty[d >> 16] = 1;
+        }
     }
+    c.sync();
+    int df = block_sum(c, fresh, sh.scan);
+    const int nbig = sh.bcast[5] < BIGQ ? sh.bcast[5] : BIGQ;
+    for (int k = 0; k < nbig; k++) { int ord = sh.bprefix[k]; int64_t r0 = ix.row_ptr[ord], r1 = ix.row_ptr[ord + 1]; df += or_list_into_bits(c, ix.post_doc + r0, r1 - r0, ws, sh); }
     c.sync();
     QTerm& t = p.terms[fr.term_slot];
     if (df == 0) { if (c.tid() == 0) { t.df = 0; t.list_len = 0; } c.sync(); return; }
@@ -613,99 +698,94 @@ IFX_FN void stage1_query(const Ctx& c, const DevIndex& ix, const QueryPlan& p, c
     }
 
     // ---- BM25 scoring over chunks (ProcessBlockedCandidates / ProcessChunk / ScoreBlockStruct)
+    // The top-K heap is inherently sequential (one thread replays .NET's PriorityQueue), everything else is block-parallel.
+    // To keep both busy the chunk loop is software-pipelined: the survivors of chunk i are compacted into `surv`, and while
+    // thread 0 (warp 0 = "heap warp") drains them into the heap, warps 1.. ("workers") already run chunk i+1's set-up and the
+    // score-independent membership lookups (phase A). The two sides meet at the barrier in front of phase B, which is the first
+    // place chunk i+1 needs the threshold chunk i produced. Workers synchronise among themselves on named barrier 1.
     const int NW = c.nwarps();
-    long long tph[6] = {0, 0, 0, 0, 0, 0}; long long tmark = 0;
+    const int hw = NT > Ctx::WS ? Ctx::WS : 0;                 // threads of the heap warp (0: single-warp build, everything sequential)
+    const bool worker = c.tid() >= hw; const int wt = c.tid() - hw, NTW = NT - hw;
+    int pend = 0;                                              // survivors of the previous chunk waiting in sh.surv (uniform)
+    long long tph[6] = {0, 0, 0, 0, 0, 0}; long long tmark = 0; long long wph[8] = {0, 0, 0, 0, 0, 0, 0, 0}; long long wmark = 0; (void)wmark;
 #ifndef IFX_EMU
-#define IFX_TICK(k) do { if (c.tid() == 0) { long long now_ = clock64(); tph[k] += now_ - tmark; tmark = now_; } } while (0)
-    if (c.tid() == 0) tmark = clock64();
+    // phase timers (debug records only): thread 0 = heap warp's view, thread `hw` = the workers' view. The "memory" clobber keeps
+    // the clock reads from being scheduled across the barriers they bracket.
+    auto rdclock = []() -> long long { long long t_; asm volatile("mov.u64 %0, %%clock64;" : "=l"(t_) :: "memory"); return t_; };
+#define IFX_TICK(k) do { if (c.tid() == 0) { long long now_ = rdclock(); tph[k] += now_ - tmark; tmark = now_; } } while (0)
+#define IFX_WTICK(k) do { if (c.tid() == hw) { long long now_ = rdclock(); wph[k] += now_ - wmark; wmark = now_; } } while (0)
+    if (c.tid() == 0) tmark = rdclock();
+    if (c.tid() == hw) wmark = rdclock();
 #else
 #define IFX_TICK(k) do { } while (0)
+#define IFX_WTICK(k) do { } while (0)
 #endif
+    auto drain = [&]() {                                       // Bm25Scorer.cs:316-329 over the compacted survivors, in candidate order
+        for (int i = 0; i < pend; i++) { unsigned long long kv = sh.surv[i]; float s = kv_score(kv); tph[5] += 1; if (sh.heap_size < K || s > sh.thr) { update_topk(sh, (int)(kv >> 32), s, K); tph[5] += 1 << 20; } }
+    };
     for (int64_t pos = 0; pos < n_cand;) {
-        // container run: candidates sharing id >> 16, cut into sub-chunks of 4096
-        if (c.warp() == 0) {
-            int hb = cand[pos] >> 16; int64_t lim = ((int64_t)hb + 1) << 16;
-            int64_t ce = lim > 0x7fffffffLL ? n_cand : warp_lower_bound(c, cand, pos, n_cand, (int32_t)lim);
-            if (c.lane() == 0) {
-            int64_t cnt = ce - pos; sh.bcast[4] = (cnt <= CHUNK && (pos == 0 || (cand[pos - 1] >> 16) != hb)) ? 1 : 0;   // chunk == all candidates of the container
-            if (cnt > CHUNK) cnt = CHUNK; sh.bcast[2] = (int)cnt;
+        if (c.tid() == 0 && pend) drain();
+        IFX_TICK(4);   // heap drain of the previous chunk (overlapped with the workers below)
+        if (worker) {
+            IFX_WTICK(7);  // everything after the join (phase B, eligibility, compaction)
+            // container run: candidates sharing id >> 16, cut into sub-chunks of 4096
+            if (c.warp() == hw / Ctx::WS) {
+                int hb = cand[pos] >> 16; int64_t lim = ((int64_t)hb + 1) << 16;
+                int64_t ce = lim > 0x7fffffffLL ? n_cand : warp_lower_bound(c, cand, pos, n_cand, (int32_t)lim);
+                if (c.lane() == 0) {
+                    int64_t cnt = ce - pos; sh.bcast[4] = (cnt <= CHUNK && (pos == 0 || (cand[pos - 1] >> 16) != hb)) ? 1 : 0;   // chunk == all candidates of the container
+                    if (cnt > CHUNK) cnt = CHUNK; sh.bcast[2] = (int)cnt; sh.bcast[5] = 0;
+                }
             }
+            c.sync_workers(NTW);
+            const int cnt = sh.bcast[2]; const bool whole_container = sh.bcast[4] != 0;
+            for (int j = wt; j < cnt; j += NTW) { int d = cand[pos + j]; sh.cand_s[j] = d; float dl = ix.doc_len[d]; sh.nv_s[j] = bm25_norm_vector(dl, avgdl); sh.score[j] = 0.f; }
+            c.sync_workers(NTW);
+            IFX_WTICK(0);  // container run + candidate ids, lengths, norms
+            const int32_t first = sh.cand_s[0], last = sh.cand_s[cnt - 1];
+            for (int t = wt; t < T; t += NTW) {      // posting sub-range of every term for this chunk (monotone cursors)
+                TermS& tm = sh.terms[t];
+                int64_t lo = tm.cursor, hi = tm.len;
+                if (tm.skip) { int cc = first >> 16; int64_t b0 = tm.skip[cc], b1 = tm.skip[cc + 1]; if (b0 > lo) lo = b0; hi = b1; if (lo > hi) lo = hi; }   // window = this container's postings
+                int64_t s0, s1;
+                if (tm.skip && whole_container) { s0 = lo; s1 = hi; }
+                else if (tm.skip || tm.len < 1024) { s0 = lower_bound_i32(tm.docs, lo, hi, first); s1 = last == 0x7fffffff ? hi : lower_bound_i32(tm.docs, s0, hi, last + 1); }
+                else { s0 = gallop_lower_bound(tm.docs, lo, hi, first); s1 = last == 0x7fffffff ? hi : gallop_lower_bound(tm.docs, s0, hi, last + 1); }
+                tm.s0 = s0; tm.s1 = s1; tm.cursor = s1;
+                if (s1 > s0 && s1 - s0 <= 16LL * cnt) sh.bcast[5] = 1;     // benign race: every writer stores 1
+            }
+            c.sync_workers(NTW);
+            IFX_WTICK(1);  // posting sub-range bounds
+            // Container-local bitmap of the chunk's candidates + per-word rank directory: posting -> candidate slot in O(1)
+            // (all candidates of a chunk share id >> 16). Built only when some term streams its posting sub-range.
+            if (sh.bcast[5] != 0) {
+                for (int w = wt; w < 2048; w += NTW) sh.cbits[w] = 0;
+                c.sync_workers(NTW);
+                for (int j = wt; j < cnt; j += NTW) { int d = sh.cand_s[j] & 0xFFFF; atomic_or(&sh.cbits[d >> 5], 1u << (d & 31)); }
+                c.sync_workers(NTW);
+                int per = (2048 + NTW - 1) / NTW; int w0 = wt * per < 2048 ? wt * per : 2048, w1 = w0 + per < 2048 ? w0 + per : 2048; int mine = 0;
+                for (int w = w0; w < w1; w++) mine += popc(sh.cbits[w]);
+                int run = worker_excl_scan(c, mine, sh.scan, hw, NTW);
+                for (int w = w0; w < w1; w++) { sh.cpref[w] = (uint16_t)run; run += popc(sh.cbits[w]); }
+                c.sync_workers(NTW);
+            }
+            IFX_WTICK(2);  // candidate bitmap + rank directory
+            stage1_phase_a(c, sh, 0, T, cnt, wt, NTW);
+            IFX_WTICK(3);  // phase A, tile 0 (this thread's share)
         }
-        c.sync();
-        const int cnt = sh.bcast[2]; const bool whole_container = sh.bcast[4] != 0;
-        for (int j = c.tid(); j < cnt; j += NT) { int d = cand[pos + j]; sh.cand_s[j] = d; float dl = ix.doc_len[d]; sh.nv_s[j] = bm25_norm_vector(dl, avgdl); sh.score[j] = 0.f; }
-        if (c.tid() == 0) sh.bcast[5] = 0;
-        c.sync();
-        const int32_t first = sh.cand_s[0], last = sh.cand_s[cnt - 1];
-        for (int t = c.tid(); t < T; t += NT) {      // posting sub-range of every term for this chunk (monotone cursors)
-            TermS& tm = sh.terms[t];
-            int64_t lo = tm.cursor, hi = tm.len;
-            if (tm.skip) { int cc = first >> 16; int64_t b0 = tm.skip[cc], b1 = tm.skip[cc + 1]; if (b0 > lo) lo = b0; hi = b1; if (lo > hi) lo = hi; }   // window = this container's postings
-            int64_t s0, s1;
-            if (tm.skip && whole_container) { s0 = lo; s1 = hi; }
-            else if (tm.skip || tm.len < 1024) { s0 = lower_bound_i32(tm.docs, lo, hi, first); s1 = last == 0x7fffffff ? hi : lower_bound_i32(tm.docs, s0, hi, last + 1); }
-            else { s0 = gallop_lower_bound(tm.docs, lo, hi, first); s1 = last == 0x7fffffff ? hi : gallop_lower_bound(tm.docs, s0, hi, last + 1); }
-            tm.s0 = s0; tm.s1 = s1; tm.cursor = s1;
-            if (s1 > s0 && s1 - s0 <= 16LL * cnt) sh.bcast[5] = 1;     // benign race: every writer stores 1
-        }
-        c.sync();
-        IFX_TICK(0);   // chunk setup + sub-range bounds
+        c.sync();      // join: heap drained, chunk staged, tile 0 looked up
+        IFX_WTICK(4);  // waiting at the join (slower workers / the heap drain)
+        IFX_TICK(0);   // heap warp waiting for the workers (set-up + phase A beyond the drain)
+        const int cnt = sh.bcast[2];
         const float thr = sh.thr; const int rounds = (cnt + NT - 1) / NT;
         const int per_thread = (CHUNK + NT - 1) / NT; const int j0 = c.tid() * per_thread < cnt ? c.tid() * per_thread : cnt; const int j1 = j0 + per_thread < cnt ? j0 + per_thread : cnt;
-        // Container-local bitmap of the chunk's candidates + per-word rank directory: posting -> candidate slot in O(1)
-        // (all candidates of a chunk share id >> 16). Built only when some term streams its posting sub-range.
-        const bool use_bitmap = sh.bcast[5] != 0;
-        if (use_bitmap) {
-            for (int w = c.tid(); w < 2048; w += NT) sh.cbits[w] = 0;
-            c.sync();
-            for (int j = c.tid(); j < cnt; j += NT) { int d = sh.cand_s[j] & 0xFFFF; atomic_or(&sh.cbits[d >> 5], 1u << (d & 31)); }
-            c.sync();
-            int per = (2048 + NT - 1) / NT; int w0 = c.tid() * per, w1 = w0 + per < 2048 ? w0 + per : 2048; int mine = 0;
-            for (int w = w0; w < w1; w++) mine += popc(sh.cbits[w]);
-            int tot; int run = block_excl_scan(c, mine, sh.scan, tot);
-            for (int w = w0; w < w1; w++) { sh.cpref[w] = (uint16_t)run; run += popc(sh.cbits[w]); }
-            c.sync();
-        }
         // Terms are processed in tiles: the membership (tf) lookups of a whole tile are issued back to back with no barrier in
         // between (independent of the scores), then the order-dependent part -- MaxScore skip, rank within the chunk, formula
         // choice, accumulation -- runs term by term with a single barrier each.
-        IFX_TICK(1);   // candidate bitmap
         for (int t0 = 0; t0 < T; t0 += S1_TILE) {
             const int tile = T - t0 < S1_TILE ? T - t0 : S1_TILE;
-            for (int tt = 0; tt < tile; tt++) {
-                const TermS& tm = sh.terms[t0 + tt];
-                const int64_t sublen = tm.s1 - tm.s0; if (tm.idf <= 0.f || sublen == 0) continue;   // uniform
-                uint8_t* tfb = sh.tfm[tt];
-                if (tm.bm && sublen > 2LL * cnt) {          // dense term, sparse chunk: O(1) bitmap probe per candidate (doc -> posting index -> tf)
-                    for (int jb = c.tid(); jb < cnt; jb += 4 * NT) {
-                        unsigned wv[4]; int rk[4]; int dd[4];
-                        for (int u = 0; u < 4; u++) { int j = jb + u * NT; dd[u] = j < cnt ? sh.cand_s[j] : -1; if (dd[u] >= 0) { wv[u] = tm.bm[dd[u] >> 5]; rk[u] = tm.bmr[dd[u] >> 5]; } }
-                        for (int u = 0; u < 4; u++) if (dd[u] >= 0) { unsigned bit = 1u << (dd[u] & 31); if (wv[u] & bit) tfb[jb + u * NT] = tm.tf[rk[u] + popc(wv[u] & (bit - 1))]; }
-                    }
-                } else if (use_bitmap && sublen <= 16LL * cnt) {   // stream the posting sub-range (coalesced), O(1) slot lookup per posting
-                    for (int64_t i0 = tm.s0 + c.tid(); i0 < tm.s1; i0 += 4LL * NT) {      // four independent loads in flight per thread
-                        int dd[4];
-                        for (int u = 0; u < 4; u++) { int64_t i = i0 + (int64_t)u * NT; dd[u] = i < tm.s1 ? tm.docs[i] : -1; }
-                        for (int u = 0; u < 4; u++) if (dd[u] >= 0) {
-                            int d = dd[u] & 0xFFFF; unsigned wv = sh.cbits[d >> 5], bit = 1u << (d & 31);
-                            if (wv & bit) tfb[sh.cpref[d >> 5] + popc(wv & (bit - 1))] = tm.tf ? tm.tf[i0 + (int64_t)u * NT] : (uint8_t)1;
-                        }
-                    }
-                } else {                                    // sparse candidates: level-synchronous binary searches, four per thread at a time
-                    for (int jb = c.tid(); jb < cnt; jb += 4 * NT) {
-                        int64_t lo[4], hi[4]; int32_t d[4];
-                        for (int u = 0; u < 4; u++) { int j = jb + u * NT; d[u] = j < cnt ? sh.cand_s[j] : 0x7fffffff; lo[u] = tm.s0; hi[u] = j < cnt ? tm.s1 : tm.s0; }
-                        for (int64_t span = sublen; span > 0; span >>= 1) {
-                            int32_t v[4]; int64_t mid[4];
-                            for (int u = 0; u < 4; u++) { mid[u] = lo[u] + ((hi[u] - lo[u]) >> 1); v[u] = lo[u] < hi[u] ? tm.docs[mid[u]] : 0; }
-                            for (int u = 0; u < 4; u++) if (lo[u] < hi[u]) { if (v[u] < d[u]) lo[u] = mid[u] + 1; else hi[u] = mid[u]; }
-                        }
-                        for (int u = 0; u < 4; u++) { int j = jb + u * NT; if (j < cnt && lo[u] < tm.s1 && tm.docs[lo[u]] == d[u]) tfb[j] = tm.tf ? tm.tf[lo[u]] : (uint8_t)1; }
-                    }
-                }
-            }
-            c.sync();
-            IFX_TICK(2);   // phase A (tf lookups)
+            if (t0 > 0) { IFX_WTICK(7); if (worker) stage1_phase_a(c, sh, t0, T, cnt, wt, NTW); IFX_WTICK(5); c.sync(); IFX_WTICK(6); }
+            IFX_TICK(2);   // phase A of the later tiles
             for (int tt = 0; tt < tile; tt++) {
                 const TermS& tm = sh.terms[t0 + tt];
                 if (tm.idf <= 0.f || tm.s1 == tm.s0) continue;
@@ -768,12 +848,12 @@ IFX_FN void stage1_query(const Ctx& c, const DevIndex& ix, const QueryPlan& p, c
             c.sync();                                    // tile buffers are rewritten by arbitrary threads in the next tile
             IFX_TICK(3);   // phase B (ranks + accumulation)
         }
-        c.sync();
-        {   // flush (Bm25Scorer.cs:316-329): eligibility in parallel (the threshold only rises during a flush, so anything not above the
-            // chunk-start threshold can never enter), then the exact sequential emulation of .NET's 4-ary PriorityQueue over the
-            // survivors in candidate order. (A set-based top-K was tried: it is only equivalent when no documents tied at the final
-            // threshold straddle the cut, and on real corpora such ties are the norm -- identical tf pattern and length -- so the
-            // heap layout, which decides which of them survive, has to be reproduced.)
+        {   // flush, part 1 (Bm25Scorer.cs:316-329): eligibility in parallel (the threshold only rises during a flush, so anything not
+            // above the chunk-start threshold can never enter), survivors compacted in candidate order. Part 2 -- the exact sequential
+            // emulation of .NET's 4-ary PriorityQueue over the survivors -- is `drain`, deferred into the next iteration.
+            // (A set-based top-K was tried: it is only equivalent when no documents tied at the final threshold straddle the cut, and
+            // on real corpora such ties are the norm -- identical tf pattern and length -- so the heap layout, which decides which of
+            // them survive, has to be reproduced.)
             const bool full = sh.heap_size >= K;
             for (int r = 0; r < rounds; r++) {
                 int j = r * NT + c.tid();
@@ -782,17 +862,40 @@ IFX_FN void stage1_query(const Ctx& c, const DevIndex& ix, const QueryPlan& p, c
                 if (c.lane() == 0) sh.ballots[0][r * NW + c.warp()] = b;
             }
             c.sync();
-            if (c.tid() == 0) {
-                const int slots = rounds * NW;
-                for (int sl = 0; sl < slots; sl++) { unsigned mk = sh.ballots[0][sl]; int jb = (sl / NW) * NT + (sl % NW) * Ctx::WS;
-                    while (mk) { int l = ffs32(mk) - 1; mk &= mk - 1; int j = jb + l; float s = sh.score[j]; tph[5] += 1; if (sh.heap_size < K || s > sh.thr) { update_topk(sh, sh.cand_s[j], s, K); tph[5] += 1 << 20; } } }
+            const int slots = rounds * NW;
+            if (c.warp() == 0) {     // exclusive prefix of the ballot popcounts (slot order == candidate order)
+                int per = (slots + Ctx::WS - 1) / Ctx::WS; int s0 = c.lane() * per < slots ? c.lane() * per : slots, s1 = s0 + per < slots ? s0 + per : slots; int mine = 0;
+                for (int sl = s0; sl < s1; sl++) mine += popc(sh.ballots[0][sl]);
+                int incl = mine;
+                for (int d = 1; d < Ctx::WS; d <<= 1) { int o = c.shfl(incl, c.lane() >= d ? c.lane() - d : 0); if (c.lane() >= d) incl += o; }
+                int run = incl - mine;
+                for (int sl = s0; sl < s1; sl++) { sh.bprefix[sl] = run; run += popc(sh.ballots[0][sl]); }
+                if (c.lane() == Ctx::WS - 1) sh.bcast[6] = incl;
+            }
+            c.sync();
+            const int n_surv = sh.bcast[6];
+            if (n_surv <= SURV_CAP) {
+                for (int r = 0; r < rounds; r++) {
+                    int j = r * NT + c.tid(); int sl = r * NW + c.warp(); unsigned bm = sh.ballots[0][sl];
+                    if ((bm >> c.lane()) & 1u) sh.surv[sh.bprefix[sl] + popc(bm & c.lanemask_lt())] = kv_pack(sh.cand_s[j], sh.score[j]);
+                }
+                pend = n_surv;
+            } else {                 // too many for the staging buffer (heap still filling up): drain in place, nothing deferred
+                pend = 0;
+                if (c.tid() == 0) {
+                    for (int sl = 0; sl < slots; sl++) { unsigned mk = sh.ballots[0][sl]; int jb = (sl / NW) * NT + (sl % NW) * Ctx::WS;
+                        while (mk) { int l = ffs32(mk) - 1; mk &= mk - 1; int j = jb + l; float s = sh.score[j]; tph[5] += 1; if (sh.heap_size < K || s > sh.thr) { update_topk(sh, sh.cand_s[j], s, K); tph[5] += 1 << 20; } } }
+                }
             }
         }
         c.sync();
-        IFX_TICK(4);   // flush
+        IFX_TICK(1);   // eligibility + compaction (+ in-place drain while the heap fills)
         pos += cnt;
     }
+    if (c.tid() == 0 && pend) drain();
+    c.sync();
     if (c.tid() == 0 && out.dbg) for (int k = 0; k < 6; k++) out.dbg[6 + k] = tph[k];
+    if (c.tid() == hw && out.dbg) for (int k = 0; k < 8; k++) out.dbg[12 + k] = wph[k];
     for (int i = c.tid(); i < MAX_CONTAINERS; i += NT) sh.dirty[i] = 0;   // `cbits` aliased the dirty flags during scoring
     c.sync();
     // ---- PopulateResultHeapFromPruning + TopKHeap.GetTopK + ConsolidateSegments: order by (score desc, key asc)

@@ -3,20 +3,22 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import infidex_b200 as ib
 from infidex_b200 import synth
-vocab = synth.make_vocab(400_000); docs = synth.gen_docs(1_000_000, vocab); qs = synth.gen_queries(1000, docs, vocab, seed=synth.SEED + 3)
+vocab = synth.make_vocab(400_000); docs = synth.gen_docs(1_000_000, vocab); qs = synth.gen_queries(1000, docs, vocab)
 schema, cols = synth.schema_and_columns(docs, False)
 e = ib.SearchEngine.CreateDefault(); e.IndexColumns(docs["keys"], schema, cols)
 h = e.UploadBatch([ib.Query(q, 10) for q in qs])
 for r in range(3): st = e.RunBatch(h)
 print({k: round(v, 2) if isinstance(v, float) else v for k, v in st.as_dict().items()})
-dbg = np.zeros((1000, 12), np.int64); e._gpu.ifx_debug_stage1_queries(h, dbg.ctypes.data_as(C.c_void_p))
+dbg = np.zeros((1000, 24), np.int64); e._gpu.ifx_debug_stage1_queries(h, dbg.ctypes.data_as(C.c_void_p))
 order = np.argsort(-dbg[:, 4])
 print("total ms by path:", {p: round(dbg[dbg[:, 3] == p, 4].sum() / 1e6, 1) for p in (0, 1, 2, 3)}, "counts", {p: int((dbg[:, 3] == p).sum()) for p in (0, 1, 2, 3)})
 print("selection share: %.1f%%" % (100 * dbg[:, 2].clip(0).sum() / dbg[:, 4].sum()))
 for i in order[:12]:
     print("%-40s cand=%8d T=%3d path=%d sel=%.2fms total=%.2fms cta=%d" % (qs[i][:40], dbg[i, 0], dbg[i, 1], dbg[i, 3], dbg[i, 2] / 1e6, dbg[i, 4] / 1e6, dbg[i, 5]))
-ph = dbg[:, 6:11].sum(0); print("scoring phase cycles share: setup+bounds %.1f%% bitmap %.1f%% phaseA %.1f%% phaseB %.1f%% flush %.1f%%" % tuple(100 * ph / ph.sum()), "| scoring cycles total %.0f M" % (ph.sum() / 1e6))
-for i in order[:3]: print("   ", qs[i][:30], (dbg[i, 6:11] / 1e3).astype(int), "kcycles", "eligible", dbg[i, 11] & 0xFFFFF, "heap updates", dbg[i, 11] >> 20)
+ph = dbg[:, 6:11].sum(0); print("scoring cycles share (thread 0 = heap warp): wait-for-workers %.1f%% eligibility+compaction %.1f%% phaseA(later tiles) %.1f%% phaseB %.1f%% heap drain %.1f%%" % tuple(100 * ph / ph.sum()), "| scoring cycles total %.0f M" % (ph.sum() / 1e6))
+for i in order[:8]: print("   ", qs[i][:30], (dbg[i, 6:11] / 1e3).astype(int), "kcycles", "eligible", dbg[i, 11] & 0xFFFFF, "heap updates", dbg[i, 11] >> 20)
+wp = dbg[:, 12:20].sum(0); print("worker-view cycles share: ids+norms %.1f%% bounds %.1f%% bitmap %.1f%% phaseA0 %.1f%% join-wait %.1f%% phaseA-later %.1f%% its-barrier %.1f%% post-join(B+elig) %.1f%%" % tuple(100 * wp / wp.sum()))
+for i in order[:8]: print("   W", qs[i][:30], (dbg[i, 12:20] / 1e3).astype(int), "kcycles")
 print("total eligible", int((dbg[:, 11] & 0xFFFFF).sum()), "total heap updates", int((dbg[:, 11] >> 20).sum()))
 c = dbg[:, 0]; print("cand percentiles", np.percentile(c, [50, 90, 99, 100]).astype(int), "mean", int(c.mean()))
 # per-CTA busy time
