@@ -235,7 +235,7 @@ extern "C" int ifx_index_create(const ifx_index_image* img, const ifx_params* pp
           ix->n_ctas = (int)std::max<size_t>(1, std::min<size_t>((size_t)want, budget / std::max<size_t>(per_cta, 1))); }
 #endif
         ix->ws.resize(ix->n_ctas);
-        for (auto& w : ix->ws) { w.bits = ix->alloc<unsigned>(nwords); dev_zero(w.bits, (size_t)nwords * 4); w.bits2 = ix->alloc<unsigned>(nwords); dev_zero(w.bits2, (size_t)nwords * 4); w.cand = ix->alloc<int32_t>((size_t)N + 1); w.cand_cap = N; w.buf_a = ix->alloc<int32_t>(max_list); w.buf_b = ix->alloc<int32_t>(max_list); w.buf_cap = max_list; }
+        for (auto& w : ix->ws) { w.bits = ix->alloc<unsigned>(nwords); dev_zero(w.bits, (size_t)nwords * 4); w.bits2 = ix->alloc<unsigned>(nwords); dev_zero(w.bits2, (size_t)nwords * 4); w.cand = ix->alloc<int32_t>((size_t)N + 1); w.cand_cap = N; w.buf_a = ix->alloc<int32_t>(max_list); w.buf_b = ix->alloc<int32_t>(max_list); w.buf_cap = max_list; w.surv_g = ix->alloc<unsigned long long>(CHUNK); }
         ix->d_ws = ix->up(ix->ws.data(), ix->ws.size());
         ix->pool_cap = (unsigned long long)std::max<int64_t>(1 << 20, std::min<int64_t>((int64_t)N * 64, (int64_t)1 << 31));
         ix->d_pool = ix->alloc<int32_t>(ix->pool_cap);

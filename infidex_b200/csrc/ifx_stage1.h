@@ -179,6 +179,7 @@ struct S1Workspace {
     unsigned* bits2;       // membership bitset of the running AND-tier intersection (all zero between uses)
     int32_t* cand;         // sorted candidate ids
     int32_t* buf_a; int32_t* buf_b;   // AND-tier ping-pong arrays
+    unsigned long long* surv_g;       // [CHUNK] flush survivors of one chunk when they exceed the shared staging buffer
     int64_t cand_cap, buf_cap;
 };
 
@@ -214,17 +215,33 @@ struct S1Shared {
 };
 
 // OR a sorted id list into the CTA's bitset; returns the number of newly set docs (block-wide).
+// Long lists: every thread takes runs of 8 consecutive ids (two 16-byte loads) and merges the ids that fall into the same 32-bit
+// word before touching memory -- dense lists average several ids per word, so this cuts the global atomics several-fold.
 IFX_FN int or_list_into_bits(const Ctx& c, const int32_t* list, int64_t n, S1Workspace& ws, S1Shared& sh) {
-    int fresh = 0; const int64_t NT4 = 4LL * c.nthreads();
-    for (int64_t i0 = c.tid(); i0 < n; i0 += NT4) {      // four independent loads in flight per thread
-        int dd[4];
-        for (int u = 0; u < 4; u++) { int64_t i = i0 + (int64_t)u * c.nthreads(); dd[u] = i < n ? list[i] : -1; }
-        for (int u = 0; u < 4; u++) if (dd[u] >= 0) {
-            int d = dd[u]; unsigned bit = 1u << (d & 31);
-            unsigned old = atomic_or(&ws.bits[d >> 5], bit);
-            if (!(old & bit)) fresh++;
-            sh.dirty[d >> 16] = 1;
+    int fresh = 0; const int NT = c.nthreads();
+    auto put = [&](int word, unsigned mask) { unsigned old = atomic_or(&ws.bits[word], mask); fresh += popc(mask & ~old); sh.dirty[word >> 11] = 1; };
+    int64_t done = 0;
+    if (n >= 4096) {
+        int64_t pre = (int64_t)((0 - (reinterpret_cast<uintptr_t>(list) >> 2)) & 3);     // ids in front of the first 16-byte boundary
+        for (int64_t i = c.tid(); i < pre; i += NT) { int d = list[i]; put(d >> 5, 1u << (d & 31)); }
+        struct alignas(16) Id4 { int32_t v[4]; };
+        const Id4* p4 = reinterpret_cast<const Id4*>(list + pre); const int64_t n8 = (n - pre) >> 3;
+        for (int64_t g0 = c.tid(); g0 < n8; g0 += 2LL * NT) {      // two runs (four loads) in flight per thread
+            Id4 q[4]; const int64_t g1 = g0 + NT; const bool two = g1 < n8;
+            q[0] = p4[2 * g0]; q[1] = p4[2 * g0 + 1]; if (two) { q[2] = p4[2 * g1]; q[3] = p4[2 * g1 + 1]; }
+            for (int h = 0; h < (two ? 2 : 1); h++) {
+                int word = q[2 * h].v[0] >> 5; unsigned mask = 0;
+                for (int k = 0; k < 8; k++) { int d = q[2 * h + (k >> 2)].v[k & 3]; if ((d >> 5) != word) { put(word, mask); word = d >> 5; mask = 0; } mask |= 1u << (d & 31); }
+                put(word, mask);
+            }
         }
+        done = pre + (n8 << 3);
+    }
+    const int64_t NT4 = 4LL * NT;
+    for (int64_t i0 = done + c.tid(); i0 < n; i0 += NT4) {      // four independent loads in flight per thread
+        int dd[4];
+        for (int u = 0; u < 4; u++) { int64_t i = i0 + (int64_t)u * NT; dd[u] = i < n ? list[i] : -1; }
+        for (int u = 0; u < 4; u++) if (dd[u] >= 0) put(dd[u] >> 5, 1u << (dd[u] & 31));
     }
     c.sync();
     return block_sum(c, fresh, sh.scan);
@@ -455,11 +472,11 @@ IFX_FN void stage1_phase_a(const Ctx& c, S1Shared& sh, int t0, int T, int cnt, i
             }
         } else if (use_bitmap && sublen <= 16LL * cnt) {   // stream the posting sub-range (coalesced), O(1) slot lookup per posting
             for (int64_t i0 = tm.s0 + wt; i0 < tm.s1; i0 += 4LL * ntw) {      // four independent loads in flight per thread
-                int dd[4];
-                for (int u = 0; u < 4; u++) { int64_t i = i0 + (int64_t)u * ntw; dd[u] = i < tm.s1 ? tm.docs[i] : -1; }
+                int dd[4]; uint8_t tv[4];                                          // tf fetched alongside the id (one latency, not two)
+                for (int u = 0; u < 4; u++) { int64_t i = i0 + (int64_t)u * ntw; bool in = i < tm.s1; dd[u] = in ? tm.docs[i] : -1; tv[u] = (in && tm.tf) ? tm.tf[i] : (uint8_t)1; }
                 for (int u = 0; u < 4; u++) if (dd[u] >= 0) {
                     int d = dd[u] & 0xFFFF; unsigned wv = sh.cbits[d >> 5], bit = 1u << (d & 31);
-                    if (wv & bit) tfb[sh.cpref[d >> 5] + popc(wv & (bit - 1))] = tm.tf ? tm.tf[i0 + (int64_t)u * ntw] : (uint8_t)1;
+                    if (wv & bit) tfb[sh.cpref[d >> 5] + popc(wv & (bit - 1))] = tv[u];
                 }
             }
         } else {                                    // sparse candidates: level-synchronous binary searches, four per thread at a time
@@ -707,9 +724,14 @@ IFX_FN void stage1_query(const Ctx& c, const DevIndex& ix, const QueryPlan& p, c
     const int hw = NT > Ctx::WS ? Ctx::WS : 0;                 // threads of the heap warp (0: single-warp build, everything sequential)
     const bool worker = c.tid() >= hw; const int wt = c.tid() - hw, NTW = NT - hw;
     int pend = 0;                                              // survivors of the previous chunk waiting in sh.surv (uniform)
-    long long tph[6] = {0, 0, 0, 0, 0, 0}; long long tmark = 0; long long wph[8] = {0, 0, 0, 0, 0, 0, 0, 0}; long long wmark = 0; (void)wmark;
-#ifndef IFX_EMU
-    // phase timers (debug records only): thread 0 = heap warp's view, thread `hw` = the workers' view. The "memory" clobber keeps
+#if !defined(IFX_EMU) && defined(IFX_S1_TIMERS)
+    long long tph[6] = {0, 0, 0, 0, 0, 0}; long long tmark = 0; long long wph[8] = {0, 0, 0, 0, 0, 0, 0, 0}; long long wmark = 0;
+#define IFX_COUNT(x) tph[5] += (x)
+#else
+#define IFX_COUNT(x) do { } while (0)
+#endif
+#if !defined(IFX_EMU) && defined(IFX_S1_TIMERS)
+    // phase timers (debug builds with -DIFX_S1_TIMERS only; they cost registers in every thread): thread 0 = heap warp's view, thread `hw` = the workers' view. The "memory" clobber keeps
     // the clock reads from being scheduled across the barriers they bracket.
     auto rdclock = []() -> long long { long long t_; asm volatile("mov.u64 %0, %%clock64;" : "=l"(t_) :: "memory"); return t_; };
 #define IFX_TICK(k) do { if (c.tid() == 0) { long long now_ = rdclock(); tph[k] += now_ - tmark; tmark = now_; } } while (0)
@@ -721,7 +743,13 @@ IFX_FN void stage1_query(const Ctx& c, const DevIndex& ix, const QueryPlan& p, c
 #define IFX_WTICK(k) do { } while (0)
 #endif
     auto drain = [&]() {                                       // Bm25Scorer.cs:316-329 over the compacted survivors, in candidate order
-        for (int i = 0; i < pend; i++) { unsigned long long kv = sh.surv[i]; float s = kv_score(kv); tph[5] += 1; if (sh.heap_size < K || s > sh.thr) { update_topk(sh, (int)(kv >> 32), s, K); tph[5] += 1 << 20; } }
+        auto one = [&](unsigned long long kv) { float s = kv_score(kv); IFX_COUNT(1); if (sh.heap_size < K || s > sh.thr) { update_topk(sh, (int)(kv >> 32), s, K); IFX_COUNT(1 << 20); } };
+        if (pend <= SURV_CAP) { for (int i = 0; i < pend; i++) one(sh.surv[i]); return; }
+        for (int i = 0; i < pend; i += 8) {                    // global staging: eight independent loads in flight, then the sequential updates
+            unsigned long long kv[8];
+            for (int u = 0; u < 8; u++) kv[u] = i + u < pend ? ws.surv_g[i + u] : 0ULL;
+            for (int u = 0; u < 8; u++) if (i + u < pend) one(kv[u]);
+        }
     };
     for (int64_t pos = 0; pos < n_cand;) {
         if (c.tid() == 0 && pend) drain();
@@ -743,16 +771,17 @@ IFX_FN void stage1_query(const Ctx& c, const DevIndex& ix, const QueryPlan& p, c
             c.sync_workers(NTW);
             IFX_WTICK(0);  // container run + candidate ids, lengths, norms
             const int32_t first = sh.cand_s[0], last = sh.cand_s[cnt - 1];
-            for (int t = wt; t < T; t += NTW) {      // posting sub-range of every term for this chunk (monotone cursors)
+            for (int t = c.warp() - hw / Ctx::WS; t < T; t += NW - hw / Ctx::WS) {   // posting sub-range of every term for this chunk (monotone cursors); one warp per term, 32-way searches
                 TermS& tm = sh.terms[t];
                 int64_t lo = tm.cursor, hi = tm.len;
                 if (tm.skip) { int cc = first >> 16; int64_t b0 = tm.skip[cc], b1 = tm.skip[cc + 1]; if (b0 > lo) lo = b0; hi = b1; if (lo > hi) lo = hi; }   // window = this container's postings
                 int64_t s0, s1;
                 if (tm.skip && whole_container) { s0 = lo; s1 = hi; }
-                else if (tm.skip || tm.len < 1024) { s0 = lower_bound_i32(tm.docs, lo, hi, first); s1 = last == 0x7fffffff ? hi : lower_bound_i32(tm.docs, s0, hi, last + 1); }
-                else { s0 = gallop_lower_bound(tm.docs, lo, hi, first); s1 = last == 0x7fffffff ? hi : gallop_lower_bound(tm.docs, s0, hi, last + 1); }
-                tm.s0 = s0; tm.s1 = s1; tm.cursor = s1;
-                if (s1 > s0 && s1 - s0 <= 16LL * cnt) sh.bcast[5] = 1;     // benign race: every writer stores 1
+                else { s0 = warp_lower_bound(c, tm.docs, lo, hi, first); s1 = last == 0x7fffffff ? hi : warp_lower_bound(c, tm.docs, s0, hi, last + 1); }
+                if (c.lane() == 0) {
+                    tm.s0 = s0; tm.s1 = s1; tm.cursor = s1;
+                    if (s1 > s0 && s1 - s0 <= 16LL * cnt) sh.bcast[5] = 1;     // benign race: every writer stores 1
+                }
             }
             c.sync_workers(NTW);
             IFX_WTICK(1);  // posting sub-range bounds
@@ -874,19 +903,12 @@ IFX_FN void stage1_query(const Ctx& c, const DevIndex& ix, const QueryPlan& p, c
             }
             c.sync();
             const int n_surv = sh.bcast[6];
-            if (n_surv <= SURV_CAP) {
-                for (int r = 0; r < rounds; r++) {
-                    int j = r * NT + c.tid(); int sl = r * NW + c.warp(); unsigned bm = sh.ballots[0][sl];
-                    if ((bm >> c.lane()) & 1u) sh.surv[sh.bprefix[sl] + popc(bm & c.lanemask_lt())] = kv_pack(sh.cand_s[j], sh.score[j]);
-                }
-                pend = n_surv;
-            } else {                 // too many for the staging buffer (heap still filling up): drain in place, nothing deferred
-                pend = 0;
-                if (c.tid() == 0) {
-                    for (int sl = 0; sl < slots; sl++) { unsigned mk = sh.ballots[0][sl]; int jb = (sl / NW) * NT + (sl % NW) * Ctx::WS;
-                        while (mk) { int l = ffs32(mk) - 1; mk &= mk - 1; int j = jb + l; float s = sh.score[j]; tph[5] += 1; if (sh.heap_size < K || s > sh.thr) { update_topk(sh, sh.cand_s[j], s, K); tph[5] += 1 << 20; } } }
-                }
+            unsigned long long* dst = n_surv <= SURV_CAP ? sh.surv : ws.surv_g;     // the rare big sets (heap still filling) go through global memory
+            for (int r = 0; r < rounds; r++) {
+                int j = r * NT + c.tid(); int sl = r * NW + c.warp(); unsigned bm = sh.ballots[0][sl];
+                if ((bm >> c.lane()) & 1u) dst[sh.bprefix[sl] + popc(bm & c.lanemask_lt())] = kv_pack(sh.cand_s[j], sh.score[j]);
             }
+            pend = n_surv;
         }
         c.sync();
         IFX_TICK(1);   // eligibility + compaction (+ in-place drain while the heap fills)
@@ -894,8 +916,10 @@ IFX_FN void stage1_query(const Ctx& c, const DevIndex& ix, const QueryPlan& p, c
     }
     if (c.tid() == 0 && pend) drain();
     c.sync();
+#if !defined(IFX_EMU) && defined(IFX_S1_TIMERS)
     if (c.tid() == 0 && out.dbg) for (int k = 0; k < 6; k++) out.dbg[6 + k] = tph[k];
     if (c.tid() == hw && out.dbg) for (int k = 0; k < 8; k++) out.dbg[12 + k] = wph[k];
+#endif
     for (int i = c.tid(); i < MAX_CONTAINERS; i += NT) sh.dirty[i] = 0;   // `cbits` aliased the dirty flags during scoring
     c.sync();
     // ---- PopulateResultHeapFromPruning + TopKHeap.GetTopK + ConsolidateSegments: order by (score desc, key asc)

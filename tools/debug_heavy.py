@@ -1,3 +1,4 @@
+# Scratch: per-query Stage-1 diagnostics. For the phase columns run with IFX_LIB=<library built with -DIFX_S1_TIMERS>.
 import sys, os, ctypes as C
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
@@ -5,7 +6,7 @@ import infidex_b200 as ib
 from infidex_b200 import synth
 vocab = synth.make_vocab(400_000); docs = synth.gen_docs(1_000_000, vocab); qs = synth.gen_queries(1000, docs, vocab)
 schema, cols = synth.schema_and_columns(docs, False)
-e = ib.SearchEngine.CreateDefault(); e.IndexColumns(docs["keys"], schema, cols)
+e = ib.SearchEngine.CreateDefault(_gpu_lib=os.environ.get('IFX_LIB')); e.IndexColumns(docs["keys"], schema, cols)
 h = e.UploadBatch([ib.Query(q, 10) for q in qs])
 for r in range(3): st = e.RunBatch(h)
 print({k: round(v, 2) if isinstance(v, float) else v for k, v in st.as_dict().items()})
