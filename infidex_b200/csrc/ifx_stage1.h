@@ -208,19 +208,18 @@ struct S1Shared {
         uint8_t dirty[MAX_CONTAINERS];    // containers of the global bitset touched by the current set operation (all zero between uses)
         unsigned cbits[2048];             // container-local bitmap of the current chunk's candidates (stream mode)
     };
-    ScanTmp scan; ScanTmp scan2[2];
+    ScanTmp scan; ScanTmp scan2[2]; alignas(16) unsigned scan3[32][4];   // scan3: packed per-warp totals of the batched rank scan
     int bcast[8]; long long bcast64[4];
     unsigned long long streamed_mask[2];   // terms whose list the selector streamed in full (roofline accounting)
     unsigned long long peq[128];           // Myers pattern masks of the word being expanded (ASCII fast path)
 };
 
-// OR a sorted id list into the CTA's bitset; returns the number of newly set docs (block-wide).
-// Long lists: every thread takes runs of 8 consecutive ids (two 16-byte loads) and merges the ids that fall into the same 32-bit
-// word before touching memory -- dense lists average several ids per word, so this cuts the global atomics several-fold.
-IFX_FN int or_list_into_bits(const Ctx& c, const int32_t* list, int64_t n, S1Workspace& ws, S1Shared& sh) {
-    int fresh = 0; const int NT = c.nthreads();
-    auto put = [&](int word, unsigned mask) { unsigned old = atomic_or(&ws.bits[word], mask); fresh += popc(mask & ~old); sh.dirty[word >> 11] = 1; };
-    int64_t done = 0;
+// Stream a sorted id list and hand it to `put(word, mask)` as per-32-bit-word masks (word = id >> 5).
+// Long lists: every thread takes runs of 8 consecutive ids (two 16-byte loads) and merges the ids that fall into the same word
+// before calling `put` -- dense lists average several ids per word, so this cuts the global atomics behind `put` several-fold.
+template <class Put>
+IFX_FN void stream_list_words(const Ctx& c, const int32_t* list, int64_t n, Put put) {
+    const int NT = c.nthreads(); int64_t done = 0;
     if (n >= 4096) {
         int64_t pre = (int64_t)((0 - (reinterpret_cast<uintptr_t>(list) >> 2)) & 3);     // ids in front of the first 16-byte boundary
         for (int64_t i = c.tid(); i < pre; i += NT) { int d = list[i]; put(d >> 5, 1u << (d & 31)); }
@@ -243,6 +242,12 @@ IFX_FN int or_list_into_bits(const Ctx& c, const int32_t* list, int64_t n, S1Wor
         for (int u = 0; u < 4; u++) { int64_t i = i0 + (int64_t)u * NT; dd[u] = i < n ? list[i] : -1; }
         for (int u = 0; u < 4; u++) if (dd[u] >= 0) put(dd[u] >> 5, 1u << (dd[u] & 31));
     }
+}
+
+// OR a sorted id list into the CTA's bitset; returns the number of newly set docs (block-wide).
+IFX_FN int or_list_into_bits(const Ctx& c, const int32_t* list, int64_t n, S1Workspace& ws, S1Shared& sh) {
+    int fresh = 0;
+    stream_list_words(c, list, n, [&](int word, unsigned mask) { unsigned old = atomic_or(&ws.bits[word], mask); fresh += popc(mask & ~old); sh.dirty[word >> 11] = 1; });
     c.sync();
     return block_sum(c, fresh, sh.scan);
 }
@@ -260,7 +265,7 @@ IFX_FN void warp_append(const Ctx& c, bool pred, int32_t value, int32_t* arr, in
 // unordered id array (ping-pong ws.buf_a / ws.buf_b) and as the membership bitset ws.bits2. Each further list either streams
 // past the bitset (coalesced, when it is not much longer than the running set) or is probed per surviving id (binary search).
 // Returns the size (-1: buffer overflow); `res` points at the surviving ids; ws.bits2 is left all-zero.
-IFX_FN int64_t intersect_terms(const Ctx& c, S1Workspace& ws, S1Shared& sh, int cnt, const int32_t*& res) {
+IFX_FN int64_t intersect_terms(const Ctx& c, const DevIndex& ix, S1Workspace& ws, S1Shared& sh, int cnt, const int32_t*& res) {
     const int NT = c.nthreads();
     int by_len[MAX_TERMS];
     for (int i = 0; i < cnt; i++) by_len[i] = sh.order[i];
@@ -268,6 +273,39 @@ IFX_FN int64_t intersect_terms(const Ctx& c, S1Workspace& ws, S1Shared& sh, int 
     const TermS& t0 = sh.terms[by_len[0]];
     int64_t n = t0.len; if (n > ws.buf_cap) return -1;
     int32_t* cur = ws.buf_a; int32_t* nxt = ws.buf_b;
+    const int bw = (int)(((int64_t)ix.n_docs + 31) >> 5);
+    if (cnt > 1 && 4 * n >= bw && ws.buf_cap >= bw) {
+        // Large running sets (>= 1/128 of the shard): keep the intersection as a bitset only. Lists with a membership bitmap are
+        // ANDed word by word; the others (fuzzy unions, mid-size lists) are streamed against the bitset into a scratch bitmap
+        // (buf_b) that then replaces it. No per-id probes or appends; ids come out ascending at the end.
+        unsigned* acc = ws.bits2; unsigned* tmp = reinterpret_cast<unsigned*>(nxt);
+        if (t0.bm) { for (int w = c.tid(); w < bw; w += NT) acc[w] = t0.bm[w]; }
+        else stream_list_words(c, t0.docs, t0.len, [&](int word, unsigned mask) { atomic_or(&acc[word], mask); });
+        c.sync();
+        for (int li = 1; li < cnt; li++) {
+            const TermS& t = sh.terms[by_len[li]];
+            if (t.bm) { for (int w = c.tid(); w < bw; w += NT) acc[w] &= t.bm[w]; }
+            else {
+                for (int w = c.tid(); w < bw; w += NT) tmp[w] = 0u;
+                c.sync();
+                stream_list_words(c, t.docs, t.len, [&](int word, unsigned mask) { unsigned hit = acc[word] & mask; if (hit) atomic_or(&tmp[word], hit); });
+                c.sync();
+                for (int w = c.tid(); w < bw; w += NT) acc[w] = tmp[w];
+            }
+            c.sync();
+        }
+        int64_t total = 0;
+        for (int w0 = 0; w0 < bw; w0 += 4 * NT) {
+            unsigned v[4]; int mine = 0; const int wb = w0 + c.tid() * 4;
+            for (int u = 0; u < 4; u++) { int w = wb + u; unsigned x = 0; if (w < bw) { x = acc[w]; acc[w] = 0u; } v[u] = x; mine += popc(x); }
+            int tot; int off = block_excl_scan(c, mine, sh.scan, tot);
+            int64_t o = total + off;
+            for (int u = 0; u < 4; u++) { unsigned x = v[u]; while (x) { int b = ffs32(x) - 1; x &= x - 1; cur[o++] = ((wb + u) << 5) | b; } }
+            total += tot;
+        }
+        res = cur; c.sync();
+        return total;
+    }
     for (int64_t i = c.tid(); i < n; i += NT) { int d = t0.docs[i]; cur[i] = d; if (cnt > 1) atomic_or(&ws.bits2[d >> 5], 1u << (d & 31)); }
     c.sync();
     for (int li = 1; li < cnt && n > 0; li++) {
@@ -415,28 +453,28 @@ IFX_FN void heap_move_up(S1Shared& sh, int doc, float pr, int idx) {
     while (idx > 0) { int parent = (idx - 1) >> 2; unsigned long long pk = sh.IFX_KV(parent); if (pr < kv_score(pk)) { sh.IFX_KV(idx) = pk; idx = parent; } else break; }
     sh.IFX_KV(idx) = kv_pack(doc, pr);
 }
-IFX_FN void heap_move_down(S1Shared& sh, int doc, float pr, int idx) {
-    const int sz = sh.heap_size; int i;
+// PriorityQueue.DequeueEnqueue on a full heap (the root is replaced and sifted down); returns the new root priority so the caller
+// can keep the threshold in a register. PriorityQueue.MoveDown picks the first strictly-smallest of the (up to) four children; here as
+// a two-level tournament with the same winner (ties keep the lower index at both levels).
+IFX_FN float heap_replace_root(S1Shared& sh, unsigned long long kv, int sz) {
+    const float pr = kv_score(kv); int idx = 0, i; float root = pr;
     while ((i = 4 * idx + 1) < sz) {
-        // first strictly-smallest of the (up to) four children, exactly as PriorityQueue.MoveDown scans them
 #ifdef IFX_EMU
         unsigned long long k0 = sh.IFX_KV(i), k1 = sh.IFX_KV(i + 1), k2 = sh.IFX_KV(i + 2), k3 = sh.IFX_KV(i + 3);
 #else
         const ulonglong2 va = *reinterpret_cast<const ulonglong2*>(&sh.heap_kv[i + 3]); const ulonglong2 vb = *reinterpret_cast<const ulonglong2*>(&sh.heap_kv[i + 5]);
         unsigned long long k0 = va.x, k1 = va.y, k2 = vb.x, k3 = vb.y;
 #endif
-        unsigned long long mk = k0; float mp = kv_score(k0); int mi = i;
-        { float x = kv_score(k1); if (x < mp) { mp = x; mk = k1; mi = i + 1; } }
-        { float x = kv_score(k2); if (x < mp) { mp = x; mk = k2; mi = i + 2; } }
-        { float x = kv_score(k3); if (x < mp) { mp = x; mk = k3; mi = i + 3; } }
-        if (!(mp < pr)) break;
-        sh.IFX_KV(idx) = mk; idx = mi;
+        const bool b01 = kv_score(k1) < kv_score(k0), b23 = kv_score(k3) < kv_score(k2);
+        const unsigned long long ka = b01 ? k1 : k0, kb = b23 ? k3 : k2;
+        const bool bb = kv_score(kb) < kv_score(ka);
+        const unsigned long long mk = bb ? kb : ka; const int mi = i + (bb ? (b23 ? 3 : 2) : (b01 ? 1 : 0));
+        if (!(kv_score(mk) < pr)) break;
+        sh.IFX_KV(idx) = mk; if (idx == 0) root = kv_score(mk);
+        idx = mi;
     }
-    sh.IFX_KV(idx) = kv_pack(doc, pr);
-}
-IFX_FN void update_topk(S1Shared& sh, int doc, float s, int K) {
-    if (sh.heap_size < K) { int i = sh.heap_size++; heap_move_up(sh, doc, s, i); if (sh.heap_size == K) sh.thr = kv_score(sh.IFX_KV(0)); }
-    else if (s > sh.thr) { heap_move_down(sh, doc, s, 0); sh.thr = kv_score(sh.IFX_KV(0)); }
+    sh.IFX_KV(idx) = kv;
+    return root;
 }
 
 // Exclusive scan over the worker threads [hw, nthreads) only (named barrier 1); every worker must call it.
@@ -641,6 +679,12 @@ IFX_FN void stage1_query(const Ctx& c, const DevIndex& ix, const QueryPlan& p, c
     const float avgdl = ix.avgdl > 0.f ? ix.avgdl : 1.f;
 
     // ---- candidate selection (TieredCandidateSelector.SelectCandidates)
+#if !defined(IFX_EMU) && defined(IFX_S1_TIMERS)
+    long long smark = 0; if (c.tid() == 0) { asm volatile("mov.u64 %0, %%clock64;" : "=l"(smark) :: "memory"); if (out.dbg) for (int k = 20; k < 24; k++) out.dbg[k] = 0; }
+#define IFX_STICK(k) do { c.sync(); if (c.tid() == 0 && out.dbg) { long long now_; asm volatile("mov.u64 %0, %%clock64;" : "=l"(now_) : "r"(sh.bcast[0]) : "memory"); out.dbg[20 + (k)] += now_ - smark; smark = now_; } } while (0)
+#else
+#define IFX_STICK(k) do { } while (0)
+#endif
     const int32_t* cand = nullptr; int64_t n_cand = 0;
     if (c.tid() == 0) {   // prefix precedence (TrySelectPrefixCandidates)
         sh.bcast64[0] = -1; sh.bcast64[1] = 0;
@@ -666,6 +710,7 @@ IFX_FN void stage1_query(const Ctx& c, const DevIndex& ix, const QueryPlan& p, c
         c.sync();
         const bool disjunctive = sh.bcast[0] != 0; const float max_idf = ((float*)sh.bcast)[1];
         int64_t g = 0;
+        IFX_STICK(0);   // prefix shortcut + idf sort
         if (disjunctive) {   // SelectCandidatesDisjunctive
             bool selective = false;
             for (int oi = 0; oi < T; oi++) {
@@ -679,11 +724,13 @@ IFX_FN void stage1_query(const Ctx& c, const DevIndex& ix, const QueryPlan& p, c
             }
         } else {
             if (c.tid() == 0) for (int i = 0; i < T; i++) sh.streamed_mask[i >> 6] |= 1ULL << (i & 63);   // every list of the AND tier
-            const int32_t* r0 = nullptr; int64_t n0 = intersect_terms(c, ws, sh, T, r0);
+            const int32_t* r0 = nullptr; int64_t n0 = intersect_terms(c, ix, ws, sh, T, r0);
             if (n0 < 0) { if (c.tid() == 0) out.n[0] = -1; return; }
             g += or_list_into_bits(c, r0, n0, ws, sh);
+            IFX_STICK(1);   // AND tier 0
             if (g < (int64_t)K * 2) {
-                if (T >= 3 && g < (int64_t)K * 3) { const int32_t* r1 = nullptr; int64_t n1 = intersect_terms(c, ws, sh, T - 1, r1); if (n1 > 0) g += or_list_into_bits(c, r1, n1, ws, sh); }
+                if (T >= 3 && g < (int64_t)K * 3) { const int32_t* r1 = nullptr; int64_t n1 = intersect_terms(c, ix, ws, sh, T - 1, r1); if (n1 > 0) g += or_list_into_bits(c, r1, n1, ws, sh); }
+                IFX_STICK(2);   // AND tier 1
                 if (g < (int64_t)K * 5) {
                     int sel[2]; int ns = 0; float cutoff = max_idf * 0.3f; int capn = T < 2 ? T : 2;
                     for (int oi = 0; oi < T && ns < capn; oi++) { const TermS& t = sh.terms[sh.order[oi]]; if (t.idf <= 0.f) continue; if (t.idf < cutoff) continue; sel[ns++] = sh.order[oi]; }
@@ -692,7 +739,9 @@ IFX_FN void stage1_query(const Ctx& c, const DevIndex& ix, const QueryPlan& p, c
             }
         }
         bool ovf = false;
+        IFX_STICK(1);   // list unions (disjunctive: everything; AND path: the top-idf lists after the tiers)
         n_cand = compact_bits(c, ix, ws, sh, ws.cand, ws.cand_cap, ovf);
+        IFX_STICK(3);   // bitset -> sorted candidate array
         if (ovf) { if (c.tid() == 0) out.n[0] = -1; return; }
         cand = ws.cand;
         algo += 2ULL * (unsigned long long)((ix.n_docs + 7) / 8);
@@ -733,7 +782,8 @@ IFX_FN void stage1_query(const Ctx& c, const DevIndex& ix, const QueryPlan& p, c
 #if !defined(IFX_EMU) && defined(IFX_S1_TIMERS)
     // phase timers (debug builds with -DIFX_S1_TIMERS only; they cost registers in every thread): thread 0 = heap warp's view, thread `hw` = the workers' view. The "memory" clobber keeps
     // the clock reads from being scheduled across the barriers they bracket.
-    auto rdclock = []() -> long long { long long t_; asm volatile("mov.u64 %0, %%clock64;" : "=l"(t_) :: "memory"); return t_; };
+    // and the dependence on a shared-memory load issued after the barrier keeps ptxas from hoisting them above it
+    auto rdclock = [&]() -> long long { long long t_; asm volatile("mov.u64 %0, %%clock64;" : "=l"(t_) : "r"(*(volatile int*)&sh.bcast[2]) : "memory"); return t_; };
 #define IFX_TICK(k) do { if (c.tid() == 0) { long long now_ = rdclock(); tph[k] += now_ - tmark; tmark = now_; } } while (0)
 #define IFX_WTICK(k) do { if (c.tid() == hw) { long long now_ = rdclock(); wph[k] += now_ - wmark; wmark = now_; } } while (0)
     if (c.tid() == 0) tmark = rdclock();
@@ -742,14 +792,20 @@ IFX_FN void stage1_query(const Ctx& c, const DevIndex& ix, const QueryPlan& p, c
 #define IFX_TICK(k) do { } while (0)
 #define IFX_WTICK(k) do { } while (0)
 #endif
-    auto drain = [&]() {                                       // Bm25Scorer.cs:316-329 over the compacted survivors, in candidate order
-        auto one = [&](unsigned long long kv) { float s = kv_score(kv); IFX_COUNT(1); if (sh.heap_size < K || s > sh.thr) { update_topk(sh, (int)(kv >> 32), s, K); IFX_COUNT(1 << 20); } };
-        if (pend <= SURV_CAP) { for (int i = 0; i < pend; i++) one(sh.surv[i]); return; }
-        for (int i = 0; i < pend; i += 8) {                    // global staging: eight independent loads in flight, then the sequential updates
+    auto drain = [&]() {                                       // Bm25Scorer.cs:316-329 + UpdateTopK (:654-670) over the compacted survivors, in candidate order
+        float thr_r = sh.thr; int hs = sh.heap_size;           // threshold and size live in registers for the whole drain
+        auto one = [&](unsigned long long kv) {
+            const float s = kv_score(kv); IFX_COUNT(1);
+            if (hs < K) { heap_move_up(sh, (int)(kv >> 32), s, hs); hs++; if (hs == K) thr_r = kv_score(sh.IFX_KV(0)); IFX_COUNT(1 << 20); }
+            else if (s > thr_r) { thr_r = heap_replace_root(sh, kv, hs); IFX_COUNT(1 << 20); }
+        };
+        if (pend <= SURV_CAP) { for (int i = 0; i < pend; i++) one(sh.surv[i]); }
+        else for (int i = 0; i < pend; i += 8) {               // global staging: eight independent loads in flight, then the sequential updates
             unsigned long long kv[8];
             for (int u = 0; u < 8; u++) kv[u] = i + u < pend ? ws.surv_g[i + u] : 0ULL;
             for (int u = 0; u < 8; u++) if (i + u < pend) one(kv[u]);
         }
+        sh.thr = thr_r; sh.heap_size = hs;
     };
     for (int64_t pos = 0; pos < n_cand;) {
         if (c.tid() == 0 && pend) drain();
@@ -815,18 +871,49 @@ IFX_FN void stage1_query(const Ctx& c, const DevIndex& ix, const QueryPlan& p, c
             const int tile = T - t0 < S1_TILE ? T - t0 : S1_TILE;
             if (t0 > 0) { IFX_WTICK(7); if (worker) stage1_phase_a(c, sh, t0, T, cnt, wt, NTW); IFX_WTICK(5); c.sync(); IFX_WTICK(6); }
             IFX_TICK(2);   // phase A of the later tiles
+            // Each thread owns the consecutive candidate slots [j0, j1). A (candidate, term) pair counts as a match only if the
+            // MaxScore test keeps it (Bm25Scorer.cs:354); its rank among the chunk's matches of this term selects the formula
+            // (first 8*floor(m/8) matches: Vector256 form, the rest: scalar form; Bm25Scorer.cs:395-444).
+            int nscan = 0;
+#ifndef IFX_EMU
+            const bool fast = per_thread == 8 && j1 - j0 == 8;      // the 8 owned slots live in registers for the whole term
+            // A term whose own bound plus the bounds of the terms after it already exceeds the threshold can never be skipped
+            // (scores are >= 0 and float addition is monotone), so its matches are exactly the non-zero tf slots, known before any
+            // score exists: the ranks of all such terms of the tile come from ONE packed block scan (16-bit fields, <= 4096 each).
+            unsigned uns = 0, ex01 = 0, ex23 = 0, ex45 = 0, m01 = 0, m23 = 0, m45 = 0;
+            for (int tt = 0; tt < tile; tt++) { const TermS& tm = sh.terms[t0 + tt]; if (tm.idf <= 0.f || tm.s1 == tm.s0) continue; if (!((0.f + tm.max_score) + tm.suffix_after <= thr)) uns |= 1u << tt; }
+            if (__popc(uns) >= 2) {
+                unsigned pk[3] = {0u, 0u, 0u};
+#pragma unroll
+                for (int tt = 0; tt < S1_TILE; tt++) if ((uns >> tt) & 1u) {
+                    const uint8_t* tfb = sh.tfm[tt]; unsigned n = 0;
+                    if (fast) { unsigned long long v = *reinterpret_cast<const unsigned long long*>(tfb + j0); v |= v >> 4; v |= v >> 2; v |= v >> 1; n = (unsigned)__popcll(v & 0x0101010101010101ULL); }
+                    else for (int j = j0; j < j1; j++) n += tfb[j] != 0;
+                    pk[tt >> 1] |= n << (16 * (tt & 1));
+                }
+                unsigned in0 = pk[0], in1 = pk[1], in2 = pk[2];
+                for (int d = 1; d < 32; d <<= 1) {
+                    unsigned o0 = __shfl_up_sync(0xffffffffu, in0, d), o1 = __shfl_up_sync(0xffffffffu, in1, d), o2 = __shfl_up_sync(0xffffffffu, in2, d);
+                    if (c.lane() >= d) { in0 += o0; in1 += o1; in2 += o2; }
+                }
+                if (c.lane() == 31) { sh.scan3[c.warp()][0] = in0; sh.scan3[c.warp()][1] = in1; sh.scan3[c.warp()][2] = in2; }
+                c.sync();
+                unsigned b0 = 0, b1 = 0, b2 = 0;
+                for (int i = 0; i < NW; i++) { const uint4 x = *reinterpret_cast<const uint4*>(sh.scan3[i]); if (i < c.warp()) { b0 += x.x; b1 += x.y; b2 += x.z; } m01 += x.x; m23 += x.y; m45 += x.z; }
+                ex01 = b0 + in0 - pk[0]; ex23 = b1 + in1 - pk[1]; ex45 = b2 + in2 - pk[2];
+            } else uns = 0;
+#else
+            const bool fast = false; const unsigned uns = 0;
+#endif
             for (int tt = 0; tt < tile; tt++) {
                 const TermS& tm = sh.terms[t0 + tt];
                 if (tm.idf <= 0.f || tm.s1 == tm.s0) continue;
                 uint8_t* tfb = sh.tfm[tt];
-                // Each thread owns the consecutive candidate slots [j0, j1). A (candidate, term) pair counts as a match only if the
-                // MaxScore test keeps it (Bm25Scorer.cs:354); its rank among the chunk's matches of this term selects the formula
-                // (first 8*floor(m/8) matches: Vector256 form, the rest: scalar form; Bm25Scorer.cs:395-444).
                 int mine = 0; const float tbound = tm.max_score; const float tsuffix = tm.suffix_after;
-                // NOTE: the block scan below contains a barrier and full-mask shuffles, so it sits at ONE convergent call site;
-                // only the per-thread counting / accumulation around it may diverge.
+                const bool ranked = (uns >> tt) & 1u;              // uniform: rank and match count already known, every non-zero tf is a match
+                // NOTE: the block scan below contains a barrier and full-mask shuffles, so it sits at ONE call site under a block-uniform
+                // condition; only the per-thread counting / accumulation around it may diverge.
 #ifndef IFX_EMU
-                const bool fast = per_thread == 8 && j1 - j0 == 8;      // the 8 owned slots live in registers for the whole term
                 unsigned long long tf8 = 0ULL; unsigned alive = 0; float sc8[8];
                 if (fast) {
                     tf8 = *reinterpret_cast<const unsigned long long*>(tfb + j0);
@@ -834,15 +921,18 @@ IFX_FN void stage1_query(const Ctx& c, const DevIndex& ix, const QueryPlan& p, c
                         float4 sa = *reinterpret_cast<const float4*>(&sh.score[j0]), sb = *reinterpret_cast<const float4*>(&sh.score[j0 + 4]);
                         sc8[0] = sa.x; sc8[1] = sa.y; sc8[2] = sa.z; sc8[3] = sa.w; sc8[4] = sb.x; sc8[5] = sb.y; sc8[6] = sb.z; sc8[7] = sb.w;
 #pragma unroll
-                        for (int k = 0; k < 8; k++) { unsigned tfv = (unsigned)(tf8 >> (8 * k)) & 0xFFu; if (tfv != 0 && !(sc8[k] + tbound + tsuffix <= thr)) alive |= 1u << k; }
+                        for (int k = 0; k < 8; k++) { unsigned tfv = (unsigned)(tf8 >> (8 * k)) & 0xFFu; if (tfv != 0 && (ranked || !(sc8[k] + tbound + tsuffix <= thr))) alive |= 1u << k; }
                         mine = __popc(alive);
                     }
                 } else
-#else
-                const bool fast = false;
 #endif
-                { for (int j = j0; j < j1; j++) if (tfb[j] != 0 && !(sh.score[j] + tbound + tsuffix <= thr)) mine++; }
-                int m; int rank = block_excl_scan_1b(c, mine, sh.scan2[tt & 1], m);
+                { for (int j = j0; j < j1; j++) if (tfb[j] != 0 && (ranked || !(sh.score[j] + tbound + tsuffix <= thr))) mine++; }
+                int m, rank;
+#ifndef IFX_EMU
+                if (ranked) { const unsigned e = tt < 2 ? ex01 : (tt < 4 ? ex23 : ex45), tm_ = tt < 2 ? m01 : (tt < 4 ? m23 : m45); rank = (int)((e >> (16 * (tt & 1))) & 0xFFFFu); m = (int)((tm_ >> (16 * (tt & 1))) & 0xFFFFu); }
+                else
+#endif
+                { rank = block_excl_scan_1b(c, mine, sh.scan2[nscan & 1], m); nscan++; }
                 const int vec_end = m - (m & 7);
 #ifndef IFX_EMU
                 if (fast) {
@@ -852,7 +942,11 @@ IFX_FN void stage1_query(const Ctx& c, const DevIndex& ix, const QueryPlan& p, c
 #pragma unroll
                         for (int k = 0; k < 8; k++) if (alive & (1u << k)) {
                             float tf = (float)((unsigned)(tf8 >> (8 * k)) & 0xFFu);
+                            #ifdef IFX_EXP_NODL   // timing experiment only (wrong scores): no global doc_len load on the scalar tail
+                            float add = rank < vec_end ? bm25_from_norm_vector(tf, nv8[k], tm.idf) : bm25_scalar(tf, nv8[k], avgdl, tm.idf);
+#else
                             float add = rank < vec_end ? bm25_from_norm_vector(tf, nv8[k], tm.idf) : bm25_scalar(tf, ix.doc_len[sh.cand_s[j0 + k]], avgdl, tm.idf);
+#endif
                             sc8[k] += add; rank++;
                         }
                         *reinterpret_cast<float4*>(&sh.score[j0]) = make_float4(sc8[0], sc8[1], sc8[2], sc8[3]);
@@ -864,7 +958,7 @@ IFX_FN void stage1_query(const Ctx& c, const DevIndex& ix, const QueryPlan& p, c
                 for (int j = j0; j < j1; j++) {
                     const uint8_t tfv = tfb[j];
                     if (tfv != 0) {
-                        if (!(sh.score[j] + tbound + tsuffix <= thr)) {
+                        if (ranked || !(sh.score[j] + tbound + tsuffix <= thr)) {
                             float tf = (float)tfv;
                             float sc = rank < vec_end ? bm25_from_norm_vector(tf, sh.nv_s[j], tm.idf) : bm25_scalar(tf, ix.doc_len[sh.cand_s[j]], avgdl, tm.idf);
                             sh.score[j] += sc; rank++;

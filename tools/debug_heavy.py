@@ -20,6 +20,7 @@ ph = dbg[:, 6:11].sum(0); print("scoring cycles share (thread 0 = heap warp): wa
 for i in order[:8]: print("   ", qs[i][:30], (dbg[i, 6:11] / 1e3).astype(int), "kcycles", "eligible", dbg[i, 11] & 0xFFFFF, "heap updates", dbg[i, 11] >> 20)
 wp = dbg[:, 12:20].sum(0); print("worker-view cycles share: ids+norms %.1f%% bounds %.1f%% bitmap %.1f%% phaseA0 %.1f%% join-wait %.1f%% phaseA-later %.1f%% its-barrier %.1f%% post-join(B+elig) %.1f%%" % tuple(100 * wp / wp.sum()))
 for i in order[:8]: print("   W", qs[i][:30], (dbg[i, 12:20] / 1e3).astype(int), "kcycles")
+for i in order[:8]: print("   S", qs[i][:30], (dbg[i, 20:24] / 1e3).astype(int), "kcycles [prefix+sort, tier0/unions, tier1, compact]")
 print("total eligible", int((dbg[:, 11] & 0xFFFFF).sum()), "total heap updates", int((dbg[:, 11] >> 20).sum()))
 c = dbg[:, 0]; print("cand percentiles", np.percentile(c, [50, 90, 99, 100]).astype(int), "mean", int(c.mean()))
 # per-CTA busy time
