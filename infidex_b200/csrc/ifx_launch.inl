@@ -6,16 +6,17 @@ __global__ void k_prepare(DevIndex ix, const uint16_t* text, const int64_t* off,
     int q = blockIdx.x * blockDim.x + threadIdx.x; if (q >= nq) return;
     prepare_query(ix, text + off[q], (int)(off[q + 1] - off[q]), par[q * 5 + 1], par[q * 5 + 0], par[q * 5 + 2], par[q * 5 + 3], par[q * 5 + 4], plans[q], items, items_cap, bc, q);
 }
-// Longest-processing-time-first order: queries bucketed by log2 of their posting volume, heaviest bucket first, so the
-// long sequential chunk chains of heavy queries start at once instead of forming the tail of the launch.
+// Longest-processing-time-first order: queries bucketed by their posting volume (log2 scale, eight steps per octave), heaviest
+// bucket first, so the long sequential chunk chains of heavy queries start at once instead of forming the tail of the launch.
 __global__ void k_order(const QueryPlan* plans, int nq, int* order) {
-    __shared__ int cnt[64]; __shared__ int base[64];
-    if (threadIdx.x < 64) cnt[threadIdx.x] = 0;
+    __shared__ int cnt[512]; __shared__ int base[512];
+    for (int i = threadIdx.x; i < 512; i += blockDim.x) cnt[i] = 0;
     __syncthreads();
-    auto bucket = [&](int q) { const QueryPlan& p = plans[q]; long long c = 1; for (int i = 0; i < p.n_terms; i++) c += p.terms[i].list_len; return 63 - __clzll(c); };
+    auto bucket = [&](int q) { const QueryPlan& p = plans[q]; long long c = 8; for (int i = 0; i < p.n_terms; i++) c += p.terms[i].list_len;
+                               int msb = 63 - __clzll(c); return msb * 8 + (int)((c >> (msb - 3)) & 7); };
     for (int q = threadIdx.x; q < nq; q += blockDim.x) atomicAdd(&cnt[bucket(q)], 1);
     __syncthreads();
-    if (threadIdx.x == 0) { int run = 0; for (int b = 63; b >= 0; b--) { base[b] = run; run += cnt[b]; } }
+    if (threadIdx.x == 0) { int run = 0; for (int b = 511; b >= 0; b--) { base[b] = run; run += cnt[b]; } }
     __syncthreads();
     for (int q = threadIdx.x; q < nq; q += blockDim.x) { int pos = atomicAdd(&base[bucket(q)], 1); order[pos] = q; }
 }

@@ -190,6 +190,8 @@ struct TermS {             // term as seen by the scorer
 constexpr int S1_TILE = 6;
 
 constexpr int SURV_CAP = 512;
+constexpr int SMALL_CHUNK = 512;                               // chunks up to this size are scored by a single warp, without block barriers
+constexpr int SMALL_TERMS = S1_TILE * CHUNK / SMALL_CHUNK;      // ... when all their terms fit the tile buffer re-cut as [term][SMALL_CHUNK]
 struct S1Shared {
     TermS terms[MAX_TERMS];
     int order[MAX_TERMS];
@@ -493,6 +495,39 @@ IFX_FN int worker_excl_scan(const Ctx& c, int v, ScanTmp& tmp, int hw, int ntw) 
 #endif
 }
 
+// tf of ONE term for every candidate slot of the chunk into tfb[0..cnt) (slots without a match are left untouched, i.e. 0),
+// executed by the `ntw` threads numbered wt. `may_stream`: the chunk's container-local bitmap (sh.cbits / sh.cpref) exists.
+IFX_FN void stage1_lookup_term(S1Shared& sh, const TermS& tm, uint8_t* tfb, int cnt, int wt, int ntw, bool may_stream) {
+    const int64_t sublen = tm.s1 - tm.s0;
+    if (tm.bm && sublen > 2LL * cnt) {          // dense term, sparse chunk: O(1) bitmap probe per candidate (doc -> posting index -> tf)
+        for (int jb = wt; jb < cnt; jb += 4 * ntw) {
+            unsigned wv[4]; int rk[4]; int dd[4];
+            for (int u = 0; u < 4; u++) { int j = jb + u * ntw; dd[u] = j < cnt ? sh.cand_s[j] : -1; if (dd[u] >= 0) { wv[u] = tm.bm[dd[u] >> 5]; rk[u] = tm.bmr[dd[u] >> 5]; } }
+            for (int u = 0; u < 4; u++) if (dd[u] >= 0) { unsigned bit = 1u << (dd[u] & 31); if (wv[u] & bit) tfb[jb + u * ntw] = tm.tf[rk[u] + popc(wv[u] & (bit - 1))]; }
+        }
+    } else if (may_stream && sublen <= 16LL * cnt) {   // stream the posting sub-range (coalesced), O(1) slot lookup per posting
+        for (int64_t i0 = tm.s0 + wt; i0 < tm.s1; i0 += 4LL * ntw) {      // four independent loads in flight per thread
+            int dd[4]; uint8_t tv[4];                                          // tf fetched alongside the id (one latency, not two)
+            for (int u = 0; u < 4; u++) { int64_t i = i0 + (int64_t)u * ntw; bool in = i < tm.s1; dd[u] = in ? tm.docs[i] : -1; tv[u] = (in && tm.tf) ? tm.tf[i] : (uint8_t)1; }
+            for (int u = 0; u < 4; u++) if (dd[u] >= 0) {
+                int d = dd[u] & 0xFFFF; unsigned wv = sh.cbits[d >> 5], bit = 1u << (d & 31);
+                if (wv & bit) tfb[sh.cpref[d >> 5] + popc(wv & (bit - 1))] = tv[u];
+            }
+        }
+    } else {                                    // sparse candidates: level-synchronous binary searches, four per thread at a time
+        for (int jb = wt; jb < cnt; jb += 4 * ntw) {
+            int64_t lo[4], hi[4]; int32_t d[4];
+            for (int u = 0; u < 4; u++) { int j = jb + u * ntw; d[u] = j < cnt ? sh.cand_s[j] : 0x7fffffff; lo[u] = tm.s0; hi[u] = j < cnt ? tm.s1 : tm.s0; }
+            for (int64_t span = sublen; span > 0; span >>= 1) {
+                int32_t v[4]; int64_t mid[4];
+                for (int u = 0; u < 4; u++) { mid[u] = lo[u] + ((hi[u] - lo[u]) >> 1); v[u] = lo[u] < hi[u] ? tm.docs[mid[u]] : 0; }
+                for (int u = 0; u < 4; u++) if (lo[u] < hi[u]) { if (v[u] < d[u]) lo[u] = mid[u] + 1; else hi[u] = mid[u]; }
+            }
+            for (int u = 0; u < 4; u++) { int j = jb + u * ntw; if (j < cnt && lo[u] < tm.s1 && tm.docs[lo[u]] == d[u]) tfb[j] = tm.tf ? tm.tf[lo[u]] : (uint8_t)1; }
+        }
+    }
+}
+
 // Phase A of one term tile: tf of every (term, candidate slot) pair of the chunk into sh.tfm (0 = no match). Independent of the
 // scores and of the threshold, so it runs on the worker threads (wt of ntw) while the heap warp is still draining the last chunk.
 IFX_FN void stage1_phase_a(const Ctx& c, S1Shared& sh, int t0, int T, int cnt, int wt, int ntw) {
@@ -500,35 +535,8 @@ IFX_FN void stage1_phase_a(const Ctx& c, S1Shared& sh, int t0, int T, int cnt, i
     const int tile = T - t0 < S1_TILE ? T - t0 : S1_TILE; const bool use_bitmap = sh.bcast[5] != 0;
     for (int tt = 0; tt < tile; tt++) {
         const TermS& tm = sh.terms[t0 + tt];
-        const int64_t sublen = tm.s1 - tm.s0; if (tm.idf <= 0.f || sublen == 0) continue;   // uniform
-        uint8_t* tfb = sh.tfm[tt];
-        if (tm.bm && sublen > 2LL * cnt) {          // dense term, sparse chunk: O(1) bitmap probe per candidate (doc -> posting index -> tf)
-            for (int jb = wt; jb < cnt; jb += 4 * ntw) {
-                unsigned wv[4]; int rk[4]; int dd[4];
-                for (int u = 0; u < 4; u++) { int j = jb + u * ntw; dd[u] = j < cnt ? sh.cand_s[j] : -1; if (dd[u] >= 0) { wv[u] = tm.bm[dd[u] >> 5]; rk[u] = tm.bmr[dd[u] >> 5]; } }
-                for (int u = 0; u < 4; u++) if (dd[u] >= 0) { unsigned bit = 1u << (dd[u] & 31); if (wv[u] & bit) tfb[jb + u * ntw] = tm.tf[rk[u] + popc(wv[u] & (bit - 1))]; }
-            }
-        } else if (use_bitmap && sublen <= 16LL * cnt) {   // stream the posting sub-range (coalesced), O(1) slot lookup per posting
-            for (int64_t i0 = tm.s0 + wt; i0 < tm.s1; i0 += 4LL * ntw) {      // four independent loads in flight per thread
-                int dd[4]; uint8_t tv[4];                                          // tf fetched alongside the id (one latency, not two)
-                for (int u = 0; u < 4; u++) { int64_t i = i0 + (int64_t)u * ntw; bool in = i < tm.s1; dd[u] = in ? tm.docs[i] : -1; tv[u] = (in && tm.tf) ? tm.tf[i] : (uint8_t)1; }
-                for (int u = 0; u < 4; u++) if (dd[u] >= 0) {
-                    int d = dd[u] & 0xFFFF; unsigned wv = sh.cbits[d >> 5], bit = 1u << (d & 31);
-                    if (wv & bit) tfb[sh.cpref[d >> 5] + popc(wv & (bit - 1))] = tv[u];
-                }
-            }
-        } else {                                    // sparse candidates: level-synchronous binary searches, four per thread at a time
-            for (int jb = wt; jb < cnt; jb += 4 * ntw) {
-                int64_t lo[4], hi[4]; int32_t d[4];
-                for (int u = 0; u < 4; u++) { int j = jb + u * ntw; d[u] = j < cnt ? sh.cand_s[j] : 0x7fffffff; lo[u] = tm.s0; hi[u] = j < cnt ? tm.s1 : tm.s0; }
-                for (int64_t span = sublen; span > 0; span >>= 1) {
-                    int32_t v[4]; int64_t mid[4];
-                    for (int u = 0; u < 4; u++) { mid[u] = lo[u] + ((hi[u] - lo[u]) >> 1); v[u] = lo[u] < hi[u] ? tm.docs[mid[u]] : 0; }
-                    for (int u = 0; u < 4; u++) if (lo[u] < hi[u]) { if (v[u] < d[u]) lo[u] = mid[u] + 1; else hi[u] = mid[u]; }
-                }
-                for (int u = 0; u < 4; u++) { int j = jb + u * ntw; if (j < cnt && lo[u] < tm.s1 && tm.docs[lo[u]] == d[u]) tfb[j] = tm.tf ? tm.tf[lo[u]] : (uint8_t)1; }
-            }
-        }
+        if (tm.idf <= 0.f || tm.s1 == tm.s0) continue;   // uniform
+        stage1_lookup_term(sh, tm, sh.tfm[tt], cnt, wt, ntw, use_bitmap);
     }
 }
 
@@ -651,6 +659,59 @@ IFX_FN void expand_fuzzy(const Ctx& c, const DevIndex& ix, QueryPlan& p, int fsl
         else { float avgdl = ix.avgdl > 0.f ? ix.avgdl : 1.f; t.df = df; t.list_len = df; t.list_off = (int64_t)b; t.idf = compute_idf(ix, df); t.max_score = max_term_score(t.idf, avgdl); }
     }
     c.sync();
+}
+
+// Scoring + flush of a small chunk (cnt <= SMALL_CHUNK) by ONE warp: lane l owns the consecutive slots [l*per, (l+1)*per), ranks come
+// from warp scans, nothing synchronises with the rest of the block. Same arithmetic and the same order as the tiled path below
+// (MaxScore test, rank -> Vector256 / scalar form, accumulation, eligibility, survivors in candidate order); tf bytes are read from
+// the tile buffer re-cut as [term][SMALL_CHUNK] (filled by the workers, one warp per term) and zeroed again after use.
+IFX_FN void stage1_small_chunk(const Ctx& c, const DevIndex& ix, S1Shared& sh, int T, int cnt, int K, float avgdl) {
+    const int per = SMALL_CHUNK / Ctx::WS;                      // 16 on the GPU (a multiple of 8 in every build)
+    const int j0 = c.lane() * per < cnt ? c.lane() * per : cnt, j1 = j0 + per < cnt ? j0 + per : cnt;
+    const float thr = sh.thr; uint8_t* tfs = &sh.tfm[0][0];
+#ifdef IFX_EMU
+    auto load8 = [](const uint8_t* p8) -> unsigned long long { unsigned long long v; memcpy(&v, p8, 8); return v; };
+    auto zero8 = [](uint8_t* p8) { const unsigned long long z = 0ULL; memcpy(p8, &z, 8); };
+#else       // 8-byte aligned by construction (tile buffer 16-aligned, SMALL_CHUNK and `per` multiples of 8)
+    auto load8 = [](const uint8_t* p8) -> unsigned long long { return *reinterpret_cast<const unsigned long long*>(p8); };
+    auto zero8 = [](uint8_t* p8) { *reinterpret_cast<unsigned long long*>(p8) = 0ULL; };
+#endif
+    auto warp_excl = [&](int mine, int& total) -> int {         // exclusive prefix over the lanes + warp total
+        int incl = mine;
+        for (int d = 1; d < Ctx::WS; d <<= 1) { int o = c.shfl(incl, c.lane() >= d ? c.lane() - d : 0); if (c.lane() >= d) incl += o; }
+        total = c.shfl(incl, Ctx::WS - 1);
+        return incl - mine;
+    };
+    for (int t = 0; t < T; t++) {
+        const TermS& tm = sh.terms[t];
+        if (tm.idf <= 0.f || tm.s1 == tm.s0) continue;          // uniform
+        uint8_t* tfb = tfs + t * SMALL_CHUNK; const float tbound = tm.max_score, tsuffix = tm.suffix_after;
+        int mine = 0;
+        for (int j = j0; j < j1; j += 8) {                       // (bytes past cnt inside the last group are zero)
+            const unsigned long long v = load8(tfb + j); if (v == 0ULL) continue;
+            for (int k = 0; k < 8; k++) if (((v >> (8 * k)) & 0xFFu) != 0 && !(sh.score[j + k] + tbound + tsuffix <= thr)) mine++;
+        }
+        int m; int rank = warp_excl(mine, m);
+        const int vec_end = m - (m & 7);
+        for (int j = j0; j < j1; j += 8) {
+            const unsigned long long v = load8(tfb + j); if (v == 0ULL) continue;
+            for (int k = 0; k < 8; k++) {
+                const unsigned tfv = (unsigned)(v >> (8 * k)) & 0xFFu;
+                if (tfv != 0 && !(sh.score[j + k] + tbound + tsuffix <= thr)) {
+                    const float tf = (float)tfv;
+                    const float add = rank < vec_end ? bm25_from_norm_vector(tf, sh.nv_s[j + k], tm.idf) : bm25_scalar(tf, ix.doc_len[sh.cand_s[j + k]], avgdl, tm.idf);
+                    sh.score[j + k] += add; rank++;
+                }
+            }
+            zero8(tfb + j);
+        }
+    }
+    // flush, part 1 (see the tiled path): eligibility against the chunk-start threshold, survivors compacted in candidate order
+    const bool full = sh.heap_size >= K; int mine = 0;
+    for (int j = j0; j < j1; j++) if (sh.score[j] > 0.f && (!full || sh.score[j] > thr) && !ix.deleted[sh.cand_s[j]]) mine++;
+    int total; int off = warp_excl(mine, total);
+    for (int j = j0; j < j1; j++) if (sh.score[j] > 0.f && (!full || sh.score[j] > thr) && !ix.deleted[sh.cand_s[j]]) sh.surv[off++] = kv_pack(sh.cand_s[j], sh.score[j]);
+    if (c.lane() == 0) sh.bcast[6] = total;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -841,6 +902,14 @@ IFX_FN void stage1_query(const Ctx& c, const DevIndex& ix, const QueryPlan& p, c
             }
             c.sync_workers(NTW);
             IFX_WTICK(1);  // posting sub-range bounds
+            if (cnt <= SMALL_CHUNK && T <= SMALL_TERMS) {
+                // small chunk: tf of ALL terms now, one warp per term (probes / binary searches only), for the single-warp scorer
+                for (int t = c.warp() - hw / Ctx::WS; t < T; t += NW - hw / Ctx::WS) {
+                    const TermS& tm = sh.terms[t];
+                    if (tm.idf <= 0.f || tm.s1 == tm.s0) continue;
+                    stage1_lookup_term(sh, tm, &sh.tfm[0][0] + t * SMALL_CHUNK, cnt, c.lane(), Ctx::WS, false);
+                }
+            } else {
             // Container-local bitmap of the chunk's candidates + per-word rank directory: posting -> candidate slot in O(1)
             // (all candidates of a chunk share id >> 16). Built only when some term streams its posting sub-range.
             if (sh.bcast[5] != 0) {
@@ -856,12 +925,20 @@ IFX_FN void stage1_query(const Ctx& c, const DevIndex& ix, const QueryPlan& p, c
             }
             IFX_WTICK(2);  // candidate bitmap + rank directory
             stage1_phase_a(c, sh, 0, T, cnt, wt, NTW);
-            IFX_WTICK(3);  // phase A, tile 0 (this thread's share)
+            }
+            IFX_WTICK(3);  // phase A, tile 0 (this thread's share) / small-chunk lookups
         }
         c.sync();      // join: heap drained, chunk staged, tile 0 looked up
         IFX_WTICK(4);  // waiting at the join (slower workers / the heap drain)
         IFX_TICK(0);   // heap warp waiting for the workers (set-up + phase A beyond the drain)
         const int cnt = sh.bcast[2];
+        if (cnt <= SMALL_CHUNK && T <= SMALL_TERMS) {
+            if (c.warp() == hw / Ctx::WS) stage1_small_chunk(c, ix, sh, T, cnt, K, avgdl);
+            c.sync();
+            pend = sh.bcast[6]; pos += cnt;
+            IFX_TICK(3);
+            continue;
+        }
         const float thr = sh.thr; const int rounds = (cnt + NT - 1) / NT;
         const int per_thread = (CHUNK + NT - 1) / NT; const int j0 = c.tid() * per_thread < cnt ? c.tid() * per_thread : cnt; const int j1 = j0 + per_thread < cnt ? j0 + per_thread : cnt;
         // Terms are processed in tiles: the membership (tf) lookups of a whole tile are issued back to back with no barrier in
@@ -880,8 +957,12 @@ IFX_FN void stage1_query(const Ctx& c, const DevIndex& ix, const QueryPlan& p, c
             // A term whose own bound plus the bounds of the terms after it already exceeds the threshold can never be skipped
             // (scores are >= 0 and float addition is monotone), so its matches are exactly the non-zero tf slots, known before any
             // score exists: the ranks of all such terms of the tile come from ONE packed block scan (16-bit fields, <= 4096 each).
-            unsigned uns = 0, ex01 = 0, ex23 = 0, ex45 = 0, m01 = 0, m23 = 0, m45 = 0;
-            for (int tt = 0; tt < tile; tt++) { const TermS& tm = sh.terms[t0 + tt]; if (tm.idf <= 0.f || tm.s1 == tm.s0) continue; if (!((0.f + tm.max_score) + tm.suffix_after <= thr)) uns |= 1u << tt; }
+            unsigned uns = 0, act = 0, ex01 = 0, ex23 = 0, ex45 = 0, m01 = 0, m23 = 0, m45 = 0;
+            {   // lane tt classifies term tt of the tile; the votes give every thread the (block-uniform) masks
+                bool a = false, u = false;
+                if (c.lane() < tile) { const TermS& tm = sh.terms[t0 + c.lane()]; a = tm.idf > 0.f && tm.s1 != tm.s0; u = a && !((0.f + tm.max_score) + tm.suffix_after <= thr); }
+                act = __ballot_sync(0xffffffffu, a); uns = __ballot_sync(0xffffffffu, u);
+            }
             if (__popc(uns) >= 2) {
                 unsigned pk[3] = {0u, 0u, 0u};
 #pragma unroll
@@ -898,16 +979,25 @@ IFX_FN void stage1_query(const Ctx& c, const DevIndex& ix, const QueryPlan& p, c
                 }
                 if (c.lane() == 31) { sh.scan3[c.warp()][0] = in0; sh.scan3[c.warp()][1] = in1; sh.scan3[c.warp()][2] = in2; }
                 c.sync();
-                unsigned b0 = 0, b1 = 0, b2 = 0;
-                for (int i = 0; i < NW; i++) { const uint4 x = *reinterpret_cast<const uint4*>(sh.scan3[i]); if (i < c.warp()) { b0 += x.x; b1 += x.y; b2 += x.z; } m01 += x.x; m23 += x.y; m45 += x.z; }
+                // lane i holds warp i's totals; a warp scan over them yields this warp's base (lane warp-1) and the block totals (lane NW-1)
+                uint4 x = make_uint4(0u, 0u, 0u, 0u); if (c.lane() < NW) x = *reinterpret_cast<const uint4*>(sh.scan3[c.lane()]);
+                for (int d = 1; d < NW; d <<= 1) {
+                    unsigned o0 = __shfl_up_sync(0xffffffffu, x.x, d), o1 = __shfl_up_sync(0xffffffffu, x.y, d), o2 = __shfl_up_sync(0xffffffffu, x.z, d);
+                    if (c.lane() >= d) { x.x += o0; x.y += o1; x.z += o2; }
+                }
+                const int src = c.warp() > 0 ? c.warp() - 1 : 0;
+                unsigned b0 = __shfl_sync(0xffffffffu, x.x, src), b1 = __shfl_sync(0xffffffffu, x.y, src), b2 = __shfl_sync(0xffffffffu, x.z, src);
+                if (c.warp() == 0) { b0 = 0; b1 = 0; b2 = 0; }
+                m01 = __shfl_sync(0xffffffffu, x.x, NW - 1); m23 = __shfl_sync(0xffffffffu, x.y, NW - 1); m45 = __shfl_sync(0xffffffffu, x.z, NW - 1);
                 ex01 = b0 + in0 - pk[0]; ex23 = b1 + in1 - pk[1]; ex45 = b2 + in2 - pk[2];
             } else uns = 0;
 #else
-            const bool fast = false; const unsigned uns = 0;
+            const bool fast = false; const unsigned uns = 0; unsigned act = 0;
+            for (int tt = 0; tt < tile; tt++) { const TermS& tm = sh.terms[t0 + tt]; if (tm.idf > 0.f && tm.s1 != tm.s0) act |= 1u << tt; }
 #endif
             for (int tt = 0; tt < tile; tt++) {
+                if (!((act >> tt) & 1u)) continue;                 // no idf or no postings inside this chunk's id range
                 const TermS& tm = sh.terms[t0 + tt];
-                if (tm.idf <= 0.f || tm.s1 == tm.s0) continue;
                 uint8_t* tfb = sh.tfm[tt];
                 int mine = 0; const float tbound = tm.max_score; const float tsuffix = tm.suffix_after;
                 const bool ranked = (uns >> tt) & 1u;              // uniform: rank and match count already known, every non-zero tf is a match
