@@ -144,6 +144,14 @@ extern "C" int ifx_index_create(const ifx_index_image* img, const ifx_params* pp
         v.df = ix->up(img->df, T); v.row_ptr = ix->up(img->row_ptr, (size_t)T + 1);
         size_t P_ = T ? (size_t)img->row_ptr[T] : 0;
         v.post_doc = ix->up(img->post_doc, P_ ? P_ : 1); v.post_tf = ix->up(img->post_tf, P_ ? P_ : 1);
+        {   // forward index: CSR transpose of the live posting lists (counting sort by doc; entries of a doc end up in term order)
+            std::vector<int64_t> fp((size_t)N + 2, 0);
+            for (int t = 0; t < T; t++) { if (img->df[t] <= 0) continue; for (int64_t i = img->row_ptr[t]; i < img->row_ptr[t + 1]; i++) fp[(size_t)img->post_doc[i] + 2]++; }
+            for (int d = 0; d < N; d++) fp[(size_t)d + 2] += fp[(size_t)d + 1];
+            const int64_t FP = fp[(size_t)N + 1]; std::vector<int32_t> ft((size_t)std::max<int64_t>(FP, 1)); std::vector<uint8_t> fw((size_t)std::max<int64_t>(FP, 1));
+            for (int t = 0; t < T; t++) { if (img->df[t] <= 0) continue; for (int64_t i = img->row_ptr[t]; i < img->row_ptr[t + 1]; i++) { int64_t at = fp[(size_t)img->post_doc[i] + 1]++; ft[(size_t)at] = t; fw[(size_t)at] = img->post_tf[i]; } }
+            v.fwd_ptr = ix->up(fp.data(), (size_t)N + 1); v.fwd_term = ix->up(ft.data(), ft.size()); v.fwd_tf = ix->up(fw.data(), fw.size());
+        }
         {   // container skip table for long posting lists: turns the per-chunk sub-range search of the scorer into a lookup
             const int ncont = (N + 65535) >> 16; const int64_t SKIP_MIN = 512; v.n_cont = ncont;
             std::vector<int32_t> sid(std::max(T, 1), -1); std::vector<int32_t> sp; int ns = 0;

@@ -61,6 +61,8 @@ struct DevIndex {
     StrDict terms; const int32_t* df; const int64_t* row_ptr; const int32_t* post_doc; const uint8_t* post_tf;
     const int32_t* term_sorted;      // term ordinals in ordinal-lexicographic order (trie DFS order)
     const unsigned long long* term_sig;   // per sorted position: 64-bit character-set signature (LD1 pre-filter)
+    // forward index (doc -> its (term, tf) pairs, terms with df > 0 only): one lookup latency per candidate for the sparse chunks
+    const int64_t* fwd_ptr; const int32_t* fwd_term; const uint8_t* fwd_tf;
     // the same dictionary grouped by term length (stable, so lexicographic inside a group): LD1 scans touch lengths m-1..m+1 only
     const int32_t* len_ptr;          // [257] group start per length (255 = 255 or longer), [256] = n terms
     const unsigned long long* len_sig;   // signature per grouped position
@@ -117,6 +119,7 @@ struct Ctx {
     int tid() const { return 0; } int nthreads() const { return 1; } int lane() const { return 0; } int warp() const { return 0; } int nwarps() const { return 1; }
     void sync() const {}
     void sync_workers(int) const {}
+    void sync_team(int) const {}
     unsigned ballot(bool p) const { return p ? 1u : 0u; }
     unsigned lanemask_lt() const { return 0u; }
     template <class T> T shfl(T v, int) const { return v; }
@@ -137,6 +140,8 @@ struct Ctx {
     __device__ void sync() const { __syncthreads(); }
     // named barrier 1 over the `n` worker threads of a warp-specialised region (n: multiple of 32; every worker warp calls it)
     __device__ void sync_workers(int n) const { asm volatile("bar.sync 1, %0;" :: "r"(n) : "memory"); }
+    // named barrier 2 over the `n` threads of the small-chunk team
+    __device__ void sync_team(int n) const { asm volatile("bar.sync 2, %0;" :: "r"(n) : "memory"); }
     __device__ unsigned ballot(bool p) const { return __ballot_sync(0xffffffffu, p); }
     __device__ unsigned lanemask_lt() const { return (1u << (threadIdx.x & 31)) - 1u; }
     template <class T> __device__ T shfl(T v, int src) const { return __shfl_sync(0xffffffffu, v, src); }

@@ -6,13 +6,16 @@ __global__ void k_prepare(DevIndex ix, const uint16_t* text, const int64_t* off,
     int q = blockIdx.x * blockDim.x + threadIdx.x; if (q >= nq) return;
     prepare_query(ix, text + off[q], (int)(off[q + 1] - off[q]), par[q * 5 + 1], par[q * 5 + 0], par[q * 5 + 2], par[q * 5 + 3], par[q * 5 + 4], plans[q], items, items_cap, bc, q);
 }
-// Longest-processing-time-first order: queries bucketed by their posting volume (log2 scale, eight steps per octave), heaviest
+// Longest-processing-time-first order: queries bucketed by their estimated work (posting volume, or the candidate count when the
+// prefix shortcut will apply; log2 scale, eight steps per octave), heaviest
 // bucket first, so the long sequential chunk chains of heavy queries start at once instead of forming the tail of the launch.
-__global__ void k_order(const QueryPlan* plans, int nq, int* order) {
+__global__ void k_order(DevIndex ix, const QueryPlan* plans, int nq, int* order) {
     __shared__ int cnt[512]; __shared__ int base[512];
     for (int i = threadIdx.x; i < 512; i += blockDim.x) cnt[i] = 0;
     __syncthreads();
-    auto bucket = [&](int q) { const QueryPlan& p = plans[q]; long long c = 8; for (int i = 0; i < p.n_terms; i++) c += p.terms[i].list_len;
+    auto bucket = [&](int q) { const QueryPlan& p = plans[q]; long long c = 8; int64_t r0, pop;
+                               if (p.status == 0 && p.n_terms > 0 && prefix_shortcut(ix, p, p.depth, r0, pop)) c += pop * 16;     // few candidates whatever the lists' lengths
+                               else for (int i = 0; i < p.n_terms; i++) c += p.terms[i].list_len;
                                int msb = 63 - __clzll(c); return msb * 8 + (int)((c >> (msb - 3)) & 7); };
     for (int q = threadIdx.x; q < nq; q += blockDim.x) atomicAdd(&cnt[bucket(q)], 1);
     __syncthreads();
@@ -83,7 +86,7 @@ static void run_stage1_phase(ifx_batch* b, ifx_stats* st) {
     k_expand<<<ix->n_ctas, kS1Threads, smem>>>(ix->v, b->d_plans, b->d_items, b->d_bc, ix->d_ws, ix->d_pool, ix->pool_cap, ix->d_sorted_len, b->d_work);
     float ms_exp = t.stop();
     t.start();
-    k_order<<<1, 1024>>>(b->d_plans, nq, b->d_order);
+    k_order<<<1, 1024>>>(ix->v, b->d_plans, nq, b->d_order);
     k_stage1<<<std::min(ix->n_ctas, nq), IFX_S1_THREADS, smem>>>(ix->v, b->d_plans, nq, ix->d_pool, ix->d_ws, b->d_bc, b->d_s1_key, b->d_s1_doc, b->d_s1_score, b->d_s1_n, K, b->d_work + 1, b->d_order, b->d_qdbg);
     float ms_s1 = t.stop();
     CUDA_TRY(cudaGetLastError());

@@ -184,14 +184,16 @@ struct S1Workspace {
 };
 
 struct TermS {             // term as seen by the scorer
-    const int32_t* docs; const uint8_t* tf; const int32_t* skip; const unsigned* bm; const int32_t* bmr; int32_t len; int32_t df; float idf, max_score, suffix_after; int64_t cursor, s0, s1;
+    const int32_t* docs; const uint8_t* tf; const int32_t* skip; const unsigned* bm; const int32_t* bmr; int32_t len; int32_t df; float idf, max_score, suffix_after; int32_t term_id; int64_t cursor, s0, s1;
 };
 
 constexpr int S1_TILE = 6;
 
 constexpr int SURV_CAP = 512;
+constexpr int QH_SIZE = 256;
 constexpr int SMALL_CHUNK = 512;                               // chunks up to this size are scored by a single warp, without block barriers
 constexpr int SMALL_TERMS = S1_TILE * CHUNK / SMALL_CHUNK;      // ... when all their terms fit the tile buffer re-cut as [term][SMALL_CHUNK]
+IFX_FN unsigned qh_hash(int32_t term_id) { return ((unsigned)term_id * 2654435761u) >> 24; }     // 8 bits = QH_SIZE
 struct S1Shared {
     TermS terms[MAX_TERMS];
     int order[MAX_TERMS];
@@ -205,6 +207,7 @@ struct S1Shared {
     // .NET PriorityQueue nodes packed as (doc << 32 | float bits of the priority), stored with a +3 shift so the four children of
     // node i (4i+1..4i+4) form one aligned 32-byte group; slots beyond the current size hold +huge sentinels
     alignas(32) unsigned long long heap_kv[MAX_K + 8];
+    int32_t qh_key[QH_SIZE]; uint8_t qh_slot[QH_SIZE];   // term id -> slot in `terms` (open addressing; terms with idf > 0 only), for the forward-index lookups
     unsigned long long surv[SURV_CAP];     // (doc, score) of the last chunk's flush survivors, drained into the heap while the next chunk is staged
     union {                               // never live at the same time: selection/compaction vs. chunk scoring
         uint8_t dirty[MAX_CONTAINERS];    // containers of the global bitset touched by the current set operation (all zero between uses)
@@ -661,57 +664,69 @@ IFX_FN void expand_fuzzy(const Ctx& c, const DevIndex& ix, QueryPlan& p, int fsl
     c.sync();
 }
 
-// Scoring + flush of a small chunk (cnt <= SMALL_CHUNK) by ONE warp: lane l owns the consecutive slots [l*per, (l+1)*per), ranks come
-// from warp scans, nothing synchronises with the rest of the block. Same arithmetic and the same order as the tiled path below
-// (MaxScore test, rank -> Vector256 / scalar form, accumulation, eligibility, survivors in candidate order); tf bytes are read from
-// the tile buffer re-cut as [term][SMALL_CHUNK] (filled by the workers, one warp per term) and zeroed again after use.
-IFX_FN void stage1_small_chunk(const Ctx& c, const DevIndex& ix, S1Shared& sh, int T, int cnt, int K, float avgdl) {
-    const int per = SMALL_CHUNK / Ctx::WS;                      // 16 on the GPU (a multiple of 8 in every build)
-    const int j0 = c.lane() * per < cnt ? c.lane() * per : cnt, j1 = j0 + per < cnt ? j0 + per : cnt;
-    const float thr = sh.thr; uint8_t* tfs = &sh.tfm[0][0];
+// Scoring + flush of a small chunk (cnt <= SMALL_CHUNK) by a team of SMALL_TEAM warps: team thread i owns the consecutive slots
+// [i*PER, (i+1)*PER), ranks come from a warp scan plus the team's per-warp totals (named barrier 2), nothing synchronises with the
+// rest of the block. Same arithmetic and the same order as the tiled path below (MaxScore test, rank -> Vector256 / scalar form,
+// accumulation, eligibility, survivors in candidate order); tf bytes are read from the tile buffer re-cut as [term][SMALL_CHUNK]
+// (filled by the workers) and zeroed again after use. `tw0`: first warp of the team.
 #ifdef IFX_EMU
-    auto load8 = [](const uint8_t* p8) -> unsigned long long { unsigned long long v; memcpy(&v, p8, 8); return v; };
-    auto zero8 = [](uint8_t* p8) { const unsigned long long z = 0ULL; memcpy(p8, &z, 8); };
-#else       // 8-byte aligned by construction (tile buffer 16-aligned, SMALL_CHUNK and `per` multiples of 8)
-    auto load8 = [](const uint8_t* p8) -> unsigned long long { return *reinterpret_cast<const unsigned long long*>(p8); };
-    auto zero8 = [](uint8_t* p8) { *reinterpret_cast<unsigned long long*>(p8) = 0ULL; };
+constexpr int SMALL_TEAM = 1;
+#else
+constexpr int SMALL_TEAM = 4;
 #endif
-    auto warp_excl = [&](int mine, int& total) -> int {         // exclusive prefix over the lanes + warp total
+IFX_FN void stage1_small_chunk(const Ctx& c, const DevIndex& ix, S1Shared& sh, int T, int cnt, int K, float avgdl, int tw0) {
+    constexpr int PER = SMALL_CHUNK / (SMALL_TEAM * Ctx::WS);     // 4 slots per thread on the GPU
+    const int wi = c.warp() - tw0, ti = wi * Ctx::WS + c.lane();
+    const int j0 = ti * PER < cnt ? ti * PER : cnt, j1 = j0 + PER < cnt ? j0 + PER : cnt, nj = j1 - j0;
+    const float thr = sh.thr; uint8_t* tfs = &sh.tfm[0][0]; int nscan = 0;
+    auto team_excl = [&](int mine, int& total) -> int {           // exclusive prefix over the team's threads + team total
         int incl = mine;
         for (int d = 1; d < Ctx::WS; d <<= 1) { int o = c.shfl(incl, c.lane() >= d ? c.lane() - d : 0); if (c.lane() >= d) incl += o; }
-        total = c.shfl(incl, Ctx::WS - 1);
-        return incl - mine;
+        const int buf = nscan & 1; nscan++;
+        if (c.lane() == Ctx::WS - 1) sh.scan3[wi][buf] = (unsigned)incl;
+        c.sync_team(SMALL_TEAM * Ctx::WS);
+        int base = 0, tot = 0;
+        for (int i = 0; i < SMALL_TEAM; i++) { int x = (int)sh.scan3[i][buf]; if (i < wi) base += x; tot += x; }
+        total = tot;
+        return base + incl - mine;
     };
     for (int t = 0; t < T; t++) {
         const TermS& tm = sh.terms[t];
-        if (tm.idf <= 0.f || tm.s1 == tm.s0) continue;          // uniform
+        if (tm.idf <= 0.f || (tm.term_id < 0 && tm.s1 == tm.s0)) continue;          // uniform (dictionary terms came through the forward index: no sub-range)
         uint8_t* tfb = tfs + t * SMALL_CHUNK; const float tbound = tm.max_score, tsuffix = tm.suffix_after;
-        int mine = 0;
-        for (int j = j0; j < j1; j += 8) {                       // (bytes past cnt inside the last group are zero)
-            const unsigned long long v = load8(tfb + j); if (v == 0ULL) continue;
-            for (int k = 0; k < 8; k++) if (((v >> (8 * k)) & 0xFFu) != 0 && !(sh.score[j + k] + tbound + tsuffix <= thr)) mine++;
-        }
-        int m; int rank = warp_excl(mine, m);
+        uint8_t tfv[PER]; bool alive[PER]; int mine = 0;
+        for (int k = 0; k < PER; k++) { tfv[k] = k < nj ? tfb[j0 + k] : (uint8_t)0; alive[k] = tfv[k] != 0 && !(sh.score[j0 + k] + tbound + tsuffix <= thr); mine += alive[k] ? 1 : 0; }
+        int m; int rank = team_excl(mine, m);
         const int vec_end = m - (m & 7);
-        for (int j = j0; j < j1; j += 8) {
-            const unsigned long long v = load8(tfb + j); if (v == 0ULL) continue;
-            for (int k = 0; k < 8; k++) {
-                const unsigned tfv = (unsigned)(v >> (8 * k)) & 0xFFu;
-                if (tfv != 0 && !(sh.score[j + k] + tbound + tsuffix <= thr)) {
-                    const float tf = (float)tfv;
-                    const float add = rank < vec_end ? bm25_from_norm_vector(tf, sh.nv_s[j + k], tm.idf) : bm25_scalar(tf, ix.doc_len[sh.cand_s[j + k]], avgdl, tm.idf);
-                    sh.score[j + k] += add; rank++;
-                }
+        for (int k = 0; k < PER; k++) {
+            if (alive[k]) {
+                const float tf = (float)tfv[k];
+                const float add = rank < vec_end ? bm25_from_norm_vector(tf, sh.nv_s[j0 + k], tm.idf) : bm25_scalar(tf, ix.doc_len[sh.cand_s[j0 + k]], avgdl, tm.idf);
+                sh.score[j0 + k] += add; rank++;
             }
-            zero8(tfb + j);
+            if (tfv[k] != 0) tfb[j0 + k] = 0;
         }
     }
     // flush, part 1 (see the tiled path): eligibility against the chunk-start threshold, survivors compacted in candidate order
-    const bool full = sh.heap_size >= K; int mine = 0;
-    for (int j = j0; j < j1; j++) if (sh.score[j] > 0.f && (!full || sh.score[j] > thr) && !ix.deleted[sh.cand_s[j]]) mine++;
-    int total; int off = warp_excl(mine, total);
-    for (int j = j0; j < j1; j++) if (sh.score[j] > 0.f && (!full || sh.score[j] > thr) && !ix.deleted[sh.cand_s[j]]) sh.surv[off++] = kv_pack(sh.cand_s[j], sh.score[j]);
-    if (c.lane() == 0) sh.bcast[6] = total;
+    const bool full = sh.heap_size >= K; int mine = 0; bool el[PER];
+    for (int k = 0; k < PER; k++) { el[k] = k < nj && sh.score[j0 + k] > 0.f && (!full || sh.score[j0 + k] > thr) && !ix.deleted[sh.cand_s[j0 + k]]; mine += el[k] ? 1 : 0; }
+    int total; int off = team_excl(mine, total);
+    for (int k = 0; k < PER; k++) if (el[k]) sh.surv[off++] = kv_pack(sh.cand_s[j0 + k], sh.score[j0 + k]);
+    if (ti == 0) sh.bcast[6] = total;
+}
+
+// Prefix precedence (TieredCandidateSelector.TrySelectPrefixCandidates): the candidates are the doc set of the query's first 1-3
+// characters when that set is small enough. Returns its range in ix.prefix.doc_id.
+IFX_FN bool prefix_shortcut(const DevIndex& ix, const QueryPlan& p, int K, int64_t& r0, int64_t& pop) {
+    int maxl = p.tlen < 3 ? p.tlen : 3;
+    for (int len = maxl; len >= 1; len--) {
+        int k = dict_lookup(ix.prefix.keys, p.ttext, len); if (k < 0) continue;
+        r0 = ix.prefix.row_ptr[k]; pop = ix.prefix.row_ptr[k + 1] - r0;
+        if (pop == 0) continue;
+        if (pop > (int64_t)K * 20) continue;
+        if (pop <= (int64_t)K * 10) { int lim = K * 2 < 100 ? K * 2 : 100; return pop >= lim; }
+    }
+    return false;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -723,13 +738,16 @@ IFX_FN void stage1_query(const Ctx& c, const DevIndex& ix, const QueryPlan& p, c
         for (int i = 0; i < p.n_terms; i++) {
             const QTerm& q = p.terms[i];
             if (q.df <= 0 || q.df > ix.stop_term_limit) continue;      // VectorModel.cs:521
-            TermS& t = sh.terms[n]; t.len = q.list_len; t.df = q.df; t.idf = q.idf; t.max_score = q.max_score; t.cursor = 0;
+            TermS& t = sh.terms[n]; t.len = q.list_len; t.df = q.df; t.idf = q.idf; t.max_score = q.max_score; t.cursor = 0; t.term_id = q.term_id;
             if (q.term_id >= 0) { t.docs = ix.post_doc + q.list_off; t.tf = ix.post_tf + q.list_off; int sk = ix.skip_id[q.term_id]; t.skip = sk >= 0 ? ix.skip_ptr + (size_t)sk * (ix.n_cont + 1) : nullptr;
                 int bi = ix.bm_id[q.term_id]; t.bm = bi >= 0 ? ix.bm_bits + (size_t)bi * ix.bm_words : nullptr; t.bmr = bi >= 0 ? ix.bm_rank + (size_t)bi * ix.bm_words : nullptr; }
             else { t.docs = pool + q.list_off; t.tf = nullptr; t.skip = nullptr; t.bm = nullptr; t.bmr = nullptr; }
             n++;
         }
         float suf = 0.f; for (int i = n - 1; i >= 0; i--) { sh.terms[i].suffix_after = suf; suf = suf + sh.terms[i].max_score; }   // ComputeSuffixSums
+        for (int i = 0; i < QH_SIZE; i++) sh.qh_key[i] = -1;
+        for (int i = 0; i < n; i++) { const TermS& t = sh.terms[i]; if (t.term_id < 0 || t.idf <= 0.f) continue;      // (ids are unique within a query)
+            unsigned h = qh_hash(t.term_id); while (sh.qh_key[h] >= 0) h = (h + 1) & (QH_SIZE - 1); sh.qh_key[h] = t.term_id; sh.qh_slot[h] = (uint8_t)i; }
         sh.n_terms = n; sh.heap_size = 0; sh.thr = 0.f; sh.streamed_mask[0] = sh.streamed_mask[1] = 0;
         for (int i = 0; i < MAX_K + 8; i++) sh.heap_kv[i] = kv_pack(0, 3.0e38f);    // sentinels (any real BM25 score is far smaller)
         out.n[0] = 0;
@@ -747,17 +765,7 @@ IFX_FN void stage1_query(const Ctx& c, const DevIndex& ix, const QueryPlan& p, c
 #define IFX_STICK(k) do { } while (0)
 #endif
     const int32_t* cand = nullptr; int64_t n_cand = 0;
-    if (c.tid() == 0) {   // prefix precedence (TrySelectPrefixCandidates)
-        sh.bcast64[0] = -1; sh.bcast64[1] = 0;
-        int maxl = p.tlen < 3 ? p.tlen : 3;
-        for (int len = maxl; len >= 1; len--) {
-            int k = dict_lookup(ix.prefix.keys, p.ttext, len); if (k < 0) continue;
-            int64_t r0 = ix.prefix.row_ptr[k], pop = ix.prefix.row_ptr[k + 1] - r0;
-            if (pop == 0) continue;
-            if (pop > (int64_t)K * 20) continue;
-            if (pop <= (int64_t)K * 10) { int lim = K * 2 < 100 ? K * 2 : 100; if (pop >= lim) { sh.bcast64[0] = r0; sh.bcast64[1] = pop; } break; }
-        }
-    }
+    if (c.tid() == 0) { sh.bcast64[0] = -1; sh.bcast64[1] = 0; int64_t r0, pop; if (prefix_shortcut(ix, p, K, r0, pop)) { sh.bcast64[0] = r0; sh.bcast64[1] = pop; } }
     c.sync();
     unsigned long long algo = 0;
     if (sh.bcast64[0] >= 0) { cand = ix.prefix.doc_id + sh.bcast64[0]; n_cand = sh.bcast64[1]; algo += 4ULL * (unsigned long long)n_cand; }
@@ -884,12 +892,19 @@ IFX_FN void stage1_query(const Ctx& c, const DevIndex& ix, const QueryPlan& p, c
             }
             c.sync_workers(NTW);
             const int cnt = sh.bcast[2]; const bool whole_container = sh.bcast[4] != 0;
-            for (int j = wt; j < cnt; j += NTW) { int d = cand[pos + j]; sh.cand_s[j] = d; float dl = ix.doc_len[d]; sh.nv_s[j] = bm25_norm_vector(dl, avgdl); sh.score[j] = 0.f; }
+            for (int jb = wt; jb < cnt; jb += 4 * NTW) {             // four candidates per thread in flight (id -> length is a dependent load)
+                int d[4]; float dl[4];
+                for (int u = 0; u < 4; u++) { int j = jb + u * NTW; d[u] = j < cnt ? cand[pos + j] : -1; }
+                for (int u = 0; u < 4; u++) dl[u] = d[u] >= 0 ? ix.doc_len[d[u]] : 0.f;
+                for (int u = 0; u < 4; u++) if (d[u] >= 0) { int j = jb + u * NTW; sh.cand_s[j] = d[u]; sh.nv_s[j] = bm25_norm_vector(dl[u], avgdl); sh.score[j] = 0.f; }
+            }
             c.sync_workers(NTW);
             IFX_WTICK(0);  // container run + candidate ids, lengths, norms
             const int32_t first = sh.cand_s[0], last = sh.cand_s[cnt - 1];
+            const bool small = cnt <= SMALL_CHUNK && T <= SMALL_TERMS;
             for (int t = c.warp() - hw / Ctx::WS; t < T; t += NW - hw / Ctx::WS) {   // posting sub-range of every term for this chunk (monotone cursors); one warp per term, 32-way searches
                 TermS& tm = sh.terms[t];
+                if (small && tm.term_id >= 0) continue;          // small chunks reach dictionary terms through the forward index
                 int64_t lo = tm.cursor, hi = tm.len;
                 if (tm.skip) { int cc = first >> 16; int64_t b0 = tm.skip[cc], b1 = tm.skip[cc + 1]; if (b0 > lo) lo = b0; hi = b1; if (lo > hi) lo = hi; }   // window = this container's postings
                 int64_t s0, s1;
@@ -902,12 +917,23 @@ IFX_FN void stage1_query(const Ctx& c, const DevIndex& ix, const QueryPlan& p, c
             }
             c.sync_workers(NTW);
             IFX_WTICK(1);  // posting sub-range bounds
-            if (cnt <= SMALL_CHUNK && T <= SMALL_TERMS) {
-                // small chunk: tf of ALL terms now, one warp per term (probes / binary searches only), for the single-warp scorer
+            if (small) {
+                // Small chunk: tf of ALL terms now, for the single-warp scorer. Dictionary terms: one warp per candidate walks the doc's
+                // forward list (a few dozen (term, tf) pairs, one coalesced read) and keeps the pairs whose term is in the query's hash --
+                // one memory latency per candidate instead of a binary search per (candidate, term). Fuzzy unions have no term id: they
+                // are searched in their pool list, one warp per term.
+                uint8_t* tfs = &sh.tfm[0][0];
+                for (int j = c.warp() - hw / Ctx::WS; j < cnt; j += NW - hw / Ctx::WS) {
+                    const int d = sh.cand_s[j]; const int64_t r0 = ix.fwd_ptr[d], r1 = ix.fwd_ptr[d + 1];
+                    for (int64_t i = r0 + c.lane(); i < r1; i += Ctx::WS) {
+                        const int32_t tid = ix.fwd_term[i]; unsigned h = qh_hash(tid);
+                        for (;;) { const int32_t k = sh.qh_key[h]; if (k == tid) { tfs[(int)sh.qh_slot[h] * SMALL_CHUNK + j] = ix.fwd_tf[i]; break; } if (k < 0) break; h = (h + 1) & (QH_SIZE - 1); }
+                    }
+                }
                 for (int t = c.warp() - hw / Ctx::WS; t < T; t += NW - hw / Ctx::WS) {
                     const TermS& tm = sh.terms[t];
-                    if (tm.idf <= 0.f || tm.s1 == tm.s0) continue;
-                    stage1_lookup_term(sh, tm, &sh.tfm[0][0] + t * SMALL_CHUNK, cnt, c.lane(), Ctx::WS, false);
+                    if (tm.term_id >= 0 || tm.idf <= 0.f || tm.s1 == tm.s0) continue;
+                    stage1_lookup_term(sh, tm, tfs + t * SMALL_CHUNK, cnt, c.lane(), Ctx::WS, false);
                 }
             } else {
             // Container-local bitmap of the chunk's candidates + per-word rank directory: posting -> candidate slot in O(1)
@@ -933,7 +959,7 @@ IFX_FN void stage1_query(const Ctx& c, const DevIndex& ix, const QueryPlan& p, c
         IFX_TICK(0);   // heap warp waiting for the workers (set-up + phase A beyond the drain)
         const int cnt = sh.bcast[2];
         if (cnt <= SMALL_CHUNK && T <= SMALL_TERMS) {
-            if (c.warp() == hw / Ctx::WS) stage1_small_chunk(c, ix, sh, T, cnt, K, avgdl);
+            if (c.warp() >= hw / Ctx::WS && c.warp() < hw / Ctx::WS + SMALL_TEAM) stage1_small_chunk(c, ix, sh, T, cnt, K, avgdl, hw / Ctx::WS);
             c.sync();
             pend = sh.bcast[6]; pos += cnt;
             IFX_TICK(3);

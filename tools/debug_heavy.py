@@ -22,6 +22,9 @@ wp = dbg[:, 12:20].sum(0); print("worker-view cycles share: ids+norms %.1f%% bou
 for i in order[:8]: print("   W", qs[i][:30], (dbg[i, 12:20] / 1e3).astype(int), "kcycles")
 for i in order[:8]: print("   S", qs[i][:30], (dbg[i, 20:24] / 1e3).astype(int), "kcycles [prefix+sort, tier0/unions, tier1, compact]")
 print("total eligible", int((dbg[:, 11] & 0xFFFFF).sum()), "total heap updates", int((dbg[:, 11] >> 20).sum()))
+for pth in (1, 2, 3):
+    sel = dbg[:, 3] == pth
+    if sel.any(): print("path", pth, "n", int(sel.sum()), "mean cand", int(dbg[sel, 0].mean()), "mean T %.1f" % dbg[sel, 1].mean(), "mean total kcyc", int(dbg[sel, 4].mean() * 1.92e-3 * 1e3 / 1e3), "| heap-warp view kcyc", (dbg[sel, 6:11].mean(0) / 1e3).astype(int), "| worker view kcyc", (dbg[sel, 12:20].mean(0) / 1e3).astype(int), "| sel kcyc", (dbg[sel, 20:24].mean(0) / 1e3).astype(int))
 c = dbg[:, 0]; print("cand percentiles", np.percentile(c, [50, 90, 99, 100]).astype(int), "mean", int(c.mean()))
 # per-CTA busy time
 busy = {}
