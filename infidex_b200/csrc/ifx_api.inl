@@ -30,7 +30,6 @@ static void h2d(void* d, const void* s, size_t n) { if (n) memcpy(d, s, n); }
 static void d2h(void* d, const void* s, size_t n) { if (n) memcpy(d, s, n); }
 static void dev_zero(void* d, size_t n) { if (n) memset(d, 0, n); }
 struct Timer { void start() {} float stop() { return 0.f; } };
-static const int kS1Threads = 1;
 #else
 #define CUDA_TRY(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) throw std::string(#x ": ") + cudaGetErrorString(e_); } while (0)
 static bool dev_ok() { int n = 0; return cudaGetDeviceCount(&n) == cudaSuccess && n > 0; }
@@ -42,7 +41,9 @@ static void dev_zero(void* d, size_t n) { if (n) CUDA_TRY(cudaMemset(d, 0, n)); 
 struct Timer { cudaEvent_t a = nullptr, b = nullptr; cudaStream_t s = 0;
     void start() { if (!a) { cudaEventCreate(&a); cudaEventCreate(&b); } cudaEventRecord(a, s); }
     float stop() { cudaEventRecord(b, s); cudaEventSynchronize(b); float ms = 0; cudaEventElapsedTime(&ms, a, b); return ms; } };
-static const int kS1Threads = 256;
+#ifndef IFX_EXPAND_THREADS
+#define IFX_EXPAND_THREADS 512
+#endif
 #ifndef IFX_S1_THREADS
 #define IFX_S1_THREADS 512
 #endif

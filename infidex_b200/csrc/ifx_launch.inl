@@ -23,7 +23,7 @@ __global__ void k_order(DevIndex ix, const QueryPlan* plans, int nq, int* order)
     __syncthreads();
     for (int q = threadIdx.x; q < nq; q += blockDim.x) { int pos = atomicAdd(&base[bucket(q)], 1); order[pos] = q; }
 }
-__global__ void __launch_bounds__(256) k_expand(DevIndex ix, QueryPlan* plans, const FuzzyItem* items, BatchCounters* bc, S1Workspace* wss,
+__global__ void __launch_bounds__(IFX_EXPAND_THREADS, 2) k_expand(DevIndex ix, QueryPlan* plans, const FuzzyItem* items, BatchCounters* bc, S1Workspace* wss,
                                                 int32_t* pool, unsigned long long pool_cap, const uint8_t* sorted_len, int* work) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     S1Shared& sh = *reinterpret_cast<S1Shared*>(smem_raw); Ctx c; S1Workspace ws = wss[blockIdx.x];
@@ -83,7 +83,7 @@ static void run_stage1_phase(ifx_batch* b, ifx_stats* st) {
     float ms_prep = t.stop();
     t.start();
     CUDA_TRY(cudaMemsetAsync(b->d_work, 0, 2 * sizeof(int)));
-    k_expand<<<ix->n_ctas, kS1Threads, smem>>>(ix->v, b->d_plans, b->d_items, b->d_bc, ix->d_ws, ix->d_pool, ix->pool_cap, ix->d_sorted_len, b->d_work);
+    k_expand<<<ix->n_ctas, IFX_EXPAND_THREADS, smem>>>(ix->v, b->d_plans, b->d_items, b->d_bc, ix->d_ws, ix->d_pool, ix->pool_cap, ix->d_sorted_len, b->d_work);
     float ms_exp = t.stop();
     t.start();
     k_order<<<1, 1024>>>(ix->v, b->d_plans, nq, b->d_order);
