@@ -127,6 +127,8 @@ struct Ctx {
 inline unsigned atomic_or(unsigned* p, unsigned v) { unsigned o = *p; *p = o | v; return o; }
 inline int atomic_add(int* p, int v) { int o = *p; *p = o + v; return o; }
 inline unsigned atomic_and(unsigned* p, unsigned v) { unsigned o = *p; *p = o & v; return o; }
+inline int atomic_min(int* p, int v) { int o = *p; if (v < o) *p = v; return o; }
+inline int atomic_max(int* p, int v) { int o = *p; if (v > o) *p = v; return o; }
 inline unsigned long long atomic_add64(unsigned long long* p, unsigned long long v) { unsigned long long o = *p; *p = o + v; return o; }
 inline int popc(unsigned v) { return __builtin_popcount(v); }
 inline int ffs32(unsigned v) { return __builtin_ffs((int)v); }
@@ -149,6 +151,8 @@ struct Ctx {
 __device__ __forceinline__ unsigned atomic_or(unsigned* p, unsigned v) { return atomicOr(p, v); }
 __device__ __forceinline__ int atomic_add(int* p, int v) { return atomicAdd(p, v); }
 __device__ __forceinline__ unsigned atomic_and(unsigned* p, unsigned v) { return atomicAnd(p, v); }
+__device__ __forceinline__ int atomic_min(int* p, int v) { return atomicMin(p, v); }
+__device__ __forceinline__ int atomic_max(int* p, int v) { return atomicMax(p, v); }
 __device__ __forceinline__ unsigned long long atomic_add64(unsigned long long* p, unsigned long long v) { return atomicAdd(p, v); }
 __device__ __forceinline__ int popc(unsigned v) { return __popc(v); }
 __device__ __forceinline__ int ffs32(unsigned v) { return __ffs((int)v); }

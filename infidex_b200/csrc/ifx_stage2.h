@@ -300,7 +300,10 @@ struct FinShared {
     float score[2 * MAX_K]; int32_t idx[2 * MAX_K]; int32_t pos[2 * MAX_K];
     int32_t keep_doc[MAX_K]; float keep_score[MAX_K]; uint8_t keep_tie[MAX_K];
     int n_keep; int bcast[8]; ScanTmp scan;
-    int32_t fv[MAX_K]; int32_t fc[MAX_K];
+    union {                                                   // never live at the same time: sort keys vs. facet scratch
+        struct { int64_t ekey[2 * MAX_K]; uint8_t etie[2 * MAX_K]; };   // per entry: document key and tiebreaker (the sort's comparator reads them on score ties)
+        struct { int32_t fv[MAX_K]; int32_t fc[MAX_K]; };
+    };
 };
 
 IFX_FN void finalize_query(const Ctx& c, const DevIndex& ix, const QueryPlan& p, const int32_t* s1_doc, const float* s1_score, int n1,
@@ -315,7 +318,7 @@ IFX_FN void finalize_query(const Ctx& c, const DevIndex& ix, const QueryPlan& p,
         int n2 = 1; while (n2 < ne) n2 <<= 1;
         int mh = 0, ovf = 0;
         for (int i = c.tid(); i < n2; i += NT) {
-            if (i < ne) { int h = B.ent_hits[eo + i]; sh.idx[i] = h < 0 ? -1 : i; sh.score[i] = h < 0 ? -2.f : B.ent_score[eo + i]; if (h >= 0) { if (h & 0x40000000) ovf = 1; h &= 0x3fffffff; if (h > mh) mh = h; } }
+            if (i < ne) { int h = B.ent_hits[eo + i]; sh.etie[i] = B.ent_tie[eo + i]; sh.ekey[i] = ix.doc_key[B.ent_doc[eo + i]]; sh.idx[i] = h < 0 ? -1 : i; sh.score[i] = h < 0 ? -2.f : B.ent_score[eo + i]; if (h >= 0) { if (h & 0x40000000) ovf = 1; h &= 0x3fffffff; if (h > mh) mh = h; } }
             else { sh.idx[i] = -1; sh.score[i] = -2.f; }
         }
         c.sync();
@@ -337,8 +340,8 @@ IFX_FN void finalize_query(const Ctx& c, const DevIndex& ix, const QueryPlan& p,
             int ia = sh.idx[a], ib = sh.idx[b];
             if (ia < 0 || ib < 0) return ia >= 0 && ib < 0;
             float sa = sh.score[a], sb = sh.score[b]; if (sa != sb) return sa > sb;
-            uint8_t ta = B.ent_tie[eo + ia], tb = B.ent_tie[eo + ib]; if (ta != tb) return ta > tb;
-            int64_t ka = ix.doc_key[B.ent_doc[eo + ia]], kb = ix.doc_key[B.ent_doc[eo + ib]]; if (ka != kb) return ka < kb;
+            uint8_t ta = sh.etie[ia], tb = sh.etie[ib]; if (ta != tb) return ta > tb;
+            int64_t ka = sh.ekey[ia], kb = sh.ekey[ib]; if (ka != kb) return ka < kb;
             return ia < ib;
         };
         for (int k = 2; k <= n2; k <<= 1) for (int j = k >> 1; j > 0; j >>= 1) {
@@ -349,25 +352,43 @@ IFX_FN void finalize_query(const Ctx& c, const DevIndex& ix, const QueryPlan& p,
         c.sync();
         for (int i = c.tid(); i < n2; i += NT) if (sh.idx[i] >= 0) sh.pos[sh.idx[i]] = i;
         c.sync();
-        // TopKHeap(K) keeps the K best entries; ConsolidateSegments keeps the better of two entries with the same key
+        // TopKHeap(K) keeps the K best entries; ConsolidateSegments keeps the better of two entries with the same key.
+        // Valid entries sort in front of the invalid ones, so "the first K valid positions" is a prefix: per-position keep flags
+        // and an ordered compaction, round by round.
+        const int lim = n2 < K ? n2 : K; int nk = 0;
+        for (int base = 0; base < lim; base += NT) {
+            const int i = base + c.tid(); int e = -1; bool keep = false;
+            if (i < lim) { e = sh.idx[i]; if (e >= 0) { int tw = B.ent_twin[eo + e]; keep = !(tw >= 0 && sh.pos[tw] < i); } }
+            int tot; int off = block_excl_scan(c, keep ? 1 : 0, sh.scan, tot);
+            if (keep) { sh.keep_doc[nk + off] = B.ent_doc[eo + e]; sh.keep_score[nk + off] = sh.score[i]; sh.keep_tie[nk + off] = sh.etie[e]; }
+            nk += tot;
+        }
+        // ResultProcessor.CalculateTruncationIndex: only docIndex 0/1 have stored word hits / lcs (Span2D height-2 quirk): for each of
+        // the two docs, the word hits of its first entry with non-zero hits and the lcs of its last entry (in entry order)
+        const int d0 = B.di_doc[q * 2], d1 = B.di_doc[q * 2 + 1];
+        if (c.tid() == 0) { sh.bcast[0] = 0x7fffffff; sh.bcast[1] = -1; sh.bcast[2] = 0x7fffffff; sh.bcast[3] = -1; sh.bcast[4] = -1; }
+        c.sync();
+        auto clamp_hits = [&](int e) { int h = B.ent_hits[eo + e] & 0x3fffffff; return h > 255 ? 255 : h; };
+        for (int e = c.tid(); e < ne; e += NT) {
+            if (B.ent_hits[eo + e] < 0) continue;
+            const int dd = B.ent_doc[eo + e];
+            if (dd == d0) { if (clamp_hits(e) != 0) atomic_min(&sh.bcast[0], e); atomic_max(&sh.bcast[1], e); }
+            else if (dd == d1) { if (clamp_hits(e) != 0) atomic_min(&sh.bcast[2], e); atomic_max(&sh.bcast[3], e); }
+        }
+        c.sync();
+        const int wh0 = sh.bcast[0] != 0x7fffffff ? clamp_hits(sh.bcast[0]) : 0, l0 = sh.bcast[1] >= 0 ? (int)B.ent_lcs[eo + sh.bcast[1]] : 0;
+        const int wh1 = sh.bcast[2] != 0x7fffffff ? clamp_hits(sh.bcast[2]) : 0, l1 = sh.bcast[3] >= 0 ? (int)B.ent_lcs[eo + sh.bcast[3]] : 0;
+        const int min_hits = max_hits > 1 ? max_hits : 1;
+        for (int i = c.tid(); i < nk; i += NT) {                     // last kept record that clears the truncation test
+            int dd = sh.keep_doc[i]; int wh = dd == d0 ? wh0 : (dd == d1 ? wh1 : 0); int lb = dd == d0 ? l0 : (dd == d1 ? l1 : 0);
+            if (wh >= min_hits || lb > 0 || sh.keep_score[i] >= 254.f) atomic_max(&sh.bcast[4], i);
+        }
+        c.sync();
         if (c.tid() == 0) {
-            int nk = 0;
-            for (int i = 0; i < n2 && i < K; i++) {
-                int e = sh.idx[i]; if (e < 0) break;
-                int tw = B.ent_twin[eo + e];
-                if (tw >= 0 && sh.pos[tw] < i) continue;
-                sh.keep_doc[nk] = B.ent_doc[eo + e]; sh.keep_score[nk] = sh.score[i]; sh.keep_tie[nk] = B.ent_tie[eo + e]; nk++;
-            }
             int result = nk;
             if (max_hits == 0 && !B.wm_any[q]) result = -1;                 // SearchPipeline.cs:418-419 -> coverage returned []
             else if (nk > 0) {
-                // ResultProcessor.CalculateTruncationIndex: only docIndex 0/1 have stored word hits / lcs (Span2D height-2 quirk)
-                int d0 = B.di_doc[q * 2], d1 = B.di_doc[q * 2 + 1]; int wh0 = 0, wh1 = 0, l0 = 0, l1 = 0;
-                for (int e = 0; e < ne; e++) { int h = B.ent_hits[eo + e]; if (h < 0) continue; h &= 0x3fffffff; if (h > 255) h = 255; int dd = B.ent_doc[eo + e];
-                    if (dd == d0) { if (wh0 == 0) wh0 = h; l0 = B.ent_lcs[eo + e]; } else if (dd == d1) { if (wh1 == 0) wh1 = h; l1 = B.ent_lcs[eo + e]; } }
-                int min_hits = max_hits > 1 ? max_hits : 1; int trunc = -1;
-                for (int i = nk - 1; i >= 0; i--) { int dd = sh.keep_doc[i]; int wh = dd == d0 ? wh0 : (dd == d1 ? wh1 : 0); int lb = dd == d0 ? l0 : (dd == d1 ? l1 : 0);
-                    if (wh >= min_hits || lb > 0 || sh.keep_score[i] >= 254.f) { trunc = i; break; } }
+                const int trunc = sh.bcast[4];
                 int count = trunc == -1 ? p.max_results : (trunc + 1 < p.max_results ? trunc + 1 : p.max_results);
                 if (result > count) result = count;
             }
