@@ -210,6 +210,7 @@ extern "C" int ifx_index_create(const ifx_index_image* img, const ifx_params* pp
             const uint16_t dl[] = {' ', '-', '/', '.', ',', ':', ';', '\'', '`', 0x2013, 0x2014, '*', '&', '\\', '_', '(', ')', '{', '}', '[', ']', '\t'};
             for (uint16_t c : dl) fl[c] |= 4;
             v.lower = ix->up(lo.data(), 65536); v.upper = ix->up(upv.data(), 65536); v.cflags = ix->up(fl.data(), 65536);
+            for (int k = 0; k < 4; k++) v.delim_ascii[k] = 0u; for (int ch = 0; ch < 128; ch++) if (fl[ch] & 4) v.delim_ascii[ch >> 5] |= 1u << (ch & 31);
             std::vector<float> l2(1024); for (int i = 0; i < 1024; i++) l2[i] = std::log2((float)(i + 1));
             v.log2_len = ix->up(l2.data(), 1024);
             int tn = std::max(1, std::min(img->n_live, P.stop_term_limit)) + 1; std::vector<float> idf(tn, 0.f);

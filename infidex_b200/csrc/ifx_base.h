@@ -81,6 +81,7 @@ struct DevIndex {
     const int32_t* affix_rev;        // indices into `affix`, ordered by the reversed string
     const int32_t* affix_rev_doc;    // last doc, in reverse-trie order
     const uint16_t* lower; const uint16_t* upper; const uint8_t* cflags;   // 65536-entry tables
+    unsigned delim_ascii[4];         // bit c set: ASCII char c is a token delimiter (cflags[c] & 4), kept in the kernel parameters
     const float* log2_len;           // MathF.Log2(len + 1) for len < 1024 (host glibc)
     const float* idf_table;          // Bm25Scorer.ComputeIdf(n_live, df) for df in [0, idf_table_n): evaluated on the host with the
     int32_t idf_table_n;             // C runtime's logf (what MathF.Log calls), so device scores cannot drift from the reference by an ulp

@@ -17,11 +17,15 @@ struct Str { const uint16_t* p; int n; };
 
 IFX_FN uint16_t up_c(const DevIndex& ix, uint16_t c) { return c < 128 ? (uint16_t)((c >= 'a' && c <= 'z') ? c - 32 : c) : ix.upper[c]; }
 IFX_FN uint16_t lo_c(const DevIndex& ix, uint16_t c) { return c < 128 ? (uint16_t)((c >= 'A' && c <= 'Z') ? c + 32 : c) : ix.lower[c]; }
-IFX_FN bool delim_c(const DevIndex& ix, uint16_t c) { return ix.cflags[c] & 4; }
+IFX_FN bool delim_c(const DevIndex& ix, uint16_t c) { return c < 128 ? ((ix.delim_ascii[c >> 5] >> (c & 31)) & 1u) != 0 : (ix.cflags[c] & 4) != 0; }
 
 IFX_FN bool eq_ic(const DevIndex& ix, Str a, Str b) {
     if (a.n != b.n) return false;
-    for (int i = 0; i < a.n; i++) if (a.p[i] != b.p[i] && up_c(ix, a.p[i]) != up_c(ix, b.p[i])) return false;
+    for (int i = 0; i < a.n; i++) {
+        const unsigned x = a.p[i], y = b.p[i]; if (x == y) continue;
+        if ((x | y) < 128u) { const unsigned l = x | 0x20u; if ((x ^ y) != 0x20u || l < 'a' || l > 'z') return false; }   // ASCII: equal ignoring case = same letter, other case
+        else if (up_c(ix, (uint16_t)x) != up_c(ix, (uint16_t)y)) return false;
+    }
     return true;
 }
 IFX_FN Str sub(Str s, int off, int n) { Str r; r.p = s.p + off; r.n = n; return r; }
@@ -41,13 +45,14 @@ IFX_FN int lev(const DevIndex& ix, Str pattern, Str text, int max_errors, bool i
     if (pattern.n > text.n) { Str t = pattern; pattern = text; text = t; }
     int m = pattern.n, n = text.n;
     if (m > MAX_TOKLEN) return max_errors + 1;
-    int costs[MAX_TOKLEN + 1];
+    int costs[MAX_TOKLEN + 1]; uint16_t pat[MAX_TOKLEN];          // the (case-folded) pattern is read n times: fold it once
     for (int i = 0; i <= m; i++) costs[i] = i;
+    for (int i = 0; i < m; i++) pat[i] = ic ? up_c(ix, pattern.p[i]) : pattern.p[i];
     for (int j = 0; j < n; j++) {
         uint16_t tv = ic ? up_c(ix, text.p[j]) : text.p[j];
         int diag = costs[0]; costs[0] = j + 1; int minc = costs[0];
         for (int i = 0; i < m; i++) {
-            int left = costs[i + 1], upv = costs[i]; uint16_t pv = ic ? up_c(ix, pattern.p[i]) : pattern.p[i]; int cost;
+            int left = costs[i + 1], upv = costs[i]; uint16_t pv = pat[i]; int cost;
             if (tv == pv) cost = diag; else { cost = upv + 1; if (left + 1 < cost) cost = left + 1; if (diag + 1 < cost) cost = diag + 1; }
             diag = left; costs[i + 1] = cost; if (cost < minc) minc = cost;
         }

@@ -206,7 +206,7 @@ struct S1Shared {
     int heap_size; float thr;
     // .NET PriorityQueue nodes packed as (doc << 32 | float bits of the priority), stored with a +3 shift so the four children of
     // node i (4i+1..4i+4) form one aligned 32-byte group; slots beyond the current size hold +huge sentinels
-    alignas(32) unsigned long long heap_kv[MAX_K + 8];
+    alignas(16) float heap_pr[MAX_K + 8]; int32_t heap_doc[MAX_K + 8];   // split so that one 16-byte load fetches the four child priorities
     int32_t qh_key[QH_SIZE]; uint8_t qh_slot[QH_SIZE];   // term id -> slot in `terms` (open addressing; terms with idf > 0 only), for the forward-index lookups
     unsigned long long surv[SURV_CAP];     // (doc, score) of the last chunk's flush survivors, drained into the heap while the next chunk is staged
     union {                               // never live at the same time: selection/compaction vs. chunk scoring
@@ -453,32 +453,31 @@ IFX_FN unsigned long long kv_pack(int doc, float pr) {
     return ((unsigned long long)(unsigned)doc << 32) | __float_as_uint(pr);
 #endif
 }
-#define IFX_KV(i) heap_kv[(i) + 3]
+#define IFX_HP(i) heap_pr[(i) + 3]
+#define IFX_HD(i) heap_doc[(i) + 3]
 IFX_FN void heap_move_up(S1Shared& sh, int doc, float pr, int idx) {
-    while (idx > 0) { int parent = (idx - 1) >> 2; unsigned long long pk = sh.IFX_KV(parent); if (pr < kv_score(pk)) { sh.IFX_KV(idx) = pk; idx = parent; } else break; }
-    sh.IFX_KV(idx) = kv_pack(doc, pr);
+    while (idx > 0) { int parent = (idx - 1) >> 2; float pp = sh.IFX_HP(parent); if (pr < pp) { sh.IFX_HP(idx) = pp; sh.IFX_HD(idx) = sh.IFX_HD(parent); idx = parent; } else break; }
+    sh.IFX_HP(idx) = pr; sh.IFX_HD(idx) = doc;
 }
 // PriorityQueue.DequeueEnqueue on a full heap (the root is replaced and sifted down); returns the new root priority so the caller
 // can keep the threshold in a register. PriorityQueue.MoveDown picks the first strictly-smallest of the (up to) four children; here as
-// a two-level tournament with the same winner (ties keep the lower index at both levels).
-IFX_FN float heap_replace_root(S1Shared& sh, unsigned long long kv, int sz) {
-    const float pr = kv_score(kv); int idx = 0, i; float root = pr;
+// a two-level tournament with the same winner (ties keep the lower index at both levels). Only the priorities are on the
+// dependent chain; the document id of a moved node follows with one load/store off it.
+IFX_FN float heap_replace_root(S1Shared& sh, int doc, float pr, int sz) {
+    int idx = 0, i; float root = pr;
     while ((i = 4 * idx + 1) < sz) {
 #ifdef IFX_EMU
-        unsigned long long k0 = sh.IFX_KV(i), k1 = sh.IFX_KV(i + 1), k2 = sh.IFX_KV(i + 2), k3 = sh.IFX_KV(i + 3);
+        const float p0 = sh.IFX_HP(i), p1 = sh.IFX_HP(i + 1), p2 = sh.IFX_HP(i + 2), p3 = sh.IFX_HP(i + 3);
 #else
-        const ulonglong2 va = *reinterpret_cast<const ulonglong2*>(&sh.heap_kv[i + 3]); const ulonglong2 vb = *reinterpret_cast<const ulonglong2*>(&sh.heap_kv[i + 5]);
-        unsigned long long k0 = va.x, k1 = va.y, k2 = vb.x, k3 = vb.y;
+        const float4 v = *reinterpret_cast<const float4*>(&sh.heap_pr[i + 3]); const float p0 = v.x, p1 = v.y, p2 = v.z, p3 = v.w;
 #endif
-        const bool b01 = kv_score(k1) < kv_score(k0), b23 = kv_score(k3) < kv_score(k2);
-        const unsigned long long ka = b01 ? k1 : k0, kb = b23 ? k3 : k2;
-        const bool bb = kv_score(kb) < kv_score(ka);
-        const unsigned long long mk = bb ? kb : ka; const int mi = i + (bb ? (b23 ? 3 : 2) : (b01 ? 1 : 0));
-        if (!(kv_score(mk) < pr)) break;
-        sh.IFX_KV(idx) = mk; if (idx == 0) root = kv_score(mk);
+        const bool b01 = p1 < p0, b23 = p3 < p2; const float pa = b01 ? p1 : p0, pb = b23 ? p3 : p2;
+        const bool bb = pb < pa; const float mp = bb ? pb : pa; const int mi = i + (bb ? (b23 ? 3 : 2) : (b01 ? 1 : 0));
+        if (!(mp < pr)) break;
+        sh.IFX_HP(idx) = mp; sh.IFX_HD(idx) = sh.IFX_HD(mi); if (idx == 0) root = mp;
         idx = mi;
     }
-    sh.IFX_KV(idx) = kv;
+    sh.IFX_HP(idx) = pr; sh.IFX_HD(idx) = doc;
     return root;
 }
 
@@ -749,7 +748,7 @@ IFX_FN void stage1_query(const Ctx& c, const DevIndex& ix, const QueryPlan& p, c
         for (int i = 0; i < n; i++) { const TermS& t = sh.terms[i]; if (t.term_id < 0 || t.idf <= 0.f) continue;      // (ids are unique within a query)
             unsigned h = qh_hash(t.term_id); while (sh.qh_key[h] >= 0) h = (h + 1) & (QH_SIZE - 1); sh.qh_key[h] = t.term_id; sh.qh_slot[h] = (uint8_t)i; }
         sh.n_terms = n; sh.heap_size = 0; sh.thr = 0.f; sh.streamed_mask[0] = sh.streamed_mask[1] = 0;
-        for (int i = 0; i < MAX_K + 8; i++) sh.heap_kv[i] = kv_pack(0, 3.0e38f);    // sentinels (any real BM25 score is far smaller)
+        for (int i = 0; i < MAX_K + 8; i++) { sh.heap_pr[i] = 3.0e38f; sh.heap_doc[i] = 0; }    // sentinels (any real BM25 score is far smaller)
         out.n[0] = 0;
     }
     c.sync();
@@ -865,8 +864,8 @@ IFX_FN void stage1_query(const Ctx& c, const DevIndex& ix, const QueryPlan& p, c
         float thr_r = sh.thr; int hs = sh.heap_size;           // threshold and size live in registers for the whole drain
         auto one = [&](unsigned long long kv) {
             const float s = kv_score(kv); IFX_COUNT(1);
-            if (hs < K) { heap_move_up(sh, (int)(kv >> 32), s, hs); hs++; if (hs == K) thr_r = kv_score(sh.IFX_KV(0)); IFX_COUNT(1 << 20); }
-            else if (s > thr_r) { thr_r = heap_replace_root(sh, kv, hs); IFX_COUNT(1 << 20); }
+            if (hs < K) { heap_move_up(sh, (int)(kv >> 32), s, hs); hs++; if (hs == K) thr_r = sh.IFX_HP(0); IFX_COUNT(1 << 20); }
+            else if (s > thr_r) { thr_r = heap_replace_root(sh, (int)(kv >> 32), s, hs); IFX_COUNT(1 << 20); }
         };
         if (pend <= SURV_CAP) { for (int i = 0; i < pend; i++) one(sh.surv[i]); }
         else for (int i = 0; i < pend; i += 8) {               // global staging: eight independent loads in flight, then the sequential updates
@@ -1135,7 +1134,7 @@ IFX_FN void stage1_query(const Ctx& c, const DevIndex& ix, const QueryPlan& p, c
     // ---- PopulateResultHeapFromPruning + TopKHeap.GetTopK + ConsolidateSegments: order by (score desc, key asc)
     const int n = sh.heap_size; int n2 = 1; while (n2 < n) n2 <<= 1;
     float* ks = sh.score; int32_t* kd = sh.cand_s;            // reuse chunk arrays (CHUNK >= MAX_K)
-    for (int i = c.tid(); i < n2; i += NT) { if (i < n) { ks[i] = kv_score(sh.IFX_KV(i)); kd[i] = (int)(sh.IFX_KV(i) >> 32); } else { ks[i] = -1.f; kd[i] = 0x7fffffff; } }
+    for (int i = c.tid(); i < n2; i += NT) { if (i < n) { ks[i] = sh.IFX_HP(i); kd[i] = sh.IFX_HD(i); } else { ks[i] = -1.f; kd[i] = 0x7fffffff; } }
     c.sync();
     auto before = [&](int a, int b) -> bool {   // a ranks before b
         if (ks[a] != ks[b]) return ks[a] > ks[b];
