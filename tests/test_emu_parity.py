@@ -44,3 +44,30 @@ def test_emu_synthetic(emu, multi):
     if multi:
         flt = ib.Filter.Parse("year >= 2000 AND rating > 7.0")
         assert not compare_search(eng, orc, qs[:80], flt=flt, facets=True)
+
+
+def test_emu_ld1_more_than_1024_matches(emu):
+    """An unknown word with > 1024 dictionary terms at edit distance 1: the reference keeps the first 1024 in trie (ordinal) order
+    (VectorModel.cs:662); the unordered fast scan must fall back to the ordered one."""
+    alpha = [chr(c) for c in range(0x4E00, 0x4E00 + 330)]          # 330 distinct letters
+    words = [a + "bcd" for a in alpha] + ["a" + a + "cd" for a in alpha] + ["ab" + a + "d" for a in alpha] + ["abc" + a for a in alpha]
+    titles = [w + " filler%d" % (i % 7) for i, w in enumerate(words)]
+    eng = ib.SearchEngine(_gpu_lib=emu); eng.IndexColumns(np.arange(len(titles)), [ib.Field("content")], [titles])
+    orc = OracleEngine(); orc.index_texts(titles, keys=np.arange(len(titles)))
+    qs = ["abcd", "abcd filler3", "xbcd"]
+    assert not compare_stage1(eng, orc, qs)
+    assert not compare_search(eng, orc, qs)
+
+
+def test_emu_dense_terms_and_full_chunks(emu):
+    """Few distinct words over many docs: every list is dense (bitmap AND tiers, bitset-mode intersections), chunks are full
+    (4096 candidates, > 512 flush survivors while the heap fills, ties at the threshold)."""
+    rng = np.random.Generator(np.random.PCG64(7))
+    vocab = ["alpha", "alphabet", "beta", "betamax", "gamma", "gammas", "delta", "deltas", "omega", "omegas", "sigma", "sigmas"]
+    n = 40_000
+    titles = [" ".join(vocab[j] for j in rng.integers(0, len(vocab), int(rng.integers(1, 5)))) for _ in range(n)]
+    eng = ib.SearchEngine(_gpu_lib=emu); eng.IndexColumns(np.arange(n), [ib.Field("content")], [titles])
+    orc = OracleEngine(); orc.index_texts(titles, keys=np.arange(n))
+    qs = ["alpha beta", "alphabet gamma delta", "omegas sigma", "gama", "betamax alpha omega sigma", "delt sigm", "alpha"]
+    assert not compare_stage1(eng, orc, qs)
+    assert not compare_search(eng, orc, qs)
