@@ -91,7 +91,10 @@ __global__ void k_cov_prepare(DevIndex ix, const QueryPlan* plans, int nq, Stage
     int q = blockIdx.x * blockDim.x + threadIdx.x; if (q >= nq) return;
     if (B.mode[q] == 0) prepare_cov_query(ix, plans[q].qtext, plans[q].qlen, B.covq[q]);
 }
-__global__ void __launch_bounds__(128) k_cov_eval(DevIndex ix, const QueryPlan* plans, int nq, Stage2Buffers B) {
+#ifndef IFX_COV_THREADS
+#define IFX_COV_THREADS 512
+#endif
+__global__ void __launch_bounds__(IFX_COV_THREADS) k_cov_eval(DevIndex ix, const QueryPlan* plans, int nq, Stage2Buffers B) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; int q = (int)(i / B.ent_cap), e = (int)(i % B.ent_cap);
     if (q >= nq || B.mode[q] != 0 || e >= B.ent_n[q]) return;
     cov_eval_entry(ix, plans[q], B, q, e);
@@ -124,7 +127,7 @@ static void run_stage2_phase(ifx_batch* b, ifx_stats* st) {
     t.start();
     k_cov_prepare<<<(nq + 63) / 64, 64>>>(ix->v, b->d_plans, nq, b->s2);
     long long total = (long long)nq * b->s2.ent_cap;
-    k_cov_eval<<<(unsigned)((total + 127) / 128), 128>>>(ix->v, b->d_plans, nq, b->s2);
+    k_cov_eval<<<(unsigned)((total + IFX_COV_THREADS - 1) / IFX_COV_THREADS), IFX_COV_THREADS>>>(ix->v, b->d_plans, nq, b->s2);
     float ms_cov = t.stop();
     t.start();
     k_finalize<<<nq, 256, sizeof(FinShared)>>>(ix->v, b->d_plans, nq, b->d_s1_doc, b->d_s1_score, b->d_s1_n, K, b->s2, ix->d_filters, (int)ix->h_filters.size(), b->fin);

@@ -671,7 +671,10 @@ IFX_FN void expand_fuzzy(const Ctx& c, const DevIndex& ix, QueryPlan& p, int fsl
 #ifdef IFX_EMU
 constexpr int SMALL_TEAM = 1;
 #else
-constexpr int SMALL_TEAM = 4;
+#ifndef IFX_SMALL_TEAM
+#define IFX_SMALL_TEAM 8
+#endif
+constexpr int SMALL_TEAM = IFX_SMALL_TEAM;
 #endif
 IFX_FN void stage1_small_chunk(const Ctx& c, const DevIndex& ix, S1Shared& sh, int T, int cnt, int K, float avgdl, int tw0) {
     constexpr int PER = SMALL_CHUNK / (SMALL_TEAM * Ctx::WS);     // 4 slots per thread on the GPU
