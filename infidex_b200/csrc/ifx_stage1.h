@@ -144,13 +144,6 @@ IFX_FN int64_t lower_bound_i32(const int32_t* a, int64_t lo, int64_t hi, int32_t
     while (lo < hi) { int64_t mid = lo + ((hi - lo) >> 1); if (a[mid] < target) lo = mid + 1; else hi = mid; }
     return lo;
 }
-IFX_FN int64_t gallop_lower_bound(const int32_t* a, int64_t from, int64_t n, int32_t target) {
-    if (from >= n || a[from] >= target) return from;
-    int64_t step = 1, lo = from, hi = from + 1;
-    while (hi < n && a[hi] < target) { lo = hi; step <<= 1; hi = lo + step; }
-    if (hi > n) hi = n;
-    return lower_bound_i32(a, lo + 1, hi, target);
-}
 
 // lower bound executed by one full warp: 32-way splits instead of binary halving (log32 n dependent loads).
 // Every lane of the calling warp must participate; the result is uniform across the warp.
@@ -376,25 +369,6 @@ IFX_FN int64_t compact_bits(const Ctx& c, const DevIndex& ix, S1Workspace& ws, S
     return total;
 }
 
-// dst <- elements of src[0..n) that occur in list[0..len) (both ascending). Ordered. Returns count.
-IFX_FN int64_t filter_members(const Ctx& c, const int32_t* src, int64_t n, const int32_t* list, int64_t len, int32_t* dst, S1Shared& sh) {
-    const int E = 8; int64_t total = 0;
-    for (int64_t base = 0; base < n; base += (int64_t)c.nthreads() * E) {
-        int64_t b = base + (int64_t)c.tid() * E, e = b + E; if (e > n) e = n;
-        int32_t keep[E]; int cnt = 0; int64_t lo = 0;
-        for (int64_t i = b; i < e; i++) {
-            int32_t d = src[i];
-            lo = (i == b) ? lower_bound_i32(list, 0, len, d) : gallop_lower_bound(list, lo, len, d);
-            if (lo < len && list[lo] == d) keep[cnt++] = d;
-        }
-        int tot; int off = block_excl_scan(c, cnt, sh.scan, tot);
-        for (int k = 0; k < cnt; k++) dst[total + off + k] = keep[k];
-        total += tot;
-    }
-    c.sync();
-    return total;
-}
-
 // .NET ArraySortHelper<T>.IntrospectiveSort with comparison (b.Idf.CompareTo(a.Idf)) over term indices -- unstable,
 // reproduced exactly because idf ties decide which lists the selector unions (TieredCandidateSelector.cs:128,253).
 struct IdfSorter {
@@ -544,16 +518,9 @@ IFX_FN void stage1_phase_a(const Ctx& c, S1Shared& sh, int t0, int T, int cnt, i
 
 // Bm25Scorer.cs:395-433 (Vector256 lanes) and :643-652 (scalar remainder); must not be contracted into FMAs.
 // The document-length part of both forms depends only on the candidate, so it is evaluated once per chunk and slot:
-//   vector form  norm = K1 * ((1 - B) + (B / avgdl) * dl)        scalar form  norm = K1 * (1 - B + B * (dl / avgdl)), dl <= 0 -> 1
+//   vector form  norm = K1 * ((1 - B) + (B / avgdl) * dl)        (the scalar form, needed for < 8 matches per term and chunk, is recomputed)
 IFX_FN float bm25_norm_vector(float dl, float avgdl) { const float K1 = 1.2f, B = 0.75f; float bdiv = B / avgdl; return K1 * ((1.f - B) + bdiv * dl); }
-IFX_FN float bm25_norm_scalar(float dl, float avgdl) { const float K1 = 1.2f, B = 0.75f; if (dl <= 0.f) dl = 1.f; return K1 * (1.f - B + B * (dl / avgdl)); }
 IFX_FN float bm25_from_norm_vector(float tf, float norm, float idf) { const float K1 = 1.2f, Delta = 1.0f; float denom = tf + norm; float core = (tf * (K1 + 1.0f)) / denom; return idf * (core + Delta); }
-IFX_FN float bm25_from_norm_scalar(float tf, float norm, float idf) { const float K1 = 1.2f, Delta = 1.0f; float denom = tf + norm; if (denom <= 0.f) return 0.f; float core = (tf * (K1 + 1.f)) / denom; return idf * (core + Delta); }
-IFX_FN float bm25_vector(float tf, float dl, float avgdl, float idf) {
-    const float K1 = 1.2f, B = 0.75f, Delta = 1.0f;
-    float bdiv = B / avgdl; float norm = K1 * ((1.f - B) + bdiv * dl); float denom = tf + norm;
-    float core = (tf * (K1 + 1.0f)) / denom; return idf * (core + Delta);
-}
 IFX_FN float bm25_scalar(float tf, float dl, float avgdl, float idf) {
     const float K1 = 1.2f, B = 0.75f, Delta = 1.0f;
     if (dl <= 0.f) dl = 1.f;
@@ -1060,11 +1027,7 @@ IFX_FN void stage1_query(const Ctx& c, const DevIndex& ix, const QueryPlan& p, c
 #pragma unroll
                         for (int k = 0; k < 8; k++) if (alive & (1u << k)) {
                             float tf = (float)((unsigned)(tf8 >> (8 * k)) & 0xFFu);
-                            #ifdef IFX_EXP_NODL   // timing experiment only (wrong scores): no global doc_len load on the scalar tail
-                            float add = rank < vec_end ? bm25_from_norm_vector(tf, nv8[k], tm.idf) : bm25_scalar(tf, nv8[k], avgdl, tm.idf);
-#else
-                            float add = rank < vec_end ? bm25_from_norm_vector(tf, nv8[k], tm.idf) : bm25_scalar(tf, ix.doc_len[sh.cand_s[j0 + k]], avgdl, tm.idf);
-#endif
+                                                        float add = rank < vec_end ? bm25_from_norm_vector(tf, nv8[k], tm.idf) : bm25_scalar(tf, ix.doc_len[sh.cand_s[j0 + k]], avgdl, tm.idf);
                             sc8[k] += add; rank++;
                         }
                         *reinterpret_cast<float4*>(&sh.score[j0]) = make_float4(sc8[0], sc8[1], sc8[2], sc8[3]);
