@@ -44,16 +44,16 @@ def compare_stage1(eng, orc, queries, depth=500):
     return bad
 
 
-def compare_search(eng, orc, queries, max_results=10, flt=None, facets=False, depth=500):
+def compare_search(eng, orc, queries, max_results=10, flt=None, facets=False, depth=500, coverage=True):
     """Identical DocumentId order, Score bits (stricter than the 1e-5 relative tolerance of the north star),
     Tiebreaker bytes, TotalCandidates and facet tables."""
     qs = []
     for q in queries:
-        x = ib.Query(q, max_results); x.Filter = flt; x.EnableFacets = facets; x.CoverageDepth = depth; qs.append(x)
+        x = ib.Query(q, max_results); x.Filter = flt; x.EnableFacets = facets; x.CoverageDepth = depth; x.EnableCoverage = coverage; qs.append(x)
     res = eng.SearchBatch(qs)
     bad = []
     for q, r in zip(queries, res):
-        x = orc.search(q, max_results, depth=depth, filter_bytes=flt.bytecode() if flt else None, facets=facets)
+        x = orc.search(q, max_results, depth=depth, coverage=coverage, filter_bytes=flt.bytecode() if flt else None, facets=facets)
         k = [t.DocumentId for t in r.Records]; s = np.array([t.Score for t in r.Records], np.float32); ti = [t.Tiebreaker for t in r.Records]
         st = r.Status & ~8
         if x["status"] != 0 or st != 0:

@@ -71,3 +71,17 @@ def test_emu_dense_terms_and_full_chunks(emu):
     qs = ["alpha beta", "alphabet gamma delta", "omegas sigma", "gama", "betamax alpha omega sigma", "delt sigm", "alpha"]
     assert not compare_stage1(eng, orc, qs)
     assert not compare_search(eng, orc, qs)
+
+
+def test_emu_query_parameter_edges(emu, movie_titles, oracle_movies):
+    """Result limits and depths of QueryTests.cs (1, 3, more than there are matches), coverage off, very long / degenerate queries."""
+    eng = ib.SearchEngine(_gpu_lib=emu)
+    eng.IndexColumns(np.arange(len(movie_titles)), [ib.Field("content")], [movie_titles])
+    qs = ["star wars", "the lord of the rings", "godfather", "zzzzqqqq", "   ", "", "matrix reloaded revolutions", "q" * 60, "love " * 40]
+    for mr, depth in ((1, 500), (3, 50), (1000, 500), (10, 10)):
+        assert not compare_search(eng, oracle_movies, qs, max_results=mr, depth=depth), (mr, depth)
+    assert not compare_search(eng, oracle_movies, qs, coverage=False)
+    assert not compare_stage1(eng, oracle_movies, qs, depth=64)
+    # beyond the fixed query buffer (256 UTF-16 units) the product must say so instead of answering something else
+    r = eng.SearchBatch([ib.Query("a" * 300, 10)])[0]
+    assert r.Status & 4 and not r.Records
