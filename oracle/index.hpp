@@ -197,6 +197,8 @@ struct Index {
     std::vector<str> first_token; std::vector<uint16_t> token_count;   // DocumentMetadataCache
     Trie term_trie;
     StrMap<std::vector<int>> prefix_docs;         // PositionalPrefixIndex DocSet per 1..3-char prefix
+    struct PrefixPost { int doc; uint16_t pos; };
+    StrMap<std::vector<PrefixPost>> prefix_post; // PositionalPrefixIndex postings (doc, token index), ascending (doc, pos); every posting is a word start
     StrMap<std::vector<int>> wm_exact, wm_ld1;    // WordMatcher exact / deletion-variant dictionaries
     StrMap<int> wm_affix_last;                    // word -> last doc containing it (Q4)
     Trie wm_fwd, wm_rev;
@@ -249,9 +251,12 @@ struct Index {
             } else { t.df = -1; t.w.clear(); t.docs.clear(); }
         });
         // PositionalPrefixIndex.IndexDocument: prefixes (len 1..3) of every word
-        for (sv w : split_words(index_text)) {
-            int ml = std::min<int>(3, (int)w.size());
-            for (int l = 1; l <= ml; l++) { auto& v = prefix_docs[str(w.substr(0, l))]; if (v.empty() || v.back() != id) v.push_back(id); }
+        {   int token_index = 0;
+            for (sv w : split_words(index_text)) {
+                int ml = std::min<int>(3, (int)w.size());
+                for (int l = 1; l <= ml; l++) { str k(w.substr(0, l)); auto& v = prefix_docs[k]; if (v.empty() || v.back() != id) v.push_back(id); prefix_post[k].push_back({id, (uint16_t)token_index}); }
+                token_index++;
+            }
         }
         // WordMatcher.Load (lower first, then normalize)
         str wm_text = normalize(to_lower(text));

@@ -11,6 +11,7 @@
 //   Scoring/SearchPipeline.cs:49-206,298-576, Scoring/ResultProcessor.cs:146-178
 #pragma once
 #include "stage1.hpp"
+#include "shortquery.hpp"
 
 namespace ifxo {
 
@@ -505,11 +506,11 @@ inline std::pair<float, uint8_t> fusion_score(sv query, sv doc, const Features& 
     return {(float)prec + sem, tie};
 }
 
-struct SearchOut { std::vector<ScoreEntry> records; int stage = 0; bool unsupported = false; };
+struct SearchOut { std::vector<ScoreEntry> records; int stage = 0; bool unsupported = false; bool short_path = false; };
 
 struct Pipeline {
-    const Index& ix; Stage1 s1; Coverage cov;
-    explicit Pipeline(const Index& i) : ix(i), s1(i), cov(i) {}
+    const Index& ix; Stage1 s1; Coverage cov; ShortQuery sq;
+    explicit Pipeline(const Index& i) : ix(i), s1(i), cov(i), sq(i) {}
 
     static void union_into(std::vector<int>& acc, const std::vector<int>& b) { std::vector<int> r; r.reserve(acc.size() + b.size()); std::set_union(acc.begin(), acc.end(), b.begin(), b.end(), std::back_inserter(r)); acc.swap(r); }
 
@@ -548,16 +549,17 @@ struct Pipeline {
         if (is_blank(search_in)) return out;
         str search = normalize(search_in);
         QueryAnalysis qa = analyze_query(search);
-        if (!qa.can_use_ngrams) { out.unsupported = true; return out; }   // short-query path: SURVEY 8(f) "next"
-        str tfidf_q = qa.mixed ? qa.long_words : search; if (is_blank(tfidf_q)) tfidf_q = search;
-        std::vector<ScoreEntry> stage1 = s1.search(tfidf_q, depth, st);
+        std::vector<ScoreEntry> stage1;
+        if (!qa.can_use_ngrams) { out.short_path = true; stage1 = sq.stage1(search, max_results); }   // no word of >= 3 chars: SURVEY 8(f)-1, oracle/shortquery.hpp
+        else { str tfidf_q = qa.mixed ? qa.long_words : search; if (is_blank(tfidf_q)) tfidf_q = search; stage1 = s1.search(tfidf_q, depth, st); }
         if (stage1_out) *stage1_out = stage1;
         bool short_q = !search.empty() && search.size() <= 3; for (char16_t c : search) if (is_delim(c)) short_q = false;
         if (short_q && (long long)stage1.size() >= max_results && max_results < INT32_MAX) { stage1.resize(max_results); out.records = stage1; out.stage = 1; return out; }
         int sq_count = 0; bool sq_known = false;
         if (short_q) { auto it = ix.prefix_docs.find(search); sq_count = it == ix.prefix_docs.end() ? 0 : (int)it->second.size(); sq_known = true; }
         bool skip_cap = short_q && sq_known && sq_count > 500;
-        if (!enable_coverage || skip_cap) { out.records = stage1; out.stage = 1; return out; }
+        bool allow_short_cov = short_q && sq_known && sq_count > 0 && sq_count <= 500;      // SearchPipeline.cs:133-137
+        if (!enable_coverage || skip_cap || (!qa.can_use_ngrams && !allow_short_cov)) { out.records = stage1; out.stage = 1; return out; }
         std::vector<ScoreEntry> covr = coverage_stage(search, depth, max_results, stage1);
         if (covr.empty() && !stage1.empty()) { out.records = stage1; out.stage = 1; return out; }
         out.records = covr; out.stage = 2; return out;

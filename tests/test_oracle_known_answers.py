@@ -103,6 +103,26 @@ def check_movie_case(c, keys, scores, titles_all):
         assert a in titles and titles.index(a) < k
 
 
-def test_short_query_path_is_flagged_not_faked(oracle_movies):
-    # queries with no word >= 3 chars take ShortQueryProcessor (SURVEY 8f "next"): status 1, never a silent answer
-    assert oracle_movies.search("as am", 20)["status"] == 1
+def test_short_query_known_answers(oracle_movies, movie_titles):
+    """Queries without a word of >= 3 characters (ShortQueryProcessor / ShortQueryResolver, oracle/shortquery.hpp): the reference's
+    own assertions, MovieSearchParityTests.cs:557-622."""
+    def titles_of(q, k=10):
+        r = oracle_movies.search(q, k); assert r["status"] == 0
+        return [movie_titles[i] for i in r["keys"]]
+    t = titles_of("a"); assert t                                           # Search_SingleLetter_ReturnsResults
+    for title in t[:5]:
+        low = title.lower(); assert low.startswith("a") or " a" in low
+    assert titles_of("x")[0] == "X"                                        # SingleLetter_X_PrefersExactTitle
+    assert titles_of("th")                                                 # Search_TwoLetters_ReturnsResults
+    assert titles_of("io")[0] == "IO"                                      # Io_PrefersExactTitleOverPrefixes
+    assert oracle_movies.search("as am", 20)["status"] == 0                # several short words: SearchShortQuery, no coverage stage
+
+
+def test_short_query_small_corpora():
+    """MovieSearchParityTests.cs:1085-1140 (ShortQuery_SingleLetter_ReturnsAllMatches, ShortQuery_TwoLetters_NoExactMatch_ReturnsPartial)."""
+    import numpy as np
+    from oracle.oracle import OracleEngine
+    o = OracleEngine(); o.index_texts(["alpha", "beta", "gamma", "delta"], keys=np.arange(1, 5))
+    r = o.search("a", 10); assert r["status"] == 0 and len(r["keys"]) >= 3
+    o = OracleEngine(); o.index_texts(["table", "chair", "desk", "lamp"], keys=np.arange(1, 5))
+    r = o.search("ab", 10); assert r["status"] == 0 and len(r["keys"]) > 0 and r["keys"][0] == 1     # only "table" has both letters
