@@ -9,6 +9,8 @@
 #include <numeric>
 #include <cstring>
 #include <cstdio>
+#include <cstdlib>
+#include <chrono>
 #include <cmath>
 #include <mutex>
 
@@ -91,10 +93,13 @@ static uint64_t hash_host(const uint16_t* s, int n) {
     return h | 1ULL;
 }
 
-static StrDict upload_dict(ifx_index* ix, const ifx_strings& s) {
+// `with_hash = false`: a plain indexed string array (never looked up by key; its entries may repeat, which would degrade the
+// open-addressing build to quadratic probing)
+static StrDict upload_dict(ifx_index* ix, const ifx_strings& s, bool with_hash = true) {
     StrDict d{}; d.n = s.n;
     size_t nchars = s.n ? s.off[s.n] : 0;
     d.chars = ix->up(s.chars, nchars ? nchars : 1); d.off = ix->up(s.off, (size_t)s.n + 1);
+    if (!with_hash) { static const uint64_t z64 = 0; static const int32_t z32 = 0; d.hkeys = ix->up(&z64, 1); d.hvals = ix->up(&z32, 1); d.hmask = 0; return d; }
     uint32_t cap = 8; while (cap < (uint32_t)s.n * 2u + 2u) cap <<= 1;
     std::vector<uint64_t> hk(cap, 0); std::vector<int32_t> hv(cap, -1);
     for (int i = 0; i < s.n; i++) {
@@ -131,6 +136,8 @@ extern "C" int ifx_index_create(const ifx_index_image* img, const ifx_params* pp
     ifx_params P; if (pp) P = *pp; else ifx_params_default(&P);
     if (img->n_docs < 0 || ((int64_t)img->n_docs + 65535) / 65536 > MAX_CONTAINERS) return fail(IFX_ERR_INVALID, "n_docs out of range");
     ifx_index* ix = new ifx_index();
+    const bool timing = getenv("IFX_CREATE_TIMING") != nullptr; auto t_last = std::chrono::steady_clock::now();
+    auto stage = [&](const char* what) { if (!timing) return; auto now = std::chrono::steady_clock::now(); fprintf(stderr, "[ifx_index_create] %-28s %.2f s\n", what, std::chrono::duration<double>(now - t_last).count()); t_last = now; };
     try {
 #ifndef IFX_EMU
         CUDA_TRY(cudaSetDevice(P.device)); ix->device = P.device;
@@ -140,11 +147,13 @@ extern "C" int ifx_index_create(const ifx_index_image* img, const ifx_params* pp
         v.doc_key = ix->up(img->doc_key, N); v.deleted = ix->up(img->deleted, N); v.doc_len = ix->up(img->doc_len, N);
         size_t ntext = N ? (size_t)img->text_off[N] : 0;
         v.text = ix->up(img->text_chars, ntext ? ntext : 1); v.text_off = ix->up(img->text_off, (size_t)N + 1);
-        v.first_token = upload_dict(ix, img->first_token); v.token_count = ix->up(img->token_count, N);
+        v.first_token = upload_dict(ix, img->first_token, false); v.token_count = ix->up(img->token_count, N);
+        stage("docs + text");
         v.terms = upload_dict(ix, img->terms); const int T = img->terms.n;
         v.df = ix->up(img->df, T); v.row_ptr = ix->up(img->row_ptr, (size_t)T + 1);
         size_t P_ = T ? (size_t)img->row_ptr[T] : 0;
         v.post_doc = ix->up(img->post_doc, P_ ? P_ : 1); v.post_tf = ix->up(img->post_tf, P_ ? P_ : 1);
+        stage("term dictionary + postings");
         {   // forward index: CSR transpose of the live posting lists (counting sort by doc; entries of a doc end up in term order)
             std::vector<int64_t> fp((size_t)N + 2, 0);
             for (int t = 0; t < T; t++) { if (img->df[t] <= 0) continue; for (int64_t i = img->row_ptr[t]; i < img->row_ptr[t + 1]; i++) fp[(size_t)img->post_doc[i] + 2]++; }
@@ -162,6 +171,7 @@ extern "C" int ifx_index_create(const ifx_index_image* img, const ifx_params* pp
             if (sp.empty()) sp.push_back(0);
             v.skip_id = ix->up(sid.data(), sid.size()); v.skip_ptr = ix->up(sp.data(), sp.size());
         }
+        stage("forward index + skip table");
         {   // dense terms additionally get a membership bitmap + rank directory: O(1) probes (doc -> posting index -> tf) in the scorer
             const int bw = (N + 31) / 32; v.bm_words = bw; const int64_t dense = std::max<int64_t>(1024, N / 32);
             std::vector<int32_t> bid(std::max(T, 1), -1); int nb = 0;
@@ -172,6 +182,7 @@ extern "C" int ifx_index_create(const ifx_index_image* img, const ifx_params* pp
                 int run = 0; for (int w = 0; w < bw; w++) { r[w] = run; run += __builtin_popcount(b[w]); } }
             v.bm_id = ix->up(bid.data(), bid.size()); v.bm_bits = ix->up(bits.data(), bits.size()); v.bm_rank = ix->up(rank.data(), rank.size());
         }
+        stage("dense bitmaps");
         // trie DFS order == ordinal-lexicographic order of the term texts (FstBuilder.CompactTrie sorts arcs by label)
         std::vector<int32_t> order(T); std::iota(order.begin(), order.end(), 0);
         auto term_sv = [&](int i) { return std::u16string_view((const char16_t*)img->terms.chars + img->terms.off[i], img->terms.off[i + 1] - img->terms.off[i]); };
@@ -184,6 +195,7 @@ extern "C" int ifx_index_create(const ifx_index_image* img, const ifx_params* pp
             std::vector<int32_t> cur(lp.begin(), lp.end() - 1), lord(std::max(T, 1), 0); std::vector<unsigned long long> lsig(std::max(T, 1), 0ULL);
             for (int i = 0; i < T; i++) { int at = cur[slen[i]]++; lord[at] = order[i]; lsig[at] = sig[i]; }
             v.len_ptr = ix->up(lp.data(), lp.size()); v.len_sig = ix->up(lsig.data(), lsig.size()); v.len_ord = ix->up(lord.data(), lord.size()); }
+        stage("sorted / length-grouped dictionary");
         v.words = upload_dict(ix, img->words); v.word_idf = ix->up(img->word_idf, img->words.n ? img->words.n : 1);
         v.prefix = upload_docset(ix, img->prefix); v.wm_exact = upload_docset(ix, img->wm_exact); v.wm_ld1 = upload_docset(ix, img->wm_ld1);
         {   // affix words: forward (prefix) order and reverse-string (suffix) order, each with the doc its trie output resolves to
@@ -200,6 +212,7 @@ extern "C" int ifx_index_create(const ifx_index_image* img, const ifx_params* pp
             std::vector<int32_t> rdoc(A); for (int i = 0; i < A; i++) rdoc[i] = fdoc[ro[i]];
             v.affix_rev = ix->up(ro.data(), A ? A : 1); v.affix_rev_doc = ix->up(rdoc.data(), A ? A : 1);
         }
+        stage("word + prefix + wordmatcher dictionaries");
         {   // character tables (tools/gen_chartables.py) + host-evaluated MathF.Log2(len + 1)
             std::vector<uint16_t> lo(65536), upv(65536); std::vector<uint8_t> fl(65536, 0);
             for (int i = 0; i < 65536; i++) lo[i] = upv[i] = (uint16_t)i;
