@@ -29,7 +29,7 @@ __global__ void __launch_bounds__(IFX_EXPAND_THREADS, 2) k_expand(DevIndex ix, Q
     S1Shared& sh = *reinterpret_cast<S1Shared*>(smem_raw); Ctx c; S1Workspace ws = wss[blockIdx.x];
     for (int i = threadIdx.x; i < MAX_CONTAINERS; i += blockDim.x) sh.dirty[i] = 0;
     __syncthreads();
-    const int n_items = min(bc->n_fuzzy_items, (int)(gridDim.x * 0 + 0x7fffffff));
+    const int n_items = bc->n_fuzzy_items;
     for (;;) {
         if (threadIdx.x == 0) sh.bcast[7] = atomicAdd(work, 1);
         __syncthreads();
