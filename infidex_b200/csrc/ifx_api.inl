@@ -66,8 +66,9 @@ struct ifx_index {
     std::vector<Column> h_columns; std::vector<std::u16string> column_names;
     std::mutex mu; std::mutex call_mu; struct ifx_batch* cached = nullptr;   // batch workspace reused by ifx_search_batch
     ~ifx_index();
-    template <class T> T* up(const T* src, size_t n) { T* d = (T*)dev_alloc(n * sizeof(T)); allocs.push_back(d); if (src && n) h2d(d, src, n * sizeof(T)); return d; }
-    template <class T> T* alloc(size_t n) { T* d = (T*)dev_alloc(n * sizeof(T)); allocs.push_back(d); return d; }
+    size_t bytes = 0;                   // device bytes held by this index (reported by IFX_CREATE_TIMING)
+    template <class T> T* up(const T* src, size_t n) { T* d = (T*)dev_alloc(n * sizeof(T)); allocs.push_back(d); bytes += n * sizeof(T); if (src && n) h2d(d, src, n * sizeof(T)); return d; }
+    template <class T> T* alloc(size_t n) { T* d = (T*)dev_alloc(n * sizeof(T)); allocs.push_back(d); bytes += n * sizeof(T); return d; }
 };
 
 struct ifx_batch {
@@ -257,12 +258,16 @@ extern "C" int ifx_index_create(const ifx_index_image* img, const ifx_params* pp
           int want = prop.multiProcessorCount * 3; size_t budget = free_b / 3;
           ix->n_ctas = (int)std::max<size_t>(1, std::min<size_t>((size_t)want, budget / std::max<size_t>(per_cta, 1))); }
 #endif
+        const size_t index_bytes = ix->bytes;
         ix->ws.resize(ix->n_ctas);
         for (auto& w : ix->ws) { w.bits = ix->alloc<unsigned>(nwords); dev_zero(w.bits, (size_t)nwords * 4); w.bits2 = ix->alloc<unsigned>(nwords); dev_zero(w.bits2, (size_t)nwords * 4); w.cand = ix->alloc<int32_t>((size_t)N + 1); w.cand_cap = N; w.buf_a = ix->alloc<int32_t>(max_list); w.buf_b = ix->alloc<int32_t>(max_list); w.buf_cap = max_list; w.surv_g = ix->alloc<unsigned long long>(CHUNK); }
         ix->d_ws = ix->up(ix->ws.data(), ix->ws.size());
         ix->pool_cap = (unsigned long long)std::max<int64_t>(1 << 20, std::min<int64_t>((int64_t)N * 64, (int64_t)1 << 31));
         ix->d_pool = ix->alloc<int32_t>(ix->pool_cap);
         ix->max_batch = P.max_batch > 0 ? P.max_batch : 16384;
+        stage("workspaces");
+        if (timing) fprintf(stderr, "[ifx_index_create] device memory: index %.1f MB, workspaces %d x %.1f MB, fuzzy pool %.1f MB\n", index_bytes / 1e6, ix->n_ctas,
+                            (ix->bytes - index_bytes - (size_t)ix->pool_cap * 4) / 1e6 / ix->n_ctas, ix->pool_cap * 4 / 1e6);
     } catch (const std::string& e) { delete ix; return fail(IFX_ERR_CUDA, e); }
     catch (const std::bad_alloc&) { delete ix; return fail(IFX_ERR_OOM, "host allocation failed"); }
     *out = ix; return IFX_OK;
