@@ -85,3 +85,22 @@ def test_emu_query_parameter_edges(emu, movie_titles, oracle_movies):
     # beyond the fixed query buffer (256 UTF-16 units) the product must say so instead of answering something else
     r = eng.SearchBatch([ib.Query("a" * 300, 10)])[0]
     assert r.Status & 4 and not r.Records
+
+
+def test_emu_small_reference_corpora(emu):
+    """The small corpora of SearchEngineTests.cs / QueryTests.cs, including twenty identical documents (every score ties; only the
+    heap layout and the key order decide who survives) -- product logic against the oracle, bit for bit."""
+    corpora = [
+        (["hello world", "goodbye world", "hello there"], 1, ["hello world", "hello", "wrld", "goodby"]),
+        (["batman and robin", "superman flies high", "spiderman swings"], 1, ["batmam", "superman", "swings high"]),
+        (["the quick brown fox", "the lazy brown dog", "a quick decision", "quick brown"], 1, ["quick brown", "brown", "quick decision"]),
+        (["batman saves the day"] * 20, 0, ["batman", "saves the day", "batmen"]),
+        (["batman saves the day story %d" % i for i in range(20)], 0, ["batman", "story 7", "day story"]),
+    ]
+    for texts, k0, qs in corpora:
+        keys = np.arange(k0, k0 + len(texts))
+        eng = ib.SearchEngine(_gpu_lib=emu); eng.IndexColumns(keys, [ib.Field("content")], [texts])
+        orc = OracleEngine(); orc.index_texts(texts, keys=keys)
+        for mr in (5, 8, 10):
+            assert not compare_search(eng, orc, qs, max_results=mr), (texts[0], mr)
+        assert not compare_stage1(eng, orc, qs)

@@ -126,3 +126,35 @@ def test_short_query_small_corpora():
     r = o.search("a", 10); assert r["status"] == 0 and len(r["keys"]) >= 3
     o = OracleEngine(); o.index_texts(["table", "chair", "desk", "lamp"], keys=np.arange(1, 5))
     r = o.search("ab", 10); assert r["status"] == 0 and len(r["keys"]) > 0 and r["keys"][0] == 1     # only "table" has both letters
+
+
+# ---- SearchEngineTests.cs:12-129 and QueryTests.cs:128-215: small corpora through the whole pipeline --------------------------------
+def _engine(texts, first_key=1):
+    import numpy as np
+    from oracle.oracle import OracleEngine
+    o = OracleEngine(); o.index_texts(texts, keys=np.arange(first_key, first_key + len(texts)))
+    return o
+
+
+def test_search_engine_tests():
+    o = _engine(["The quick brown fox jumps over the lazy dog", "A journey of a thousand miles begins with a single step",
+                 "To be or not to be that is the question", "The fox was quick and clever"])
+    r = o.search("fox", 10); assert r["keys"] and 1 in r["keys"] and 4 in r["keys"]                     # IndexAndSearch_FindsDocuments
+    o = _engine(["hello world", "goodbye world", "hello there"])
+    r = o.search("hello world", 10); assert r["keys"][0] == 1 and r["scores"][0] > 200                   # Search_ExactMatch_ReturnsHighScore
+    o = _engine(["batman and robin", "superman flies high", "spiderman swings"])
+    assert o.search("batmam", 10)["keys"][0] == 1                                                        # Search_FuzzyMatch_FindsSimilar
+    assert o.search("", 10)["keys"] == []                                                                # Search_EmptyQuery_ReturnsNoResults
+    o = _engine(["hello world", "goodbye world"])
+    r = o.search("xyzabc", 10); assert not r["keys"] or r["scores"][0] < 50                              # Search_NoMatches_ReturnsEmptyResults
+    o = _engine(["the quick brown fox", "the lazy brown dog", "a quick decision", "quick brown"])
+    assert o.search("quick brown", 10)["keys"][0] in (4, 1)                                              # Search_MultiWordQuery_RanksRelevance
+
+
+def test_query_tests_result_limits():
+    o = _engine(["The quick brown fox", "The lazy dog", "Quick thinking"])
+    assert o.search("quick", 10)["keys"]                                                                 # SearchEngine_QuerySearch_ReturnsResult
+    o = _engine(["batman saves the day"] * 20, first_key=0)
+    assert len(o.search("batman", 5)["keys"]) == 5                                                       # ..._LimitsResults_IdenticalDocuments
+    o = _engine(["batman saves the day story %d" % i for i in range(20)], first_key=0)
+    assert len(o.search("batman", 8)["keys"]) == 8                                                       # ..._LimitsResults_VariedDocuments
