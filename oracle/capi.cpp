@@ -149,6 +149,12 @@ int ifxo_dict_docs(void* h, int kind, const uint16_t* s, int n, int* out, int ca
 int ifxo_affix_last(void* h, const uint16_t* s, int n) { auto& m = ((Engine*)h)->ix.wm_affix_last; auto it = m.find(str((const char16_t*)s, (size_t)n)); return it == m.end() ? -1 : it->second; }
 
 // ---- component-level entry points (known-answer tests of the reference's unit tests)
+// WordMatcher.Lookup (kind 0) / LookupAffix (kind 1) for one word: ascending internal doc ids
+int ifxo_wm_lookup(void* h, int kind, const uint16_t* s, int n, int* out, int cap) {
+    Engine* e = (Engine*)h; if (!e->pipe) return -1;
+    sv w((const char16_t*)s, (size_t)n); std::vector<int> r = kind == 0 ? e->pipe->wm_lookup(w) : e->pipe->wm_affix(w);
+    int m = std::min((int)r.size(), cap); std::memcpy(out, r.data(), (size_t)m * sizeof(int)); return (int)r.size();
+}
 int ifxo_levenshtein(const uint16_t* a, int na, const uint16_t* b, int nb, int max_errors, int ic) { return lev(sv((const char16_t*)a, na), sv((const char16_t*)b, nb), max_errors, ic != 0); }
 int ifxo_damerau(const uint16_t* a, int na, const uint16_t* b, int nb, int maxd, int ic) { return damerau(sv((const char16_t*)a, na), sv((const char16_t*)b, nb), maxd, ic != 0); }
 int ifxo_normalize(const uint16_t* a, int na, uint16_t* out, int cap) { str r = normalize(sv((const char16_t*)a, na)); int n = std::min((int)r.size(), cap); std::memcpy(out, r.data(), n * 2); return (int)r.size(); }

@@ -152,6 +152,10 @@ class OracleEngine:
     def avgdl(self):
         return float(lib().ifxo_avgdl(self.h))
 
+    def wm_lookup(self, word, affix=False):
+        a = u16(word); out = np.zeros(4096, np.int32); n = lib().ifxo_wm_lookup(self.h, int(affix), _p(a), len(a), _p(out), len(out))
+        return out[:max(n, 0)].tolist()
+
     def coverage(self, query, doc, lcs=0.0, bm25=0.0):
         q, d = u16(query), u16(doc); out = np.zeros(4, np.int32)
         lib().ifxo_coverage(self.h, _p(q), len(q), _p(d), len(d), C.c_double(lcs), C.c_float(bm25), _p(out))

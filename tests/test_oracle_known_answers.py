@@ -158,3 +158,10 @@ def test_query_tests_result_limits():
     assert len(o.search("batman", 5)["keys"]) == 5                                                       # ..._LimitsResults_IdenticalDocuments
     o = _engine(["batman saves the day story %d" % i for i in range(20)], first_key=0)
     assert len(o.search("batman", 8)["keys"]) == 8                                                       # ..._LimitsResults_VariedDocuments
+
+
+def test_word_matcher_tests():
+    """WordMatcherTests.cs:9-73 (default WordMatcherSetup sizes: exact 2..8, LD1 3..8, affix >= 3); doc ids are insertion indices."""
+    o = _engine(["hello world test", "goodbye world"]); assert o.wm_lookup("world") == [0, 1]           # Lookup_ExactMatch_FindsDocument
+    o = _engine(["batman is here"]); assert 0 in o.wm_lookup("batmam")                                   # Lookup_LD1Support_FindsFuzzyMatches
+    o = _engine(["batman superman spiderman"]); assert 0 in o.wm_lookup("bat", affix=True)               # LookupAffix_FindsPrefixMatches
