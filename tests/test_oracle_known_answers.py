@@ -165,3 +165,12 @@ def test_word_matcher_tests():
     o = _engine(["hello world test", "goodbye world"]); assert o.wm_lookup("world") == [0, 1]           # Lookup_ExactMatch_FindsDocument
     o = _engine(["batman is here"]); assert 0 in o.wm_lookup("batmam")                                   # Lookup_LD1Support_FindsFuzzyMatches
     o = _engine(["batman superman spiderman"]); assert 0 in o.wm_lookup("bat", affix=True)               # LookupAffix_FindsPrefixMatches
+
+
+def test_tokenizer_tests_through_the_index():
+    """TokenizerTests.cs:20-33 (words of >= 3 characters are tokens) with configuration 400 (3-grams after two pad characters,
+    Tokenizer.cs:89-139): observable through the term dictionary of an indexed document."""
+    o = _engine(["hello world"])
+    for term in ("hello", "world", "hel", "ell", "llo", "lo ", "o w", " wo", "wor", "orld"[:3], "rld", "￿￿h", "￿he"):
+        assert o.lookup_term(term) >= 0, term
+    assert o.lookup_term("￿￿￿") < 0 and o.lookup_term("he") < 0 and o.lookup_term("hello world") < 0
