@@ -149,6 +149,16 @@ int ifxo_dict_docs(void* h, int kind, const uint16_t* s, int n, int* out, int ca
 int ifxo_affix_last(void* h, const uint16_t* s, int n) { auto& m = ((Engine*)h)->ix.wm_affix_last; auto it = m.find(str((const char16_t*)s, (size_t)n)); return it == m.end() ? -1 : it->second; }
 
 // ---- component-level entry points (known-answer tests of the reference's unit tests)
+// FstIndex over an ad-hoc term list (FstIndexTests.cs): mode 0 MatchWithinEditDistance1, mode 1 GetByPrefix. Returns the reference's
+// return value (total match count / number written), fills up to `cap` outputs.
+int ifxo_fst_query(const uint16_t* blob, const int* off, const int* outs, int n, int mode, const uint16_t* q, int qn, int* out, int cap) {
+    std::vector<std::pair<str, int>> items; for (int i = 0; i < n; i++) items.emplace_back(str((const char16_t*)blob + off[i], (size_t)(off[i + 1] - off[i])), outs[i]);
+    std::sort(items.begin(), items.end());
+    Trie t; t.build(items); std::vector<int> r; sv qs((const char16_t*)q, (size_t)qn); int ret;
+    if (mode == 0) ret = t.match_ld1(qs, cap, r); else { int node = t.walk(qs); ret = t.collect(node, cap, r); }
+    for (size_t i = 0; i < r.size() && (int)i < cap; i++) out[i] = r[i];
+    return ret;
+}
 // WordMatcher.Lookup (kind 0) / LookupAffix (kind 1) for one word: ascending internal doc ids
 int ifxo_wm_lookup(void* h, int kind, const uint16_t* s, int n, int* out, int cap) {
     Engine* e = (Engine*)h; if (!e->pipe) return -1;

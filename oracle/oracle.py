@@ -59,6 +59,14 @@ class Field:
         self.name, self.weight, self.indexable, self.filterable, self.facetable = name, weight, indexable, filterable, facetable
 
 
+def fst_query(terms, query, cap=10, prefix=False):
+    """FstIndex built from {term: output}: MatchWithinEditDistance1 (or GetByPrefix) -> (return value, outputs written)."""
+    keys = list(terms); blob = u16("".join(keys)); off = np.zeros(len(keys) + 1, np.int32); off[1:] = np.cumsum([len(k) for k in keys])
+    outs = np.array([terms[k] for k in keys], np.int32); q = u16(query); out = np.full(max(cap, 1), -1, np.int32)
+    n = lib().ifxo_fst_query(_p(blob), _p(off), _p(outs), len(keys), int(prefix), _p(q), len(q), _p(out), cap)
+    return n, [int(x) for x in out[:min(n, cap)]]
+
+
 class OracleEngine:
     """SearchEngine.CreateDefault() restated (config 400)."""
 

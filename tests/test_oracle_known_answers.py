@@ -174,3 +174,14 @@ def test_tokenizer_tests_through_the_index():
     for term in ("hello", "world", "hel", "ell", "llo", "lo ", "o w", " wo", "wor", "orld"[:3], "rld", "￿￿h", "￿he"):
         assert o.lookup_term(term) >= 0, term
     assert o.lookup_term("￿￿￿") < 0 and o.lookup_term("he") < 0 and o.lookup_term("hello world") < 0
+
+
+def test_fst_index_tests():
+    """FstIndexTests.cs:20-124 -- exact counts of the Myers / trie LD1 match (the "search variant" the LD1 kernel reproduces)."""
+    from oracle.oracle import fst_query
+    terms = {"apple": 10, "apples": 20, "apply": 30, "bpple": 40}
+    n, r = fst_query(terms, "applz"); assert n == 2 and sorted(r) == [10, 30]                       # MatchWithinEditDistance1_FindsMatches
+    n, r = fst_query(terms, "apple"); assert n == 4 and sorted(r) == [10, 20, 30, 40]
+    n, r = fst_query({"apple": 1, "apply": 2, "bpple": 3}, "apple", cap=1); assert n == 3           # ..._BufferOverflow: total count
+    n, r = fst_query({"apple": 1, "apply": 2, "bpple": 3}, "app", cap=1, prefix=True); assert n == 1 and r[0] in (1, 2)   # GetByPrefix_FillsBufferAndStops
+    n, r = fst_query({"apple": 1, "apply": 2, "bpple": 3}, "app", cap=5, prefix=True); assert n == 2 and sorted(r) == [1, 2]
