@@ -48,6 +48,10 @@ class _Pool:
         return bytes(out)
 
 
+class FilterParseError(ValueError):
+    """Api/FilterParseException.cs"""
+
+
 class Filter:
     """AST node. kind in: value, range, in, string, null, and, or, not."""
 
@@ -129,8 +133,8 @@ class Filter:
 
     def __eq__(self, o): return isinstance(o, Filter) and self.bytecode() == o.bytecode()
 
-    # ---- Filter.Parse (subset)
-    _TOK = re.compile(r"\s*(?:(<=|>=|!=|=|<|>|\(|\)|,)|'((?:[^']|'')*)'|\"((?:[^\"]|\"\")*)\"|([A-Za-z_][A-Za-z0-9_\.]*)|(-?\d+(?:\.\d+)?(?:[eE][+-]?\d+)?))")
+    # ---- Filter.Parse: the Infiscript grammar (Api/Infiscript.bnf, Api/FilterParser.cs) without the ternary form
+    _TOK = re.compile(r"\s*(?:(<=|>=|!=|&&|\|\||=|<|>|\(|\)|,|&|\||!|\?|:)|'((?:[^']|'')*)'|\"((?:[^\"]|\"\")*)\"|([A-Za-z_][A-Za-z0-9_\.]*)|(-?\d+(?:\.\d+)?(?:[eE][+-]?\d+)?))")
 
     @staticmethod
     def Parse(expr):
@@ -140,7 +144,7 @@ class Filter:
                 break
             m = Filter._TOK.match(expr, pos)
             if not m:
-                raise ValueError("cannot tokenize filter at %d: %r" % (pos, expr[pos:pos + 20]))
+                raise FilterParseError("cannot tokenize filter at %d: %r" % (pos, expr[pos:pos + 20]))
             pos = m.end()
             if m.group(1): toks.append(("op", m.group(1)))
             elif m.group(2) is not None: toks.append(("val", m.group(2).replace("''", "'")))
@@ -155,54 +159,66 @@ class Filter:
 
         def take(): t = peek(); p[0] += 1; return t
 
+        def is_op(*ops): return peek()[0] == "op" and peek()[1] in ops
+
+        def need(cond, msg):
+            if not cond:
+                raise FilterParseError(msg)
+
+        def value():
+            t = take(); need(t[0] in ("val", "id"), "expected a value"); return t[1]
+
         def parse_or():
             left = parse_and()
-            while kw("OR"):
+            while kw("OR") or is_op("||", "|"):
                 take(); left = Filter.Or(left, parse_and())
             return left
 
         def parse_and():
             left = parse_not()
-            while kw("AND"):
+            while kw("AND") or is_op("&&", "&"):
                 take(); left = Filter.And(left, parse_not())
             return left
 
         def parse_not():
-            if kw("NOT"):
-                take(); return Filter.Not(parse_not())
+            if kw("NOT") or is_op("!"):
+                take(); return Filter.Not(parse_atom())      # <not_operator> <primary_expression>
             return parse_atom()
 
         def parse_atom():
             t = take()
             if t == ("op", "("):
-                e = parse_or(); assert take() == ("op", ")"), "expected )"; return e
-            assert t[0] == "id", "expected field name"
+                e = parse_or(); need(take() == ("op", ")"), "expected )"); return e
+            need(t[0] == "id", "expected field name")
             field = t[1]
             if kw("BETWEEN"):
-                take(); a = take()[1]; assert kw("AND"); take(); b = take()[1]; return Filter.Range(field, a, b)
+                take(); a = value(); need(kw("AND"), "expected AND in BETWEEN"); take(); b = value(); return Filter.Range(field, a, b)
             if kw("IN"):
-                take(); assert take() == ("op", "("); vals = []
-                while peek() != ("op", ")"):
-                    v = take();
-                    if v != ("op", ","): vals.append(v[1])
-                take(); return Filter.In(field, vals)
+                take(); need(take() == ("op", "("), "expected ( after IN"); vals = [value()]
+                while is_op(","):
+                    take(); vals.append(value())
+                need(take() == ("op", ")"), "expected ) after IN list"); return Filter.In(field, vals)
             if kw("IS"):
                 take(); neg = False
                 if kw("NOT"): take(); neg = True
-                assert kw("NULL"); take(); return Filter.Null(field, not neg)
-            for word, op in (("CONTAINS", "CONTAINS"), ("LIKE", "LIKE")):
+                need(kw("NULL"), "expected NULL"); take(); return Filter.Null(field, not neg)
+            for word, op in (("CONTAINS", "CONTAINS"), ("LIKE", "LIKE"), ("MATCHES", "MATCHES")):
                 if kw(word):
-                    take(); return Filter.String(field, op, take()[1])
+                    take(); return Filter.String(field, op, value())
             if kw("STARTS"):
-                take(); assert kw("WITH"); take(); return Filter.String(field, "STARTS_WITH", take()[1])
+                take(); need(kw("WITH"), "expected WITH"); take(); return Filter.String(field, "STARTS_WITH", value())
             if kw("ENDS"):
-                take(); assert kw("WITH"); take(); return Filter.String(field, "ENDS_WITH", take()[1])
-            op = take(); assert op[0] == "op", "expected comparison operator"; v = take()[1]
+                take(); need(kw("WITH"), "expected WITH"); take(); return Filter.String(field, "ENDS_WITH", value())
+            op = take(); need(op[0] == "op" and op[1] in ("=", "!=", ">", ">=", "<", "<="), "expected comparison operator"); v = value()
             return {"=": lambda: Filter.Value(field, v), "!=": lambda: Filter.Not(Filter.Value(field, v)),
                     ">": lambda: Filter.Range(field, min=v, include_min=False), ">=": lambda: Filter.Range(field, min=v, include_min=True),
                     "<": lambda: Filter.Range(field, max=v, include_max=False), "<=": lambda: Filter.Range(field, max=v, include_max=True)}[op[1]]()
 
+        if not toks:
+            raise FilterParseError("empty filter expression")
         e = parse_or()
+        if is_op("?"):
+            raise FilterParseError("the ternary form (cond ? a : b) is not supported by this binding")
         if p[0] != len(toks):
-            raise ValueError("trailing tokens in filter expression")
+            raise FilterParseError("trailing tokens in filter expression")
         return e
