@@ -169,6 +169,12 @@ int ifxo_levenshtein(const uint16_t* a, int na, const uint16_t* b, int nb, int m
 int ifxo_damerau(const uint16_t* a, int na, const uint16_t* b, int nb, int maxd, int ic) { return damerau(sv((const char16_t*)a, na), sv((const char16_t*)b, nb), maxd, ic != 0); }
 int ifxo_normalize(const uint16_t* a, int na, uint16_t* out, int cap) { str r = normalize(sv((const char16_t*)a, na)); int n = std::min((int)r.size(), cap); std::memcpy(out, r.data(), n * 2); return (int)r.size(); }
 // coverage of one (query, doc) pair with the engine's corpus statistics: out = [coverage_score, word_hits, fusion score bits, tie]
+// CoverageEngine.SetWordIdfCache (BugReproductionTests.cs:24-31): replace the word-level idf cache of an (empty) engine
+int ifxo_set_word_idf(void* h, const uint16_t* blob, const int* off, const float* idf, int n) {
+    Engine* e = (Engine*)h; e->ix.word_idf.clear();
+    for (int i = 0; i < n; i++) e->ix.word_idf[str((const char16_t*)blob + off[i], (size_t)(off[i + 1] - off[i]))] = idf[i];
+    return 0;
+}
 int ifxo_coverage(void* h, const uint16_t* q, int nq, const uint16_t* d, int nd, double lcs, float bm25, int* out) {
     Engine* e = (Engine*)h; Coverage cov(e->ix); QueryCtx ctx = cov.prepare(sv((const char16_t*)q, nq));
     Features f = cov.features(ctx, sv((const char16_t*)d, nd), lcs, -1);

@@ -164,6 +164,10 @@ class OracleEngine:
         a = u16(word); out = np.zeros(4096, np.int32); n = lib().ifxo_wm_lookup(self.h, int(affix), _p(a), len(a), _p(out), len(out))
         return out[:max(n, 0)].tolist()
 
+    def set_word_idf(self, cache):
+        keys = list(cache); blob = u16("".join(keys)); off = np.zeros(len(keys) + 1, np.int32); off[1:] = np.cumsum([len(k) for k in keys])
+        lib().ifxo_set_word_idf(self.h, _p(blob), _p(off), _p(np.array([cache[k] for k in keys], np.float32)), len(keys))
+
     def coverage(self, query, doc, lcs=0.0, bm25=0.0):
         q, d = u16(query), u16(doc); out = np.zeros(4, np.int32)
         lib().ifxo_coverage(self.h, _p(q), len(q), _p(d), len(d), C.c_double(lcs), C.c_float(bm25), _p(out))

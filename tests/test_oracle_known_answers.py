@@ -185,3 +185,12 @@ def test_fst_index_tests():
     n, r = fst_query({"apple": 1, "apply": 2, "bpple": 3}, "apple", cap=1); assert n == 3           # ..._BufferOverflow: total count
     n, r = fst_query({"apple": 1, "apply": 2, "bpple": 3}, "app", cap=1, prefix=True); assert n == 1 and r[0] in (1, 2)   # GetByPrefix_FillsBufferAndStops
     n, r = fst_query({"apple": 1, "apply": 2, "bpple": 3}, "app", cap=5, prefix=True); assert n == 2 and sorted(r) == [1, 2]
+
+
+def test_bug_reproduction_prefix_preference():
+    """BugReproductionTests.cs:12-67 (CoverageEngine + FusionScorer with a fixed word-idf cache, bm25 0.5): "the matrix rev" must
+    score "The Matrix Revisited" above "The Matrix Reloaded"."""
+    from oracle.oracle import OracleEngine
+    o = OracleEngine(); o.set_word_idf({"the": 1.574, "matrix": 9.544, "rev": 9.515})
+    reloaded = o.coverage("the matrix rev", "The Matrix Reloaded", 0.0, 0.5); revisited = o.coverage("the matrix rev", "The Matrix Revisited", 0.0, 0.5)
+    assert revisited["score"] > reloaded["score"]
