@@ -58,7 +58,7 @@ def test_levenshtein_within():
     assert O.levenshtein("batman", "ratmin", 1) > 1
 
 
-# CoverageEngineTests.cs:19-75 (engine without corpus statistics: IDF falls back to log2(len+1))
+# CoverageEngineTests.cs:18-120, all seven tests (engine without corpus statistics: IDF falls back to log2(len+1))
 def test_coverage_engine_known_answers():
     e = O.OracleEngine()
     c = e.coverage("hello world", "this is hello world text")
@@ -68,6 +68,9 @@ def test_coverage_engine_known_answers():
     assert c["coverage"] > 100 and c["word_hits"] == 2
     c = e.coverage("batmam", "batman is a superhero")
     assert c["coverage"] > 150 and c["word_hits"] > 0
+    assert e.coverage("new york", "I live in newyork city")["coverage"] > 100          # :77-90 JoinedWords_DetectsCompound
+    assert e.coverage("bat", "batman is a superhero")["coverage"] > 50                 # :92-105 PrefixMatch_FindsPartialWord
+    c = e.coverage("", "hello world"); assert c["coverage"] == 0 and c["word_hits"] == 0   # :107-120 EmptyQuery_ReturnsZero
 
 
 # MovieSearchParityTests.cs (33 tests; the n-gram-path ones are restated in movie_known_answers.json)
