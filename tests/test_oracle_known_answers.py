@@ -48,7 +48,8 @@ def test_fuzzy_regression_matrix_above_mat():
 
 # LevenshteinDistanceTests.cs:11-79
 @pytest.mark.parametrize("a,b,d", [("hello", "hello", 0), ("hello", "hallo", 1), ("bat", "brat", 1), ("batman", "batma", 1), ("", "", 0),
-                                   ("hello", "", 5), ("", "hello", 5), ("kitten", "sitting", 3), ("saturday", "sunday", 3)])
+                                   ("hello", "", 5), ("", "hello", 5), ("kitten", "sitting", 3), ("saturday", "sunday", 3), ("abc", "xyz", 3),
+                                   ("a" * 70 + "test", "a" * 70 + "best", 1)])
 def test_levenshtein(a, b, d):
     assert O.levenshtein(a, b) == d
 
