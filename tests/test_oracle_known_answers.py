@@ -198,3 +198,51 @@ def test_bug_reproduction_prefix_preference():
     o = OracleEngine(); o.set_word_idf({"the": 1.574, "matrix": 9.544, "rev": 9.515})
     reloaded = o.coverage("the matrix rev", "The Matrix Reloaded", 0.0, 0.5); revisited = o.coverage("the matrix rev", "The Matrix Revisited", 0.0, 0.5)
     assert revisited["score"] > reloaded["score"]
+
+
+# ---- the MovieSearchParityTests whose assertions are invariants over the whole list (not expressible in movie_known_answers.json) -------
+def _movie_search(oracle_movies, movie_titles, q, k):
+    r = oracle_movies.search(q, k); assert r["status"] == 0
+    return [movie_titles[i] for i in r["keys"]], list(r["scores"])
+
+
+def test_movie_sap_and_de_prefix_at_title_start(oracle_movies, movie_titles):
+    t, _ = _movie_search(oracle_movies, movie_titles, "sap", 200); assert t            # Sap_PrefersPrefixAtTitleStart (:381-427)
+    seen_other = False
+    for title in t:
+        low = title.lower(); starts = low.startswith("sap") and (len(low) == 3 or not low[3].isalpha())
+        if not starts: seen_other = True
+        else: assert not seen_other, title
+    t, _ = _movie_search(oracle_movies, movie_titles, "de", 200); assert t              # De_PrefersPrefixAtTitleStart (:510-555)
+    seen_other = False
+    for title in t:
+        if not title.lower().startswith("de"): seen_other = True
+        else: assert not seen_other, title
+
+
+def test_movie_eatrix_f(oracle_movies, movie_titles):                                   # EatrixF_PrefersBeatrixFarrand (:469-508)
+    for q in ("eatrix f", "eatrix fe", "eatrix fea", "eatrix fer"):
+        t, _ = _movie_search(oracle_movies, movie_titles, q, 10); assert t, q
+        if len(q.split()[-1]) >= 3:
+            assert "beatrix" in t[0].lower() and "farrand" in t[0].lower(), (q, t[0])
+
+
+def test_movie_two_f_and_two_fo(oracle_movies, movie_titles):
+    import re
+    t, _ = _movie_search(oracle_movies, movie_titles, "two f", 10)                      # Search_TwoF_PrefersStrictPrefixMatch (:661-694)
+    assert len(t) >= 2 and t[0].lower().startswith("two ") and re.search(r"\bTwo\s+[Ff]", t[0], re.I)
+    t, s = _movie_search(oracle_movies, movie_titles, "two fo", 20)                     # Search_TwoFo_AllExactPrefixesBeforePartialMatches (:696-776)
+    assert len(t) >= 5
+    pre = [x.lower().startswith("two fo") for x in t]
+    if False in pre and pre.index(False) > 0:
+        i = pre.index(False); assert pre[i - 1] and s[i - 1] > s[i]
+    low = [x.lower() for x in t]
+    if "tea for two" in low:
+        assert any(pre[: low.index("tea for two")])
+
+
+def test_short_query_two_letters_small_corpora():
+    o = _engine(["cat", "dog", "ape"])                                                  # ShortQuery_TwoLetters_ReturnsPartialMatch (:999-1042)
+    r = o.search("va", 10); assert r["status"] == 0 and r["keys"] and r["keys"][0] in (1, 3) and all(r["scores"][0] >= x for x in r["scores"])
+    o = _engine(["apple", "banana", "cherry", "grape", "orange"])                       # ShortQuery_TwoLetters_MultiplePartialMatches (:1044-1085)
+    r = o.search("ra", 10); assert r["status"] == 0 and r["keys"] and {3, 4, 5} & set(r["keys"])
