@@ -104,3 +104,27 @@ def test_emu_small_reference_corpora(emu):
         for mr in (5, 8, 10):
             assert not compare_search(eng, orc, qs, max_results=mr), (texts[0], mr)
         assert not compare_stage1(eng, orc, qs)
+
+
+def test_concurrent_search_calls_are_serialised_correctly(emu, movie_titles):
+    """ThreadSafetyTests.cs in spirit: many threads call Search on one engine (readers under the C# read lock); the C-ABI serialises
+    the calls on its single batch workspace and every caller must get exactly its own answer."""
+    import threading
+    eng = ib.SearchEngine(_gpu_lib=emu)
+    eng.IndexColumns(np.arange(5000), [ib.Field("content")], [movie_titles[:5000]])
+    qs = ["star wars", "the matrix", "godfather", "lord rings", "toy story", "batman", "alien", "love", "night", "dark knight"]
+    want = {q: [(e.DocumentId, e.Score, e.Tiebreaker) for e in eng.Search(ib.Query(q, 10)).Records] for q in qs}
+    errors = []
+
+    def worker(k):
+        try:
+            for i in range(30):
+                q = qs[(i * 7 + k) % len(qs)]
+                got = [(e.DocumentId, e.Score, e.Tiebreaker) for e in eng.Search(ib.Query(q, 10)).Records]
+                if got != want[q]:
+                    errors.append((k, q))
+        except Exception as e:      # noqa: BLE001
+            errors.append((k, repr(e)))
+    ts = [threading.Thread(target=worker, args=(k,)) for k in range(6)]
+    [t.start() for t in ts]; [t.join() for t in ts]
+    assert not errors, errors[:3]
