@@ -267,6 +267,13 @@ class SearchEngine:
             return -1
         code = flt.bytecode() if isinstance(flt, Filter) else bytes(flt)
         if code not in self._filters:
+            if isinstance(flt, Filter):
+                # The reference's VM reads any field of the document (FilterVM.cs:160-165); the device only holds columns for fields
+                # flagged Filterable or Facetable. A filter on another schema field must fail loudly, not evaluate to "no match".
+                have = {c.lower() for c in self._columns}
+                missing = sorted(f for f in flt.fields() if f.lower() not in have and any(f.lower() == x.Name.lower() for x in self._schema))
+                if missing:
+                    raise ValueError("filter uses field(s) %s that are neither Filterable nor Facetable in the schema: no device column exists for them" % missing)
             fid = C.c_int(-1); buf = np.frombuffer(code, np.uint8).copy()
             self._check(self._gpu.ifx_filter_register(self._index, _p(buf), C.c_size_t(len(buf)), C.byref(fid)), "ifx_filter_register")
             self._filters[code] = fid.value

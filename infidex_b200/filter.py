@@ -84,6 +84,14 @@ class Filter:
     @staticmethod
     def Not(a): return Filter("not", left=a)
 
+    def fields(self):
+        """Names of the document fields the filter reads."""
+        out = set()
+        if self.kind in ("and", "or"): out |= self.left.fields() | self.right.fields()
+        elif self.kind == "not": out |= self.left.fields()
+        else: out.add(self.field)
+        return out
+
     # ---- FilterCompiler
     def _compile(self, pool, code):
         k = self.kind

@@ -57,3 +57,42 @@ def test_emu_random_corpora(block):
     for seed in range(block * 40, block * 40 + 40):
         bad = _case(seed, emu)
         assert not bad, (seed, bad[:1])
+
+
+def _q(text, flt):
+    q = ib.Query(text, 10); q.Filter = flt
+    return q
+
+
+def _filter_case(seed, emu):
+    """Multi-field documents with numeric / string columns, random Infiscript filters, facets on."""
+    rng = random.Random(10_000 + seed)
+    alph = rng.choice(ALPHABETS[:4]); vocab = [_word(rng, alph, 2, 8) for _ in range(rng.choice([10, 60]))]
+    nd = rng.choice([5, 60, 400])
+    titles = [" ".join(rng.choice(vocab) for _ in range(rng.randint(1, 5))) for _ in range(nd)]
+    years = np.array([rng.randint(1950, 2024) for _ in range(nd)], np.int64)
+    ratings = np.array([round(rng.randint(10, 100) / 10.0, 1) for _ in range(nd)], np.float64)
+    genres = [rng.choice(["Fantasy", "Horror", "SciFi", "drama", "", "Sci-Fi Noir"]) for _ in range(nd)]
+    schema = [ib.Field("title", None, ib.Weight.High), ib.Field("year", None, ib.Weight.Med, indexable=False, filterable=True, facetable=True),
+              ib.Field("rating", None, ib.Weight.Med, indexable=False, filterable=True), ib.Field("genre", None, ib.Weight.Low, filterable=True, facetable=True)]
+    cols = [titles, years, ratings, genres]; keys = np.arange(100, 100 + nd, dtype=np.int64)
+    eng = ib.SearchEngine(_gpu_lib=emu); eng.IndexColumns(keys, schema, cols)
+    orc = OracleEngine([OField(f.Name, f.Weight, f.Indexable, f.Filterable, f.Facetable) for f in schema]); orc.index_columns(keys, cols)
+    qs = [" ".join(rng.choice(titles).split()[:2]) for _ in range(8)]
+    exprs = ["year >= %d" % rng.randint(1950, 2024), "year BETWEEN 1980 AND %d" % rng.randint(1981, 2024), "rating > %.1f AND year < %d" % (rng.randint(10, 90) / 10, rng.randint(1960, 2024)),
+             "genre = 'fantasy' OR genre = 'HORROR'", "NOT genre = ''", "genre IN ('SciFi', 'drama') && rating <= 7.5", "genre CONTAINS 'sci'", "genre STARTS WITH 'sci' | genre ENDS WITH 'noir'",
+             "genre LIKE '%%i%%' AND ! (year < 1990)", "rating != 5.0", "genre IS NOT NULL AND (year > 2000 OR rating >= 9)"]
+    with pytest.raises(ValueError):        # `title` is indexable only: no device column -- the mirror must refuse, not answer "no match"
+        eng.Search(_q(qs[0], ib.Filter.Parse("title CONTAINS 'a'")))
+    bad = []
+    for e in rng.sample(exprs, 4):
+        bad += compare_search(eng, orc, qs, max_results=rng.choice([3, 10, 40]), flt=ib.Filter.Parse(e), facets=True)
+    return bad
+
+
+@pytest.mark.parametrize("block", range(2))
+def test_emu_random_filters_and_facets(block):
+    emu = emu_lib()
+    for seed in range(block * 30, block * 30 + 30):
+        bad = _filter_case(seed, emu)
+        assert not bad, (seed, bad[:1])
