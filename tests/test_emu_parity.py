@@ -128,3 +128,15 @@ def test_concurrent_search_calls_are_serialised_correctly(emu, movie_titles):
     ts = [threading.Thread(target=worker, args=(k,)) for k in range(6)]
     [t.start() for t in ts]; [t.join() for t in ts]
     assert not errors, errors[:3]
+
+
+def test_emu_several_containers(emu):
+    """More than 65 536 documents: container runs, per-container skip-table windows, tail chunks per container, bitset-mode tiers --
+    the multi-container control flow on the CPU (the GPU tests repeat it at 300 k documents)."""
+    vocab = synth.make_vocab(60_000)
+    docs = synth.gen_docs(150_000, vocab)
+    qs = synth.gen_queries(50, docs, vocab)
+    schema, cols = synth.schema_and_columns(docs, False)
+    eng, orc = build_pair(docs["keys"], schema, cols, gpu_lib=emu)
+    assert not compare_stage1(eng, orc, qs)
+    assert not compare_search(eng, orc, qs[:25])
