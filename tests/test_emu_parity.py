@@ -140,3 +140,14 @@ def test_emu_several_containers(emu):
     eng, orc = build_pair(docs["keys"], schema, cols, gpu_lib=emu)
     assert not compare_stage1(eng, orc, qs)
     assert not compare_search(eng, orc, qs[:25])
+
+
+def test_emu_degenerate_corpora(emu):
+    """No documents at all; documents that are empty, blank, delimiter-only or shorter than an n-gram."""
+    eng = ib.SearchEngine(_gpu_lib=emu); eng.IndexColumns(np.zeros(0, np.int64), [ib.Field("content")], [[]])
+    r = eng.Search(ib.Query("hello", 10)); assert not r.Records and not (r.Status & ~8)
+    texts = ["", "   ", "a", "ab", "---", "hello"]
+    eng = ib.SearchEngine(_gpu_lib=emu); eng.IndexColumns(np.arange(len(texts)), [ib.Field("content")], [texts])
+    orc = OracleEngine(); orc.index_texts(texts, keys=np.arange(len(texts)))
+    qs = ["hello", "hel", "a", "ab", "---", "x y z", "hellp", "hello hello"]
+    assert not compare_search(eng, orc, qs) and not compare_stage1(eng, orc, qs)
