@@ -28,6 +28,12 @@ class _Pool:
             self.index[k] = len(self.items); self.items.append(("s", s))
         return self.index[k]
 
+    def add_number(self, x):
+        k = ("n", float(x))
+        if k not in self.index:
+            self.index[k] = len(self.items); self.items.append(("n", float(x)))
+        return self.index[k]
+
     def add_array(self, values):
         self.items.append(("a", [str(v) for v in values])); return len(self.items) - 1
 
@@ -43,6 +49,8 @@ class _Pool:
         for kind, v in self.items:
             if kind == "s":
                 out += b"\x01" + self._dotnet_string(v)
+            elif kind == "n":
+                out += b"\x02" + struct.pack("<d", v)
             else:
                 out += b"\x03" + struct.pack("<i", len(v)) + b"".join(self._dotnet_string(x) for x in v)
         return bytes(out)
@@ -53,7 +61,7 @@ class FilterParseError(ValueError):
 
 
 class Filter:
-    """AST node. kind in: value, range, in, string, null, and, or, not."""
+    """AST node. kind in: value, range, in, string, null, and, or, not, ternary, literal."""
 
     def __init__(self, kind, **kw):
         self.kind = kind; self.__dict__.update(kw); self._code = None
@@ -84,11 +92,19 @@ class Filter:
     @staticmethod
     def Not(a): return Filter("not", left=a)
 
+    @staticmethod
+    def Ternary(cond, true_value, false_value): return Filter("ternary", cond=cond, left=true_value, right=false_value)
+
+    @staticmethod
+    def Literal(value): return Filter("literal", value=value)
+
     def fields(self):
         """Names of the document fields the filter reads."""
         out = set()
         if self.kind in ("and", "or"): out |= self.left.fields() | self.right.fields()
         elif self.kind == "not": out |= self.left.fields()
+        elif self.kind == "ternary": out |= self.cond.fields() | self.left.fields() | self.right.fields()
+        elif self.kind == "literal": pass
         else: out.add(self.field)
         return out
 
@@ -101,6 +117,16 @@ class Filter:
             self.right._compile(pool, code); code[jp][1] = len(code)
         elif k == "not":
             self.left._compile(pool, code); code.append([OP["NOT"], None])
+        elif k == "ternary":      # FilterCompiler.CompileTernary (:224-252)
+            self.cond._compile(pool, code); jf = len(code); code.append([OP["JUMP_IF_FALSE"], 0]); code.append([OP["POP"], None])
+            self.left._compile(pool, code); je = len(code); code.append([OP["JUMP"], 0])
+            code[jf][1] = len(code); code.append([OP["POP"], None]); self.right._compile(pool, code); code[je][1] = len(code)
+        elif k == "literal":      # CompileLiteral (:254-279)
+            v = self.value
+            if isinstance(v, bool): c = pool.add_string("True" if v else "False")
+            elif isinstance(v, (int, float)): c = pool.add_number(v)
+            else: c = pool.add_string("null" if v is None else str(v))
+            code.append([OP["PUSH_CONST"], c])
         elif k == "value":
             f = pool.add_string(self.field); v = pool.add_string("" if self.value is None else str(self.value))
             code += [[OP["PUSH_FIELD"], f], [OP["PUSH_CONST"], v], [OP["EQ"], None]]
@@ -141,7 +167,7 @@ class Filter:
 
     def __eq__(self, o): return isinstance(o, Filter) and self.bytecode() == o.bytecode()
 
-    # ---- Filter.Parse: the Infiscript grammar (Api/Infiscript.bnf, Api/FilterParser.cs) without the ternary form
+    # ---- Filter.Parse: the Infiscript grammar (Api/Infiscript.bnf, Api/FilterParser.cs)
     _TOK = re.compile(r"\s*(?:(<=|>=|!=|&&|\|\||=|<|>|\(|\)|,|&|\||!|\?|:)|'((?:[^']|'')*)'|\"((?:[^\"]|\"\")*)\"|([A-Za-z_][A-Za-z0-9_\.]*)|(-?\d+(?:\.\d+)?(?:[eE][+-]?\d+)?))")
 
     @staticmethod
@@ -176,6 +202,13 @@ class Filter:
         def value():
             t = take(); need(t[0] in ("val", "id"), "expected a value"); return t[1]
 
+        def parse_ternary():        # <or_expression> [ "?" <ternary> ":" <ternary> ], right-associative, lowest precedence
+            cond = parse_or()
+            if is_op("?"):
+                take(); tv = parse_ternary(); need(is_op(":"), "ternary format is: condition ? true_value : false_value"); take(); fv = parse_ternary()
+                return Filter.Ternary(cond, tv, fv)
+            return cond
+
         def parse_or():
             left = parse_and()
             while kw("OR") or is_op("||", "|"):
@@ -196,7 +229,10 @@ class Filter:
         def parse_atom():
             t = take()
             if t == ("op", "("):
-                e = parse_or(); need(take() == ("op", ")"), "expected )"); return e
+                e = parse_ternary(); need(take() == ("op", ")"), "expected )"); return e
+            if t[0] == "val":            # literal (ternary branches): a number when it parses as one (FilterParser.cs:179-191)
+                try: return Filter.Literal(float(t[1]))
+                except ValueError: return Filter.Literal(t[1])
             need(t[0] == "id", "expected field name")
             field = t[1]
             if kw("BETWEEN"):
@@ -224,9 +260,7 @@ class Filter:
 
         if not toks:
             raise FilterParseError("empty filter expression")
-        e = parse_or()
-        if is_op("?"):
-            raise FilterParseError("the ternary form (cond ? a : b) is not supported by this binding")
+        e = parse_ternary()
         if p[0] != len(toks):
             raise FilterParseError("trailing tokens in filter expression")
         return e

@@ -59,3 +59,44 @@ def test_meaning_through_the_oracle_vm():
     assert sel("title CONTAINS 'test'") == [2] and sel("title STARTS WITH 'The'") == [1] and sel("email ENDS WITH '.com'") == [0, 2]
     assert sel("title LIKE '%Potter%'") == [0] and sel("description IS NOT NULL") == [0, 1, 2] and sel("description IS NULL") == []
     assert sel("a = '1' OR genre = 'Horror' AND year >= '2000'") == [] and sel("(a = '1' OR genre = 'Horror') AND year >= '1970'") == [1]
+
+
+# ---- TernaryFilterTests.cs: cond ? a : b (lowest precedence, right-associative), literal branches ---------------------------------------
+def test_ternary_structure():
+    f = P("score >= 90 ? status = 'premium' : status = 'basic'"); assert f.kind == "ternary" and f.cond.kind == "range" and f.left.kind == "value"   # :26-44
+    f = P("a = '1' ? b = '2' : c = '3' ? d = '4' : e = '5'"); assert f.kind == "ternary" and f.right.kind == "ternary" and f.left.kind == "value"  # :228-246
+    f = P("a = '1' OR b = '2' ? c = '3' : d = '4'"); assert f.kind == "ternary" and f.cond.kind == "or"                                             # :197-226
+    f = P("(a = '1' ? b = '2' : c = '3') AND d = '4'"); assert f.kind == "and" and f.left.kind == "ternary"                                          # :136-157
+    f = P("age >= 18 ? 'adult' : 'minor'"); assert (f.left.kind, f.left.value, f.right.value) == ("literal", "adult", "minor")                        # :340-359
+    f = P("premium = 'yes' ? 100 : 50"); assert (f.left.value, f.right.value) == (100.0, 50.0)                                                        # :377-394
+    f = P("available = 'yes' ? price >= 100 : 'unavailable'"); assert f.left.kind == "range" and f.right.kind == "literal"                            # :396-
+    assert b"VIP" in P("premium = 'yes' ? 'VIP' : 'Standard'").bytecode() and b"Standard" in P("premium = 'yes' ? 'VIP' : 'Standard'").bytecode()     # :361-375
+
+
+@pytest.mark.parametrize("expr", ["score >= 90 ? 'high'", "? 'yes' : 'no'", "score >= 90 ? : 'low'", "score >= 90 ? 'high' :"])
+def test_ternary_errors(expr):                            # :247-282
+    with pytest.raises(ib.FilterParseError):
+        P(expr)
+
+
+def test_ternary_meaning_oracle_and_product():
+    """Execute_SimpleTernary_True (:46-60) and friends on the oracle's VM, then the product's VM (kernel emulation) on a small corpus."""
+    from parity_util import compare_search, emu_lib
+    rows = [dict(title="alpha premium member", score="95", status="premium"), dict(title="alpha basic member", score="40", status="basic"),
+            dict(title="alpha odd member", score="95", status="basic"), dict(title="alpha other member", score="10", status="premium")]
+    names = ["title", "score", "status"]
+    o = OracleEngine([OField("title", 1, True, False, False), OField("score", 1, False, True, False), OField("status", 1, False, True, True)])
+    keys = np.arange(1, len(rows) + 1); cols = [[r[n] for r in rows] for n in names]; o.index_columns(keys, cols)
+    sel = lambda e: [i + 1 for i in range(len(rows)) if o.filter_eval(P(e).bytecode(), i)]
+    assert sel("score >= 90 ? status = 'premium' : status = 'basic'") == [1, 2]
+    assert sel("score >= 90 ? status = 'premium' : score < 20 ? status = 'premium' : status = 'basic'") == [1, 2, 4]
+    assert sel("score >= 90 ? 'high' : 'low'") == []            # a literal on top of the stack is not `true` (FilterVM.cs:26-46)
+    eng = ib.SearchEngine(_gpu_lib=emu_lib())
+    eng.IndexColumns(keys, [ib.Field("title"), ib.Field("score", None, ib.Weight.Med, indexable=False, filterable=True),
+                            ib.Field("status", None, ib.Weight.Med, indexable=False, filterable=True, facetable=True)], cols)
+    for e in ("score >= 90 ? status = 'premium' : status = 'basic'", "score >= 90 ? status = 'premium' : score < 20 ? status = 'premium' : status = 'basic'",
+              "score >= 90 ? 'high' : 'low'"):
+        assert not compare_search(eng, o, ["alpha member", "premium"], flt=P(e), facets=True), e
+    # numeric constants in the pool are not executed on the device (their double.ToString() form would be needed): flagged, not guessed
+    q = ib.Query("alpha member", 10); q.Filter = P("status = 'basic' ? 1 : score > 50")
+    assert eng.Search(q).Status & 2
