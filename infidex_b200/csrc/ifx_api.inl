@@ -32,6 +32,7 @@ static void h2d(void* d, const void* s, size_t n) { if (n) memcpy(d, s, n); }
 static void d2h(void* d, const void* s, size_t n) { if (n) memcpy(d, s, n); }
 static void dev_zero(void* d, size_t n) { if (n) memset(d, 0, n); }
 struct Timer { void start() {} float stop() { return 0.f; } };
+struct DeviceGuard { explicit DeviceGuard(int) {} };
 #else
 #define CUDA_TRY(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) throw std::string(#x ": ") + cudaGetErrorString(e_); } while (0)
 static bool dev_ok() { int n = 0; return cudaGetDeviceCount(&n) == cudaSuccess && n > 0; }
@@ -43,6 +44,9 @@ static void dev_zero(void* d, size_t n) { if (n) CUDA_TRY(cudaMemset(d, 0, n)); 
 struct Timer { cudaEvent_t a = nullptr, b = nullptr; cudaStream_t s = 0;
     void start() { if (!a) { cudaEventCreate(&a); cudaEventCreate(&b); } cudaEventRecord(a, s); }
     float stop() { cudaEventRecord(b, s); cudaEventSynchronize(b); float ms = 0; cudaEventElapsedTime(&ms, a, b); return ms; } };
+// The CUDA current device is per host thread: every entry point that touches the device selects the index's device for its own
+// duration (callers may come from any thread of the C# pool) and restores the caller's.
+struct DeviceGuard { int prev = -1; explicit DeviceGuard(int dev) { cudaGetDevice(&prev); if (prev != dev) CUDA_TRY(cudaSetDevice(dev)); else prev = -1; } ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); } };
 #ifndef IFX_EXPAND_THREADS
 #define IFX_EXPAND_THREADS 512
 #endif
@@ -61,7 +65,7 @@ struct ifx_index {
     std::vector<S1Workspace> ws; S1Workspace* d_ws = nullptr;
     int32_t* d_pool = nullptr; unsigned long long pool_cap = 0;
     int max_batch = 16384;
-    int device = 0; uint8_t* d_flush = nullptr;
+    int device = 0; uint8_t* d_flush = nullptr; bool attr_s1 = false, attr_s2 = false;   // kernel attributes are per device: tracked per index (guarded by mu)
     std::vector<FilterProg> h_filters; FilterProg* d_filters = nullptr;
     std::vector<Column> h_columns; std::vector<std::u16string> column_names;
     std::mutex mu; std::mutex call_mu; struct ifx_batch* cached = nullptr;   // batch workspace reused by ifx_search_batch
@@ -273,6 +277,6 @@ extern "C" int ifx_index_create(const ifx_index_image* img, const ifx_params* pp
     *out = ix; return IFX_OK;
 }
 
-extern "C" void ifx_index_destroy(ifx_index* idx) { delete idx; }
+extern "C" void ifx_index_destroy(ifx_index* idx) { if (!idx) return; try { DeviceGuard dg(idx->device); delete idx; } catch (...) { } }
 
 #include "ifx_launch.inl"

@@ -41,6 +41,7 @@ constexpr int MAX_K = 1024;          // coverage depth supported by the on-chip 
 constexpr int AFFIX_CAP = 4096;      // WordMatcher.cs:41 MaxFstAffixTermsPerQuery
 constexpr int MAX_QTOK = 64;         // coverage query tokens (len >= 2, deduped)
 constexpr int MAX_WM_WORDS = 32;     // query words (len >= 2) looked up in the WordMatcher
+constexpr int MAX_TOKLEN = 96;       // Levenshtein row length of the coverage kernel; a query word longer than this raises IFX_Q_OVERFLOW
 constexpr int MAX_CONTAINERS = 8192; // 65536-doc containers per shard (N <= 536M)
 constexpr char16_t PAD = 0xFFFF;
 

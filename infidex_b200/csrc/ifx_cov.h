@@ -11,7 +11,6 @@
 namespace ifx {
 
 constexpr int MAX_DTOK = 192;        // document tokens handled on chip; longer documents raise IFX_Q_OVERFLOW
-constexpr int MAX_TOKLEN = 96;       // Levenshtein row length (tokens longer than this never match fuzzily)
 
 struct Str { const uint16_t* p; int n; };
 

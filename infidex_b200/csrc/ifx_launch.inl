@@ -24,12 +24,12 @@ __global__ void k_order(DevIndex ix, const QueryPlan* plans, int nq, int* order)
     for (int q = threadIdx.x; q < nq; q += blockDim.x) { int pos = atomicAdd(&base[bucket(q)], 1); order[pos] = q; }
 }
 __global__ void __launch_bounds__(IFX_EXPAND_THREADS, 2) k_expand(DevIndex ix, QueryPlan* plans, const FuzzyItem* items, BatchCounters* bc, S1Workspace* wss,
-                                                int32_t* pool, unsigned long long pool_cap, const uint8_t* sorted_len, int* work) {
+                                                int32_t* pool, unsigned long long pool_cap, const uint8_t* sorted_len, int* work, int items_cap) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     S1Shared& sh = *reinterpret_cast<S1Shared*>(smem_raw); Ctx c; S1Workspace ws = wss[blockIdx.x];
     for (int i = threadIdx.x; i < MAX_CONTAINERS; i += blockDim.x) sh.dirty[i] = 0;
     __syncthreads();
-    const int n_items = bc->n_fuzzy_items;
+    const int n_items = bc->n_fuzzy_items < items_cap ? bc->n_fuzzy_items : items_cap;   // prepare_query counts past the cap (and flags those queries)
     for (;;) {
         if (threadIdx.x == 0) sh.bcast[7] = atomicAdd(work, 1);
         __syncthreads();
@@ -64,7 +64,7 @@ __global__ void __launch_bounds__(IFX_S1_THREADS, 2) k_stage1(DevIndex ix, const
 static void run_stage1_phase(ifx_batch* b, ifx_stats* st) {
     ifx_index* ix = b->idx; const int nq = b->nq; const int K = b->depth_max;
     BatchCounters zero{}; h2d(b->d_bc, &zero, sizeof(zero));
-    int items_cap = nq * 4 + 64;
+    const int items_cap = nq * MAX_FUZZY;       // every query may carry MAX_FUZZY unknown words: the item list can never overflow
     Timer t;
 #ifdef IFX_EMU
     std::vector<int64_t> off(nq + 1); d2h(off.data(), b->d_off, (nq + 1) * 8);
@@ -76,14 +76,13 @@ static void run_stage1_phase(ifx_batch* b, ifx_stats* st) {
     (void)t;
 #else
     size_t smem = sizeof(S1Shared);
-    static bool attr_set = false;
-    if (!attr_set) { CUDA_TRY(cudaFuncSetAttribute(k_expand, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); CUDA_TRY(cudaFuncSetAttribute(k_stage1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_set = true; }
+    if (!ix->attr_s1) { CUDA_TRY(cudaFuncSetAttribute(k_expand, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); CUDA_TRY(cudaFuncSetAttribute(k_stage1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); ix->attr_s1 = true; }
     t.start();
     k_prepare<<<(nq + 127) / 128, 128>>>(ix->v, b->d_text, b->d_off, b->d_par, nq, b->d_plans, b->d_items, items_cap, b->d_bc);
     float ms_prep = t.stop();
     t.start();
     CUDA_TRY(cudaMemsetAsync(b->d_work, 0, 2 * sizeof(int)));
-    k_expand<<<ix->n_ctas, IFX_EXPAND_THREADS, smem>>>(ix->v, b->d_plans, b->d_items, b->d_bc, ix->d_ws, ix->d_pool, ix->pool_cap, ix->d_sorted_len, b->d_work);
+    k_expand<<<ix->n_ctas, IFX_EXPAND_THREADS, smem>>>(ix->v, b->d_plans, b->d_items, b->d_bc, ix->d_ws, ix->d_pool, ix->pool_cap, ix->d_sorted_len, b->d_work, items_cap);
     float ms_exp = t.stop();
     t.start();
     k_order<<<1, 1024>>>(ix->v, b->d_plans, nq, b->d_order);
@@ -109,7 +108,7 @@ static int fill_batch(ifx_batch* b, const ifx_query* q, int nq) {
     if (fresh) {
         b->nq = nq; b->depth_max = depth_max; b->cap_max = cap_max; b->text_cap = std::max<size_t>(text.size(), (size_t)nq * 64);
         b->d_text = b->alloc<uint16_t>(b->text_cap); b->d_off = b->alloc<int64_t>(nq + 1); b->d_par = b->alloc<int32_t>(par.size());
-        b->d_plans = b->alloc<QueryPlan>(nq); b->d_items = b->alloc<FuzzyItem>((size_t)nq * 4 + 64); b->d_bc = b->alloc<BatchCounters>(1); b->d_work = b->alloc<int>(8); dev_zero(b->d_work, 8 * sizeof(int));
+        b->d_plans = b->alloc<QueryPlan>(nq); b->d_items = b->alloc<FuzzyItem>((size_t)nq * MAX_FUZZY); b->d_bc = b->alloc<BatchCounters>(1); b->d_work = b->alloc<int>(8); dev_zero(b->d_work, 8 * sizeof(int));
         size_t K = b->depth_max;
         b->d_s1_key = b->alloc<int64_t>(nq * K); b->d_s1_doc = b->alloc<int32_t>(nq * K); b->d_s1_score = b->alloc<float>(nq * K); b->d_s1_n = b->alloc<int32_t>(nq); b->d_order = b->alloc<int>(nq); b->d_qdbg = b->alloc<long long>((size_t)nq * IFX_QDBG); dev_zero(b->d_qdbg, (size_t)nq * IFX_QDBG * 8);
     } else if (text.size() > b->text_cap) return fail(IFX_ERR_INVALID, "batch text outgrew its buffer");
@@ -121,11 +120,11 @@ static int fill_batch(ifx_batch* b, const ifx_query* q, int nq) {
 extern "C" int ifx_batch_upload(ifx_index* idx, const ifx_query* q, int nq, ifx_batch** out) {
     if (!idx || !q || nq <= 0 || !out) return fail(IFX_ERR_INVALID, "bad batch arguments");
     ifx_batch* b = new ifx_batch(); b->idx = idx;
-    try { int rc = fill_batch(b, q, nq); if (rc) { delete b; return rc; } }
+    try { DeviceGuard dg(idx->device); int rc = fill_batch(b, q, nq); if (rc) { delete b; return rc; } }
     catch (const std::string& e) { delete b; return fail(IFX_ERR_CUDA, e); }
     *out = b; return IFX_OK;
 }
-extern "C" void ifx_batch_free(ifx_batch* b) { delete b; }
+extern "C" void ifx_batch_free(ifx_batch* b) { if (!b) return; try { DeviceGuard dg(b->idx->device); delete b; } catch (...) { } }
 
 extern "C" int ifx_stage1_batch(ifx_index* idx, const ifx_query* q, int nq, int depth, int64_t* doc_key, float* score, int32_t* n, int32_t* status, ifx_stats* st) {
     if (!dev_ok()) return fail(IFX_ERR_NO_DEVICE, "no CUDA device available (infidex_b200 has no CPU fallback)");
@@ -133,7 +132,7 @@ extern "C" int ifx_stage1_batch(ifx_index* idx, const ifx_query* q, int nq, int 
     ifx_batch* b = nullptr; int rc = ifx_batch_upload(idx, qq.data(), nq, &b); if (rc) return rc;
     if (st) memset(st, 0, sizeof(*st));
     try {
-        std::lock_guard<std::mutex> lk(idx->mu);
+        std::lock_guard<std::mutex> lk(idx->mu); DeviceGuard dg(idx->device);
         run_stage1_phase(b, st);
         d2h(doc_key, b->d_s1_key, (size_t)nq * depth * 8); d2h(score, b->d_s1_score, (size_t)nq * depth * 4); d2h(n, b->d_s1_n, (size_t)nq * 4);
         if (status) { std::vector<QueryPlan> pl(nq); d2h(pl.data(), b->d_plans, sizeof(QueryPlan) * (size_t)nq); for (int i = 0; i < nq; i++) { status[i] = pl[i].status; if (n[i] < 0) { status[i] |= IFX_Q_OVERFLOW; n[i] = 0; } } }
@@ -144,4 +143,4 @@ extern "C" int ifx_stage1_batch(ifx_index* idx, const ifx_query* q, int nq, int 
 #include "ifx_search.inl"
 
 // debugging aid: per-query [n_cand, n_terms, selection_ns, path, total_ns, cta] of the last run's k_stage1
-extern "C" int ifx_debug_stage1_queries(ifx_batch* b, long long* out) { try { d2h(out, b->d_qdbg, (size_t)b->nq * IFX_QDBG * 8); } catch (const std::string& e) { return fail(IFX_ERR_CUDA, e); } return IFX_OK; }
+extern "C" int ifx_debug_stage1_queries(ifx_batch* b, long long* out) { try { DeviceGuard dg(b->idx->device); d2h(out, b->d_qdbg, (size_t)b->nq * IFX_QDBG * 8); } catch (const std::string& e) { return fail(IFX_ERR_CUDA, e); } return IFX_OK; }

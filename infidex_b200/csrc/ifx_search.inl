@@ -27,29 +27,33 @@ static std::u16string utf8_to_u16(const uint8_t* p, size_t n) {
     return r;
 }
 
-extern "C" int ifx_filter_register(ifx_index* idx, const uint8_t* data, size_t len, int* out_id) {
-    if (!idx || !data || !out_id) return fail(IFX_ERR_INVALID, "null argument");
-    size_t p = 0; auto need = [&](size_t n) { return p + n <= len; };
-    auto rd_i32 = [&]() { int32_t v; memcpy(&v, data + p, 4); p += 4; return v; };
-    auto rd_str = [&]() { uint32_t n = 0; int sh = 0; while (p < len) { uint8_t b = data[p++]; n |= (uint32_t)(b & 0x7F) << sh; if (!(b & 0x80)) break; sh += 7; } std::u16string s = utf8_to_u16(data + p, std::min<size_t>(n, len - p)); p += n; return s; };
+static int filter_register_impl(ifx_index* idx, const uint8_t* data, size_t len, int* out_id) {
+    size_t p = 0; bool trunc = false; auto need = [&](size_t n) { return n <= len && p <= len - n; };
+    auto rd_i32 = [&]() { int32_t v = 0; if (!need(4)) { trunc = true; p = len; return v; } memcpy(&v, data + p, 4); p += 4; return v; };
+    auto rd_str = [&]() { uint32_t n = 0; int sh = 0; bool done = false; while (p < len && sh < 35) { uint8_t b = data[p++]; n |= (uint32_t)(b & 0x7F) << sh; if (!(b & 0x80)) { done = true; break; } sh += 7; }
+                          if (!done || !need(n)) { trunc = true; p = len; return std::u16string(); } std::u16string s = utf8_to_u16(data + p, n); p += n; return s; };
     if (len < 23 || memcmp(data, "INFISCRIPT-V1", 13) != 0) return fail(IFX_ERR_INVALID, "bad INFISCRIPT magic");
     p = 13; uint16_t ver; memcpy(&ver, data + p, 2); p += 2; if (ver != 1) return fail(IFX_ERR_INVALID, "unsupported INFISCRIPT version");
-    int pool_size = rd_i32(); size_t pool_end = p + (size_t)pool_size; if (pool_end > len) return fail(IFX_ERR_INVALID, "truncated constant pool");
-    int cnt = rd_i32();
+    const int pool_size = rd_i32(); if (pool_size < 4 || !need((size_t)pool_size)) return fail(IFX_ERR_INVALID, "truncated constant pool");
+    const size_t pool_end = p + (size_t)pool_size;
+    const int cnt = rd_i32(); if (cnt < 0 || cnt > pool_size) return fail(IFX_ERR_INVALID, "constant count out of range");   // every constant takes >= 1 byte
     std::vector<FConst> consts(cnt); std::vector<uint16_t> chars; std::vector<FConst> extra;
     std::vector<std::vector<std::u16string>> arrays(cnt);
     auto add_str = [&](FConst& k, const std::u16string& s) { k.kind = 1; k.off = (int32_t)chars.size(); k.len = (int32_t)s.size(); chars.insert(chars.end(), s.begin(), s.end()); double d = 0; k.is_num = host_try_parse_double((const uint16_t*)s.data(), (int)s.size(), d) ? 1 : 0; k.num = d; k.col = -1; k.arr_start = k.arr_len = 0;
         for (size_t c = 0; c < idx->column_names.size(); c++) if (idx->column_names[c] == s) { k.col = (int32_t)c; break; } };
     for (int i = 0; i < cnt; i++) {
-        if (!need(1)) return fail(IFX_ERR_INVALID, "truncated constant"); int kind = data[p++]; FConst& k = consts[i]; memset(&k, 0, sizeof(k)); k.col = -1;
+        if (!need(1) || p >= pool_end) return fail(IFX_ERR_INVALID, "truncated constant"); int kind = data[p++]; FConst& k = consts[i]; memset(&k, 0, sizeof(k)); k.col = -1;
         if (kind == 1) add_str(k, rd_str());
-        else if (kind == 2) { k.kind = 2; memcpy(&k.num, data + p, 8); p += 8; k.is_num = 1; }
-        else if (kind == 3) { k.kind = 3; int n = rd_i32(); for (int j = 0; j < n; j++) arrays[i].push_back(rd_str()); }
+        else if (kind == 2) { if (!need(8)) return fail(IFX_ERR_INVALID, "truncated number constant"); k.kind = 2; memcpy(&k.num, data + p, 8); p += 8; k.is_num = 1; }
+        else if (kind == 3) { k.kind = 3; const int n = rd_i32(); if (n < 0 || (size_t)n > len - p) return fail(IFX_ERR_INVALID, "array constant length out of range");   // every element takes >= 1 byte
+            for (int j = 0; j < n && !trunc; j++) arrays[i].push_back(rd_str()); }
         else return fail(IFX_ERR_INVALID, "unknown constant type");
+        if (trunc) return fail(IFX_ERR_INVALID, "truncated constant");
     }
     for (int i = 0; i < cnt; i++) if (consts[i].kind == 3) { consts[i].arr_start = cnt + (int)extra.size(); consts[i].arr_len = (int)arrays[i].size(); for (auto& s : arrays[i]) { FConst e; memset(&e, 0, sizeof(e)); add_str(e, s); extra.push_back(e); } }
     consts.insert(consts.end(), extra.begin(), extra.end());
-    p = pool_end; if (!need(4)) return fail(IFX_ERR_INVALID, "truncated code"); int ic = rd_i32();
+    p = pool_end; if (!need(4)) return fail(IFX_ERR_INVALID, "truncated code"); const int ic = rd_i32();
+    if (ic < 0 || (size_t)ic > len - p) return fail(IFX_ERR_INVALID, "instruction count out of range");
     std::vector<FInstr> code;
     for (int i = 0; i < ic; i++) { if (!need(1)) return fail(IFX_ERR_INVALID, "truncated code"); FInstr in; in.op = data[p++]; in.a = 0;
         if (!op_valid((uint8_t)in.op)) return fail(IFX_ERR_INVALID, "unknown opcode");
@@ -58,16 +62,25 @@ extern "C" int ifx_filter_register(ifx_index* idx, const uint8_t* data, size_t l
         if (in.op == 0x01 && consts[in.a].kind != 1) return fail(IFX_ERR_INVALID, "PUSH_FIELD operand is not a string");
         if ((in.op == 0x60 || in.op == 0x61 || in.op == 0x62) && (in.a < 0 || in.a > ic)) return fail(IFX_ERR_INVALID, "jump target out of range");
         code.push_back(in); }
-    try {
-        std::lock_guard<std::mutex> lk(idx->mu);
-        FilterProg fp{}; if (chars.empty()) chars.push_back(0);
-        fp.consts = idx->up(consts.data(), std::max<size_t>(consts.size(), 1)); fp.code = idx->up(code.data(), std::max<size_t>(code.size(), 1)); fp.chars = idx->up(chars.data(), chars.size());
-        fp.n_consts = (int)consts.size(); fp.n_code = (int)code.size();
-        idx->h_filters.push_back(fp);
-        idx->d_filters = idx->up(idx->h_filters.data(), idx->h_filters.size());   // small; previous copies are released with the index
-        *out_id = (int)idx->h_filters.size() - 1;
-    } catch (const std::string& e) { return fail(IFX_ERR_CUDA, e); }
+    std::lock_guard<std::mutex> lk(idx->mu);
+    DeviceGuard dg(idx->device);
+    FilterProg fp{}; if (chars.empty()) chars.push_back(0);
+    fp.consts = idx->up(consts.data(), std::max<size_t>(consts.size(), 1)); fp.code = idx->up(code.data(), std::max<size_t>(code.size(), 1)); fp.chars = idx->up(chars.data(), chars.size());
+    fp.n_consts = (int)consts.size(); fp.n_code = (int)code.size();
+    idx->h_filters.push_back(fp);
+    idx->d_filters = idx->up(idx->h_filters.data(), idx->h_filters.size());   // small; previous copies are released with the index
+    *out_id = (int)idx->h_filters.size() - 1;
     return IFX_OK;
+}
+
+// Externally supplied bytecode: every size is validated against the remaining bytes before it is trusted, and nothing may unwind
+// through the C boundary.
+extern "C" int ifx_filter_register(ifx_index* idx, const uint8_t* data, size_t len, int* out_id) {
+    if (!idx || !data || !out_id) return fail(IFX_ERR_INVALID, "null argument");
+    try { return filter_register_impl(idx, data, len, out_id); }
+    catch (const std::string& e) { return fail(IFX_ERR_CUDA, e); }
+    catch (const std::bad_alloc&) { return fail(IFX_ERR_OOM, "host allocation failed while parsing the filter"); }
+    catch (...) { return fail(IFX_ERR_INVALID, "malformed INFISCRIPT bytecode"); }
 }
 
 // ---- kernels ---------------------------------------------------------------------------------------------------------------
@@ -118,8 +131,7 @@ static void run_stage2_phase(ifx_batch* b, ifx_stats* st) {
     for (int q = 0; q < nq; q++) finalize_query(c, ix->v, b->d_plans[q], b->d_s1_doc + (size_t)q * K, b->d_s1_score + (size_t)q * K, b->d_s1_n[q], b->s2, ix->d_filters, (int)ix->h_filters.size(), *fsh, b->fin, q);
     (void)t; (void)st;
 #else
-    static bool attr_set = false;
-    if (!attr_set) { CUDA_TRY(cudaFuncSetAttribute(k_wm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WmShared))); CUDA_TRY(cudaFuncSetAttribute(k_finalize, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FinShared))); attr_set = true; }
+    if (!ix->attr_s2) { CUDA_TRY(cudaFuncSetAttribute(k_wm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WmShared))); CUDA_TRY(cudaFuncSetAttribute(k_finalize, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FinShared))); ix->attr_s2 = true; }
     t.start();
     CUDA_TRY(cudaMemsetAsync(b->d_work + 2, 0, sizeof(int)));
     k_wm<<<std::min(ix->n_ctas, nq), 256, sizeof(WmShared)>>>(ix->v, b->d_plans, nq, b->d_s1_doc, b->d_s1_score, b->d_s1_n, K, ix->d_ws, b->s2, b->d_work + 2);
@@ -154,7 +166,7 @@ extern "C" int ifx_batch_run(ifx_batch* b, ifx_stats* st) {
     if (!dev_ok()) return fail(IFX_ERR_NO_DEVICE, "no CUDA device available (infidex_b200 has no CPU fallback)");
     if (st) { int64_t h = st->h2d_bytes, d = st->d2h_bytes; memset(st, 0, sizeof(*st)); st->h2d_bytes = h; st->d2h_bytes = d; }
     try {
-        std::lock_guard<std::mutex> lk(b->idx->mu);
+        std::lock_guard<std::mutex> lk(b->idx->mu); DeviceGuard dg(b->idx->device);
         if (!b->s2.ent_doc) alloc_stage2(b, std::max(b->cap_max, 1), b->fcap);
         Timer tt; tt.start();
         run_stage1_phase(b, st);
@@ -170,6 +182,7 @@ extern "C" int ifx_batch_download(ifx_batch* b, ifx_batch_result* out) {
     if (out->cap < b->fin.cap) return fail(IFX_ERR_INVALID, "result capacity smaller than the batch's max_results");
     const size_t nq = b->nq; const int cap = b->fin.cap;
     try {
+        DeviceGuard dg(b->idx->device);
         if (out->cap == cap) { d2h(out->doc_key, b->fin.key, nq * cap * 8); d2h(out->score, b->fin.score, nq * cap * 4); d2h(out->tie, b->fin.tie, nq * cap); }
         else { std::vector<int64_t> k(nq * cap); std::vector<float> s(nq * cap); std::vector<uint8_t> t(nq * cap); d2h(k.data(), b->fin.key, nq * cap * 8); d2h(s.data(), b->fin.score, nq * cap * 4); d2h(t.data(), b->fin.tie, nq * cap);
             for (size_t q = 0; q < nq; q++) { memcpy(out->doc_key + q * out->cap, k.data() + q * cap, cap * 8); memcpy(out->score + q * out->cap, s.data() + q * cap, cap * 4); memcpy(out->tie + q * out->cap, t.data() + q * cap, cap); } }
@@ -188,6 +201,7 @@ extern "C" int ifx_search_batch(ifx_index* idx, const ifx_query* q, int nq, ifx_
     std::lock_guard<std::mutex> call_lock(idx->call_mu);      // one batch in flight per index (callers queue, like writers on the C# RW lock)
     int rc = IFX_OK;
     try {
+        DeviceGuard dg(idx->device);
         ifx_batch* b = idx->cached;
         if (b) { rc = fill_batch(b, q, nq); if (rc || b->fcap != out->facet_cap) { delete b; b = nullptr; idx->cached = nullptr; } }
         if (!b) { b = new ifx_batch(); b->idx = idx; b->fcap = out->facet_cap; rc = fill_batch(b, q, nq); if (rc) { delete b; return rc; } idx->cached = b; }
@@ -202,7 +216,7 @@ extern "C" int ifx_search_batch(ifx_index* idx, const ifx_query* q, int nq, ifx_
 // Benchmark hygiene helper: evict the L2 (126 MB on B200) by overwriting a 256 MiB scratch buffer.
 extern "C" int ifx_flush_l2(ifx_index* idx) {
     if (!idx) return fail(IFX_ERR_INVALID, "null index");
-    try { if (!idx->d_flush) idx->d_flush = idx->alloc<uint8_t>((size_t)256 << 20); dev_zero(idx->d_flush, (size_t)256 << 20);
+    try { DeviceGuard dg(idx->device); if (!idx->d_flush) idx->d_flush = idx->alloc<uint8_t>((size_t)256 << 20); dev_zero(idx->d_flush, (size_t)256 << 20);
 #ifndef IFX_EMU
         CUDA_TRY(cudaDeviceSynchronize());
 #endif

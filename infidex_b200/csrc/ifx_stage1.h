@@ -45,10 +45,11 @@ IFX_FN void prepare_query(const DevIndex& ix, const uint16_t* text, int len, int
         if (i >= len) break;
         int b = i; while (i < len && !is_delim(ix, text[i])) i++;
         n_words++;
+        if (i - b > MAX_TOKLEN) p.status |= 4;      // the coverage kernel's Levenshtein row (ifx_cov.h lev) cannot hold this word: flagged, never silently unmatched
         if (i - b >= 3) { if (n_long > 0) p.ttext[tl++] = u' '; for (int k = b; k < i; k++) p.ttext[tl++] = text[k]; n_long++; } else n_short++;
     }
     bool can_ngrams = n_words == 0 ? len >= 3 : n_long > 0;
-    if (!can_ngrams) { p.status = 1; return; }
+    if (!can_ngrams) { p.status |= 1; return; }
     bool mixed = n_short > 0 && n_long > 0;
     if (!mixed) { tl = len; for (int i = 0; i < len; i++) p.ttext[i] = text[i]; }
     p.tlen = tl;

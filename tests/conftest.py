@@ -13,6 +13,28 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
 
+def _have_gpu():
+    try:
+        import ctypes
+        from infidex_b200 import _build
+        if not os.path.exists(_build.GPU_LIB):
+            return False
+        lib = ctypes.CDLL(_build.GPU_LIB); lib.ifx_device_count.restype = ctypes.c_int
+        return lib.ifx_device_count() > 0
+    except Exception:
+        return False
+
+
+def pytest_collection_modifyitems(config, items):
+    """`gpu` tests need a CUDA device: on a box without one they are skipped (never silently run on a CPU path -- there is none)."""
+    if _have_gpu():
+        return
+    skip = pytest.mark.skip(reason="no CUDA device (run on the B200 box with -m gpu)")
+    for it in items:
+        if "gpu" in it.keywords:
+            it.add_marker(skip)
+
+
 def load_movie_titles():
     p = os.path.join(ROOT, "tests", "golden", "movies_titles.txt.gz")
     return [l.rstrip("\n").replace("\\n", "\n").replace("\\\\", "\\") for l in gzip.open(p, "rt", encoding="utf-8")]

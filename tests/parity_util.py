@@ -74,3 +74,27 @@ def compare_search(eng, orc, queries, max_results=10, flt=None, facets=False, de
         if not ok:
             bad.append((q, k[:5], x["keys"][:5], s[:3].tolist(), x["scores"][:3].tolist(), ti[:3], x["ties"][:3], r.TotalCandidates, x["total"]))
     return bad
+
+
+def compare_search_batch(eng, orc, queries, max_results=10, flt=None, depth=500, threads=None):
+    """compare_search for large batches: the oracle runs the whole batch on all host threads (ids, Score bits, tie bytes, counts);
+    TotalCandidates / facets are covered by compare_search on a subset."""
+    qs = []
+    for q in queries:
+        x = ib.Query(q, max_results); x.Filter = flt; x.CoverageDepth = depth; qs.append(x)
+    res = eng.SearchBatch(qs)
+    ok, os_, ot, on, ost = orc.search_batch(queries, max_results, depth, True, flt.bytecode() if flt else None, threads=threads or (os.cpu_count() or 1))
+    bad = []
+    for i, (q, r) in enumerate(zip(queries, res)):
+        st = r.Status & ~8
+        if st & 1:
+            assert not r.Records
+            continue
+        if ost[i] != 0 or st != 0:
+            if (ost[i] != 0) != (st != 0):
+                bad.append((q, "status", int(ost[i]), r.Status))
+            continue
+        n = int(on[i]); k = [t.DocumentId for t in r.Records]; s = np.array([t.Score for t in r.Records], np.float32); ti = [t.Tiebreaker for t in r.Records]
+        if not (k == ok[i, :n].tolist() and np.array_equal(s.view(np.uint32), os_[i, :n].view(np.uint32)) and ti == ot[i, :n].tolist()):
+            bad.append((q, k[:5], ok[i, :n].tolist()[:5], s[:3].tolist(), os_[i, :3].tolist(), ti[:3], ot[i, :3].tolist()))
+    return bad
