@@ -22,7 +22,7 @@ def _sources():
 
 def build_host(force=False):
     if force or _stale(HOST_LIB, _sources()):
-        subprocess.check_call(["g++"] + GXX_FLAGS + ["-o", HOST_LIB, os.path.join(CSRC, "ifx_host_build.cpp")])
+        subprocess.check_call(["g++"] + GXX_FLAGS + ["-o", HOST_LIB, os.path.join(CSRC, "ifx_host_build.cpp"), os.path.join(CSRC, "ifx_synth.cpp")])
     return HOST_LIB
 
 

@@ -23,6 +23,9 @@
 #include <cstring>
 #include <charconv>
 #include <memory>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 
 namespace {
 #include "chartables.inc"
@@ -94,27 +97,51 @@ struct KeyedRecords {
     std::vector<uint8_t> rec_rep_last;   // did the key's latest posting see a repeat occurrence (stop-term edge rule)
 };
 
-struct Csr { std::vector<char16_t> chars; std::vector<uint32_t> off; std::vector<int64_t> row; std::vector<int32_t> docs; std::vector<uint8_t> w; std::vector<int32_t> extra; std::vector<uint8_t> rep_last; int n = 0; };
+// big flat array without the zero fill of std::vector::resize (the scatter that follows touches every element, in parallel)
+template <class T> struct RawVec {
+    T* p = nullptr; size_t n = 0;
+    RawVec() = default; RawVec(const RawVec&) = delete; RawVec& operator=(const RawVec&) = delete;
+    ~RawVec() { free(p); }
+    void resize(size_t m) { free(p); p = (T*)malloc(std::max<size_t>(m, 1) * sizeof(T)); if (!p) throw std::bad_alloc(); n = m; }
+    T* data() { return p; } const T* data() const { return p; } size_t size() const { return n; }
+    T& operator[](size_t i) { return p[i]; } const T& operator[](size_t i) const { return p[i]; }
+};
+
+template <class F> void par_for(int64_t n, int threads, F f) {       // f(begin, end, thread index)
+    threads = (int)std::max<int64_t>(1, std::min<int64_t>(threads, n));
+    if (threads == 1) { f((int64_t)0, n, 0); return; }
+    std::vector<std::thread> ts;
+    for (int t = 0; t < threads; t++) ts.emplace_back([=] { f(n * t / threads, n * (t + 1) / threads, t); });
+    for (auto& th : ts) th.join();
+}
+
+struct Csr { std::vector<char16_t> chars; std::vector<uint32_t> off; std::vector<int64_t> row; RawVec<int32_t> docs; RawVec<uint8_t> w; std::vector<int32_t> extra; std::vector<uint8_t> rep_last; int n = 0; };
 
 // merge thread-local KeyedRecords (threads own ascending doc ranges) -> global keys in first-occurrence order + CSR
-void merge_records(std::vector<std::unique_ptr<KeyedRecords>>& parts, Csr& out, bool weighted) {
+void merge_records(std::vector<std::unique_ptr<KeyedRecords>>& parts, Csr& out, bool weighted, const char* name = "") {
+    const bool timing = getenv("IFX_CREATE_TIMING") != nullptr; auto t_last = std::chrono::steady_clock::now();
+    auto stage = [&](const char* what) { if (!timing) return; auto now = std::chrono::steady_clock::now(); fprintf(stderr, "[merge %-6s] %-24s %.2f s\n", name, what, std::chrono::duration<double>(now - t_last).count()); t_last = now; };
     Interner g; std::vector<std::vector<int32_t>> l2g(parts.size());
     for (size_t t = 0; t < parts.size(); t++) { auto& p = *parts[t]; l2g[t].resize(p.keys.size()); for (int k = 0; k < p.keys.size(); k++) l2g[t][k] = g.intern(p.keys.get(k)); }
+    stage("global keys");
     int G = g.size(); out.n = G; out.chars.assign(g.arena.begin(), g.arena.end()); out.off = g.off; if (out.chars.empty()) out.chars.push_back(0);
     // per-part per-key counts -> row pointers -> every part scatters its records in parallel (parts own ascending doc ranges,
     // so placing part t's records after those of parts < t keeps every row ascending)
     const size_t NP = parts.size();
     std::vector<std::vector<int32_t>> cnt(NP);
     { std::vector<std::thread> ts; for (size_t t = 0; t < NP; t++) ts.emplace_back([&, t] { cnt[t].assign(G, 0); for (int32_t k : parts[t]->rec_key) cnt[t][l2g[t][k]]++; }); for (auto& th : ts) th.join(); }
+    stage("count");
     out.row.assign((size_t)G + 1, 0);
     for (int g2 = 0; g2 < G; g2++) { int64_t c = 0; for (size_t t = 0; t < NP; t++) c += cnt[t][g2]; out.row[g2 + 1] = out.row[g2] + c; }
-    out.docs.resize((size_t)out.row[G] ? out.row[G] : 1); if (weighted) out.w.resize(out.docs.size());
+    out.docs.resize((size_t)out.row[G]); if (weighted) out.w.resize(out.docs.size());
     std::vector<std::vector<int64_t>> start(NP);
     for (size_t t = 0; t < NP; t++) start[t].resize(G);
     for (int g2 = 0; g2 < G; g2++) { int64_t o = out.row[g2]; for (size_t t = 0; t < NP; t++) { start[t][g2] = o; o += cnt[t][g2]; } }
+    stage("rows + starts");
     { std::vector<std::thread> ts; for (size_t t = 0; t < NP; t++) ts.emplace_back([&, t] { auto& p = *parts[t]; auto& pos = start[t];
           for (size_t r = 0; r < p.rec_key.size(); r++) { int64_t o = pos[l2g[t][p.rec_key[r]]]++; out.docs[o] = p.rec_doc[r]; if (weighted) out.w[o] = p.rec_w[r]; } });
       for (auto& th : ts) th.join(); }
+    stage("scatter");
     if (weighted) {
         out.extra.assign(G, 0); out.rep_last.assign(G, 0);
         for (size_t t = 0; t < parts.size(); t++) { auto& p = *parts[t]; for (int32_t k : p.sat_keys) out.extra[l2g[t][k]]++;
@@ -169,8 +196,9 @@ int ifx_builder_add_docs(ifx_builder* b, int n, const int64_t* keys, const int32
     if (b->finished) return IFX_ERR_INVALID;
     int F = (int)b->schema.size();
     b->keys.insert(b->keys.end(), keys, keys + n);
-    for (int f = 0; f < F; f++) { auto& v = b->values[f]; auto& nl = b->is_null[f]; v.reserve(v.size() + n);
-        for (int d = 0; d < n; d++) { if (kinds[f] == 0) { v.emplace_back(); nl.push_back(1); } else { v.push_back(value_to_string(kinds[f], cols[f], offs ? offs[f] : nullptr, d)); nl.push_back(0); } } }
+    const int hw = (int)std::max(1u, std::min(std::thread::hardware_concurrency(), 64u));
+    for (int f = 0; f < F; f++) { auto& v = b->values[f]; auto& nl = b->is_null[f]; const size_t base = v.size(); v.resize(base + n); nl.resize(base + n, kinds[f] == 0 ? 1 : 0);
+        if (kinds[f] != 0) par_for(n, n >= 100000 ? hw : 1, [&, f](int64_t a, int64_t e, int) { for (int64_t d = a; d < e; d++) v[base + d] = value_to_string(kinds[f], cols[f], offs ? offs[f] : nullptr, (int)d); }); }
     return IFX_OK;
 }
 
@@ -178,6 +206,8 @@ int ifx_builder_finish(ifx_builder* b, int threads) {
     if (b->finished) return IFX_OK;
     const int N = (int)b->keys.size(); const int F = (int)b->schema.size();
     if (threads < 1) threads = 1; if (threads > N) threads = std::max(1, N);
+    const bool timing = getenv("IFX_CREATE_TIMING") != nullptr; auto t_last = std::chrono::steady_clock::now();
+    auto stage = [&](const char* what) { if (!timing) return; auto now = std::chrono::steady_clock::now(); fprintf(stderr, "[ifx_builder_finish] %-28s %.2f s\n", what, std::chrono::duration<double>(now - t_last).count()); t_last = now; };
     // indexable fields ordered by Weight (stable): GetSearchAbleFieldList
     std::vector<int> order; for (int w = 0; w < 3; w++) for (int f = 0; f < F; f++) if ((b->schema[f].flags & IFX_FIELD_INDEXABLE) && b->schema[f].weight == w) order.push_back(f);
     struct Part {
@@ -221,17 +251,43 @@ int ifx_builder_finish(ifx_builder* b, int threads) {
         }
     };
     { std::vector<std::thread> ts; for (int t = 0; t < threads; t++) ts.emplace_back(work, t); for (auto& t : ts) t.join(); }
+    stage("tokenise (parallel)");
     // ---- merge
-    b->deleted.assign(N, 0); b->text_off.assign(1, 0); b->ft_off.assign(1, 0);
-    for (auto& P : parts) { b->text.insert(b->text.end(), P.text.begin(), P.text.end()); for (auto l : P.text_len) b->text_off.push_back(b->text_off.back() + l);
-        b->ft_chars.insert(b->ft_chars.end(), P.ft.begin(), P.ft.end()); for (auto l : P.ft_len) b->ft_off.push_back(b->ft_off.back() + l); b->tok_count.insert(b->tok_count.end(), P.tokc.begin(), P.tokc.end()); }
-    if (b->text.empty()) b->text.push_back(0); if (b->ft_chars.empty()) b->ft_chars.push_back(0);
-    {   // the four keyed-record sets merge independently
+    b->deleted.assign(N, 0);
+    {   std::vector<size_t> tbase(threads + 1, 0), fbase(threads + 1, 0), dbase(threads + 1, 0);
+        for (int t = 0; t < threads; t++) { tbase[t + 1] = tbase[t] + parts[t].text.size(); fbase[t + 1] = fbase[t] + parts[t].ft.size(); dbase[t + 1] = dbase[t] + parts[t].text_len.size(); }
+        b->text.resize(std::max<size_t>(tbase[threads], 1)); b->ft_chars.resize(std::max<size_t>(fbase[threads], 1)); b->text_off.resize((size_t)N + 1); b->ft_off.resize((size_t)N + 1); b->tok_count.resize(N);
+        par_for(threads, threads, [&](int64_t a, int64_t e, int) { for (int64_t t = a; t < e; t++) { Part& P = parts[t];
+            if (!P.text.empty()) std::memcpy(b->text.data() + tbase[t], P.text.data(), P.text.size() * 2); if (!P.ft.empty()) std::memcpy(b->ft_chars.data() + fbase[t], P.ft.data(), P.ft.size() * 2);
+            int64_t to = (int64_t)tbase[t]; uint32_t fo = (uint32_t)fbase[t];
+            for (size_t i = 0; i < P.text_len.size(); i++) { to += P.text_len[i]; fo += P.ft_len[i]; b->text_off[dbase[t] + i + 1] = to; b->ft_off[dbase[t] + i + 1] = fo; b->tok_count[dbase[t] + i] = P.tokc[i]; }
+            std::vector<char16_t>().swap(P.text); std::vector<char16_t>().swap(P.ft); } });
+    }
+    stage("text concat");
+    auto small_dicts = [&] {
+    // word idf
+        { Interner g; std::vector<int32_t> gdf; for (auto& P : parts) for (int k = 0; k < P.words.size(); k++) { bool nw; int id = g.intern(P.words.get(k), &nw); if (nw) gdf.push_back(0); gdf[id] += P.word_df[k]; }
+          b->word_chars.assign(g.arena.begin(), g.arena.end()); if (b->word_chars.empty()) b->word_chars.push_back(0); b->word_off = g.off; b->word_idf.resize(gdf.size());
+          for (size_t i = 0; i < gdf.size(); i++) b->word_idf[i] = (gdf[i] > 0 && gdf[i] <= N) ? compute_idf_host(N, gdf[i]) : 0.f; }
+        // affix words: last doc wins (WordMatcher.IndexWordInFst quirk Q4)
+        { Interner g; for (auto& P : parts) for (int k = 0; k < P.affix.size(); k++) { bool nw; int id = g.intern(P.affix.get(k), &nw); if (nw) b->affix_last.push_back(P.affix_last[k]); else b->affix_last[id] = P.affix_last[k]; }
+          b->affix_chars.assign(g.arena.begin(), g.arena.end()); if (b->affix_chars.empty()) b->affix_chars.push_back(0); b->affix_off = g.off; if (b->affix_last.empty()) b->affix_last.push_back(0); }
+        // filter / facet columns
+        for (int f = 0; f < F; f++) {
+            if (!(b->schema[f].flags & (IFX_FIELD_FILTERABLE | IFX_FIELD_FACETABLE))) continue;
+            Interner g; std::vector<int32_t> ids(N);
+            for (int d = 0; d < N; d++) ids[d] = b->is_null[f][d] ? -1 : g.intern(b->values[f][d]);
+            b->col_ids.push_back(std::move(ids)); b->col_chars.emplace_back(g.arena.begin(), g.arena.end()); if (b->col_chars.back().empty()) b->col_chars.back().push_back(0); b->col_off.push_back(g.off); b->col_names.push_back(b->schema[f].name);
+        }
+    };
+    {   // the four keyed-record sets merge independently; the small dictionaries (word idf, affix words, columns) alongside
         std::vector<std::unique_ptr<KeyedRecords>> v0, v1, v2, v3;
         for (auto& P : parts) { v0.push_back(std::move(P.terms)); v1.push_back(std::move(P.prefix)); v2.push_back(std::move(P.exact)); v3.push_back(std::move(P.ld1)); }
-        std::thread t0([&] { merge_records(v0, b->terms, true); }), t1([&] { merge_records(v1, b->prefix, false); }), t2([&] { merge_records(v2, b->wm_exact, false); }), t3([&] { merge_records(v3, b->wm_ld1, false); });
-        t0.join(); t1.join(); t2.join(); t3.join();
+        std::thread t0([&] { merge_records(v0, b->terms, true, "terms"); }), t1([&] { merge_records(v1, b->prefix, false, "prefix"); }), t2([&] { merge_records(v2, b->wm_exact, false, "exact"); }), t3([&] { merge_records(v3, b->wm_ld1, false, "ld1"); });
+        std::thread t4(small_dicts);
+        t0.join(); t1.join(); t2.join(); t3.join(); t4.join();
     }
+    stage("merge records -> CSR");
     // stop terms + df (Term.IncrementTermUsageCounter / FirstCycleAdd): df = postings + saturated repeats; a term dies when df would exceed the limit
     const int T = b->terms.n; b->df.assign(T, 0);
     std::vector<int64_t> new_row((size_t)T + 1, 0); int64_t wpos = 0;
@@ -245,29 +301,18 @@ int ifx_builder_finish(ifx_builder* b, int threads) {
         wpos += cnt;
     }
     new_row[T] = wpos; b->terms.row.swap(new_row);
+    stage("stop terms");
     // doc lengths (integer sums) and avgdl (sequential float sum, VectorModel.cs:212-216)
     std::vector<uint32_t> dl(N, 0);
-    for (int64_t i = 0; i < wpos; i++) dl[b->terms.docs[i]] += b->terms.w[i];
+    par_for(wpos, threads, [&](int64_t a, int64_t e, int) { for (int64_t i = a; i < e; i++) __atomic_fetch_add(&dl[b->terms.docs[i]], (uint32_t)b->terms.w[i], __ATOMIC_RELAXED); });   // integer sums: order-free
     b->doc_len.resize(N); float total = 0.f; for (int d = 0; d < N; d++) { b->doc_len[d] = (float)dl[d]; total += b->doc_len[d]; }
     float avgdl = N > 0 ? total / (float)N : 0.f;
-    // word idf
-    { Interner g; std::vector<int32_t> gdf; for (auto& P : parts) for (int k = 0; k < P.words.size(); k++) { bool nw; int id = g.intern(P.words.get(k), &nw); if (nw) gdf.push_back(0); gdf[id] += P.word_df[k]; }
-      b->word_chars.assign(g.arena.begin(), g.arena.end()); if (b->word_chars.empty()) b->word_chars.push_back(0); b->word_off = g.off; b->word_idf.resize(gdf.size());
-      for (size_t i = 0; i < gdf.size(); i++) b->word_idf[i] = (gdf[i] > 0 && gdf[i] <= N) ? compute_idf_host(N, gdf[i]) : 0.f; }
-    // affix words: last doc wins (WordMatcher.IndexWordInFst quirk Q4)
-    { Interner g; for (auto& P : parts) for (int k = 0; k < P.affix.size(); k++) { bool nw; int id = g.intern(P.affix.get(k), &nw); if (nw) b->affix_last.push_back(P.affix_last[k]); else b->affix_last[id] = P.affix_last[k]; }
-      b->affix_chars.assign(g.arena.begin(), g.arena.end()); if (b->affix_chars.empty()) b->affix_chars.push_back(0); b->affix_off = g.off; if (b->affix_last.empty()) b->affix_last.push_back(0); }
-    // filter / facet columns
-    for (int f = 0; f < F; f++) {
-        if (!(b->schema[f].flags & (IFX_FIELD_FILTERABLE | IFX_FIELD_FACETABLE))) continue;
-        Interner g; std::vector<int32_t> ids(N);
-        for (int d = 0; d < N; d++) ids[d] = b->is_null[f][d] ? -1 : g.intern(b->values[f][d]);
-        b->col_ids.push_back(std::move(ids)); b->col_chars.emplace_back(g.arena.begin(), g.arena.end()); if (b->col_chars.back().empty()) b->col_chars.back().push_back(0); b->col_off.push_back(g.off); b->col_names.push_back(b->schema[f].name);
-    }
+    stage("doc lengths");
     b->cols.resize(b->col_ids.size());
     { int ci = 0; for (int f = 0; f < F; f++) { if (!(b->schema[f].flags & (IFX_FIELD_FILTERABLE | IFX_FIELD_FACETABLE))) continue; ifx_column& c = b->cols[ci];
         c.name = (const uint16_t*)b->col_names[ci].data(); c.name_len = (int)b->col_names[ci].size(); c.flags = ((b->schema[f].flags & IFX_FIELD_FILTERABLE) ? IFX_COL_FILTERABLE : 0) | ((b->schema[f].flags & IFX_FIELD_FACETABLE) ? IFX_COL_FACETABLE : 0);
         c.value_id = b->col_ids[ci].data(); c.dict = {(const uint16_t*)b->col_chars[ci].data(), b->col_off[ci].data(), (int)b->col_off[ci].size() - 1}; ci++; } }
+    stage("columns");
     // ---- image
     ifx_index_image& I = b->img; auto S = [](std::vector<char16_t>& c, std::vector<uint32_t>& o) { return ifx_strings{(const uint16_t*)c.data(), o.data(), (int)o.size() - 1}; };
     I.n_docs = N; I.n_live = N; I.avgdl = avgdl; I.doc_key = b->keys.data(); I.deleted = b->deleted.data(); I.doc_len = b->doc_len.data();

@@ -880,6 +880,9 @@ IFX_FN void stage1_query(const Ctx& c, const DevIndex& ix, const QueryPlan& p, c
                 int64_t s0, s1;
                 if (tm.skip && whole_container) { s0 = lo; s1 = hi; }
                 else { s0 = warp_lower_bound(c, tm.docs, lo, hi, first); s1 = last == 0x7fffffff ? hi : warp_lower_bound(c, tm.docs, s0, hi, last + 1); }
+#ifndef IFX_EMU
+                __syncwarp();                                    // every lane has read tm.cursor / tm.len before lane 0 overwrites them (racecheck)
+#endif
                 if (c.lane() == 0) {
                     tm.s0 = s0; tm.s1 = s1; tm.cursor = s1;
                     if (s1 > s0 && s1 - s0 <= 16LL * cnt) sh.bcast[5] = 1;     // benign race: every writer stores 1

@@ -5,7 +5,8 @@ Docs     : title = 1 + Poisson(2.7) words (cap 12); description = 8 + Poisson(7)
            rating U{1.0..10.0} step 0.1; genre in 20 categories (Zipf).
 Queries  : 1-3 consecutive title words of a random doc; p=0.30 one edit (sub/ins/del/transpose) in a word of len >= 4;
            p=0.20 last word cut to a prefix of >= 3 chars; p=0.05 a word absent from the doc prepended.
-All draws come from numpy Generator(PCG64(seed)) with seed 0x1F1DEC5 (documented substitute for the survey's SplitMix64).
+Documents come from csrc/ifx_synth.cpp (multi-threaded; one SplitMix64 stream per document, seed 0x1F1DEC5); the vocabulary and the
+queries from numpy Generator(PCG64(seed)).
 """
 import numpy as np
 
@@ -39,43 +40,58 @@ def make_vocab(V=400_000, seed=SEED):
     return {"words": words, "blob": blob, "offs": offs, "lens": lens, "cdf": cdf}
 
 
-def _join_words(vocab, ids, doc_off):
-    """UTF-16 blob + offsets of docs whose words (ids, ragged by doc_off) are joined by single spaces."""
-    n = len(doc_off) - 1
-    wl = vocab["lens"][ids].astype(np.int64)
-    out_len = wl + 1                                   # word + trailing space
-    last = np.zeros(len(ids), bool); last[doc_off[1:][doc_off[1:] > doc_off[:-1]] - 1] = True
-    out_len[last] -= 1                                 # no space after a doc's last word
-    wstart = np.zeros(len(ids) + 1, np.int64); np.cumsum(out_len, out=wstart[1:])
-    total = int(wstart[-1])
-    blob = np.full(total, 32, np.uint16)
-    # char index gather: for every output char of every word, its source index in the vocab blob
-    rep = np.repeat(np.arange(len(ids)), wl)
-    within = np.arange(int(wl.sum()), dtype=np.int64) - np.repeat(np.cumsum(wl) - wl, wl)
-    blob[wstart[:-1][rep] + within] = vocab["blob"][vocab["offs"][ids][rep] + within]
-    offs = np.zeros(n + 1, np.int64); offs[:] = wstart[doc_off]
-    return blob, offs
+_hostlib = None
 
 
-def gen_docs(n, vocab, seed=SEED, with_description=False, start=0):
-    """Columns for docs [start, start+n). Deterministic per (seed, start)."""
-    rng = np.random.Generator(np.random.PCG64([seed, start]))
-    V = len(vocab["lens"])
-    tcount = np.minimum(1 + rng.poisson(2.7, n), 12).astype(np.int64)
-    toff = np.zeros(n + 1, np.int64); np.cumsum(tcount, out=toff[1:])
-    tids = np.minimum(np.searchsorted(vocab["cdf"], rng.random(int(toff[-1]))), V - 1).astype(np.int64)
-    title = _join_words(vocab, tids, toff)
-    out = {"n": n, "keys": np.arange(start, start + n, dtype=np.int64), "title": title, "title_ids": tids, "title_off": toff}
-    if with_description:
-        dcount = (8 + rng.poisson(7.0, n)).astype(np.int64)
-        doff = np.zeros(n + 1, np.int64); np.cumsum(dcount, out=doff[1:])
-        dids = np.minimum(np.searchsorted(vocab["cdf"], rng.random(int(doff[-1]))), V - 1).astype(np.int64)
-        out["description"] = _join_words(vocab, dids, doff)
-    out["year"] = rng.integers(1950, 2025, n).astype(np.int64)
-    out["rating"] = np.round(rng.integers(10, 101, n) / 10.0, 1).astype(np.float64)
-    gr = np.arange(1, 21, dtype=np.float64) ** -1.07; gc = np.cumsum(gr) / gr.sum()
-    out["genre_id"] = np.minimum(np.searchsorted(gc, rng.random(n)), 19)
+def _host():
+    global _hostlib
+    if _hostlib is None:
+        import ctypes as C
+        from . import _build
+        _hostlib = C.CDLL(_build.build_host())
+    return _hostlib
+
+
+def _p(a):
+    import ctypes as C
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def gen_docs(n, vocab, seed=SEED, with_description=False, start=0, threads=None):
+    """Columns for docs [start, start+n) of the corpus `seed` (csrc/ifx_synth.cpp: every document has its own SplitMix64 stream, so any
+    range / thread count / shard split yields the same documents)."""
+    import ctypes as C
+    import os
+    lib = _host(); th = threads or min(os.cpu_count() or 1, 64); multi = 1 if with_description else 0
+    V = len(vocab["lens"]); lens = np.ascontiguousarray(vocab["lens"], np.int32); cdf = np.ascontiguousarray(vocab["cdf"], np.float64)
+    twoff = np.zeros(n + 1, np.int64); tcoff = np.zeros(n + 1, np.int64)
+    dwoff = np.zeros(n + 1 if multi else 1, np.int64); dcoff = np.zeros(n + 1 if multi else 1, np.int64)
+    lib.ifx_synth_sizes(C.c_int64(n), C.c_int64(start), C.c_uint64(seed), multi, th, _p(lens), _p(cdf), V, _p(twoff), _p(tcoff), _p(dwoff), _p(dcoff))
+    tids = np.zeros(max(int(twoff[-1]), 1), np.int32); tblob = np.zeros(max(int(tcoff[-1]), 1), np.uint16)
+    dblob = np.zeros(max(int(dcoff[-1]), 1) if multi else 1, np.uint16)
+    year = np.zeros(n, np.int64); rating = np.zeros(n, np.float64); genre = np.zeros(n, np.int64)
+    blob = np.ascontiguousarray(vocab["blob"], np.uint16); offs = np.ascontiguousarray(vocab["offs"], np.int64)
+    lib.ifx_synth_fill(C.c_int64(n), C.c_int64(start), C.c_uint64(seed), multi, th, _p(blob), _p(offs), _p(lens), _p(cdf), V,
+                       _p(twoff), _p(tcoff), _p(dwoff), _p(dcoff), _p(tids), _p(tblob), _p(dblob), _p(year), _p(rating), _p(genre))
+    out = {"n": n, "start": start, "seed": seed, "keys": np.arange(start, start + n, dtype=np.int64), "title": (tblob, tcoff), "title_ids": tids[: int(twoff[-1])], "title_off": twoff,
+           "year": year, "rating": rating, "genre_id": genre}
+    if multi:
+        out["description"] = (dblob, dcoff)
     return out
+
+
+def corpus_ref(n, seed=SEED):
+    """A handle on the corpus `seed` of n documents that holds no documents: enough for gen_queries (titles are regenerated on demand)."""
+    return {"n": n, "seed": seed, "virtual": True}
+
+
+def _title_ids(docs, vocab, d):
+    if not docs.get("virtual"):
+        return docs["title_ids"][int(docs["title_off"][d]): int(docs["title_off"][d + 1])]
+    import ctypes as C
+    out = np.zeros(12, np.int32); cdf = vocab["cdf"]
+    k = _host().ifx_synth_title_ids(C.c_int64(d), C.c_uint64(docs["seed"]), _p(cdf), len(cdf), _p(out))
+    return out[:k]
 
 
 def gen_queries(nq, docs, vocab, seed=SEED):
@@ -85,9 +101,9 @@ def gen_queries(nq, docs, vocab, seed=SEED):
     alpha = "abcdefghijklmnopqrstuvwxyz"
     for _ in range(nq):
         d = int(rng.integers(0, docs["n"]))
-        a, b = int(docs["title_off"][d]), int(docs["title_off"][d + 1])
-        k = int(min(rng.integers(1, 4), b - a)); s = int(rng.integers(a, b - k + 1))
-        ws = [words[i] for i in docs["title_ids"][s:s + k]]
+        tid = _title_ids(docs, vocab, d); nt = len(tid)
+        k = int(min(rng.integers(1, 4), nt)); s = int(rng.integers(0, nt - k + 1))
+        ws = [words[i] for i in tid[s:s + k]]
         if rng.random() < 0.30:
             cand = [i for i, w in enumerate(ws) if len(w) >= 4]
             if cand:
@@ -102,7 +118,7 @@ def gen_queries(nq, docs, vocab, seed=SEED):
         if rng.random() < 0.20 and len(ws[-1]) > 3:
             ws[-1] = ws[-1][: int(rng.integers(3, len(ws[-1])))]
         if rng.random() < 0.05:
-            title_set = set(docs["title_ids"][a:b].tolist())
+            title_set = set(int(x) for x in tid)
             while True:
                 x = int(min(np.searchsorted(vocab["cdf"], rng.random()), len(words) - 1))
                 if x not in title_set:
@@ -123,31 +139,3 @@ def schema_and_columns(docs, multi_field):
               Field("rating", None, Weight.Med, indexable=False, filterable=True),
               Field("genre", None, Weight.Med, indexable=False, filterable=True, facetable=True)]
     return schema, [docs["title"], docs["description"], docs["year"], docs["rating"], genre]
-
-
-class ChunkedCorpus:
-    """Streams a large synthetic corpus chunk by chunk (deterministic per chunk) and keeps only what query sampling needs."""
-
-    def __init__(self, n_docs, vocab, multi_field, chunk=500_000, seed=SEED):
-        self.n, self.vocab, self.multi, self.chunk, self.seed = n_docs, vocab, multi_field, chunk, seed
-        self.title_ids, self.title_off = [], [np.zeros(1, np.int64)]
-        self.schema = schema_and_columns({"title": None, "description": None, "year": None, "rating": None, "genre_id": np.zeros(0, np.int64)}, multi_field)[0]
-        self.text_chars = 0
-
-    def chunks(self, workers=1):
-        """Yields (keys, columns) in document order; chunk generation (numpy, releases the GIL) runs `workers` chunks ahead."""
-        from concurrent.futures import ThreadPoolExecutor
-        starts = list(range(0, self.n, self.chunk))
-        gen = lambda st: gen_docs(min(self.chunk, self.n - st), self.vocab, seed=self.seed, with_description=self.multi, start=st)
-        with ThreadPoolExecutor(max_workers=max(1, workers)) as ex:
-            pending = [ex.submit(gen, st) for st in starts[:workers]]; nxt = workers
-            for _ in starts:
-                d = pending.pop(0).result()
-                if nxt < len(starts):
-                    pending.append(ex.submit(gen, starts[nxt])); nxt += 1
-                self.title_ids.append(d["title_ids"].astype(np.int32)); self.title_off.append(d["title_off"][1:] + self.title_off[-1][-1])
-                self.text_chars += int(d["title"][1][-1]) + (int(d["description"][1][-1]) if self.multi else 0)
-                yield d["keys"], schema_and_columns(d, self.multi)[1]
-
-    def docs_for_queries(self):
-        return {"n": self.n, "title_ids": np.concatenate(self.title_ids), "title_off": np.concatenate(self.title_off)}
