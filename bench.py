@@ -1,15 +1,17 @@
 #!/usr/bin/env python3
 """bench.py -- queries/sec of the Infidex search path on B200 (BASELINE.json metric), one JSON line on rank 0.
 
-  python bench.py --gpus 1 --steps K --warmup W            # our CUDA path
+  python bench.py --gpus 1 --steps K --warmup W            # our CUDA path; default workload = the metric's own config:
+                                                            # BASELINE.json configs[2], 10M multi-field docs, 10k-query batch
   python bench.py --impl reference ...                      # the reference algorithm on the host cores (oracle port; the
                                                             # C# reference itself cannot run here -- no dotnet in the image)
-A "step" is one pass of the hot path over one batch of synthetic queries (workload below). `value` times the
-device-resident batch (ifx_batch_run, CUDA events inside the library); `e2e` times the reference-facing call
-ifx_search_batch with host buffers (host->device query upload + device->host result download inside the region).
-N > 1: one process per GPU (torchrun), each rank holds a replica of the index and runs its own batch per step
-(weak scaling, queries are independent); per-rank results are all-gathered to rank 0 with NCCL. The doc-id-sharded
-100M-doc configuration (configs[4]) is not built this round -- see DESIGN.md "multi-GPU".
+A "step" is one pass of the hot path over one batch of synthetic queries. `value` times the device-resident batch
+(ifx_batch_run, CUDA events inside the library); `e2e` times the reference-facing call ifx_search_batch with host buffers
+(host->device query upload + device->host result download inside the region). Every run ends with a PARITY assertion: a bounded
+sample of a timed batch is answered by the oracle (CPU restatement of the reference) on the host cores -- that run is also the
+`cpu_baseline` -- and the GPU's records for those queries must be identical (DocumentId order, Score bits, Tiebreaker bytes);
+a mismatch fails the run instead of printing a line.
+N > 1: see `run_ours` (one process per GPU under torchrun).
 """
 import argparse
 import json
@@ -26,11 +28,26 @@ sys.path.insert(0, ROOT)
 
 WORKLOADS = {
     # BASELINE.json configs[1]: 1M synthetic single-field docs, 1k-query batch, top-10
-    "c2": dict(n_docs=1_000_000, nq=1000, multi=False, vocab=400_000, label="configs[1]: 1M single-field docs, 1k-query batch, top-10, coverage depth 500"),
-    # BASELINE.json configs[2]/[3]: 10M docs title(High)+description(Low), 10k-query batch (+ filter/facets with --filter)
-    "c3": dict(n_docs=10_000_000, nq=10_000, multi=True, vocab=400_000, label="configs[2]: 10M multi-field docs, 10k-query batch, top-10"),
-    "tiny": dict(n_docs=50_000, nq=200, multi=False, vocab=50_000, label="smoke workload (not a benchmark)"),
+    "c2": dict(n_docs=1_000_000, nq=1000, multi=False, vocab=400_000, filter=False, label="configs[1]: 1M single-field docs, 1k-query batch, top-10, coverage depth 500"),
+    # BASELINE.json configs[2] -- the configuration the metric is quoted on
+    "c3": dict(n_docs=10_000_000, nq=10_000, multi=True, vocab=400_000, filter=False, label="configs[2]: 10M multi-field docs (title High / description Low), 10k-query batch, top-10, coverage depth 500"),
+    # BASELINE.json configs[3]: + Filter.Parse("year >= 2000 AND rating > 7.0") + EnableFacets
+    "c4": dict(n_docs=10_000_000, nq=10_000, multi=True, vocab=400_000, filter=True, label="configs[3]: 10M multi-field docs + Filter.Parse('year >= 2000 AND rating > 7.0') + EnableFacets, 10k-query batch, top-10"),
+    "tiny": dict(n_docs=50_000, nq=200, multi=True, vocab=50_000, filter=False, label="smoke workload (not a benchmark)"),
 }
+C4_FILTER = "year >= 2000 AND rating > 7.0"
+
+
+def effective_cpus():
+    """CPUs this process may actually use: the affinity mask, capped by the cgroup quota (os.cpu_count() ignores both)."""
+    n = len(os.sched_getaffinity(0))
+    try:
+        q, p = open("/sys/fs/cgroup/cpu.max").read().split()
+        if q != "max":
+            n = max(1, min(n, int(float(q) / float(p))))
+    except Exception:
+        pass
+    return n
 
 
 def clocks_sampler(stop, out, gpu_index):
@@ -53,7 +70,7 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def make_corpus(wl, seed_shift=0):
+def make_corpus(wl):
     from infidex_b200 import synth
     vocab = synth.make_vocab(wl["vocab"])
     docs = synth.gen_docs(wl["n_docs"], vocab, with_description=wl["multi"])
@@ -61,57 +78,81 @@ def make_corpus(wl, seed_shift=0):
     return vocab, docs, schema, cols
 
 
-def run_reference(args, wl, rank, world):
-    """Reference arm: the reference's algorithm (oracle port) on the host cores, all threads, bounded sample per step."""
-    if rank != 0:
-        return
+def batch_queries(wl, docs, vocab, step, rank=0):
+    from infidex_b200 import dist as ifxd
     from infidex_b200 import synth
+    return synth.gen_queries(wl["nq"], docs, vocab, seed=ifxd.rank_batch_seed(synth.SEED, step, rank))
+
+
+def oracle_from_image(eng, schema):
+    """The oracle over the same index: its state is taken from the flattened image of the host builder (Index::load_image; checked equal
+    to the oracle's own sequential build by tests/test_oracle_image.py and tests/test_host_builder.py -- re-indexing 10M documents with
+    the restatement takes ~20 min), every search-time structure and all search code are the oracle's own."""
     from oracle.oracle import Field as OField
     from oracle.oracle import OracleEngine
-    vocab, docs, schema, cols = make_corpus(wl)
     orc = OracleEngine([OField(f.Name, f.Weight, f.Indexable, f.Filterable, f.Facetable) for f in schema])
-    orc.index_columns(docs["keys"], cols)
-    cores = os.cpu_count() or 1
+    orc.load_image(eng.image_ptr())
+    return orc
+
+
+def run_reference(args, wl, rank, world):
+    """Reference arm: the reference's algorithm (oracle port) on the host cores, all threads, bounded sample of the batch per step."""
+    if rank != 0:
+        return
+    import infidex_b200 as ib
+    vocab, docs, schema, cols = make_corpus(wl)
+    eng = ib.SearchEngine.__new__(ib.SearchEngine); eng._host = ib.engine._load_host(); eng._builder = None; eng._index = None; eng._gpu = None   # host builder only: no device, no GPU library
+    t0 = time.time(); eng.IndexColumns(docs["keys"], schema, cols, upload=False); orc = oracle_from_image(eng, schema); t_index = time.time() - t0
+    cores = effective_cpus()
     sample = min(wl["nq"], args.ref_sample)
-    flt = None
-    if args.filter:
-        import infidex_b200 as ib
-        flt = ib.Filter.Parse("year >= 2000 AND rating > 7.0").bytecode()
+    fb = ib.Filter.Parse(C4_FILTER).bytecode() if wl["filter"] else None
     times = []
     for s in range(args.warmup + args.steps):
-        qs = synth.gen_queries(sample, docs, vocab, seed=synth.SEED + s)
-        t0 = time.perf_counter(); orc.search_batch(qs, 10, 500, True, flt, threads=cores); dt = time.perf_counter() - t0
+        qs = batch_queries(wl, docs, vocab, s)[:sample]
+        t0 = time.perf_counter(); orc.search_batch(qs, 10, 500, True, fb, threads=cores); dt = time.perf_counter() - t0
         if s >= args.warmup:
             times.append(dt)
     total = sum(times); qps = sample * len(times) / total
     line = {"impl": "reference", "metric": "queries/sec", "value": qps, "unit": "queries/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": wl["label"], "batch": sample, "filter": bool(args.filter)},
-            "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": cores, "kind": "port",
-                             "sample": "%d-query sample of the batch per step, oracle (C++ restatement of the C# reference), %d host threads" % (sample, cores)},
+            "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": wl["label"], "batch": sample, "filter": bool(wl["filter"]), "index_build_s": round(t_index, 1)},
+            "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": cores, "os_cpu_count": os.cpu_count(), "kind": "port",
+                             "sample": "first %d queries of every step's batch, oracle (C++ restatement of the C# reference; dotnet absent), %d host threads" % (sample, cores)},
             "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c2", choices=list(WORKLOADS))
-    ap.add_argument("--filter", action="store_true", help="configs[3]: Filter.Parse('year >= 2000 AND rating > 7.0') + EnableFacets (multi-field workloads)")
-    ap.add_argument("--ref-sample", type=int, default=1000, help="queries per step of the CPU arms (bounded sample)")
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    args = ap.parse_args()
-    wl = WORKLOADS[args.workload]
-    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
-    if args.impl == "reference":
-        return run_reference(args, wl, rank, world)
+def parity_and_cpu_baseline(eng, schema, wl, qs, gpu_bufs, flt, args):
+    """Answers the first `sample` queries of one timed batch with the oracle on all host cores (timed: the cpu_baseline) and compares the
+    GPU's records for the same queries, bit for bit. Returns (cpu_baseline dict, parity dict)."""
+    orc = oracle_from_image(eng, schema)
+    cores = effective_cpus()
+    sample = min(len(qs), args.ref_sample)
+    fb = flt.bytecode() if flt else None
+    orc.search_batch(qs[: max(8, sample // 16)], 10, 500, True, fb, threads=cores)       # warm-up
+    t0 = time.perf_counter(); ok, osc, ot, on, ost = orc.search_batch(qs[:sample], 10, 500, True, fb, threads=cores); dt = time.perf_counter() - t0
+    n1 = max(8, sample // 16)
+    t1 = time.perf_counter(); orc.search_batch(qs[:n1], 10, 500, True, fb, threads=1); dt1 = time.perf_counter() - t1
+    bad = []
+    for i in range(sample):
+        st = int(gpu_bufs["status"][i]) & ~8
+        if ost[i] != 0 or st != 0:
+            if (ost[i] != 0) != (st != 0):
+                bad.append((qs[i], "status", int(ost[i]), st))
+            continue
+        n = int(on[i])
+        same = n == int(gpu_bufs["n"][i]) and np.array_equal(gpu_bufs["keys"][i, :n], ok[i, :n]) and \
+            np.array_equal(gpu_bufs["scores"][i, :n].view(np.uint32), osc[i, :n].view(np.uint32)) and np.array_equal(gpu_bufs["ties"][i, :n], ot[i, :n])
+        if not same:
+            bad.append((qs[i], gpu_bufs["keys"][i, :3].tolist(), ok[i, :3].tolist()))
+    cpu = {"value": sample / dt, "unit": "queries/s", "cores": cores, "os_cpu_count": os.cpu_count(), "kind": "port", "single_thread_value": n1 / dt1,
+           "sample": "first %d queries of the first timed batch, oracle (C++ restatement of the C# reference; dotnet absent), %d threads; index state loaded from the builder image" % (sample, cores)}
+    return cpu, {"checked": sample, "mismatches": len(bad), "what": "DocumentId order, float32 Score bits, Tiebreaker bytes vs the oracle"}, bad
 
+
+def run_ours(args, wl, rank, world, local):
     import infidex_b200 as ib
     from infidex_b200 import dist as ifxd
-    from infidex_b200 import synth
     dist = None
     if world > 1:
         import torch
@@ -119,25 +160,19 @@ def main():
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     t_setup = time.time()
+    vocab, docs, schema, cols = make_corpus(wl); t_gen = time.time() - t_setup
     eng = ib.SearchEngine.CreateDefault(device=local)
-    if wl["n_docs"] > 2_000_000:          # large corpora are generated and indexed chunk by chunk
-        vocab = synth.make_vocab(wl["vocab"])
-        cc = synth.ChunkedCorpus(wl["n_docs"], vocab, wl["multi"], chunk=250_000)
-        eng.IndexChunks(cc.schema, cc.chunks())     # numpy generation is fastest single-threaded (measured)
-        docs = cc.docs_for_queries(); schema = cc.schema; cols = None; text_mb = cc.text_chars * 2 / 1e6
-    else:
-        vocab, docs, schema, cols = make_corpus(wl)
-        eng.IndexColumns(docs["keys"], schema, cols); text_mb = docs["title"][1][-1] * 2 / 1e6
-    t_index = time.time() - t_setup
-    flt = ib.Filter.Parse("year >= 2000 AND rating > 7.0") if args.filter else None
+    t0 = time.time(); eng.IndexColumns(docs["keys"], schema, cols); t_index = time.time() - t0
+    text_mb = (docs["title"][1][-1] + (docs["description"][1][-1] if wl["multi"] else 0)) * 2 / 1e6
+    flt = ib.Filter.Parse(C4_FILTER) if wl["filter"] else None
     n_total = args.warmup + args.steps
-    batches = []
-    for s in range(n_total):   # a distinct batch per step and per rank
-        qs = synth.gen_queries(wl["nq"], docs, vocab, seed=ifxd.rank_batch_seed(synth.SEED, s, rank))
+    batches, texts = [], []
+    for s in range(n_total):   # a distinct batch per step (and per rank: replicas answer independent batches)
+        qs = batch_queries(wl, docs, vocab, s, rank)
         qq = []
         for t in qs:
             x = ib.Query(t, 10); x.Filter = flt; x.EnableFacets = bool(flt); qq.append(x)
-        batches.append(qq)
+        batches.append(qq); texts.append(qs)
     t_setup = time.time() - t_setup
 
     def barrier():
@@ -160,6 +195,8 @@ def main():
                 agg[k] += getattr(st, k)
             algo += st.algo_bytes_stage1; launches += st.kernel_launches; q_max = max(q_max, st.s1_query_ms_max); q_sum += st.s1_query_ms_sum
     barrier()
+    for h in handles:
+        eng.FreeBatch(h)
     # ---- e2e: host buffers in / out through the C-ABI call ifx_search_batch (query upload + result download inside the region) --
     packed = [eng.PackBatch(b) for b in batches]
     e2e_t = 0.0; h2d = d2h = 0
@@ -168,18 +205,17 @@ def main():
         st = ib.Stats(); t0 = time.perf_counter(); eng.SearchPacked(packed[s], st); dt = time.perf_counter() - t0
         if s >= args.warmup:
             e2e_t += dt; h2d, d2h = st.h2d_bytes, st.d2h_bytes
-    res_status = packed[-1]["bufs"]["status"]
     stop.set()
-    bad = int(((res_status & ~8) != 0).sum())
-    dev_ms = agg["ms_total"]; step_ms = dev_ms / args.steps
+    bad_status = int(sum(((p["bufs"]["status"] & ~8) != 0).sum() for p in packed[args.warmup:]))
+    dev_ms = agg["ms_total"]
     if dist is not None:
-        import torch
-        dev_ms, e2e_t = ifxd.max_over_ranks(dist, [dev_ms, e2e_t], device="cuda"); step_ms = dev_ms / args.steps
-        gathered = ifxd.gather_results(dist, packed[-1]["bufs"]["keys"], device="cuda")      # per-batch result exchange over NCCL
+        dev_ms, e2e_t = ifxd.max_over_ranks(dist, [dev_ms, e2e_t], device="cuda")
+        ifxd.gather_results(dist, packed[-1]["bufs"]["keys"], device="cuda")      # per-batch result exchange over NCCL
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
-        return
+        return 0
+    step_ms = dev_ms / args.steps
     nq_all = wl["nq"] * world
     value = nq_all * args.steps / (dev_ms / 1e3)
     e2e = nq_all * args.steps / e2e_t
@@ -200,39 +236,45 @@ def main():
         clocks = {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(c[1] for c in clk), "reasons": sorted(reasons), "samples": len(clk)}
     line = {"metric": "queries/sec", "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": wl["label"], "batch_per_gpu": wl["nq"], "filter": bool(flt), "parallelism": "replica x%d (query-parallel)" % world,
-                       "l2": "256 MiB L2 flush before every timed step; the index (text alone %.0f MB) also exceeds the 126 MB L2" % text_mb, "index_build_s": round(t_index, 1),
-                       "setup_s": round(t_setup, 1), "bad_status": bad},
+            "config": {"workload": wl["label"], "batch": wl["nq"], "filter": bool(flt), "parallelism": "replica x%d (query-parallel)" % world if world > 1 else "1 GPU",
+                       "l2": "256 MiB L2 flush before every timed step; the index (text alone %.0f MB) also exceeds the 126 MB L2" % text_mb,
+                       "corpus_gen_s": round(t_gen, 1), "index_build_s": round(t_index, 1), "setup_s": round(t_setup, 1), "bad_status": bad_status},
             "phases_ms_per_step": {k: round(v / args.steps, 3) for k, v in agg.items()},
             "roofline": {"bound": "hbm", "kernel": "k_stage1", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "algo_bytes_per_launch": s1_bytes, "ms_per_launch": s1_ms, "peak_source": peak_src,
                          "longest_query_ms": q_max, "sum_query_ms_per_launch": q_sum / args.steps},
             "e2e": {"value": e2e, "unit": "queries/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
             "gpu_launches": int(launches), "clocks": clocks}
-    if not args.no_cpu_baseline and world == 1 and cols is not None:
-        line["cpu_baseline"] = cpu_baseline(wl, vocab, docs, schema, cols, flt, args)
-    print(json.dumps(line), flush=True)
+    rc = 0
+    if not args.no_cpu_baseline:
+        s0 = args.warmup                                                           # the first timed batch
+        cpu, parity, bad = parity_and_cpu_baseline(eng, schema, wl, texts[s0], packed[s0]["bufs"], flt, args)
+        line["cpu_baseline"] = cpu; line["parity"] = parity
+        if bad:
+            print("PARITY FAILURE: %d of %d sampled queries differ from the oracle, e.g. %r" % (len(bad), parity["checked"], bad[:3]), file=sys.stderr, flush=True)
+            rc = 1
+    if rc == 0:
+        print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()
+    return rc
 
 
-def cpu_baseline(wl, vocab, docs, schema, cols, flt, args):
-    """The oracle (CPU restatement of the reference) timed on this box's host cores over a bounded sample of the same workload."""
-    from infidex_b200 import synth
-    from oracle.oracle import Field as OField
-    from oracle.oracle import OracleEngine
-    orc = OracleEngine([OField(f.Name, f.Weight, f.Indexable, f.Filterable, f.Facetable) for f in schema])
-    orc.index_columns(docs["keys"], cols)
-    cores = os.cpu_count() or 1
-    sample = min(wl["nq"], args.ref_sample)
-    qs = synth.gen_queries(sample, docs, vocab, seed=synth.SEED + 1)
-    fb = flt.bytecode() if flt else None
-    orc.search_batch(qs[: max(8, sample // 20)], 10, 500, True, fb, threads=cores)       # warm-up
-    t0 = time.perf_counter(); orc.search_batch(qs, 10, 500, True, fb, threads=cores); dt = time.perf_counter() - t0
-    t1 = time.perf_counter(); orc.search_batch(qs[: max(50, sample // 10)], 10, 500, True, fb, threads=1); dt1 = time.perf_counter() - t1
-    return {"value": sample / dt, "unit": "queries/s", "cores": cores, "kind": "port",
-            "single_thread_value": max(50, sample // 10) / dt1,
-            "sample": "%d queries of the step-1 batch, oracle (C++ restatement of the C# reference; dotnet absent), %d threads" % (sample, cores)}
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c3", choices=list(WORKLOADS), help="default: c3 = BASELINE.json configs[2], the configuration the metric is quoted on")
+    ap.add_argument("--ref-sample", type=int, default=512, help="queries per step of the CPU arms (bounded sample of the batch)")
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the oracle leg (cpu_baseline + parity assertion)")
+    args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        return run_reference(args, wl, rank, world)
+    sys.exit(run_ours(args, wl, rank, world, local))
 
 
 if __name__ == "__main__":

@@ -3,6 +3,9 @@
 #include "../../include/infidex_gpu.h"
 #include "ifx_stage1.h"
 #include "ifx_stage2.h"
+#include "ifx_build.h"
+#include <thread>
+#include <functional>
 #include <vector>
 #include <string>
 #include <algorithm>
@@ -100,23 +103,27 @@ static uint64_t hash_host(const uint16_t* s, int n) {
 
 // `with_hash = false`: a plain indexed string array (never looked up by key; its entries may repeat, which would degrade the
 // open-addressing build to quadratic probing)
-static StrDict upload_dict(ifx_index* ix, const ifx_strings& s, bool with_hash = true) {
+struct HostHash { std::vector<uint64_t> hk; std::vector<int32_t> hv; uint32_t cap = 0; };
+static void build_hash(const ifx_strings& s, HostHash& H) {      // host only: the big dictionaries are hashed on parallel host threads, then uploaded
+    uint32_t cap = 8; while (cap < (uint32_t)s.n * 2u + 2u) cap <<= 1;
+    H.cap = cap; H.hk.assign(cap, 0); H.hv.assign(cap, -1);
+    for (int i = 0; i < s.n; i++) {
+        uint64_t h = hash_host(s.chars + s.off[i], (int)(s.off[i + 1] - s.off[i])); uint32_t slot = (uint32_t)(h >> 7) & (cap - 1);
+        while (H.hk[slot] != 0) slot = (slot + 1) & (cap - 1);
+        H.hk[slot] = h; H.hv[slot] = i;
+    }
+}
+static StrDict upload_dict(ifx_index* ix, const ifx_strings& s, bool with_hash = true, const HostHash* pre = nullptr) {
     StrDict d{}; d.n = s.n;
     size_t nchars = s.n ? s.off[s.n] : 0;
     d.chars = ix->up(s.chars, nchars ? nchars : 1); d.off = ix->up(s.off, (size_t)s.n + 1);
     if (!with_hash) { static const uint64_t z64 = 0; static const int32_t z32 = 0; d.hkeys = ix->up(&z64, 1); d.hvals = ix->up(&z32, 1); d.hmask = 0; return d; }
-    uint32_t cap = 8; while (cap < (uint32_t)s.n * 2u + 2u) cap <<= 1;
-    std::vector<uint64_t> hk(cap, 0); std::vector<int32_t> hv(cap, -1);
-    for (int i = 0; i < s.n; i++) {
-        uint64_t h = hash_host(s.chars + s.off[i], (int)(s.off[i + 1] - s.off[i])); uint32_t slot = (uint32_t)(h >> 7) & (cap - 1);
-        while (hk[slot] != 0) slot = (slot + 1) & (cap - 1);
-        hk[slot] = h; hv[slot] = i;
-    }
-    d.hkeys = ix->up(hk.data(), cap); d.hvals = ix->up(hv.data(), cap); d.hmask = cap - 1;
+    HostHash local; if (!pre) { build_hash(s, local); pre = &local; }
+    d.hkeys = ix->up(pre->hk.data(), pre->cap); d.hvals = ix->up(pre->hv.data(), pre->cap); d.hmask = pre->cap - 1;
     return d;
 }
-static DocsetDict upload_docset(ifx_index* ix, const ifx_docset_dict& s) {
-    DocsetDict d{}; d.keys = upload_dict(ix, s.keys);
+static DocsetDict upload_docset(ifx_index* ix, const ifx_docset_dict& s, const HostHash* pre = nullptr) {
+    DocsetDict d{}; d.keys = upload_dict(ix, s.keys, true, pre);
     size_t np = s.keys.n ? (size_t)s.row_ptr[s.keys.n] : 0;
     static const int64_t zero = 0;
     d.row_ptr = ix->up(s.keys.n ? s.row_ptr : &zero, (size_t)s.keys.n + 1); d.doc_id = ix->up(s.doc_id, np ? np : 1);
@@ -147,18 +154,58 @@ extern "C" int ifx_index_create(const ifx_index_image* img, const ifx_params* pp
 #ifndef IFX_EMU
         CUDA_TRY(cudaSetDevice(P.device)); ix->device = P.device;
 #endif
-        DevIndex& v = ix->v; const int N = img->n_docs;
+        DevIndex& v = ix->v; const int N = img->n_docs; const int T = img->terms.n;
+        // ---- host-side preparation of the dictionaries on parallel threads (hash tables, the two sort orders of the term and the
+        //      affix dictionaries) while this thread uploads the bulk arrays and derives the posting-side structures on the device
+        HostHash hh_terms, hh_words, hh_prefix, hh_exact, hh_ld1;
+        std::vector<int32_t> order(T); std::vector<uint8_t> slen(T); std::vector<unsigned long long> sig(std::max(T, 1), 0ULL);
+        std::vector<int32_t> lp(257, 0), lord(std::max(T, 1), 0); std::vector<unsigned long long> lsig(std::max(T, 1), 0ULL);
+        auto term_sv = [&](int i) { return std::u16string_view((const char16_t*)img->terms.chars + img->terms.off[i], img->terms.off[i + 1] - img->terms.off[i]); };
+        const int A = img->affix_words.n;
+        std::vector<uint16_t> achars; std::vector<uint32_t> aoff(A + 1, 0); std::vector<int32_t> fdoc(std::max(A, 1)), ro(std::max(A, 1)), rdoc(std::max(A, 1)); HostHash hh_affix;
+        std::vector<std::function<void()>> jobs;
+        jobs.push_back([&] { build_hash(img->terms, hh_terms); });
+        jobs.push_back([&] { build_hash(img->words, hh_words); });
+        jobs.push_back([&] { build_hash(img->prefix.keys, hh_prefix); });
+        jobs.push_back([&] { build_hash(img->wm_exact.keys, hh_exact); });
+        jobs.push_back([&] { build_hash(img->wm_ld1.keys, hh_ld1); });
+        jobs.push_back([&] {   // trie DFS order == ordinal-lexicographic order of the term texts (FstBuilder.CompactTrie sorts arcs by label)
+            std::iota(order.begin(), order.end(), 0);
+            std::sort(order.begin(), order.end(), [&](int x, int y) { return term_sv(x) < term_sv(y); });
+            for (int i = 0; i < T; i++) { auto sv = term_sv(order[i]); size_t l = sv.size(); slen[i] = (uint8_t)(l > 255 ? 255 : l); unsigned long long g = 0; for (char16_t ch : sv) g |= 1ULL << (((uint16_t)ch * 0x9E37u >> 4) & 63); sig[i] = g; }
+            for (int i = 0; i < T; i++) lp[slen[i] + 1]++; for (int l = 0; l < 256; l++) lp[l + 1] += lp[l];       // counting sort of the sorted positions by length
+            std::vector<int32_t> cur(lp.begin(), lp.end() - 1);
+            for (int i = 0; i < T; i++) { int at = cur[slen[i]]++; lord[at] = order[i]; lsig[at] = sig[i]; } });
+        jobs.push_back([&] {   // affix words: forward (prefix) order and reverse-string (suffix) order, each with the doc its trie output resolves to
+            auto aw = [&](int i) { return std::u16string_view((const char16_t*)img->affix_words.chars + img->affix_words.off[i], img->affix_words.off[i + 1] - img->affix_words.off[i]); };
+            std::vector<int32_t> fo(A); std::iota(fo.begin(), fo.end(), 0); std::sort(fo.begin(), fo.end(), [&](int x, int y) { return aw(x) < aw(y); });
+            for (int i = 0; i < A; i++) { auto w = aw(fo[i]); achars.insert(achars.end(), w.begin(), w.end()); aoff[i + 1] = (uint32_t)achars.size(); fdoc[i] = img->affix_last_doc[fo[i]]; }
+            if (achars.empty()) achars.push_back(0);
+            auto rev_less = [&](int x2, int y2) { auto x = std::u16string_view((const char16_t*)achars.data() + aoff[x2], aoff[x2 + 1] - aoff[x2]), y = std::u16string_view((const char16_t*)achars.data() + aoff[y2], aoff[y2 + 1] - aoff[y2]);
+                size_t n = std::min(x.size(), y.size()); for (size_t k = 0; k < n; k++) { char16_t p = x[x.size() - 1 - k], q = y[y.size() - 1 - k]; if (p != q) return p < q; } return x.size() < y.size(); };
+            std::iota(ro.begin(), ro.begin() + A, 0); std::sort(ro.begin(), ro.begin() + A, rev_less);
+            for (int i = 0; i < A; i++) rdoc[i] = fdoc[ro[i]];
+            ifx_strings ss{achars.data(), aoff.data(), A}; build_hash(ss, hh_affix); });
+        std::vector<std::thread> workers; for (auto& j : jobs) workers.emplace_back(j);
+        struct Joiner { std::vector<std::thread>& w; ~Joiner() { for (auto& t : w) if (t.joinable()) t.join(); } } joiner{workers};
+
         v.n_docs = N; v.n_live = img->n_live; v.avgdl = img->avgdl; v.stop_term_limit = P.stop_term_limit;
         v.doc_key = ix->up(img->doc_key, N); v.deleted = ix->up(img->deleted, N); v.doc_len = ix->up(img->doc_len, N);
         size_t ntext = N ? (size_t)img->text_off[N] : 0;
         v.text = ix->up(img->text_chars, ntext ? ntext : 1); v.text_off = ix->up(img->text_off, (size_t)N + 1);
         v.first_token = upload_dict(ix, img->first_token, false); v.token_count = ix->up(img->token_count, N);
         stage("docs + text");
-        v.terms = upload_dict(ix, img->terms); const int T = img->terms.n;
-        v.df = ix->up(img->df, T); v.row_ptr = ix->up(img->row_ptr, (size_t)T + 1);
+        v.df = ix->up(img->df, T ? T : 1); v.row_ptr = ix->up(img->row_ptr, (size_t)T + 1);
         size_t P_ = T ? (size_t)img->row_ptr[T] : 0;
         v.post_doc = ix->up(img->post_doc, P_ ? P_ : 1); v.post_tf = ix->up(img->post_tf, P_ ? P_ : 1);
-        stage("term dictionary + postings");
+        stage("postings");
+        const int ncont = (N + 65535) >> 16; const int64_t SKIP_MIN = 512; v.n_cont = ncont;
+        const int bw = (N + 31) / 32; v.bm_words = bw; const int64_t dense = std::max<int64_t>(1024, N / 32);
+        std::vector<int32_t> sid(std::max(T, 1), -1), bid(std::max(T, 1), -1), skip_terms, bm_terms;
+        for (int t = 0; t < T; t++) { const int64_t len = img->row_ptr[t + 1] - img->row_ptr[t]; if (len >= SKIP_MIN) { sid[t] = (int)skip_terms.size(); skip_terms.push_back(t); } if (len >= dense) { bid[t] = (int)bm_terms.size(); bm_terms.push_back(t); } }
+        const int ns = (int)skip_terms.size(), nb = (int)bm_terms.size();
+        v.skip_id = ix->up(sid.data(), sid.size()); v.bm_id = ix->up(bid.data(), bid.size());
+#ifdef IFX_EMU
         {   // forward index: CSR transpose of the live posting lists (counting sort by doc; entries of a doc end up in term order)
             std::vector<int64_t> fp((size_t)N + 2, 0);
             for (int t = 0; t < T; t++) { if (img->df[t] <= 0) continue; for (int64_t i = img->row_ptr[t]; i < img->row_ptr[t + 1]; i++) fp[(size_t)img->post_doc[i] + 2]++; }
@@ -168,56 +215,61 @@ extern "C" int ifx_index_create(const ifx_index_image* img, const ifx_params* pp
             v.fwd_ptr = ix->up(fp.data(), (size_t)N + 1); v.fwd_term = ix->up(ft.data(), ft.size()); v.fwd_tf = ix->up(fw.data(), fw.size());
         }
         {   // container skip table for long posting lists: turns the per-chunk sub-range search of the scorer into a lookup
-            const int ncont = (N + 65535) >> 16; const int64_t SKIP_MIN = 512; v.n_cont = ncont;
-            std::vector<int32_t> sid(std::max(T, 1), -1); std::vector<int32_t> sp; int ns = 0;
-            for (int t = 0; t < T; t++) { int64_t r0 = img->row_ptr[t], len = img->row_ptr[t + 1] - r0; if (len < SKIP_MIN) continue;
-                sid[t] = ns++; size_t base = sp.size(); sp.resize(base + ncont + 1); int64_t i = 0;
-                for (int c = 0; c <= ncont; c++) { int64_t lim = (int64_t)c << 16; while (i < len && img->post_doc[r0 + i] < lim) i++; sp[base + c] = (int32_t)i; } }
+            std::vector<int32_t> sp((size_t)std::max(ns, 0) * (ncont + 1));
+            for (int r = 0; r < ns; r++) { const int t = skip_terms[r]; int64_t r0 = img->row_ptr[t], len = img->row_ptr[t + 1] - r0; int64_t i = 0;
+                for (int c = 0; c <= ncont; c++) { int64_t lim = (int64_t)c << 16; while (i < len && img->post_doc[r0 + i] < lim) i++; sp[(size_t)r * (ncont + 1) + c] = (int32_t)i; } }
             if (sp.empty()) sp.push_back(0);
-            v.skip_id = ix->up(sid.data(), sid.size()); v.skip_ptr = ix->up(sp.data(), sp.size());
+            v.skip_ptr = ix->up(sp.data(), sp.size());
         }
-        stage("forward index + skip table");
         {   // dense terms additionally get a membership bitmap + rank directory: O(1) probes (doc -> posting index -> tf) in the scorer
-            const int bw = (N + 31) / 32; v.bm_words = bw; const int64_t dense = std::max<int64_t>(1024, N / 32);
-            std::vector<int32_t> bid(std::max(T, 1), -1); int nb = 0;
-            for (int t = 0; t < T; t++) if (img->row_ptr[t + 1] - img->row_ptr[t] >= dense) bid[t] = nb++;
             std::vector<unsigned> bits((size_t)std::max(nb, 1) * std::max(bw, 1), 0u); std::vector<int32_t> rank((size_t)std::max(nb, 1) * std::max(bw, 1), 0);
-            for (int t = 0; t < T; t++) { if (bid[t] < 0) continue; unsigned* b = bits.data() + (size_t)bid[t] * bw; int32_t* r = rank.data() + (size_t)bid[t] * bw;
-                for (int64_t i = img->row_ptr[t]; i < img->row_ptr[t + 1]; i++) { int d = img->post_doc[i]; b[d >> 5] |= 1u << (d & 31); }
-                int run = 0; for (int w = 0; w < bw; w++) { r[w] = run; run += __builtin_popcount(b[w]); } }
-            v.bm_id = ix->up(bid.data(), bid.size()); v.bm_bits = ix->up(bits.data(), bits.size()); v.bm_rank = ix->up(rank.data(), rank.size());
+            for (int k = 0; k < nb; k++) { const int t = bm_terms[k]; unsigned* bb = bits.data() + (size_t)k * bw; int32_t* r = rank.data() + (size_t)k * bw;
+                for (int64_t i = img->row_ptr[t]; i < img->row_ptr[t + 1]; i++) { int d = img->post_doc[i]; bb[d >> 5] |= 1u << (d & 31); }
+                int run = 0; for (int w = 0; w < bw; w++) { r[w] = run; run += __builtin_popcount(bb[w]); } }
+            v.bm_bits = ix->up(bits.data(), bits.size()); v.bm_rank = ix->up(rank.data(), rank.size());
         }
-        stage("dense bitmaps");
-        // trie DFS order == ordinal-lexicographic order of the term texts (FstBuilder.CompactTrie sorts arcs by label)
-        std::vector<int32_t> order(T); std::iota(order.begin(), order.end(), 0);
-        auto term_sv = [&](int i) { return std::u16string_view((const char16_t*)img->terms.chars + img->terms.off[i], img->terms.off[i + 1] - img->terms.off[i]); };
-        std::sort(order.begin(), order.end(), [&](int a, int b) { return term_sv(a) < term_sv(b); });
-        std::vector<uint8_t> slen(T); for (int i = 0; i < T; i++) { size_t l = term_sv(order[i]).size(); slen[i] = (uint8_t)(l > 255 ? 255 : l); }
+#else
+        {   // the same three structures derived on the device from the uploaded CSR (csrc/ifx_build.h)
+            const int sms = [&] { cudaDeviceProp prop; CUDA_TRY(cudaGetDeviceProperties(&prop, P.device)); return prop.multiProcessorCount; }();
+            const int grid = sms * 8;
+            unsigned* cnt = (unsigned*)dev_alloc(((size_t)N + 1) * 4); dev_zero(cnt, ((size_t)N + 1) * 4);
+            if (T > 0) k_fwd_count<<<grid, 256>>>(v.row_ptr, v.df, T, v.post_doc, cnt);
+            const int64_t n_tiles = ((int64_t)N + SCAN_TILE - 1) / SCAN_TILE;
+            unsigned long long* tile = (unsigned long long*)dev_alloc((size_t)std::max<int64_t>(n_tiles, 1) * 8);
+            int64_t* fwd_ptr = ix->alloc<int64_t>((size_t)N + 1);
+            if (N > 0) { k_scan_tile_sums<<<(unsigned)n_tiles, SCAN_THREADS>>>(cnt, N, tile); k_scan_tiles<<<1, 1024>>>(tile, n_tiles); k_scan_final<<<(unsigned)n_tiles, SCAN_THREADS>>>(cnt, N, tile, fwd_ptr); }
+            else dev_zero(fwd_ptr, 8);
+            int64_t FP = 0; d2h(&FP, fwd_ptr + N, 8);
+            int32_t* fwd_term = ix->alloc<int32_t>((size_t)std::max<int64_t>(FP, 1)); uint8_t* fwd_tf = ix->alloc<uint8_t>((size_t)std::max<int64_t>(FP, 1));
+            dev_zero(cnt, ((size_t)N + 1) * 4);
+            if (T > 0) k_fwd_scatter<<<grid, 256>>>(v.row_ptr, v.df, T, v.post_doc, v.post_tf, fwd_ptr, cnt, fwd_term, fwd_tf);
+            v.fwd_ptr = fwd_ptr; v.fwd_term = fwd_term; v.fwd_tf = fwd_tf;
+            int32_t* d_skip_terms = (int32_t*)dev_alloc((size_t)std::max(ns, 1) * 4); h2d(d_skip_terms, skip_terms.data(), (size_t)ns * 4);
+            int32_t* skip_ptr = ix->alloc<int32_t>(std::max<size_t>((size_t)ns * (ncont + 1), 1));
+            if (ns > 0) { const int64_t tot = (int64_t)ns * (ncont + 1); k_skip_table<<<(unsigned)((tot + 255) / 256), 256>>>(v.row_ptr, d_skip_terms, ns, ncont, v.post_doc, skip_ptr); }
+            v.skip_ptr = skip_ptr;
+            int32_t* d_bm_terms = (int32_t*)dev_alloc((size_t)std::max(nb, 1) * 4); h2d(d_bm_terms, bm_terms.data(), (size_t)nb * 4);
+            const size_t bmn = (size_t)std::max(nb, 1) * std::max(bw, 1);
+            unsigned* bm_bits = ix->alloc<unsigned>(bmn); int32_t* bm_rank = ix->alloc<int32_t>(bmn); dev_zero(bm_bits, bmn * 4);
+            if (nb > 0) { k_bitmap_fill<<<nb, 512>>>(v.row_ptr, d_bm_terms, bw, v.post_doc, bm_bits); k_bitmap_rank<<<nb, 512>>>(bw, bm_bits, bm_rank); } else dev_zero(bm_rank, bmn * 4);
+            v.bm_bits = bm_bits; v.bm_rank = bm_rank;
+            CUDA_TRY(cudaGetLastError()); CUDA_TRY(cudaDeviceSynchronize());
+            dev_free(cnt); dev_free(tile); dev_free(d_skip_terms); dev_free(d_bm_terms);
+        }
+#endif
+        stage("forward index + skip tables + dense bitmaps");
+        for (auto& t : workers) t.join();
+        stage("waiting for the host dictionary threads");
+        v.terms = upload_dict(ix, img->terms, true, &hh_terms);
         v.term_sorted = ix->up(order.data(), T ? T : 1); ix->d_sorted_len = ix->up(slen.data(), T ? T : 1);
-        {   std::vector<unsigned long long> sig(std::max(T, 1), 0ULL); for (int i = 0; i < T; i++) { auto sv = term_sv(order[i]); unsigned long long g = 0; for (char16_t ch : sv) g |= 1ULL << (((uint16_t)ch * 0x9E37u >> 4) & 63); sig[i] = g; } v.term_sig = ix->up(sig.data(), sig.size());
-            // counting sort of the sorted positions by length
-            std::vector<int32_t> lp(257, 0); for (int i = 0; i < T; i++) lp[slen[i] + 1]++; for (int l = 0; l < 256; l++) lp[l + 1] += lp[l];
-            std::vector<int32_t> cur(lp.begin(), lp.end() - 1), lord(std::max(T, 1), 0); std::vector<unsigned long long> lsig(std::max(T, 1), 0ULL);
-            for (int i = 0; i < T; i++) { int at = cur[slen[i]]++; lord[at] = order[i]; lsig[at] = sig[i]; }
-            v.len_ptr = ix->up(lp.data(), lp.size()); v.len_sig = ix->up(lsig.data(), lsig.size()); v.len_ord = ix->up(lord.data(), lord.size()); }
-        stage("sorted / length-grouped dictionary");
-        v.words = upload_dict(ix, img->words); v.word_idf = ix->up(img->word_idf, img->words.n ? img->words.n : 1);
-        v.prefix = upload_docset(ix, img->prefix); v.wm_exact = upload_docset(ix, img->wm_exact); v.wm_ld1 = upload_docset(ix, img->wm_ld1);
-        {   // affix words: forward (prefix) order and reverse-string (suffix) order, each with the doc its trie output resolves to
-            const int A = img->affix_words.n;
-            auto aw = [&](int i) { return std::u16string_view((const char16_t*)img->affix_words.chars + img->affix_words.off[i], img->affix_words.off[i + 1] - img->affix_words.off[i]); };
-            std::vector<int32_t> fo(A); std::iota(fo.begin(), fo.end(), 0); std::sort(fo.begin(), fo.end(), [&](int a, int b) { return aw(a) < aw(b); });
-            std::vector<uint16_t> chars; std::vector<uint32_t> off(A + 1, 0); std::vector<int32_t> fdoc(A);
-            for (int i = 0; i < A; i++) { auto s = aw(fo[i]); chars.insert(chars.end(), s.begin(), s.end()); off[i + 1] = (uint32_t)chars.size(); fdoc[i] = img->affix_last_doc[fo[i]]; }
-            ifx_strings ss{chars.data(), off.data(), A}; if (chars.empty()) chars.push_back(0); ss.chars = chars.data();
-            v.affix = upload_dict(ix, ss); v.affix_fwd_doc = ix->up(fdoc.data(), A ? A : 1);
-            auto rev_less = [&](int a, int b) { auto x = std::u16string_view((const char16_t*)chars.data() + off[a], off[a + 1] - off[a]), y = std::u16string_view((const char16_t*)chars.data() + off[b], off[b + 1] - off[b]);
-                size_t n = std::min(x.size(), y.size()); for (size_t k = 0; k < n; k++) { char16_t p = x[x.size() - 1 - k], q = y[y.size() - 1 - k]; if (p != q) return p < q; } return x.size() < y.size(); };
-            std::vector<int32_t> ro(A); std::iota(ro.begin(), ro.end(), 0); std::sort(ro.begin(), ro.end(), rev_less);
-            std::vector<int32_t> rdoc(A); for (int i = 0; i < A; i++) rdoc[i] = fdoc[ro[i]];
-            v.affix_rev = ix->up(ro.data(), A ? A : 1); v.affix_rev_doc = ix->up(rdoc.data(), A ? A : 1);
-        }
-        stage("word + prefix + wordmatcher dictionaries");
+        v.term_sig = ix->up(sig.data(), sig.size());
+        v.len_ptr = ix->up(lp.data(), lp.size()); v.len_sig = ix->up(lsig.data(), lsig.size()); v.len_ord = ix->up(lord.data(), lord.size());
+        v.words = upload_dict(ix, img->words, true, &hh_words); v.word_idf = ix->up(img->word_idf, img->words.n ? img->words.n : 1);
+        v.prefix = upload_docset(ix, img->prefix, &hh_prefix); v.wm_exact = upload_docset(ix, img->wm_exact, &hh_exact); v.wm_ld1 = upload_docset(ix, img->wm_ld1, &hh_ld1);
+        {   ifx_strings ss{achars.data(), aoff.data(), A};
+            v.affix = upload_dict(ix, ss, true, &hh_affix); v.affix_fwd_doc = ix->up(fdoc.data(), A ? A : 1);
+            v.affix_rev = ix->up(ro.data(), A ? A : 1); v.affix_rev_doc = ix->up(rdoc.data(), A ? A : 1); }
+        stage("dictionaries");
         {   // character tables (tools/gen_chartables.py) + host-evaluated MathF.Log2(len + 1)
             std::vector<uint16_t> lo(65536), upv(65536); std::vector<uint8_t> fl(65536, 0);
             for (int i = 0; i < 65536; i++) lo[i] = upv[i] = (uint16_t)i;
@@ -250,21 +302,24 @@ extern "C" int ifx_index_create(const ifx_index_image* img, const ifx_params* pp
         }
         // persistent-CTA workspaces
         int64_t max_list = 1; for (int t = 0; t < T; t++) max_list = std::max<int64_t>(max_list, img->row_ptr[t + 1] - img->row_ptr[t]);
-        for (int k = 0; k < img->prefix.keys.n; k++) (void)k;
         max_list = std::max<int64_t>(max_list, std::min<int64_t>(N, P.stop_term_limit));
         int64_t nwords = ((int64_t)N + 31) / 32 + 2048;
-        size_t per_cta = (size_t)nwords * 8 + (size_t)(N + 1) * 4 + 2 * (size_t)max_list * 4;
+        // candidate array: the selector's sets are bounded by the lists it unions (each <= stop_term_limit; the disjunctive loop stops at
+        // 100 K docs, the AND path adds at most two top-idf lists to its tiers) -- never sized by N for large shards
+        const int64_t cand_cap = std::min<int64_t>(N, 3LL * std::min<int64_t>(N, P.stop_term_limit) + 100LL * MAX_K + 4096);
+        size_t per_cta = (size_t)nwords * 8 + (size_t)(cand_cap + 1) * 4 + 2 * (size_t)max_list * 4 + CHUNK * 8;
 #ifdef IFX_EMU
         ix->n_ctas = 1;
 #else
         { cudaDeviceProp prop; CUDA_TRY(cudaGetDeviceProperties(&prop, P.device));
           size_t free_b = 0, total_b = 0; CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
-          int want = prop.multiProcessorCount * 3; size_t budget = free_b / 3;
+          int want = prop.multiProcessorCount * 2;          // = resident CTAs of the persistent kernels (__launch_bounds__(.., 2)): one workspace each
+          size_t budget = free_b / 2;
           ix->n_ctas = (int)std::max<size_t>(1, std::min<size_t>((size_t)want, budget / std::max<size_t>(per_cta, 1))); }
 #endif
         const size_t index_bytes = ix->bytes;
         ix->ws.resize(ix->n_ctas);
-        for (auto& w : ix->ws) { w.bits = ix->alloc<unsigned>(nwords); dev_zero(w.bits, (size_t)nwords * 4); w.bits2 = ix->alloc<unsigned>(nwords); dev_zero(w.bits2, (size_t)nwords * 4); w.cand = ix->alloc<int32_t>((size_t)N + 1); w.cand_cap = N; w.buf_a = ix->alloc<int32_t>(max_list); w.buf_b = ix->alloc<int32_t>(max_list); w.buf_cap = max_list; w.surv_g = ix->alloc<unsigned long long>(CHUNK); }
+        for (auto& w : ix->ws) { w.bits = ix->alloc<unsigned>(nwords); dev_zero(w.bits, (size_t)nwords * 4); w.bits2 = ix->alloc<unsigned>(nwords); dev_zero(w.bits2, (size_t)nwords * 4); w.cand = ix->alloc<int32_t>((size_t)cand_cap + 1); w.cand_cap = cand_cap; w.buf_a = ix->alloc<int32_t>(max_list); w.buf_b = ix->alloc<int32_t>(max_list); w.buf_cap = max_list; w.surv_g = ix->alloc<unsigned long long>(CHUNK); }
         ix->d_ws = ix->up(ix->ws.data(), ix->ws.size());
         ix->pool_cap = (unsigned long long)std::max<int64_t>(1 << 20, std::min<int64_t>((int64_t)N * 64, (int64_t)1 << 31));
         ix->d_pool = ix->alloc<int32_t>(ix->pool_cap);

@@ -194,8 +194,9 @@ class SearchEngine:
                 cols.append(["" if v is None else str(v) for v in vals])
         self.IndexColumns(np.array([d.DocumentKey for d in docs], np.int64), fields, cols)
 
-    def IndexColumns(self, keys, schema, columns, threads=None):
-        """Bulk form of IndexDocuments: schema = list[Field] (values ignored), columns[f] = list[str] | int64[] | float64[]."""
+    def IndexColumns(self, keys, schema, columns, threads=None, upload=True):
+        """Bulk form of IndexDocuments: schema = list[Field] (values ignored), columns[f] = list[str] | int64[] | float64[].
+        upload=False stops after the host builder (image_ptr() is valid, no device is touched)."""
         self.Dispose()
         n = len(keys)
         keys = np.ascontiguousarray(keys, np.int64)
@@ -204,7 +205,7 @@ class SearchEngine:
         fl = np.array([(1 if f.Indexable else 0) | (2 if f.Filterable else 0) | (4 if f.Facetable else 0) for f in schema], np.int32)
         self._builder = self._host.ifx_builder_create(len(schema), _p(nb), _p(no.astype(np.int32)), _p(w), _p(fl))
         self._add_columns(keys, columns)
-        self._finish(schema, threads)
+        self._finish(schema, threads, upload)
 
     def _add_columns(self, keys, columns):
         n = len(keys)
@@ -223,15 +224,16 @@ class SearchEngine:
         if rc:
             raise NativeError("ifx_builder_add_docs failed")
 
-    def _finish(self, schema, threads=None):
-        self._host.ifx_builder_finish(C.c_void_p(self._builder), threads or max(1, min(os.cpu_count() or 1, 32)))
+    def _finish(self, schema, threads=None, upload=True):
+        self._host.ifx_builder_finish(C.c_void_p(self._builder), threads or max(1, min(len(os.sched_getaffinity(0)), 64)))
         img = self._host.ifx_builder_image(C.c_void_p(self._builder))
         self._schema = list(schema)
         self._columns = []
         buf = np.zeros(4096, np.uint16); b = C.c_void_p(self._builder)
         for c in range(self._host.ifx_builder_num_columns(b)):
             n = self._host.ifx_builder_column_name(b, c, _p(buf), len(buf)); self._columns.append(buf[:n].tobytes().decode("utf-16-le"))
-        self._upload(img)
+        if upload:
+            self._upload(img)
 
     def IndexChunks(self, schema, chunks, threads=None):
         """Streaming form of IndexColumns for corpora that do not fit one numpy batch: `chunks` yields (keys, columns)."""

@@ -128,12 +128,23 @@ def gen_queries(nq, docs, vocab, seed=SEED):
     return out
 
 
+def _pack_choice(options, ids):
+    """Pre-packed (uint16 blob, int64 offsets) string column whose row i is options[ids[i]] (no per-row Python objects)."""
+    ids = np.asarray(ids, np.int64)
+    ol = np.array([len(o) for o in options], np.int64); oo = np.zeros(len(options) + 1, np.int64); np.cumsum(ol, out=oo[1:])
+    ob = np.frombuffer("".join(options).encode("utf-16-le"), np.uint16)
+    wl = ol[ids]; offs = np.zeros(len(ids) + 1, np.int64); np.cumsum(wl, out=offs[1:])
+    within = np.arange(int(offs[-1]), dtype=np.int64) - np.repeat(offs[:-1], wl)
+    blob = ob[np.repeat(oo[ids], wl) + within] if len(within) else np.zeros(1, np.uint16)
+    return np.ascontiguousarray(blob), offs
+
+
 def schema_and_columns(docs, multi_field):
     """(schema, columns) for SearchEngine.IndexColumns / the oracle, per BASELINE.json configs."""
     from .engine import Field, Weight
     if not multi_field:      # configs[1]: new Document(i, title) -> single field "content", Weight.Med
         return [Field("content", None, Weight.Med)], [docs["title"]]
-    genre = [GENRES[g] for g in docs["genre_id"]]
+    genre = _pack_choice(GENRES, docs["genre_id"])
     schema = [Field("title", None, Weight.High), Field("description", None, Weight.Low),
               Field("year", None, Weight.Med, indexable=False, filterable=True, facetable=True),
               Field("rating", None, Weight.Med, indexable=False, filterable=True),

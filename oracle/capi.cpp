@@ -5,6 +5,7 @@
 //
 // Follows /root/reference/src/Infidex/SearchEngine.cs:256-319 (Search) and :124-192 (IndexDocumentsInternal).
 #include "filter.hpp"
+#include "../include/infidex_gpu.h"     // ifx_index_image: the flattened index format of the boundary (ifxo_load_image, bench only)
 #include <thread>
 #include <atomic>
 #include <string>
@@ -79,6 +80,8 @@ int ifxo_add_docs(void* h, int n, const long long* keys, const int* kinds, const
     }
     return 0;
 }
+// bench.py only: index state from a flattened image instead of add_docs + build (see Index::load_image)
+int ifxo_load_image(void* h, const ifx_index_image* img) { Engine* e = (Engine*)h; e->ix.load_image(*img); delete e->pipe; e->pipe = new Pipeline(e->ix); return 0; }
 int ifxo_build(void* h) { Engine* e = (Engine*)h; e->ix.build(); delete e->pipe; e->pipe = new Pipeline(e->ix); return 0; }
 
 // status: 0 ok, 1 unsupported query/filter feature (short-query path, regex)

@@ -103,6 +103,10 @@ class OracleEngine:
         lib().ifxo_add_docs(self.h, n, _p(keys), _p(kinds), cols, offs)
         lib().ifxo_build(self.h)
 
+    def load_image(self, image_ptr):
+        """bench.py only: take the index state from a flattened ifx_index_image (pointer from SearchEngine.image_ptr()); see Index::load_image."""
+        lib().ifxo_load_image(self.h, C.c_void_p(image_ptr))
+
     def index_texts(self, texts, keys=None):
         keys = np.arange(len(texts), dtype=np.int64) if keys is None else keys
         self.index_columns(keys, [list(texts)])

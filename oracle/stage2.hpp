@@ -550,6 +550,7 @@ struct Pipeline {
         str search = normalize(search_in);
         QueryAnalysis qa = analyze_query(search);
         std::vector<ScoreEntry> stage1;
+        if (!qa.can_use_ngrams && ix.from_image) { out.unsupported = true; return out; }   // an image carries no token positions (champion lists)
         if (!qa.can_use_ngrams) { out.short_path = true; stage1 = sq.stage1(search, max_results); }   // no word of >= 3 chars: SURVEY 8(f)-1, oracle/shortquery.hpp
         else { str tfidf_q = qa.mixed ? qa.long_words : search; if (is_blank(tfidf_q)) tfidf_q = search; stage1 = s1.search(tfidf_q, depth, st); }
         if (stage1_out) *stage1_out = stage1;
