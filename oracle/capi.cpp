@@ -113,6 +113,15 @@ int ifxo_stage1(void* h, const uint16_t* q, int qlen, int depth, long long* out_
     return r.status;
 }
 
+// Per-chunk trace of the MaxScore threshold chain of one query (see Stage1Stats::trace); returns the number of chunks, fills <= cap rows of 6 doubles.
+int ifxo_stage1_trace(void* h, const uint16_t* q, int qlen, int depth, double* out, int cap, long long* stats) {
+    Engine* e = (Engine*)h; std::vector<ScoreEntry> s1; Stage1Stats st; std::vector<double> tr; st.trace = &tr;
+    do_search(*e, sv((const char16_t*)q, (size_t)qlen), 10, depth, false, nullptr, false, &s1, &st);
+    int n = (int)(tr.size() / 6); std::memcpy(out, tr.data(), sizeof(double) * 6 * (size_t)std::min(n, cap));
+    if (stats) { stats[0] = st.path; stats[1] = st.candidates; stats[2] = st.streamed_postings; stats[3] = st.n_terms; stats[4] = st.n_fuzzy; }
+    return n;
+}
+
 // Batch search over `threads` host threads (queries are independent; the index is immutable) -- CPU baseline timing.
 // out arrays are [nq * cap]; out_n[nq]; status[nq]
 int ifxo_search_batch(void* h, const uint16_t* qblob, const long long* qoff, int nq, int max_results, int depth, int enable_cov,

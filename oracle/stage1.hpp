@@ -72,6 +72,9 @@ struct QTerm {
 struct Stage1Stats {          // what the candidate selector did (for roofline accounting / debugging)
     int path = 0;             // 1 prefix shortcut, 2 disjunctive, 3 tiers, 4 full scan
     long long candidates = 0; long long streamed_postings = 0; int n_terms = 0; int n_fuzzy = 0;
+    // optional per-chunk trace of the MaxScore chain (tools/speculation_study.py): [threshold at chunk start, candidates, matched pairs,
+    // matched pairs the MaxScore test skipped, max over those of (score + bound + suffix), heap updates during the flush]
+    std::vector<double>* trace = nullptr;
 };
 
 struct Stage1 {
@@ -250,6 +253,7 @@ struct Stage1 {
                 while (p < ce) {
                     size_t cnt = std::min<size_t>(4096, ce - p);
                     score.assign(cnt, 0.f);
+                    const bool tracing = st && st->trace; double tr_matched = 0, tr_skipped = 0, tr_vmax = -1.0, tr_updates = 0; const float tr_thr0 = thr;
                     for (size_t t = 0; t < T; t++) {
                         const QTerm& q = terms[t];
                         if (q.idf <= 0.f) continue;
@@ -257,20 +261,24 @@ struct Stage1 {
                         midx.clear(); mtf.clear();
                         const std::vector<int>& dl = *q.docs; size_t& cur = cursor[t];
                         for (size_t j = 0; j < cnt; j++) {
-                            if (K < INT32_MAX && score[j] + q.max_score + rem <= thr) continue;
+                            if (K < INT32_MAX && score[j] + q.max_score + rem <= thr) {
+                                if (tracing && std::binary_search(dl.begin(), dl.end(), cands[p + j])) { tr_skipped++; tr_matched++; tr_vmax = std::max(tr_vmax, (double)(score[j] + q.max_score + rem)); }
+                                continue;
+                            }
                             int target = cands[p + j];
                             // Advance(target): first posting >= target from the current position
                             if (cur < dl.size() && dl[cur] < target) cur = std::lower_bound(dl.begin() + cur, dl.end(), target) - dl.begin();
                             if (cur < dl.size() && dl[cur] == target) { midx.push_back((int)j); mtf.push_back(q.fuzzy ? 1.f : (float)(*q.w)[cur]); }
                         }
-                        size_t m = midx.size(), vec_end = m - (m % 8);
+                        size_t m = midx.size(), vec_end = m - (m % 8); tr_matched += (double)m;
                         for (size_t i = 0; i < m; i++) {
                             int j = midx[i]; float d = ix.doc_len[cands[p + j]];
                             if (i < vec_end) score[j] += term_score_vector(mtf[i], d, avgdl, q.idf);
                             else { if (d <= 0.f) d = 1.f; score[j] += term_score_scalar(mtf[i], d, avgdl, q.idf); }
                         }
                     }
-                    for (size_t j = 0; j < cnt; j++) if (score[j] > 0.f) { int id = cands[p + j]; if (!ix.docs[id].deleted) update_topk(id, score[j], K, heap, thr); }
+                    for (size_t j = 0; j < cnt; j++) if (score[j] > 0.f) { int id = cands[p + j]; if (!ix.docs[id].deleted) { float before = thr; int hs = heap.size(); update_topk(id, score[j], K, heap, thr); if (thr != before || heap.size() != hs) tr_updates++; } }
+                    if (tracing) { double rec[6] = {(double)tr_thr0, (double)cnt, tr_matched, tr_skipped, tr_vmax, tr_updates}; st->trace->insert(st->trace->end(), rec, rec + 6); }
                     p += cnt;
                 }
             }
