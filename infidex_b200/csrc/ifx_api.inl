@@ -1,7 +1,7 @@
 // infidex_b200 -- implementation of the C-ABI (include/infidex_gpu.h).
 // Included by ifx_api.cu (CUDA product) and by tests/emu/emu_api.cpp (IFX_EMU host emulation of the kernels, tests only).
 #include "../../include/infidex_gpu.h"
-#include "ifx_stage1.h"
+#include "ifx_stage1_score.h"
 #include "ifx_stage2.h"
 #include "ifx_build.h"
 #include <thread>
@@ -67,6 +67,7 @@ struct ifx_index {
     int n_ctas = 1;
     std::vector<S1Workspace> ws; S1Workspace* d_ws = nullptr;
     int32_t* d_pool = nullptr; unsigned long long pool_cap = 0;
+    unsigned char* d_spool = nullptr; unsigned long long spool_cap = 0;   // Stage-1 staging pool of a batch (candidates, lengths, chunk tables, tf matrices)
     int max_batch = 16384;
     int device = 0; uint8_t* d_flush = nullptr; bool attr_s1 = false, attr_s2 = false;   // kernel attributes are per device: tracked per index (guarded by mu)
     std::vector<FilterProg> h_filters; FilterProg* d_filters = nullptr;
@@ -83,6 +84,7 @@ struct ifx_batch {
     std::vector<void*> allocs;
     uint16_t* d_text = nullptr; int64_t* d_off = nullptr; int32_t* d_par = nullptr;   // par: [nq][5] max_results, depth, enable_cov, filter_id, enable_facets
     QueryPlan* d_plans = nullptr; FuzzyItem* d_items = nullptr; BatchCounters* d_bc = nullptr; int* d_work = nullptr;
+    S1Rec* d_recs = nullptr; int32_t* d_light = nullptr; int32_t* d_heavy = nullptr;
     int* d_order = nullptr; long long* d_qdbg = nullptr;
     int64_t* d_s1_key = nullptr; int32_t* d_s1_doc = nullptr; float* d_s1_score = nullptr; int32_t* d_s1_n = nullptr;
     Stage2Buffers s2{};                 // WordMatcher + coverage outputs
@@ -213,6 +215,7 @@ extern "C" int ifx_index_create(const ifx_index_image* img, const ifx_params* pp
             const int64_t FP = fp[(size_t)N + 1]; std::vector<int32_t> ft((size_t)std::max<int64_t>(FP, 1)); std::vector<uint8_t> fw((size_t)std::max<int64_t>(FP, 1));
             for (int t = 0; t < T; t++) { if (img->df[t] <= 0) continue; for (int64_t i = img->row_ptr[t]; i < img->row_ptr[t + 1]; i++) { int64_t at = fp[(size_t)img->post_doc[i] + 1]++; ft[(size_t)at] = t; fw[(size_t)at] = img->post_tf[i]; } }
             v.fwd_ptr = ix->up(fp.data(), (size_t)N + 1); v.fwd_term = ix->up(ft.data(), ft.size()); v.fwd_tf = ix->up(fw.data(), fw.size());
+            v.fwd_avg_bytes = (int32_t)(N > 0 ? 5 * FP / N + 16 : 16);
         }
         {   // container skip table for long posting lists: turns the per-chunk sub-range search of the scorer into a lookup
             std::vector<int32_t> sp((size_t)std::max(ns, 0) * (ncont + 1));
@@ -239,7 +242,7 @@ extern "C" int ifx_index_create(const ifx_index_image* img, const ifx_params* pp
             int64_t* fwd_ptr = ix->alloc<int64_t>((size_t)N + 1);
             if (N > 0) { k_scan_tile_sums<<<(unsigned)n_tiles, SCAN_THREADS>>>(cnt, N, tile); k_scan_tiles<<<1, 1024>>>(tile, n_tiles); k_scan_final<<<(unsigned)n_tiles, SCAN_THREADS>>>(cnt, N, tile, fwd_ptr); }
             else dev_zero(fwd_ptr, 8);
-            int64_t FP = 0; d2h(&FP, fwd_ptr + N, 8);
+            int64_t FP = 0; d2h(&FP, fwd_ptr + N, 8); v.fwd_avg_bytes = (int32_t)(N > 0 ? 5 * FP / N + 16 : 16);
             int32_t* fwd_term = ix->alloc<int32_t>((size_t)std::max<int64_t>(FP, 1)); uint8_t* fwd_tf = ix->alloc<uint8_t>((size_t)std::max<int64_t>(FP, 1));
             dev_zero(cnt, ((size_t)N + 1) * 4);
             if (T > 0) k_fwd_scatter<<<grid, 256>>>(v.row_ptr, v.df, T, v.post_doc, v.post_tf, fwd_ptr, cnt, fwd_term, fwd_tf);
@@ -307,7 +310,8 @@ extern "C" int ifx_index_create(const ifx_index_image* img, const ifx_params* pp
         // candidate array: the selector's sets are bounded by the lists it unions (each <= stop_term_limit; the disjunctive loop stops at
         // 100 K docs, the AND path adds at most two top-idf lists to its tiers) -- never sized by N for large shards
         const int64_t cand_cap = std::min<int64_t>(N, 3LL * std::min<int64_t>(N, P.stop_term_limit) + 100LL * MAX_K + 4096);
-        size_t per_cta = (size_t)nwords * 8 + (size_t)(cand_cap + 1) * 4 + 2 * (size_t)max_list * 4 + CHUNK * 8;
+        (void)cand_cap;
+        size_t per_cta = (size_t)nwords * 8 + (size_t)(nwords + ncont + 2) * 4 + 2 * (size_t)(ncont + 2) * 4 + 2 * (size_t)max_list * 4 + CHUNK * 8;
 #ifdef IFX_EMU
         ix->n_ctas = 1;
 #else
@@ -319,10 +323,17 @@ extern "C" int ifx_index_create(const ifx_index_image* img, const ifx_params* pp
 #endif
         const size_t index_bytes = ix->bytes;
         ix->ws.resize(ix->n_ctas);
-        for (auto& w : ix->ws) { w.bits = ix->alloc<unsigned>(nwords); dev_zero(w.bits, (size_t)nwords * 4); w.bits2 = ix->alloc<unsigned>(nwords); dev_zero(w.bits2, (size_t)nwords * 4); w.cand = ix->alloc<int32_t>((size_t)cand_cap + 1); w.cand_cap = cand_cap; w.buf_a = ix->alloc<int32_t>(max_list); w.buf_b = ix->alloc<int32_t>(max_list); w.buf_cap = max_list; w.surv_g = ix->alloc<unsigned long long>(CHUNK); }
+        for (auto& w : ix->ws) { w.bits = ix->alloc<unsigned>(nwords); dev_zero(w.bits, (size_t)nwords * 4); w.bits2 = ix->alloc<unsigned>(nwords); dev_zero(w.bits2, (size_t)nwords * 4); w.cand = nullptr; w.cand_cap = 0; w.rank = ix->alloc<int32_t>((size_t)nwords + ncont + 2); w.cstart = ix->alloc<int32_t>((size_t)ncont + 2); w.cfirst = ix->alloc<int32_t>((size_t)ncont + 2); w.buf_a = ix->alloc<int32_t>(max_list); w.buf_b = ix->alloc<int32_t>(max_list); w.buf_cap = max_list; w.surv_g = ix->alloc<unsigned long long>(CHUNK); }
         ix->d_ws = ix->up(ix->ws.data(), ix->ws.size());
         ix->pool_cap = (unsigned long long)std::max<int64_t>(1 << 20, std::min<int64_t>((int64_t)N * 64, (int64_t)1 << 31));
         ix->d_pool = ix->alloc<int32_t>(ix->pool_cap);
+        {   // Stage-1 staging pool: per candidate 8 bytes + one tf byte per scored term; a batch that outgrows it is finished in waves
+            unsigned long long want = (unsigned long long)std::max<int64_t>(64LL << 20, std::min<int64_t>((int64_t)N * 1600, 24LL << 30));
+            if (const char* e = getenv("IFX_S1_POOL_MB")) want = (unsigned long long)atoll(e) << 20;
+#ifndef IFX_EMU
+            size_t free_b = 0, total_b = 0; CUDA_TRY(cudaMemGetInfo(&free_b, &total_b)); want = std::min<unsigned long long>(want, free_b / 2);
+#endif
+            ix->spool_cap = want; ix->d_spool = ix->alloc<unsigned char>(want); }
         ix->max_batch = P.max_batch > 0 ? P.max_batch : 16384;
         stage("workspaces");
         if (timing) fprintf(stderr, "[ifx_index_create] device memory: index %.1f MB, workspaces %d x %.1f MB, fuzzy pool %.1f MB\n", index_bytes / 1e6, ix->n_ctas,

@@ -83,6 +83,7 @@ struct DevIndex {
     const int32_t* affix_rev_doc;    // last doc, in reverse-trie order
     const uint16_t* lower; const uint16_t* upper; const uint8_t* cflags;   // 65536-entry tables
     unsigned delim_ascii[4];         // bit c set: ASCII char c is a token delimiter (cflags[c] & 4), kept in the kernel parameters
+    int32_t fwd_avg_bytes;           // average bytes of one document's forward list (+ its pointers): cost model of the per-candidate lookup mode
     const float* log2_len;           // MathF.Log2(len + 1) for len < 1024 (host glibc)
     const float* idf_table;          // Bm25Scorer.ComputeIdf(n_live, df) for df in [0, idf_table_n): evaluated on the host with the
     int32_t idf_table_n;             // C runtime's logf (what MathF.Log calls), so device scores cannot drift from the reference by an ulp
@@ -122,6 +123,7 @@ struct Ctx {
     void sync() const {}
     void sync_workers(int) const {}
     void sync_team(int) const {}
+    void syncwarp() const {}
     unsigned ballot(bool p) const { return p ? 1u : 0u; }
     unsigned lanemask_lt() const { return 0u; }
     template <class T> T shfl(T v, int) const { return v; }
@@ -146,6 +148,7 @@ struct Ctx {
     __device__ void sync_workers(int n) const { asm volatile("bar.sync 1, %0;" :: "r"(n) : "memory"); }
     // named barrier 2 over the `n` threads of the small-chunk team
     __device__ void sync_team(int n) const { asm volatile("bar.sync 2, %0;" :: "r"(n) : "memory"); }
+    __device__ void syncwarp() const { __syncwarp(); }
     __device__ unsigned ballot(bool p) const { return __ballot_sync(0xffffffffu, p); }
     __device__ unsigned lanemask_lt() const { return (1u << (threadIdx.x & 31)) - 1u; }
     template <class T> __device__ T shfl(T v, int src) const { return __shfl_sync(0xffffffffu, v, src); }
@@ -200,7 +203,8 @@ struct QueryPlan {
     FuzzyReq fuzzy[MAX_FUZZY];
 };
 
-struct BatchCounters { int32_t n_fuzzy_items; int32_t overflow; unsigned long long fuzzy_pool_used; unsigned long long algo_bytes; unsigned long long s1_ns_sum; unsigned long long s1_ns_max; unsigned long long s1_cand_sum; };
+struct BatchCounters { int32_t n_fuzzy_items; int32_t overflow; unsigned long long fuzzy_pool_used; unsigned long long algo_bytes; unsigned long long s1_ns_sum; unsigned long long s1_ns_max; unsigned long long s1_cand_sum;
+                       unsigned long long s1_pool_used; int32_t s1_deferred, s1_n_light, s1_n_heavy, s1_wave; };
 
 struct FuzzyItem { int32_t query; int32_t slot; };
 

@@ -39,12 +39,14 @@ __global__ void __launch_bounds__(IFX_EXPAND_THREADS, 2) k_expand(DevIndex ix, Q
         expand_fuzzy(c, ix, plans[fi.query], fi.slot, ws, sh, pool, pool_cap, bc, sorted_len, sh.cand_s);
     }
 }
-__global__ void __launch_bounds__(IFX_S1_THREADS, 2) k_stage1(DevIndex ix, const QueryPlan* plans, int nq, const int32_t* pool, S1Workspace* wss, BatchCounters* bc,
-                                                int64_t* s1_key, int32_t* s1_doc, float* s1_score, int32_t* s1_n, int K, int* work, const int* order, long long* qdbg) {
+// Stage 1, kernel 1: candidate selection + tf lookups of one query per CTA (persistent, LPT order). `wave` > 0: only the queries an earlier
+// wave deferred because the staging pool was full.
+__global__ void __launch_bounds__(IFX_S1_THREADS, 2) k_select_lookup(DevIndex ix, const QueryPlan* plans, int nq, const int32_t* pool, S1Workspace* wss, BatchCounters* bc,
+                                                int32_t* s1_n, int* work, const int* order, long long* qdbg, S1Rec* recs, unsigned char* spool, unsigned long long spool_cap,
+                                                S1Queues queues, int wave, int force_mode) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     S1Shared& sh = *reinterpret_cast<S1Shared*>(smem_raw); Ctx c; S1Workspace ws = wss[blockIdx.x];
     for (int i = threadIdx.x; i < MAX_CONTAINERS; i += blockDim.x) sh.dirty[i] = 0;
-    for (int i = threadIdx.x; i < S1_TILE * CHUNK; i += blockDim.x) (&sh.tfm[0][0])[i] = 0;
     __syncthreads();
     for (;;) {
         if (threadIdx.x == 0) sh.bcast[7] = atomicAdd(work, 1);
@@ -52,46 +54,123 @@ __global__ void __launch_bounds__(IFX_S1_THREADS, 2) k_stage1(DevIndex ix, const
         int qi = sh.bcast[7]; __syncthreads();
         if (qi >= nq) break;
         const int q = order[qi];
-        Stage1Out o{s1_key + (size_t)q * K, s1_doc + (size_t)q * K, s1_score + (size_t)q * K, s1_n + q, qdbg + (size_t)q * IFX_QDBG};
+        if (wave > 0 && recs[q].state != 2) continue;
+        Stage1Out o{nullptr, nullptr, nullptr, s1_n + q, qdbg + (size_t)q * IFX_QDBG};
         unsigned long long t0 = 0; if (threadIdx.x == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-        stage1_query(c, ix, plans[q], pool, ws, sh, o, bc);
+        const int path = stage1_select(c, ix, plans[q], pool, ws, sh, o);
+        stage1_lookup(c, ix, plans[q], path, q, ws, sh, recs, spool, spool_cap, queues, bc, o, ix.fwd_avg_bytes, force_mode);
         __syncthreads();
         if (threadIdx.x == 0) { unsigned long long t1; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1)); atomicAdd(&bc->s1_ns_sum, t1 - t0); atomicMax(&bc->s1_ns_max, t1 - t0); qdbg[(size_t)q * IFX_QDBG + 4] = (long long)(t1 - t0); qdbg[(size_t)q * IFX_QDBG + 2] -= (long long)t0; qdbg[(size_t)q * IFX_QDBG + 5] = blockIdx.x; }
     }
 }
+// Stage 1, kernel 2a: one warp per light query (persistent warps pulling from the light queue).
+#ifndef IFX_SW_WARPS
+#define IFX_SW_WARPS 16
 #endif
+__global__ void __launch_bounds__(IFX_SW_WARPS * 32, 1) k_score_warp(DevIndex ix, const S1Rec* recs, const unsigned char* spool, const int32_t* light, const BatchCounters* bc, int* work,
+                                                                     int32_t* s1_doc, float* s1_score, int32_t* s1_n, int K, long long* qdbg) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Ctx c; WarpScoreShared& sh = reinterpret_cast<WarpScoreShared*>(smem_raw)[threadIdx.x >> 5];
+    const int n = bc->s1_n_light;
+    for (;;) {
+        int qi = 0; if (c.lane() == 0) qi = atomicAdd(work, 1); qi = __shfl_sync(0xffffffffu, qi, 0);
+        if (qi >= n) break;
+        const int q = light[qi];
+        unsigned long long t0 = 0; if (c.lane() == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        score_warp(c, ix.avgdl, recs[q], spool, sh, s1_doc + (size_t)q * K, s1_score + (size_t)q * K, s1_n + q);
+        if (c.lane() == 0) { unsigned long long t1; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1)); qdbg[(size_t)q * IFX_QDBG + 10] = (long long)(t1 - t0); }
+    }
+}
+// Stage 1, kernel 2b: one CTA per heavy query.
+__global__ void __launch_bounds__(IFX_S1_THREADS, 2) k_score_cta(DevIndex ix, const S1Rec* recs, const unsigned char* spool, const int32_t* heavy, const BatchCounters* bc, int* work, S1Workspace* wss,
+                                                                 int32_t* s1_doc, float* s1_score, int32_t* s1_n, int K, long long* qdbg) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    S1Shared& sh = *reinterpret_cast<S1Shared*>(smem_raw); Ctx c; S1Workspace ws = wss[blockIdx.x];
+    const int n = bc->s1_n_heavy;
+    for (;;) {
+        if (threadIdx.x == 0) sh.bcast[7] = atomicAdd(work, 1);
+        __syncthreads();
+        int qi = sh.bcast[7]; __syncthreads();
+        if (qi >= n) break;
+        const int q = heavy[qi];
+        unsigned long long t0 = 0; if (threadIdx.x == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        score_cta(c, ix.avgdl, recs[q], spool, ws, sh, s1_doc + (size_t)q * K, s1_score + (size_t)q * K, s1_n + q);
+        if (threadIdx.x == 0) { unsigned long long t1; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1)); qdbg[(size_t)q * IFX_QDBG + 10] = (long long)(t1 - t0); }
+    }
+}
+// Stage 1, kernel 3: final order of every query scored in this wave.
+__global__ void __launch_bounds__(256) k_s1_finish(DevIndex ix, const BatchCounters* bc, const int32_t* light, const int32_t* heavy, int64_t* s1_key, int32_t* s1_doc, float* s1_score, int32_t* s1_n, int K) {
+    __shared__ FinishShared sh; Ctx c; const int nl = bc->s1_n_light, nh = bc->s1_n_heavy; const int b = blockIdx.x;
+    if (b >= nl + nh) return;
+    const int q = b < nl ? light[b] : heavy[b - nl];
+    s1_finish(c, ix, sh, s1_key + (size_t)q * K, s1_doc + (size_t)q * K, s1_score + (size_t)q * K, s1_n + q);
+}
+#endif
+
+static int s1_force_mode() { const char* e = getenv("IFX_S1_LOOKUP"); return e ? atoi(e) : 0; }      // 1 forward-index lookups, 2 streamed lists (tests / A-B runs)
 
 static void run_stage1_phase(ifx_batch* b, ifx_stats* st) {
     ifx_index* ix = b->idx; const int nq = b->nq; const int K = b->depth_max;
     BatchCounters zero{}; h2d(b->d_bc, &zero, sizeof(zero));
     const int items_cap = nq * MAX_FUZZY;       // every query may carry MAX_FUZZY unknown words: the item list can never overflow
+    const int force_mode = s1_force_mode(); S1Queues queues{b->d_light, b->d_heavy};
     Timer t;
 #ifdef IFX_EMU
     std::vector<int64_t> off(nq + 1); d2h(off.data(), b->d_off, (nq + 1) * 8);
     for (int q = 0; q < nq; q++) prepare_query(ix->v, b->d_text + off[q], (int)(off[q + 1] - off[q]), b->d_par[q * 5 + 1], b->d_par[q * 5 + 0], b->d_par[q * 5 + 2], b->d_par[q * 5 + 3], b->d_par[q * 5 + 4], b->d_plans[q], b->d_items, items_cap, b->d_bc, q);
-    static S1Shared* sh = new S1Shared(); memset(sh->dirty, 0, sizeof(sh->dirty));
+    static S1Shared* sh = new S1Shared(); memset(sh->dirty, 0, sizeof(sh->dirty)); static WarpScoreShared* wsh = new WarpScoreShared(); static FinishShared* fsh = new FinishShared();
     Ctx c; int nit = std::min(b->d_bc->n_fuzzy_items, items_cap);
     for (int i = 0; i < nit; i++) expand_fuzzy(c, ix->v, b->d_plans[b->d_items[i].query], b->d_items[i].slot, ix->ws[0], *sh, ix->d_pool, ix->pool_cap, b->d_bc, ix->d_sorted_len, sh->cand_s);
-    for (int q = 0; q < nq; q++) { Stage1Out o{b->d_s1_key + (size_t)q * K, b->d_s1_doc + (size_t)q * K, b->d_s1_score + (size_t)q * K, b->d_s1_n + q, nullptr}; stage1_query(c, ix->v, b->d_plans[q], ix->d_pool, ix->ws[0], *sh, o, b->d_bc); }
+    const bool no_warp = getenv("IFX_S1_NO_WARP") != nullptr;      // tests: force every query through the block-wide scorer
+    for (int wave = 0; wave < 64; wave++) {
+        b->d_bc->s1_pool_used = 0; b->d_bc->s1_deferred = 0; b->d_bc->s1_n_light = 0; b->d_bc->s1_n_heavy = 0; b->d_bc->s1_wave = wave;
+        for (int q = 0; q < nq; q++) {
+            if (wave > 0 && b->d_recs[q].state != 2) continue;
+            Stage1Out o{nullptr, nullptr, nullptr, b->d_s1_n + q, nullptr};
+            const int path = stage1_select(c, ix->v, b->d_plans[q], ix->d_pool, ix->ws[0], *sh, o);
+            stage1_lookup(c, ix->v, b->d_plans[q], path, q, ix->ws[0], *sh, b->d_recs, ix->d_spool, ix->spool_cap, queues, b->d_bc, o, ix->v.fwd_avg_bytes, force_mode);
+        }
+        for (int i = 0; i < b->d_bc->s1_n_light; i++) { const int q = b->d_light[i];
+            if (no_warp) score_cta(c, ix->v.avgdl, b->d_recs[q], ix->d_spool, ix->ws[0], *sh, b->d_s1_doc + (size_t)q * K, b->d_s1_score + (size_t)q * K, b->d_s1_n + q);
+            else score_warp(c, ix->v.avgdl, b->d_recs[q], ix->d_spool, *wsh, b->d_s1_doc + (size_t)q * K, b->d_s1_score + (size_t)q * K, b->d_s1_n + q); }
+        for (int i = 0; i < b->d_bc->s1_n_heavy; i++) { const int q = b->d_heavy[i]; score_cta(c, ix->v.avgdl, b->d_recs[q], ix->d_spool, ix->ws[0], *sh, b->d_s1_doc + (size_t)q * K, b->d_s1_score + (size_t)q * K, b->d_s1_n + q); }
+        for (int i = 0; i < b->d_bc->s1_n_light + b->d_bc->s1_n_heavy; i++) { const int q = i < b->d_bc->s1_n_light ? b->d_light[i] : b->d_heavy[i - b->d_bc->s1_n_light];
+            s1_finish(c, ix->v, *fsh, b->d_s1_key + (size_t)q * K, b->d_s1_doc + (size_t)q * K, b->d_s1_score + (size_t)q * K, b->d_s1_n + q); }
+        if (b->d_bc->s1_deferred == 0) break;
+    }
     (void)t;
 #else
-    size_t smem = sizeof(S1Shared);
-    if (!ix->attr_s1) { CUDA_TRY(cudaFuncSetAttribute(k_expand, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); CUDA_TRY(cudaFuncSetAttribute(k_stage1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); ix->attr_s1 = true; }
+    const size_t smem = sizeof(S1Shared), smem_w = sizeof(WarpScoreShared) * IFX_SW_WARPS;
+    if (!ix->attr_s1) { CUDA_TRY(cudaFuncSetAttribute(k_expand, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); CUDA_TRY(cudaFuncSetAttribute(k_select_lookup, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUDA_TRY(cudaFuncSetAttribute(k_score_cta, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); CUDA_TRY(cudaFuncSetAttribute(k_score_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_w)); ix->attr_s1 = true; }
     t.start();
     k_prepare<<<(nq + 127) / 128, 128>>>(ix->v, b->d_text, b->d_off, b->d_par, nq, b->d_plans, b->d_items, items_cap, b->d_bc);
     float ms_prep = t.stop();
     t.start();
-    CUDA_TRY(cudaMemsetAsync(b->d_work, 0, 2 * sizeof(int)));
+    CUDA_TRY(cudaMemsetAsync(b->d_work, 0, 8 * sizeof(int)));
     k_expand<<<ix->n_ctas, IFX_EXPAND_THREADS, smem>>>(ix->v, b->d_plans, b->d_items, b->d_bc, ix->d_ws, ix->d_pool, ix->pool_cap, ix->d_sorted_len, b->d_work, items_cap);
     float ms_exp = t.stop();
-    t.start();
-    k_order<<<1, 1024>>>(ix->v, b->d_plans, nq, b->d_order);
-    k_stage1<<<std::min(ix->n_ctas, nq), IFX_S1_THREADS, smem>>>(ix->v, b->d_plans, nq, ix->d_pool, ix->d_ws, b->d_bc, b->d_s1_key, b->d_s1_doc, b->d_s1_score, b->d_s1_n, K, b->d_work + 1, b->d_order, b->d_qdbg);
-    float ms_s1 = t.stop();
+    float ms_sel = 0.f, ms_sw = 0.f, ms_sc = 0.f, ms_fin = 0.f; int launches = 2; const int sms = ix->n_ctas / 2 > 0 ? ix->n_ctas / 2 : 1;
+    k_order<<<1, 1024>>>(ix->v, b->d_plans, nq, b->d_order); launches++;
+    for (int wave = 0; wave < 64; wave++) {
+        if (wave > 0) { BatchCounters bc; d2h(&bc, b->d_bc, sizeof(bc)); bc.s1_pool_used = 0; bc.s1_deferred = 0; bc.s1_n_light = 0; bc.s1_n_heavy = 0; bc.s1_wave = wave; h2d(b->d_bc, &bc, sizeof(bc)); CUDA_TRY(cudaMemsetAsync(b->d_work + 1, 0, 4 * sizeof(int))); }
+        t.start();
+        k_select_lookup<<<std::min(ix->n_ctas, nq), IFX_S1_THREADS, smem>>>(ix->v, b->d_plans, nq, ix->d_pool, ix->d_ws, b->d_bc, b->d_s1_n, b->d_work + 1, b->d_order, b->d_qdbg, b->d_recs, ix->d_spool, ix->spool_cap, queues, wave, force_mode);
+        ms_sel += t.stop(); t.start();
+        k_score_cta<<<std::min(ix->n_ctas, nq), IFX_S1_THREADS, smem>>>(ix->v, b->d_recs, ix->d_spool, b->d_heavy, b->d_bc, b->d_work + 2, ix->d_ws, b->d_s1_doc, b->d_s1_score, b->d_s1_n, K, b->d_qdbg);
+        ms_sc += t.stop(); t.start();
+        k_score_warp<<<sms, IFX_SW_WARPS * 32, smem_w>>>(ix->v, b->d_recs, ix->d_spool, b->d_light, b->d_bc, b->d_work + 3, b->d_s1_doc, b->d_s1_score, b->d_s1_n, K, b->d_qdbg);
+        ms_sw += t.stop(); t.start();
+        k_s1_finish<<<nq, 256>>>(ix->v, b->d_bc, b->d_light, b->d_heavy, b->d_s1_key, b->d_s1_doc, b->d_s1_score, b->d_s1_n, K);
+        ms_fin += t.stop(); launches += 4;
+        int deferred = 0; d2h(&deferred, &b->d_bc->s1_deferred, sizeof(int));
+        if (deferred == 0) break;
+    }
     CUDA_TRY(cudaGetLastError());
-    if (st) { st->ms_prepare += ms_prep; st->ms_expand += ms_exp; st->ms_stage1 += ms_s1; st->kernel_launches += 4; }
+    if (st) { st->ms_prepare += ms_prep; st->ms_expand += ms_exp; st->ms_stage1 += ms_sel + ms_sc + ms_sw + ms_fin; st->ms_s1_select += ms_sel; st->ms_s1_score_cta += ms_sc; st->ms_s1_score_warp += ms_sw; st->ms_s1_finish += ms_fin; st->kernel_launches += launches; }
 #endif
-    if (st) { BatchCounters bc; d2h(&bc, b->d_bc, sizeof(bc)); st->algo_bytes_stage1 += (int64_t)bc.algo_bytes; st->s1_query_ms_max = (float)(bc.s1_ns_max * 1e-6); st->s1_query_ms_sum = (float)(bc.s1_ns_sum * 1e-6); }
+    if (st) { BatchCounters bc; d2h(&bc, b->d_bc, sizeof(bc)); st->algo_bytes_stage1 += (int64_t)bc.algo_bytes; st->s1_query_ms_max = (float)(bc.s1_ns_max * 1e-6); st->s1_query_ms_sum = (float)(bc.s1_ns_sum * 1e-6);
+        st->s1_light = bc.s1_n_light; st->s1_heavy = bc.s1_n_heavy; st->s1_waves = bc.s1_wave + 1; st->s1_pool_bytes = (int64_t)bc.s1_pool_used; }
 }
 
 // (re)fill the per-batch inputs; allocates on first use or when the batch outgrows its buffers
@@ -110,6 +189,7 @@ static int fill_batch(ifx_batch* b, const ifx_query* q, int nq) {
         b->d_text = b->alloc<uint16_t>(b->text_cap); b->d_off = b->alloc<int64_t>(nq + 1); b->d_par = b->alloc<int32_t>(par.size());
         b->d_plans = b->alloc<QueryPlan>(nq); b->d_items = b->alloc<FuzzyItem>((size_t)nq * MAX_FUZZY); b->d_bc = b->alloc<BatchCounters>(1); b->d_work = b->alloc<int>(8); dev_zero(b->d_work, 8 * sizeof(int));
         size_t K = b->depth_max;
+        b->d_recs = b->alloc<S1Rec>(nq); dev_zero(b->d_recs, sizeof(S1Rec) * (size_t)nq); b->d_light = b->alloc<int32_t>(nq); b->d_heavy = b->alloc<int32_t>(nq);
         b->d_s1_key = b->alloc<int64_t>(nq * K); b->d_s1_doc = b->alloc<int32_t>(nq * K); b->d_s1_score = b->alloc<float>(nq * K); b->d_s1_n = b->alloc<int32_t>(nq); b->d_order = b->alloc<int>(nq); b->d_qdbg = b->alloc<long long>((size_t)nq * IFX_QDBG); dev_zero(b->d_qdbg, (size_t)nq * IFX_QDBG * 8);
     } else if (text.size() > b->text_cap) return fail(IFX_ERR_INVALID, "batch text outgrew its buffer");
     h2d(b->d_text, text.data(), text.size() * 2); h2d(b->d_off, off.data(), (nq + 1) * 8); h2d(b->d_par, par.data(), par.size() * 4);

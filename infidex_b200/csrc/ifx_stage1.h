@@ -174,6 +174,9 @@ struct S1Workspace {
     int32_t* cand;         // sorted candidate ids
     int32_t* buf_a; int32_t* buf_b;   // AND-tier ping-pong arrays
     unsigned long long* surv_g;       // [CHUNK] flush survivors of one chunk when they exceed the shared staging buffer
+    int32_t* rank;         // rank directory of `bits` (candidates before word w), valid between the compaction and the tf lookups of a query
+    int32_t* cstart;       // [n_cont + 1] candidates before container c
+    int32_t* cfirst;       // [n_cont + 1] chunks before container c
     int64_t cand_cap, buf_cap;
 };
 
@@ -430,7 +433,7 @@ IFX_FN unsigned long long kv_pack(int doc, float pr) {
 }
 #define IFX_HP(i) heap_pr[(i) + 3]
 #define IFX_HD(i) heap_doc[(i) + 3]
-IFX_FN void heap_move_up(S1Shared& sh, int doc, float pr, int idx) {
+template <class H> IFX_FN void heap_move_up(H& sh, int doc, float pr, int idx) {
     while (idx > 0) { int parent = (idx - 1) >> 2; float pp = sh.IFX_HP(parent); if (pr < pp) { sh.IFX_HP(idx) = pp; sh.IFX_HD(idx) = sh.IFX_HD(parent); idx = parent; } else break; }
     sh.IFX_HP(idx) = pr; sh.IFX_HD(idx) = doc;
 }
@@ -438,7 +441,7 @@ IFX_FN void heap_move_up(S1Shared& sh, int doc, float pr, int idx) {
 // can keep the threshold in a register. PriorityQueue.MoveDown picks the first strictly-smallest of the (up to) four children; here as
 // a two-level tournament with the same winner (ties keep the lower index at both levels). Only the priorities are on the
 // dependent chain; the document id of a moved node follows with one load/store off it.
-IFX_FN float heap_replace_root(S1Shared& sh, int doc, float pr, int sz) {
+template <class H> IFX_FN float heap_replace_root(H& sh, int doc, float pr, int sz) {
     int idx = 0, i; float root = pr;
     while ((i = 4 * idx + 1) < sz) {
 #ifdef IFX_EMU
@@ -700,8 +703,10 @@ IFX_FN bool prefix_shortcut(const DevIndex& ix, const QueryPlan& p, int K, int64
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-IFX_FN void stage1_query(const Ctx& c, const DevIndex& ix, const QueryPlan& p, const int32_t* pool, S1Workspace& ws, S1Shared& sh,
-                         Stage1Out out, BatchCounters* bc) {
+// Candidate selection of one query (TieredCandidateSelector.SelectCandidates). Leaves the candidate set as bits in ws.bits (dirty
+// containers flagged in sh.dirty), the scored terms in sh.terms / sh.n_terms; `path`: 0 nothing to score, 1 prefix shortcut, 2 disjunctive,
+// 3 AND tiers, -1 workspace overflow.
+IFX_FN int stage1_select(const Ctx& c, const DevIndex& ix, const QueryPlan& p, const int32_t* pool, S1Workspace& ws, S1Shared& sh, Stage1Out out) {
     const int K = p.depth; const int NT = c.nthreads();
     if (c.tid() == 0) {
         int n = 0;
@@ -724,7 +729,7 @@ IFX_FN void stage1_query(const Ctx& c, const DevIndex& ix, const QueryPlan& p, c
     }
     c.sync();
     const int T = sh.n_terms;
-    if (T == 0 || ix.n_live == 0 || p.status != 0) return;
+    if (T == 0 || ix.n_live == 0 || p.status != 0) return 0;
     const float avgdl = ix.avgdl > 0.f ? ix.avgdl : 1.f;
 
     // ---- candidate selection (TieredCandidateSelector.SelectCandidates)
@@ -734,11 +739,10 @@ IFX_FN void stage1_query(const Ctx& c, const DevIndex& ix, const QueryPlan& p, c
 #else
 #define IFX_STICK(k) do { } while (0)
 #endif
-    const int32_t* cand = nullptr; int64_t n_cand = 0;
+    int path = 0;
     if (c.tid() == 0) { sh.bcast64[0] = -1; sh.bcast64[1] = 0; int64_t r0, pop; if (prefix_shortcut(ix, p, K, r0, pop)) { sh.bcast64[0] = r0; sh.bcast64[1] = pop; } }
     c.sync();
-    unsigned long long algo = 0;
-    if (sh.bcast64[0] >= 0) { cand = ix.prefix.doc_id + sh.bcast64[0]; n_cand = sh.bcast64[1]; algo += 4ULL * (unsigned long long)n_cand; }
+    if (sh.bcast64[0] >= 0) { path = 1; or_list_into_bits(c, ix.prefix.doc_id + sh.bcast64[0], sh.bcast64[1], ws, sh); }
     else {
         if (c.tid() == 0) {
             bool typo = false; float max_idf = 0.f;
@@ -764,7 +768,7 @@ IFX_FN void stage1_query(const Ctx& c, const DevIndex& ix, const QueryPlan& p, c
         } else {
             if (c.tid() == 0) for (int i = 0; i < T; i++) sh.streamed_mask[i >> 6] |= 1ULL << (i & 63);   // every list of the AND tier
             const int32_t* r0 = nullptr; int64_t n0 = intersect_terms(c, ix, ws, sh, T, r0);
-            if (n0 < 0) { if (c.tid() == 0) out.n[0] = -1; return; }
+            if (n0 < 0) { if (c.tid() == 0) out.n[0] = -1; return -1; }
             g += or_list_into_bits(c, r0, n0, ws, sh);
             IFX_STICK(1);   // AND tier 0
             if (g < (int64_t)K * 2) {
@@ -777,347 +781,15 @@ IFX_FN void stage1_query(const Ctx& c, const DevIndex& ix, const QueryPlan& p, c
                 }
             }
         }
-        bool ovf = false;
         IFX_STICK(1);   // list unions (disjunctive: everything; AND path: the top-idf lists after the tiers)
-        n_cand = compact_bits(c, ix, ws, sh, ws.cand, ws.cand_cap, ovf);
-        IFX_STICK(3);   // bitset -> sorted candidate array
-        if (ovf) { if (c.tid() == 0) out.n[0] = -1; return; }
-        cand = ws.cand;
-        algo += 2ULL * (unsigned long long)((ix.n_docs + 7) / 8);
+        path = disjunctive ? 2 : 3;
     }
-    if (c.tid() == 0 && out.dbg) { out.dbg[0] = n_cand; out.dbg[1] = T; out.dbg[3] = sh.bcast64[0] >= 0 ? 1 : (sh.bcast[0] ? 2 : 3);
+    if (c.tid() == 0 && out.dbg) { out.dbg[1] = T; out.dbg[3] = path;
 #ifndef IFX_EMU
         unsigned long long tn; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tn)); out.dbg[2] = (long long)tn;
 #endif
     }
-    // ---- roofline accounting: full-stream lists 5 B/posting, probe-only lists min(5 df, 32 |C|), 4 B doc_len per candidate
-    if (c.tid() == 0) {
-        for (int i = 0; i < T; i++) {
-            unsigned long long full = (sh.terms[i].tf ? 5ULL : 4ULL) * (unsigned long long)sh.terms[i].len;
-            bool streamed = (sh.streamed_mask[i >> 6] >> (i & 63)) & 1ULL;
-            unsigned long long probe = 32ULL * (unsigned long long)n_cand;
-            algo += streamed ? full : (full < probe ? full : probe);
-        }
-        algo += 4ULL * (unsigned long long)n_cand;
-        atomic_add64(&bc->algo_bytes, algo);
-    }
-
-    // ---- BM25 scoring over chunks (ProcessBlockedCandidates / ProcessChunk / ScoreBlockStruct)
-    // The top-K heap is inherently sequential (one thread replays .NET's PriorityQueue), everything else is block-parallel.
-    // To keep both busy the chunk loop is software-pipelined: the survivors of chunk i are compacted into `surv`, and while
-    // thread 0 (warp 0 = "heap warp") drains them into the heap, warps 1.. ("workers") already run chunk i+1's set-up and the
-    // score-independent membership lookups (phase A). The two sides meet at the barrier in front of phase B, which is the first
-    // place chunk i+1 needs the threshold chunk i produced. Workers synchronise among themselves on named barrier 1.
-    const int NW = c.nwarps();
-    const int hw = NT > Ctx::WS ? Ctx::WS : 0;                 // threads of the heap warp (0: single-warp build, everything sequential)
-    const bool worker = c.tid() >= hw; const int wt = c.tid() - hw, NTW = NT - hw;
-    int pend = 0;                                              // survivors of the previous chunk waiting in sh.surv (uniform)
-#if !defined(IFX_EMU) && defined(IFX_S1_TIMERS)
-    long long tph[6] = {0, 0, 0, 0, 0, 0}; long long tmark = 0; long long wph[8] = {0, 0, 0, 0, 0, 0, 0, 0}; long long wmark = 0;
-#define IFX_COUNT(x) tph[5] += (x)
-#else
-#define IFX_COUNT(x) do { } while (0)
-#endif
-#if !defined(IFX_EMU) && defined(IFX_S1_TIMERS)
-    // phase timers (debug builds with -DIFX_S1_TIMERS only; they cost registers in every thread): thread 0 = heap warp's view, thread `hw` = the workers' view. The "memory" clobber keeps
-    // the clock reads from being scheduled across the barriers they bracket.
-    // and the dependence on a shared-memory load issued after the barrier keeps ptxas from hoisting them above it
-    auto rdclock = [&]() -> long long { long long t_; asm volatile("mov.u64 %0, %%clock64;" : "=l"(t_) : "r"(*(volatile int*)&sh.bcast[2]) : "memory"); return t_; };
-#define IFX_TICK(k) do { if (c.tid() == 0) { long long now_ = rdclock(); tph[k] += now_ - tmark; tmark = now_; } } while (0)
-#define IFX_WTICK(k) do { if (c.tid() == hw) { long long now_ = rdclock(); wph[k] += now_ - wmark; wmark = now_; } } while (0)
-    if (c.tid() == 0) tmark = rdclock();
-    if (c.tid() == hw) wmark = rdclock();
-#else
-#define IFX_TICK(k) do { } while (0)
-#define IFX_WTICK(k) do { } while (0)
-#endif
-    auto drain = [&]() {                                       // Bm25Scorer.cs:316-329 + UpdateTopK (:654-670) over the compacted survivors, in candidate order
-        float thr_r = sh.thr; int hs = sh.heap_size;           // threshold and size live in registers for the whole drain
-        auto one = [&](unsigned long long kv) {
-            const float s = kv_score(kv); IFX_COUNT(1);
-            if (hs < K) { heap_move_up(sh, (int)(kv >> 32), s, hs); hs++; if (hs == K) thr_r = sh.IFX_HP(0); IFX_COUNT(1 << 20); }
-            else if (s > thr_r) { thr_r = heap_replace_root(sh, (int)(kv >> 32), s, hs); IFX_COUNT(1 << 20); }
-        };
-        if (pend <= SURV_CAP) { for (int i = 0; i < pend; i++) one(sh.surv[i]); }
-        else for (int i = 0; i < pend; i += 8) {               // global staging: eight independent loads in flight, then the sequential updates
-            unsigned long long kv[8];
-            for (int u = 0; u < 8; u++) kv[u] = i + u < pend ? ws.surv_g[i + u] : 0ULL;
-            for (int u = 0; u < 8; u++) if (i + u < pend) one(kv[u]);
-        }
-        sh.thr = thr_r; sh.heap_size = hs;
-    };
-    for (int64_t pos = 0; pos < n_cand;) {
-        if (c.tid() == 0 && pend) drain();
-        IFX_TICK(4);   // heap drain of the previous chunk (overlapped with the workers below)
-        if (worker) {
-            IFX_WTICK(7);  // everything after the join (phase B, eligibility, compaction)
-            // container run: candidates sharing id >> 16, cut into sub-chunks of 4096
-            if (c.warp() == hw / Ctx::WS) {
-                int hb = cand[pos] >> 16; int64_t lim = ((int64_t)hb + 1) << 16;
-                int64_t ce = lim > 0x7fffffffLL ? n_cand : warp_lower_bound(c, cand, pos, n_cand, (int32_t)lim);
-                if (c.lane() == 0) {
-                    int64_t cnt = ce - pos; sh.bcast[4] = (cnt <= CHUNK && (pos == 0 || (cand[pos - 1] >> 16) != hb)) ? 1 : 0;   // chunk == all candidates of the container
-                    if (cnt > CHUNK) cnt = CHUNK; sh.bcast[2] = (int)cnt; sh.bcast[5] = 0;
-                }
-            }
-            c.sync_workers(NTW);
-            const int cnt = sh.bcast[2]; const bool whole_container = sh.bcast[4] != 0;
-            for (int jb = wt; jb < cnt; jb += 4 * NTW) {             // four candidates per thread in flight (id -> length is a dependent load)
-                int d[4]; float dl[4];
-                for (int u = 0; u < 4; u++) { int j = jb + u * NTW; d[u] = j < cnt ? cand[pos + j] : -1; }
-                for (int u = 0; u < 4; u++) dl[u] = d[u] >= 0 ? ix.doc_len[d[u]] : 0.f;
-                for (int u = 0; u < 4; u++) if (d[u] >= 0) { int j = jb + u * NTW; sh.cand_s[j] = d[u]; sh.nv_s[j] = bm25_norm_vector(dl[u], avgdl); sh.score[j] = 0.f; }
-            }
-            c.sync_workers(NTW);
-            IFX_WTICK(0);  // container run + candidate ids, lengths, norms
-            const int32_t first = sh.cand_s[0], last = sh.cand_s[cnt - 1];
-            const bool small = cnt <= SMALL_CHUNK && T <= SMALL_TERMS;
-            for (int t = c.warp() - hw / Ctx::WS; t < T; t += NW - hw / Ctx::WS) {   // posting sub-range of every term for this chunk (monotone cursors); one warp per term, 32-way searches
-                TermS& tm = sh.terms[t];
-                if (small && tm.term_id >= 0) continue;          // small chunks reach dictionary terms through the forward index
-                int64_t lo = tm.cursor, hi = tm.len;
-                if (tm.skip) { int cc = first >> 16; int64_t b0 = tm.skip[cc], b1 = tm.skip[cc + 1]; if (b0 > lo) lo = b0; hi = b1; if (lo > hi) lo = hi; }   // window = this container's postings
-                int64_t s0, s1;
-                if (tm.skip && whole_container) { s0 = lo; s1 = hi; }
-                else { s0 = warp_lower_bound(c, tm.docs, lo, hi, first); s1 = last == 0x7fffffff ? hi : warp_lower_bound(c, tm.docs, s0, hi, last + 1); }
-#ifndef IFX_EMU
-                __syncwarp();                                    // every lane has read tm.cursor / tm.len before lane 0 overwrites them (racecheck)
-#endif
-                if (c.lane() == 0) {
-                    tm.s0 = s0; tm.s1 = s1; tm.cursor = s1;
-                    if (s1 > s0 && s1 - s0 <= 16LL * cnt) sh.bcast[5] = 1;     // benign race: every writer stores 1
-                }
-            }
-            c.sync_workers(NTW);
-            IFX_WTICK(1);  // posting sub-range bounds
-            if (small) {
-                // Small chunk: tf of ALL terms now, for the single-warp scorer. Dictionary terms: one warp per candidate walks the doc's
-                // forward list (a few dozen (term, tf) pairs, one coalesced read) and keeps the pairs whose term is in the query's hash --
-                // one memory latency per candidate instead of a binary search per (candidate, term). Fuzzy unions have no term id: they
-                // are searched in their pool list, one warp per term.
-                uint8_t* tfs = &sh.tfm[0][0];
-                for (int j = c.warp() - hw / Ctx::WS; j < cnt; j += NW - hw / Ctx::WS) {
-                    const int d = sh.cand_s[j]; const int64_t r0 = ix.fwd_ptr[d], r1 = ix.fwd_ptr[d + 1];
-                    for (int64_t i = r0 + c.lane(); i < r1; i += Ctx::WS) {
-                        const int32_t tid = ix.fwd_term[i]; unsigned h = qh_hash(tid);
-                        for (;;) { const int32_t k = sh.qh_key[h]; if (k == tid) { tfs[(int)sh.qh_slot[h] * SMALL_CHUNK + j] = ix.fwd_tf[i]; break; } if (k < 0) break; h = (h + 1) & (QH_SIZE - 1); }
-                    }
-                }
-                for (int t = c.warp() - hw / Ctx::WS; t < T; t += NW - hw / Ctx::WS) {
-                    const TermS& tm = sh.terms[t];
-                    if (tm.term_id >= 0 || tm.idf <= 0.f || tm.s1 == tm.s0) continue;
-                    stage1_lookup_term(sh, tm, tfs + t * SMALL_CHUNK, cnt, c.lane(), Ctx::WS, false);
-                }
-            } else {
-            // Container-local bitmap of the chunk's candidates + per-word rank directory: posting -> candidate slot in O(1)
-            // (all candidates of a chunk share id >> 16). Built only when some term streams its posting sub-range.
-            if (sh.bcast[5] != 0) {
-                for (int w = wt; w < 2048; w += NTW) sh.cbits[w] = 0;
-                c.sync_workers(NTW);
-                for (int j = wt; j < cnt; j += NTW) { int d = sh.cand_s[j] & 0xFFFF; atomic_or(&sh.cbits[d >> 5], 1u << (d & 31)); }
-                c.sync_workers(NTW);
-                int per = (2048 + NTW - 1) / NTW; int w0 = wt * per < 2048 ? wt * per : 2048, w1 = w0 + per < 2048 ? w0 + per : 2048; int mine = 0;
-                for (int w = w0; w < w1; w++) mine += popc(sh.cbits[w]);
-                int run = worker_excl_scan(c, mine, sh.scan, hw, NTW);
-                for (int w = w0; w < w1; w++) { sh.cpref[w] = (uint16_t)run; run += popc(sh.cbits[w]); }
-                c.sync_workers(NTW);
-            }
-            IFX_WTICK(2);  // candidate bitmap + rank directory
-            stage1_phase_a(c, sh, 0, T, cnt, wt, NTW);
-            }
-            IFX_WTICK(3);  // phase A, tile 0 (this thread's share) / small-chunk lookups
-        }
-        c.sync();      // join: heap drained, chunk staged, tile 0 looked up
-        IFX_WTICK(4);  // waiting at the join (slower workers / the heap drain)
-        IFX_TICK(0);   // heap warp waiting for the workers (set-up + phase A beyond the drain)
-        const int cnt = sh.bcast[2];
-        if (cnt <= SMALL_CHUNK && T <= SMALL_TERMS) {
-            if (c.warp() >= hw / Ctx::WS && c.warp() < hw / Ctx::WS + SMALL_TEAM) stage1_small_chunk(c, ix, sh, T, cnt, K, avgdl, hw / Ctx::WS);
-            c.sync();
-            pend = sh.bcast[6]; pos += cnt;
-            IFX_TICK(3);
-            continue;
-        }
-        const float thr = sh.thr; const int rounds = (cnt + NT - 1) / NT;
-        const int per_thread = (CHUNK + NT - 1) / NT; const int j0 = c.tid() * per_thread < cnt ? c.tid() * per_thread : cnt; const int j1 = j0 + per_thread < cnt ? j0 + per_thread : cnt;
-        // Terms are processed in tiles: the membership (tf) lookups of a whole tile are issued back to back with no barrier in
-        // between (independent of the scores), then the order-dependent part -- MaxScore skip, rank within the chunk, formula
-        // choice, accumulation -- runs term by term with a single barrier each.
-        for (int t0 = 0; t0 < T; t0 += S1_TILE) {
-            const int tile = T - t0 < S1_TILE ? T - t0 : S1_TILE;
-            if (t0 > 0) { IFX_WTICK(7); if (worker) stage1_phase_a(c, sh, t0, T, cnt, wt, NTW); IFX_WTICK(5); c.sync(); IFX_WTICK(6); }
-            IFX_TICK(2);   // phase A of the later tiles
-            // Each thread owns the consecutive candidate slots [j0, j1). A (candidate, term) pair counts as a match only if the
-            // MaxScore test keeps it (Bm25Scorer.cs:354); its rank among the chunk's matches of this term selects the formula
-            // (first 8*floor(m/8) matches: Vector256 form, the rest: scalar form; Bm25Scorer.cs:395-444).
-            int nscan = 0;
-#ifndef IFX_EMU
-            const bool fast = per_thread == 8 && j1 - j0 == 8;      // the 8 owned slots live in registers for the whole term
-            // A term whose own bound plus the bounds of the terms after it already exceeds the threshold can never be skipped
-            // (scores are >= 0 and float addition is monotone), so its matches are exactly the non-zero tf slots, known before any
-            // score exists: the ranks of all such terms of the tile come from ONE packed block scan (16-bit fields, <= 4096 each).
-            unsigned uns = 0, act = 0, ex01 = 0, ex23 = 0, ex45 = 0, m01 = 0, m23 = 0, m45 = 0;
-            {   // lane tt classifies term tt of the tile; the votes give every thread the (block-uniform) masks
-                bool a = false, u = false;
-                if (c.lane() < tile) { const TermS& tm = sh.terms[t0 + c.lane()]; a = tm.idf > 0.f && tm.s1 != tm.s0; u = a && !((0.f + tm.max_score) + tm.suffix_after <= thr); }
-                act = __ballot_sync(0xffffffffu, a); uns = __ballot_sync(0xffffffffu, u);
-            }
-            if (__popc(uns) >= 2) {
-                unsigned pk[3] = {0u, 0u, 0u};
-#pragma unroll
-                for (int tt = 0; tt < S1_TILE; tt++) if ((uns >> tt) & 1u) {
-                    const uint8_t* tfb = sh.tfm[tt]; unsigned n = 0;
-                    if (fast) { unsigned long long v = *reinterpret_cast<const unsigned long long*>(tfb + j0); v |= v >> 4; v |= v >> 2; v |= v >> 1; n = (unsigned)__popcll(v & 0x0101010101010101ULL); }
-                    else for (int j = j0; j < j1; j++) n += tfb[j] != 0;
-                    pk[tt >> 1] |= n << (16 * (tt & 1));
-                }
-                unsigned in0 = pk[0], in1 = pk[1], in2 = pk[2];
-                for (int d = 1; d < 32; d <<= 1) {
-                    unsigned o0 = __shfl_up_sync(0xffffffffu, in0, d), o1 = __shfl_up_sync(0xffffffffu, in1, d), o2 = __shfl_up_sync(0xffffffffu, in2, d);
-                    if (c.lane() >= d) { in0 += o0; in1 += o1; in2 += o2; }
-                }
-                if (c.lane() == 31) { sh.scan3[c.warp()][0] = in0; sh.scan3[c.warp()][1] = in1; sh.scan3[c.warp()][2] = in2; }
-                c.sync();
-                // lane i holds warp i's totals; a warp scan over them yields this warp's base (lane warp-1) and the block totals (lane NW-1)
-                uint4 x = make_uint4(0u, 0u, 0u, 0u); if (c.lane() < NW) x = *reinterpret_cast<const uint4*>(sh.scan3[c.lane()]);
-                for (int d = 1; d < NW; d <<= 1) {
-                    unsigned o0 = __shfl_up_sync(0xffffffffu, x.x, d), o1 = __shfl_up_sync(0xffffffffu, x.y, d), o2 = __shfl_up_sync(0xffffffffu, x.z, d);
-                    if (c.lane() >= d) { x.x += o0; x.y += o1; x.z += o2; }
-                }
-                const int src = c.warp() > 0 ? c.warp() - 1 : 0;
-                unsigned b0 = __shfl_sync(0xffffffffu, x.x, src), b1 = __shfl_sync(0xffffffffu, x.y, src), b2 = __shfl_sync(0xffffffffu, x.z, src);
-                if (c.warp() == 0) { b0 = 0; b1 = 0; b2 = 0; }
-                m01 = __shfl_sync(0xffffffffu, x.x, NW - 1); m23 = __shfl_sync(0xffffffffu, x.y, NW - 1); m45 = __shfl_sync(0xffffffffu, x.z, NW - 1);
-                ex01 = b0 + in0 - pk[0]; ex23 = b1 + in1 - pk[1]; ex45 = b2 + in2 - pk[2];
-            } else uns = 0;
-#else
-            const bool fast = false; const unsigned uns = 0; unsigned act = 0;
-            for (int tt = 0; tt < tile; tt++) { const TermS& tm = sh.terms[t0 + tt]; if (tm.idf > 0.f && tm.s1 != tm.s0) act |= 1u << tt; }
-#endif
-            for (int tt = 0; tt < tile; tt++) {
-                if (!((act >> tt) & 1u)) continue;                 // no idf or no postings inside this chunk's id range
-                const TermS& tm = sh.terms[t0 + tt];
-                uint8_t* tfb = sh.tfm[tt];
-                int mine = 0; const float tbound = tm.max_score; const float tsuffix = tm.suffix_after;
-                const bool ranked = (uns >> tt) & 1u;              // uniform: rank and match count already known, every non-zero tf is a match
-                // NOTE: the block scan below contains a barrier and full-mask shuffles, so it sits at ONE call site under a block-uniform
-                // condition; only the per-thread counting / accumulation around it may diverge.
-#ifndef IFX_EMU
-                unsigned long long tf8 = 0ULL; unsigned alive = 0; float sc8[8];
-                if (fast) {
-                    tf8 = *reinterpret_cast<const unsigned long long*>(tfb + j0);
-                    if (tf8 != 0ULL) {
-                        float4 sa = *reinterpret_cast<const float4*>(&sh.score[j0]), sb = *reinterpret_cast<const float4*>(&sh.score[j0 + 4]);
-                        sc8[0] = sa.x; sc8[1] = sa.y; sc8[2] = sa.z; sc8[3] = sa.w; sc8[4] = sb.x; sc8[5] = sb.y; sc8[6] = sb.z; sc8[7] = sb.w;
-#pragma unroll
-                        for (int k = 0; k < 8; k++) { unsigned tfv = (unsigned)(tf8 >> (8 * k)) & 0xFFu; if (tfv != 0 && (ranked || !(sc8[k] + tbound + tsuffix <= thr))) alive |= 1u << k; }
-                        mine = __popc(alive);
-                    }
-                } else
-#endif
-                { for (int j = j0; j < j1; j++) if (tfb[j] != 0 && (ranked || !(sh.score[j] + tbound + tsuffix <= thr))) mine++; }
-                int m, rank;
-#ifndef IFX_EMU
-                if (ranked) { const unsigned e = tt < 2 ? ex01 : (tt < 4 ? ex23 : ex45), tm_ = tt < 2 ? m01 : (tt < 4 ? m23 : m45); rank = (int)((e >> (16 * (tt & 1))) & 0xFFFFu); m = (int)((tm_ >> (16 * (tt & 1))) & 0xFFFFu); }
-                else
-#endif
-                { rank = block_excl_scan_1b(c, mine, sh.scan2[nscan & 1], m); nscan++; }
-                const int vec_end = m - (m & 7);
-#ifndef IFX_EMU
-                if (fast) {
-                    if (alive) {
-                        float4 da = *reinterpret_cast<const float4*>(&sh.nv_s[j0]), db = *reinterpret_cast<const float4*>(&sh.nv_s[j0 + 4]);
-                        float nv8[8] = {da.x, da.y, da.z, da.w, db.x, db.y, db.z, db.w};
-#pragma unroll
-                        for (int k = 0; k < 8; k++) if (alive & (1u << k)) {
-                            float tf = (float)((unsigned)(tf8 >> (8 * k)) & 0xFFu);
-                                                        float add = rank < vec_end ? bm25_from_norm_vector(tf, nv8[k], tm.idf) : bm25_scalar(tf, ix.doc_len[sh.cand_s[j0 + k]], avgdl, tm.idf);
-                            sc8[k] += add; rank++;
-                        }
-                        *reinterpret_cast<float4*>(&sh.score[j0]) = make_float4(sc8[0], sc8[1], sc8[2], sc8[3]);
-                        *reinterpret_cast<float4*>(&sh.score[j0 + 4]) = make_float4(sc8[4], sc8[5], sc8[6], sc8[7]);
-                    }
-                    if (tf8 != 0ULL) *reinterpret_cast<unsigned long long*>(tfb + j0) = 0ULL;
-                } else
-#endif
-                for (int j = j0; j < j1; j++) {
-                    const uint8_t tfv = tfb[j];
-                    if (tfv != 0) {
-                        if (ranked || !(sh.score[j] + tbound + tsuffix <= thr)) {
-                            float tf = (float)tfv;
-                            float sc = rank < vec_end ? bm25_from_norm_vector(tf, sh.nv_s[j], tm.idf) : bm25_scalar(tf, ix.doc_len[sh.cand_s[j]], avgdl, tm.idf);
-                            sh.score[j] += sc; rank++;
-                        }
-                        tfb[j] = 0;
-                    }
-                }
-                // no further barrier: score[j] / tfm[.][j] of these slots are private to this thread throughout the tile
-            }
-            c.sync();                                    // tile buffers are rewritten by arbitrary threads in the next tile
-            IFX_TICK(3);   // phase B (ranks + accumulation)
-        }
-        {   // flush, part 1 (Bm25Scorer.cs:316-329): eligibility in parallel (the threshold only rises during a flush, so anything not
-            // above the chunk-start threshold can never enter), survivors compacted in candidate order. Part 2 -- the exact sequential
-            // emulation of .NET's 4-ary PriorityQueue over the survivors -- is `drain`, deferred into the next iteration.
-            // (A set-based top-K was tried: it is only equivalent when no documents tied at the final threshold straddle the cut, and
-            // on real corpora such ties are the norm -- identical tf pattern and length -- so the heap layout, which decides which of
-            // them survive, has to be reproduced.)
-            const bool full = sh.heap_size >= K;
-            for (int r = 0; r < rounds; r++) {
-                int j = r * NT + c.tid();
-                bool e = j < cnt && sh.score[j] > 0.f && (!full || sh.score[j] > thr) && !ix.deleted[sh.cand_s[j]];
-                unsigned b = c.ballot(e);
-                if (c.lane() == 0) sh.ballots[0][r * NW + c.warp()] = b;
-            }
-            c.sync();
-            const int slots = rounds * NW;
-            if (c.warp() == 0) {     // exclusive prefix of the ballot popcounts (slot order == candidate order)
-                int per = (slots + Ctx::WS - 1) / Ctx::WS; int s0 = c.lane() * per < slots ? c.lane() * per : slots, s1 = s0 + per < slots ? s0 + per : slots; int mine = 0;
-                for (int sl = s0; sl < s1; sl++) mine += popc(sh.ballots[0][sl]);
-                int incl = mine;
-                for (int d = 1; d < Ctx::WS; d <<= 1) { int o = c.shfl(incl, c.lane() >= d ? c.lane() - d : 0); if (c.lane() >= d) incl += o; }
-                int run = incl - mine;
-                for (int sl = s0; sl < s1; sl++) { sh.bprefix[sl] = run; run += popc(sh.ballots[0][sl]); }
-                if (c.lane() == Ctx::WS - 1) sh.bcast[6] = incl;
-            }
-            c.sync();
-            const int n_surv = sh.bcast[6];
-            unsigned long long* dst = n_surv <= SURV_CAP ? sh.surv : ws.surv_g;     // the rare big sets (heap still filling) go through global memory
-            for (int r = 0; r < rounds; r++) {
-                int j = r * NT + c.tid(); int sl = r * NW + c.warp(); unsigned bm = sh.ballots[0][sl];
-                if ((bm >> c.lane()) & 1u) dst[sh.bprefix[sl] + popc(bm & c.lanemask_lt())] = kv_pack(sh.cand_s[j], sh.score[j]);
-            }
-            pend = n_surv;
-        }
-        c.sync();
-        IFX_TICK(1);   // eligibility + compaction (+ in-place drain while the heap fills)
-        pos += cnt;
-    }
-    if (c.tid() == 0 && pend) drain();
-    c.sync();
-#if !defined(IFX_EMU) && defined(IFX_S1_TIMERS)
-    if (c.tid() == 0 && out.dbg) for (int k = 0; k < 6; k++) out.dbg[6 + k] = tph[k];
-    if (c.tid() == hw && out.dbg) for (int k = 0; k < 8; k++) out.dbg[12 + k] = wph[k];
-#endif
-    for (int i = c.tid(); i < MAX_CONTAINERS; i += NT) sh.dirty[i] = 0;   // `cbits` aliased the dirty flags during scoring
-    c.sync();
-    // ---- PopulateResultHeapFromPruning + TopKHeap.GetTopK + ConsolidateSegments: order by (score desc, key asc)
-    const int n = sh.heap_size; int n2 = 1; while (n2 < n) n2 <<= 1;
-    float* ks = sh.score; int32_t* kd = sh.cand_s;            // reuse chunk arrays (CHUNK >= MAX_K)
-    for (int i = c.tid(); i < n2; i += NT) { if (i < n) { ks[i] = sh.IFX_HP(i); kd[i] = sh.IFX_HD(i); } else { ks[i] = -1.f; kd[i] = 0x7fffffff; } }
-    c.sync();
-    auto before = [&](int a, int b) -> bool {   // a ranks before b
-        if (ks[a] != ks[b]) return ks[a] > ks[b];
-        if (kd[a] == 0x7fffffff || kd[b] == 0x7fffffff) return kd[a] < kd[b];
-        return ix.doc_key[kd[a]] < ix.doc_key[kd[b]];
-    };
-    for (int k = 2; k <= n2; k <<= 1) for (int j = k >> 1; j > 0; j >>= 1) {
-        for (int i = c.tid(); i < n2; i += NT) { int l = i ^ j; if (l > i) { bool up = (i & k) == 0; bool sw = up ? before(l, i) : before(i, l); if (sw) { float x = ks[i]; ks[i] = ks[l]; ks[l] = x; int y = kd[i]; kd[i] = kd[l]; kd[l] = y; } } }
-        c.sync();
-    }
-    for (int i = c.tid(); i < n; i += NT) { out.doc[i] = kd[i]; out.score[i] = ks[i]; out.key[i] = ix.doc_key[kd[i]]; }
-    if (c.tid() == 0) out.n[0] = n;
-    c.sync();
+    return path;
 }
 
 }  // namespace ifx
