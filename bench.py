@@ -183,8 +183,8 @@ def run_ours(args, wl, rank, world, local):
     handles = [eng.UploadBatch(b) for b in batches]
     stop = threading.Event(); clk = []
     th = threading.Thread(target=clocks_sampler, args=(stop, clk, local), daemon=True)
-    agg = {k: 0.0 for k in ("ms_total", "ms_prepare", "ms_expand", "ms_stage1", "ms_wordmatch", "ms_stage2", "ms_final")}
-    algo = 0; launches = 0; q_max = 0.0; q_sum = 0.0
+    agg = {k: 0.0 for k in ("ms_total", "ms_prepare", "ms_expand", "ms_stage1", "ms_s1_select", "ms_s1_score_warp", "ms_s1_score_cta", "ms_s1_finish", "ms_wordmatch", "ms_stage2", "ms_final")}
+    algo = 0; launches = 0; q_max = 0.0; q_sum = 0.0; s1_info = {}
     for s in range(n_total):
         if s == args.warmup:
             barrier(); th.start()
@@ -194,6 +194,7 @@ def run_ours(args, wl, rank, world, local):
             for k in agg:
                 agg[k] += getattr(st, k)
             algo += st.algo_bytes_stage1; launches += st.kernel_launches; q_max = max(q_max, st.s1_query_ms_max); q_sum += st.s1_query_ms_sum
+            s1_info = {"queries_scored_per_warp": st.s1_light, "queries_scored_per_cta": st.s1_heavy, "waves": st.s1_waves, "staging_pool_bytes": int(st.s1_pool_bytes)}
     barrier()
     for h in handles:
         eng.FreeBatch(h)
@@ -240,8 +241,10 @@ def run_ours(args, wl, rank, world, local):
                        "l2": "256 MiB L2 flush before every timed step; the index (text alone %.0f MB) also exceeds the 126 MB L2" % text_mb,
                        "corpus_gen_s": round(t_gen, 1), "index_build_s": round(t_index, 1), "setup_s": round(t_setup, 1), "bad_status": bad_status},
             "phases_ms_per_step": {k: round(v / args.steps, 3) for k, v in agg.items()},
-            "roofline": {"bound": "hbm", "kernel": "k_stage1", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+            "stage1": s1_info,
+            "roofline": {"bound": "hbm", "kernel": "Stage 1 = k_select_lookup (posting streams, selection) + k_score_cta + k_score_warp + k_s1_finish", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "algo_bytes_per_launch": s1_bytes, "ms_per_launch": s1_ms, "peak_source": peak_src,
+                         "select_lookup_ms_per_launch": agg["ms_s1_select"] / args.steps,
                          "longest_query_ms": q_max, "sum_query_ms_per_launch": q_sum / args.steps},
             "e2e": {"value": e2e, "unit": "queries/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
             "gpu_launches": int(launches), "clocks": clocks}

@@ -276,41 +276,52 @@ IFX_FN int64_t intersect_terms(const Ctx& c, const DevIndex& ix, S1Workspace& ws
     int64_t n = t0.len; if (n > ws.buf_cap) return -1;
     int32_t* cur = ws.buf_a; int32_t* nxt = ws.buf_b;
     const int bw = (int)(((int64_t)ix.n_docs + 31) >> 5);
+    int li_start = 1; bool seeded = false;
     if (cnt > 1 && 4 * n >= bw && ws.buf_cap >= bw) {
         // Large running sets (>= 1/128 of the shard): keep the intersection as a bitset only. Lists with a membership bitmap are
         // ANDed word by word; the others (fuzzy unions, mid-size lists) are streamed against the bitset into a scratch bitmap
-        // (buf_b) that then replaces it. No per-id probes or appends; ids come out ascending at the end.
+        // (buf_b) that then replaces it. No per-id probes or appends. As soon as the set has thinned out (< 1/512 of the shard) the
+        // survivors are expanded into the id array and the remaining lists are probed per survivor below -- an AND over the 3-grams
+        // of several words collapses after two or three lists, and streaming twenty more lists past a nearly empty bitset was the
+        // most expensive part of the heaviest queries.
         unsigned* acc = ws.bits2; unsigned* tmp = reinterpret_cast<unsigned*>(nxt);
         if (t0.bm) { for (int w = c.tid(); w < bw; w += NT) acc[w] = t0.bm[w]; }
         else stream_list_words(c, t0.docs, t0.len, [&](int word, unsigned mask) { atomic_or(&acc[word], mask); });
         c.sync();
+        auto expand = [&](bool clear) -> int64_t {
+            int64_t total = 0;
+            for (int w0 = 0; w0 < bw; w0 += 4 * NT) {
+                unsigned v[4]; int mine = 0; const int wb = w0 + c.tid() * 4;
+                for (int u = 0; u < 4; u++) { int w = wb + u; unsigned x = 0; if (w < bw) { x = acc[w]; if (clear) acc[w] = 0u; } v[u] = x; mine += popc(x); }
+                int tot; int off = block_excl_scan(c, mine, sh.scan, tot);
+                int64_t o = total + off;
+                for (int u = 0; u < 4; u++) { unsigned x = v[u]; while (x) { int b = ffs32(x) - 1; x &= x - 1; cur[o++] = ((wb + u) << 5) | b; } }
+                total += tot;
+            }
+            c.sync();
+            return total;
+        };
         for (int li = 1; li < cnt; li++) {
-            const TermS& t = sh.terms[by_len[li]];
-            if (t.bm) { for (int w = c.tid(); w < bw; w += NT) acc[w] &= t.bm[w]; }
+            const TermS& t = sh.terms[by_len[li]]; int mine = 0;
+            if (t.bm) { for (int w = c.tid(); w < bw; w += NT) { const unsigned x = acc[w] & t.bm[w]; acc[w] = x; mine += popc(x); } }
             else {
                 for (int w = c.tid(); w < bw; w += NT) tmp[w] = 0u;
                 c.sync();
                 stream_list_words(c, t.docs, t.len, [&](int word, unsigned mask) { unsigned hit = acc[word] & mask; if (hit) atomic_or(&tmp[word], hit); });
                 c.sync();
-                for (int w = c.tid(); w < bw; w += NT) acc[w] = tmp[w];
+                for (int w = c.tid(); w < bw; w += NT) { const unsigned x = tmp[w]; acc[w] = x; mine += popc(x); }
             }
             c.sync();
+            const int64_t nbits = block_sum(c, mine, sh.scan);
+            if (li + 1 < cnt && 16 * nbits < bw) { n = expand(false); li_start = li + 1; seeded = true; break; }      // bits2 keeps the membership: the invariant of the loop below
         }
-        int64_t total = 0;
-        for (int w0 = 0; w0 < bw; w0 += 4 * NT) {
-            unsigned v[4]; int mine = 0; const int wb = w0 + c.tid() * 4;
-            for (int u = 0; u < 4; u++) { int w = wb + u; unsigned x = 0; if (w < bw) { x = acc[w]; acc[w] = 0u; } v[u] = x; mine += popc(x); }
-            int tot; int off = block_excl_scan(c, mine, sh.scan, tot);
-            int64_t o = total + off;
-            for (int u = 0; u < 4; u++) { unsigned x = v[u]; while (x) { int b = ffs32(x) - 1; x &= x - 1; cur[o++] = ((wb + u) << 5) | b; } }
-            total += tot;
-        }
-        res = cur; c.sync();
-        return total;
+        if (!seeded) { const int64_t total = expand(true); res = cur; return total; }
     }
-    for (int64_t i = c.tid(); i < n; i += NT) { int d = t0.docs[i]; cur[i] = d; if (cnt > 1) atomic_or(&ws.bits2[d >> 5], 1u << (d & 31)); }
-    c.sync();
-    for (int li = 1; li < cnt && n > 0; li++) {
+    if (!seeded) {
+        for (int64_t i = c.tid(); i < n; i += NT) { int d = t0.docs[i]; cur[i] = d; if (cnt > 1) atomic_or(&ws.bits2[d >> 5], 1u << (d & 31)); }
+        c.sync();
+    }
+    for (int li = li_start; li < cnt && n > 0; li++) {
         const TermS& t = sh.terms[by_len[li]];
         if (c.tid() == 0) sh.bcast[6] = 0;
         c.sync();
