@@ -177,6 +177,7 @@ struct S1Workspace {
     int32_t* rank;         // rank directory of `bits` (candidates before word w), valid between the compaction and the tf lookups of a query
     int32_t* cstart;       // [n_cont + 1] candidates before container c
     int32_t* cfirst;       // [n_cont + 1] chunks before container c
+    int32_t* ctab;         // [n_cont] packed S1Cont records (16 bytes each) for the tf lookups
     int64_t cand_cap, buf_cap;
 };
 

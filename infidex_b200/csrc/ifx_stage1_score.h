@@ -21,7 +21,8 @@ struct S1Rec {
     int32_t state;                                                            // 0 nothing to score, 1 light (score_warp), 3 heavy (score_cta), 2 deferred (pool full), -1 overflow
     int32_t K, path, pad;
 };
-struct S1Queues { int32_t* light; int32_t* heavy; };                           // query ids appended by stage1_lookup (counters in BatchCounters)
+struct S1Queues { int32_t* light; int32_t* heavy; };
+struct alignas(16) S1Cont { int32_t cstart, cnt, cpad, cfirst; };                // per container: candidates before it, its candidates, padded tf slots before it, chunks before it                           // query ids appended by stage1_lookup (counters in BatchCounters)
 
 IFX_FN int pad16(int x) { return (x + 15) & ~15; }
 constexpr int DEL_BIT = (int)0x80000000;
@@ -96,7 +97,8 @@ IFX_FN void stage1_lookup(const Ctx& c, const DevIndex& ix, const QueryPlan& p, 
         const int cc = c0 + c.tid(); const int cntc = cc < ncont ? ws.cstart[cc + 1] - ws.cstart[cc] : 0;
         const int nch = (cntc + CHUNK - 1) / CHUNK; const int slots = (cntc / CHUNK) * CHUNK + pad16(cntc % CHUNK);
         int t1, t2; const int e1 = block_excl_scan(c, nch, sh.scan, t1); const int e2 = block_excl_scan(c, slots, sh.scan, t2);
-        if (cc < ncont) { ws.cfirst[cc] = n_chunks + e1; ws.rank[nwords + cc] = n_slots + e2; }      // padded slots before container cc: kept behind the rank directory
+        if (cc < ncont) { ws.cfirst[cc] = n_chunks + e1; ws.rank[nwords + cc] = n_slots + e2;      // padded slots before container cc: kept behind the rank directory
+                          S1Cont ct; ct.cstart = ws.cstart[cc]; ct.cnt = cntc; ct.cpad = n_slots + e2; ct.cfirst = n_chunks + e1; reinterpret_cast<S1Cont*>(ws.ctab)[cc] = ct; }
         if (cntc > 0) atomic_max(&sh.bcast[1], cntc < CHUNK ? cntc : CHUNK);
         n_chunks += t1; n_slots += t2;
     }
@@ -122,31 +124,64 @@ IFX_FN void stage1_lookup(const Ctx& c, const DevIndex& ix, const QueryPlan& p, 
     unsigned long long cost_s = 0; int n_dict = 0;
     for (int t = 0; t < T; t++) if (sh.order[t] >= 0 && sh.terms[t].term_id >= 0) { cost_s += 5ULL * (unsigned long long)sh.terms[t].len; n_dict++; }
     const bool forward = force_mode == 1 ? true : (force_mode == 2 ? false : (n_dict > 0 && (unsigned long long)n_cand * (unsigned long long)fwd_avg_bytes < cost_s));
+    const S1Cont* ctab = reinterpret_cast<const S1Cont*>(ws.ctab);
+    auto put_hit = [&](int d, unsigned wv, int a, uint8_t tfv) {      // candidate d (bit set in wv) of row a
+        const unsigned bit = 1u << (d & 31); const int idx = ws.rank[d >> 5] + popc(wv & (bit - 1)); const S1Cont ct = ctab[d >> 16];
+        const int jc = idx - ct.cstart, sub = jc / CHUNK; const int cnt_k = ct.cnt - sub * CHUNK < CHUNK ? ct.cnt - sub * CHUNK : CHUNK;
+        tfb[(int64_t)Ta * (ct.cpad + sub * CHUNK) + (int64_t)a * pad16(cnt_k) + (jc - sub * CHUNK)] = tfv;
+    };
     auto stream_term = [&](const TermS& tm, int a) {      // every posting of one list against the candidate bitset
-        const int64_t len = tm.len; const int64_t NT4 = 4LL * NT;
-        for (int64_t i0 = c.tid(); i0 < len; i0 += NT4) {
+        const int64_t len = tm.len; int64_t done = 0;
+#ifndef IFX_EMU
+        if (len >= 2048) {
+            // aligned middle of the list: 16 postings per thread in flight (four 16-byte id loads + four 4-byte tf loads), then their
+            // 16 bitset probes, then the hits
+            const int64_t pre = (int64_t)((0 - (reinterpret_cast<uintptr_t>(tm.docs) >> 2)) & 3);
+            for (int64_t i = c.tid(); i < pre; i += NT) { const int d = tm.docs[i]; const unsigned wv = ws.bits[d >> 5]; if ((wv >> (d & 31)) & 1u) put_hit(d, wv, a, tm.tf ? tm.tf[i] : (uint8_t)1); }
+            const int4* p4 = reinterpret_cast<const int4*>(tm.docs + pre); const unsigned* t4 = tm.tf ? reinterpret_cast<const unsigned*>(tm.tf + pre) : nullptr;
+            const int64_t n4 = (len - pre) >> 2;
+            for (int64_t g0 = c.tid(); g0 < n4; g0 += 4LL * NT) {
+                int4 dv[4]; unsigned tw[4]; unsigned wv[16];
+#pragma unroll
+                for (int u = 0; u < 4; u++) { const int64_t g = g0 + (int64_t)u * NT; if (g < n4) { dv[u] = p4[g]; tw[u] = t4 ? t4[g] : 0x01010101u; } else { dv[u] = make_int4(-1, -1, -1, -1); tw[u] = 0u; } }
+#pragma unroll
+                for (int u = 0; u < 4; u++) { const int dd[4] = {dv[u].x, dv[u].y, dv[u].z, dv[u].w};
+#pragma unroll
+                    for (int k = 0; k < 4; k++) wv[4 * u + k] = dd[k] >= 0 ? ws.bits[dd[k] >> 5] : 0u; }
+#pragma unroll
+                for (int u = 0; u < 4; u++) { const int dd[4] = {dv[u].x, dv[u].y, dv[u].z, dv[u].w};
+#pragma unroll
+                    for (int k = 0; k < 4; k++) if (dd[k] >= 0 && ((wv[4 * u + k] >> (dd[k] & 31)) & 1u)) put_hit(dd[k], wv[4 * u + k], a, (uint8_t)(tw[u] >> (8 * k))); }
+            }
+            done = pre + (n4 << 2);
+        }
+#endif
+        const int64_t NT4 = 4LL * NT;
+        for (int64_t i0 = done + c.tid(); i0 < len; i0 += NT4) {
             int dd[4]; uint8_t tv[4]; unsigned wv[4];
             for (int u = 0; u < 4; u++) { int64_t i = i0 + (int64_t)u * NT; const bool in = i < len; dd[u] = in ? tm.docs[i] : -1; tv[u] = (in && tm.tf) ? tm.tf[i] : (uint8_t)1; }
             for (int u = 0; u < 4; u++) wv[u] = dd[u] >= 0 ? ws.bits[dd[u] >> 5] : 0u;
-            for (int u = 0; u < 4; u++) if (dd[u] >= 0) {
-                const unsigned bit = 1u << (dd[u] & 31);
-                if (wv[u] & bit) {
-                    const int idx = ws.rank[dd[u] >> 5] + popc(wv[u] & (bit - 1)); const int cc = dd[u] >> 16;
-                    const int cs = ws.cstart[cc], jc = idx - cs, sub = jc / CHUNK, cntc = ws.cstart[cc + 1] - cs;
-                    const int cnt_k = cntc - sub * CHUNK < CHUNK ? cntc - sub * CHUNK : CHUNK;
-                    tfb[(int64_t)Ta * (cpad[cc] + sub * CHUNK) + (int64_t)a * pad16(cnt_k) + (jc - sub * CHUNK)] = tv[u];
-                }
-            }
+            for (int u = 0; u < 4; u++) if (dd[u] >= 0 && ((wv[u] >> (dd[u] & 31)) & 1u)) put_hit(dd[u], wv[u], a, tv[u]);
         }
     };
-    if (forward) {   // one warp per candidate walks the document's forward list; the query's term hash maps term id -> row
+    if (forward) {
+        // Batches of FW_G candidates per warp: their forward lists (a few dozen to a few hundred (term, tf) pairs each) are walked as ONE
+        // concatenated range, so a lane has several independent loads in flight instead of one dependent chain per candidate. The
+        // query's term hash maps term id -> row.
+        constexpr int FW_G = Ctx::WS >= 4 ? 4 : 1;      // (the single-lane test build walks one candidate at a time)
         for (int k = 0; k < n_chunks; k++) {
             const S1Chunk ch = chunks[k]; const int rowlen = pad16(ch.cnt);
-            for (int j = c.warp(); j < ch.cnt; j += NW) {
-                const int d = cand[ch.start + j] & ~DEL_BIT; const int64_t r0 = ix.fwd_ptr[d], r1 = ix.fwd_ptr[d + 1];
-                for (int64_t i = r0 + c.lane(); i < r1; i += WS) {
-                    const int32_t tid = ix.fwd_term[i]; unsigned h = qh_hash(tid);
-                    for (;;) { const int32_t kk = sh.qh_key[h]; if (kk == tid) { tfb[ch.tf_off + (int64_t)sh.order[sh.qh_slot[h]] * rowlen + j] = ix.fwd_tf[i]; break; } if (kk < 0) break; h = (h + 1) & (QH_SIZE - 1); }
+            for (int jb = c.warp() * FW_G; jb < ch.cnt; jb += NW * FW_G) {
+                int64_t r0 = 0, r1 = 0;
+                if (c.lane() < FW_G && jb + c.lane() < ch.cnt) { const int d = cand[ch.start + jb + c.lane()] & ~DEL_BIT; r0 = ix.fwd_ptr[d]; r1 = ix.fwd_ptr[d + 1]; }
+                int64_t b0[FW_G]; int pre[FW_G + 1]; pre[0] = 0;
+                for (int g = 0; g < FW_G; g++) { b0[g] = c.shfl(r0, g); const int64_t e1 = c.shfl(r1, g); pre[g + 1] = pre[g] + (int)(e1 - b0[g]); }
+                const int E = pre[FW_G];
+                for (int e0 = c.lane(); e0 < E; e0 += 4 * WS) {
+                    int32_t tid[4]; uint8_t tfv[4]; int gj[4];
+                    for (int u = 0; u < 4; u++) { const int e = e0 + u * WS; tid[u] = -1; gj[u] = 0; if (e < E) { int g = 0; for (int x = 1; x < FW_G; x++) if (e >= pre[x]) g = x; const int64_t i = b0[g] + (e - pre[g]); tid[u] = ix.fwd_term[i]; tfv[u] = ix.fwd_tf[i]; gj[u] = g; } }
+                    for (int u = 0; u < 4; u++) if (tid[u] >= 0) { unsigned h = qh_hash(tid[u]);
+                        for (;;) { const int32_t kk = sh.qh_key[h]; if (kk == tid[u]) { tfb[ch.tf_off + (int64_t)sh.order[sh.qh_slot[h]] * rowlen + jb + gj[u]] = tfv[u]; break; } if (kk < 0) break; h = (h + 1) & (QH_SIZE - 1); } }
                 }
             }
         }
