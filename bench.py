@@ -194,7 +194,7 @@ def run_ours(args, wl, rank, world, local):
             for k in agg:
                 agg[k] += getattr(st, k)
             algo += st.algo_bytes_stage1; launches += st.kernel_launches; q_max = max(q_max, st.s1_query_ms_max); q_sum += st.s1_query_ms_sum
-            s1_info = {"queries_scored_per_warp": st.s1_light, "queries_scored_per_cta": st.s1_heavy, "waves": st.s1_waves, "staging_pool_bytes": int(st.s1_pool_bytes)}
+            s1_info = {"queries_scored_per_warp": st.s1_light + st.s1_mid, "queries_scored_per_cta": st.s1_heavy, "waves": st.s1_waves, "staging_pool_bytes": int(st.s1_pool_bytes)}
     barrier()
     for h in handles:
         eng.FreeBatch(h)

@@ -132,9 +132,9 @@ typedef struct ifx_stats {            /* filled by ifx_search_batch / ifx_batch_
     float s1_query_ms_max;            /* longest single query inside k_select_lookup (device globaltimer) */
     float s1_query_ms_sum;            /* sum over queries of their time inside k_select_lookup */
     float ms_s1_select, ms_s1_score_warp, ms_s1_score_cta, ms_s1_finish;   /* the four Stage-1 launches that make up ms_stage1 */
-    int32_t s1_light, s1_heavy;       /* queries scored one per warp / one per CTA (last wave) */
+    int32_t s1_light, s1_heavy;       /* queries scored one per warp (8 slots per lane) / one per CTA (last wave) */
     int32_t s1_waves;                 /* > 1: the batch outgrew the Stage-1 staging pool and was finished in waves */
-    int32_t reserved0;
+    int32_t s1_mid;                   /* queries scored one per warp with 32 slots per lane (last wave) */
     int64_t s1_pool_bytes;            /* staging pool bytes used (last wave) */
 } ifx_stats;
 

@@ -204,7 +204,7 @@ struct QueryPlan {
 };
 
 struct BatchCounters { int32_t n_fuzzy_items; int32_t overflow; unsigned long long fuzzy_pool_used; unsigned long long algo_bytes; unsigned long long s1_ns_sum; unsigned long long s1_ns_max; unsigned long long s1_cand_sum;
-                       unsigned long long s1_pool_used; int32_t s1_deferred, s1_n_light, s1_n_heavy, s1_wave; };
+                       unsigned long long s1_pool_used; int32_t s1_deferred, s1_n_light, s1_n_heavy, s1_wave, s1_n_mid, s1_pad; };
 
 struct FuzzyItem { int32_t query; int32_t slot; };
 

@@ -63,21 +63,25 @@ __global__ void __launch_bounds__(IFX_S1_THREADS, 2) k_select_lookup(DevIndex ix
         if (threadIdx.x == 0) { unsigned long long t1; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1)); atomicAdd(&bc->s1_ns_sum, t1 - t0); atomicMax(&bc->s1_ns_max, t1 - t0); qdbg[(size_t)q * IFX_QDBG + 4] = (long long)(t1 - t0); qdbg[(size_t)q * IFX_QDBG + 2] -= (long long)t0; qdbg[(size_t)q * IFX_QDBG + 5] = blockIdx.x; }
     }
 }
-// Stage 1, kernel 2a: one warp per light query (persistent warps pulling from the light queue).
+// Stage 1, kernel 2a: one warp per light / mid query (persistent warps pulling from the class's queue).
 #ifndef IFX_SW_WARPS
 #define IFX_SW_WARPS 16
 #endif
-__global__ void __launch_bounds__(IFX_SW_WARPS * 32, 1) k_score_warp(DevIndex ix, const S1Rec* recs, const unsigned char* spool, const int32_t* light, const BatchCounters* bc, int* work,
-                                                                     int32_t* s1_doc, float* s1_score, int32_t* s1_n, int K, long long* qdbg) {
+#ifndef IFX_SW_WARPS_MID
+#define IFX_SW_WARPS_MID 12
+#endif
+template <int CAPW, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, 1) k_score_warp(DevIndex ix, const S1Rec* recs, const unsigned char* spool, const int32_t* queue, const int32_t* n_queue, int* work,
+                                                              int32_t* s1_doc, float* s1_score, int32_t* s1_n, int K, long long* qdbg) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Ctx c; WarpScoreShared& sh = reinterpret_cast<WarpScoreShared*>(smem_raw)[threadIdx.x >> 5];
-    const int n = bc->s1_n_light;
+    const int n = *n_queue;
     for (;;) {
         int qi = 0; if (c.lane() == 0) qi = atomicAdd(work, 1); qi = __shfl_sync(0xffffffffu, qi, 0);
         if (qi >= n) break;
-        const int q = light[qi];
+        const int q = queue[qi];
         unsigned long long t0 = 0; if (c.lane() == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-        score_warp(c, ix.avgdl, recs[q], spool, sh, s1_doc + (size_t)q * K, s1_score + (size_t)q * K, s1_n + q);
+        score_warp<CAPW>(c, ix.avgdl, recs[q], spool, sh, s1_doc + (size_t)q * K, s1_score + (size_t)q * K, s1_n + q);
         if (c.lane() == 0) { unsigned long long t1; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1)); qdbg[(size_t)q * IFX_QDBG + 10] = (long long)(t1 - t0); }
     }
 }
@@ -99,10 +103,10 @@ __global__ void __launch_bounds__(IFX_S1_THREADS, 2) k_score_cta(DevIndex ix, co
     }
 }
 // Stage 1, kernel 3: final order of every query scored in this wave.
-__global__ void __launch_bounds__(256) k_s1_finish(DevIndex ix, const BatchCounters* bc, const int32_t* light, const int32_t* heavy, int64_t* s1_key, int32_t* s1_doc, float* s1_score, int32_t* s1_n, int K) {
-    __shared__ FinishShared sh; Ctx c; const int nl = bc->s1_n_light, nh = bc->s1_n_heavy; const int b = blockIdx.x;
-    if (b >= nl + nh) return;
-    const int q = b < nl ? light[b] : heavy[b - nl];
+__global__ void __launch_bounds__(256) k_s1_finish(DevIndex ix, const BatchCounters* bc, S1Queues queues, int64_t* s1_key, int32_t* s1_doc, float* s1_score, int32_t* s1_n, int K) {
+    __shared__ FinishShared sh; Ctx c; const int nl = bc->s1_n_light, nm = bc->s1_n_mid, nh = bc->s1_n_heavy; const int b = blockIdx.x;
+    if (b >= nl + nm + nh) return;
+    const int q = b < nl ? queues.light[b] : (b < nl + nm ? queues.mid[b - nl] : queues.heavy[b - nl - nm]);
     s1_finish(c, ix, sh, s1_key + (size_t)q * K, s1_doc + (size_t)q * K, s1_score + (size_t)q * K, s1_n + q);
 }
 #endif
@@ -113,7 +117,7 @@ static void run_stage1_phase(ifx_batch* b, ifx_stats* st) {
     ifx_index* ix = b->idx; const int nq = b->nq; const int K = b->depth_max;
     BatchCounters zero{}; h2d(b->d_bc, &zero, sizeof(zero));
     const int items_cap = nq * MAX_FUZZY;       // every query may carry MAX_FUZZY unknown words: the item list can never overflow
-    const int force_mode = s1_force_mode(); S1Queues queues{b->d_light, b->d_heavy};
+    const int force_mode = s1_force_mode(); S1Queues queues{b->d_light, b->d_mid, b->d_heavy};
     Timer t;
 #ifdef IFX_EMU
     std::vector<int64_t> off(nq + 1); d2h(off.data(), b->d_off, (nq + 1) * 8);
@@ -123,7 +127,7 @@ static void run_stage1_phase(ifx_batch* b, ifx_stats* st) {
     for (int i = 0; i < nit; i++) expand_fuzzy(c, ix->v, b->d_plans[b->d_items[i].query], b->d_items[i].slot, ix->ws[0], *sh, ix->d_pool, ix->pool_cap, b->d_bc, ix->d_sorted_len, sh->cand_s);
     const bool no_warp = getenv("IFX_S1_NO_WARP") != nullptr;      // tests: force every query through the block-wide scorer
     for (int wave = 0; wave < 64; wave++) {
-        b->d_bc->s1_pool_used = 0; b->d_bc->s1_deferred = 0; b->d_bc->s1_n_light = 0; b->d_bc->s1_n_heavy = 0; b->d_bc->s1_wave = wave;
+        b->d_bc->s1_pool_used = 0; b->d_bc->s1_deferred = 0; b->d_bc->s1_n_light = 0; b->d_bc->s1_n_mid = 0; b->d_bc->s1_n_heavy = 0; b->d_bc->s1_wave = wave;
         for (int q = 0; q < nq; q++) {
             if (wave > 0 && b->d_recs[q].state != 2) continue;
             Stage1Out o{nullptr, nullptr, nullptr, b->d_s1_n + q, nullptr};
@@ -132,17 +136,22 @@ static void run_stage1_phase(ifx_batch* b, ifx_stats* st) {
         }
         for (int i = 0; i < b->d_bc->s1_n_light; i++) { const int q = b->d_light[i];
             if (no_warp) score_cta(c, ix->v.avgdl, b->d_recs[q], ix->d_spool, ix->ws[0], *sh, b->d_s1_doc + (size_t)q * K, b->d_s1_score + (size_t)q * K, b->d_s1_n + q);
-            else score_warp(c, ix->v.avgdl, b->d_recs[q], ix->d_spool, *wsh, b->d_s1_doc + (size_t)q * K, b->d_s1_score + (size_t)q * K, b->d_s1_n + q); }
+            else score_warp<W_CAP>(c, ix->v.avgdl, b->d_recs[q], ix->d_spool, *wsh, b->d_s1_doc + (size_t)q * K, b->d_s1_score + (size_t)q * K, b->d_s1_n + q); }
+        for (int i = 0; i < b->d_bc->s1_n_mid; i++) { const int q = b->d_mid[i];
+            if (no_warp) score_cta(c, ix->v.avgdl, b->d_recs[q], ix->d_spool, ix->ws[0], *sh, b->d_s1_doc + (size_t)q * K, b->d_s1_score + (size_t)q * K, b->d_s1_n + q);
+            else score_warp<W_CAP_MID>(c, ix->v.avgdl, b->d_recs[q], ix->d_spool, *wsh, b->d_s1_doc + (size_t)q * K, b->d_s1_score + (size_t)q * K, b->d_s1_n + q); }
         for (int i = 0; i < b->d_bc->s1_n_heavy; i++) { const int q = b->d_heavy[i]; score_cta(c, ix->v.avgdl, b->d_recs[q], ix->d_spool, ix->ws[0], *sh, b->d_s1_doc + (size_t)q * K, b->d_s1_score + (size_t)q * K, b->d_s1_n + q); }
-        for (int i = 0; i < b->d_bc->s1_n_light + b->d_bc->s1_n_heavy; i++) { const int q = i < b->d_bc->s1_n_light ? b->d_light[i] : b->d_heavy[i - b->d_bc->s1_n_light];
+        const int nl_ = b->d_bc->s1_n_light, nm_ = b->d_bc->s1_n_mid, nh_ = b->d_bc->s1_n_heavy;
+        for (int i = 0; i < nl_ + nm_ + nh_; i++) { const int q = i < nl_ ? b->d_light[i] : (i < nl_ + nm_ ? b->d_mid[i - nl_] : b->d_heavy[i - nl_ - nm_]);
             s1_finish(c, ix->v, *fsh, b->d_s1_key + (size_t)q * K, b->d_s1_doc + (size_t)q * K, b->d_s1_score + (size_t)q * K, b->d_s1_n + q); }
         if (b->d_bc->s1_deferred == 0) break;
     }
     (void)t;
 #else
-    const size_t smem = sizeof(S1Shared), smem_w = sizeof(WarpScoreShared) * IFX_SW_WARPS;
+    const size_t smem = sizeof(S1Shared), smem_w = sizeof(WarpScoreShared) * IFX_SW_WARPS, smem_m = sizeof(WarpScoreShared) * IFX_SW_WARPS_MID;
+    auto k_light = k_score_warp<W_CAP, IFX_SW_WARPS>; auto k_mid = k_score_warp<W_CAP_MID, IFX_SW_WARPS_MID>;
     if (!ix->attr_s1) { CUDA_TRY(cudaFuncSetAttribute(k_expand, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); CUDA_TRY(cudaFuncSetAttribute(k_select_lookup, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        CUDA_TRY(cudaFuncSetAttribute(k_score_cta, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); CUDA_TRY(cudaFuncSetAttribute(k_score_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_w)); ix->attr_s1 = true; }
+        CUDA_TRY(cudaFuncSetAttribute(k_score_cta, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); CUDA_TRY(cudaFuncSetAttribute(k_light, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_w)); CUDA_TRY(cudaFuncSetAttribute(k_mid, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_m)); ix->attr_s1 = true; }
     t.start();
     k_prepare<<<(nq + 127) / 128, 128>>>(ix->v, b->d_text, b->d_off, b->d_par, nq, b->d_plans, b->d_items, items_cap, b->d_bc);
     float ms_prep = t.stop();
@@ -153,16 +162,17 @@ static void run_stage1_phase(ifx_batch* b, ifx_stats* st) {
     float ms_sel = 0.f, ms_sw = 0.f, ms_sc = 0.f, ms_fin = 0.f; int launches = 2; const int sms = ix->n_ctas / 2 > 0 ? ix->n_ctas / 2 : 1;
     k_order<<<1, 1024>>>(ix->v, b->d_plans, nq, b->d_order); launches++;
     for (int wave = 0; wave < 64; wave++) {
-        if (wave > 0) { BatchCounters bc; d2h(&bc, b->d_bc, sizeof(bc)); bc.s1_pool_used = 0; bc.s1_deferred = 0; bc.s1_n_light = 0; bc.s1_n_heavy = 0; bc.s1_wave = wave; h2d(b->d_bc, &bc, sizeof(bc)); CUDA_TRY(cudaMemsetAsync(b->d_work + 1, 0, 4 * sizeof(int))); }
+        if (wave > 0) { BatchCounters bc; d2h(&bc, b->d_bc, sizeof(bc)); bc.s1_pool_used = 0; bc.s1_deferred = 0; bc.s1_n_light = 0; bc.s1_n_mid = 0; bc.s1_n_heavy = 0; bc.s1_wave = wave; h2d(b->d_bc, &bc, sizeof(bc)); CUDA_TRY(cudaMemsetAsync(b->d_work + 1, 0, 5 * sizeof(int))); }
         t.start();
         k_select_lookup<<<std::min(ix->n_ctas, nq), IFX_S1_THREADS, smem>>>(ix->v, b->d_plans, nq, ix->d_pool, ix->d_ws, b->d_bc, b->d_s1_n, b->d_work + 1, b->d_order, b->d_qdbg, b->d_recs, ix->d_spool, ix->spool_cap, queues, wave, force_mode);
         ms_sel += t.stop(); t.start();
         k_score_cta<<<std::min(ix->n_ctas, nq), IFX_S1_THREADS, smem>>>(ix->v, b->d_recs, ix->d_spool, b->d_heavy, b->d_bc, b->d_work + 2, ix->d_ws, b->d_s1_doc, b->d_s1_score, b->d_s1_n, K, b->d_qdbg);
         ms_sc += t.stop(); t.start();
-        k_score_warp<<<sms, IFX_SW_WARPS * 32, smem_w>>>(ix->v, b->d_recs, ix->d_spool, b->d_light, b->d_bc, b->d_work + 3, b->d_s1_doc, b->d_s1_score, b->d_s1_n, K, b->d_qdbg);
+        k_mid<<<sms, IFX_SW_WARPS_MID * 32, smem_m>>>(ix->v, b->d_recs, ix->d_spool, b->d_mid, &b->d_bc->s1_n_mid, b->d_work + 4, b->d_s1_doc, b->d_s1_score, b->d_s1_n, K, b->d_qdbg);
+        k_light<<<sms, IFX_SW_WARPS * 32, smem_w>>>(ix->v, b->d_recs, ix->d_spool, b->d_light, &b->d_bc->s1_n_light, b->d_work + 3, b->d_s1_doc, b->d_s1_score, b->d_s1_n, K, b->d_qdbg);
         ms_sw += t.stop(); t.start();
-        k_s1_finish<<<nq, 256>>>(ix->v, b->d_bc, b->d_light, b->d_heavy, b->d_s1_key, b->d_s1_doc, b->d_s1_score, b->d_s1_n, K);
-        ms_fin += t.stop(); launches += 4;
+        k_s1_finish<<<nq, 256>>>(ix->v, b->d_bc, queues, b->d_s1_key, b->d_s1_doc, b->d_s1_score, b->d_s1_n, K);
+        ms_fin += t.stop(); launches += 5;
         int deferred = 0; d2h(&deferred, &b->d_bc->s1_deferred, sizeof(int));
         if (deferred == 0) break;
     }
@@ -170,7 +180,7 @@ static void run_stage1_phase(ifx_batch* b, ifx_stats* st) {
     if (st) { st->ms_prepare += ms_prep; st->ms_expand += ms_exp; st->ms_stage1 += ms_sel + ms_sc + ms_sw + ms_fin; st->ms_s1_select += ms_sel; st->ms_s1_score_cta += ms_sc; st->ms_s1_score_warp += ms_sw; st->ms_s1_finish += ms_fin; st->kernel_launches += launches; }
 #endif
     if (st) { BatchCounters bc; d2h(&bc, b->d_bc, sizeof(bc)); st->algo_bytes_stage1 += (int64_t)bc.algo_bytes; st->s1_query_ms_max = (float)(bc.s1_ns_max * 1e-6); st->s1_query_ms_sum = (float)(bc.s1_ns_sum * 1e-6);
-        st->s1_light = bc.s1_n_light; st->s1_heavy = bc.s1_n_heavy; st->s1_waves = bc.s1_wave + 1; st->s1_pool_bytes = (int64_t)bc.s1_pool_used; }
+        st->s1_light = bc.s1_n_light; st->s1_mid = bc.s1_n_mid; st->s1_heavy = bc.s1_n_heavy; st->s1_waves = bc.s1_wave + 1; st->s1_pool_bytes = (int64_t)bc.s1_pool_used; }
 }
 
 // (re)fill the per-batch inputs; allocates on first use or when the batch outgrows its buffers
@@ -189,7 +199,7 @@ static int fill_batch(ifx_batch* b, const ifx_query* q, int nq) {
         b->d_text = b->alloc<uint16_t>(b->text_cap); b->d_off = b->alloc<int64_t>(nq + 1); b->d_par = b->alloc<int32_t>(par.size());
         b->d_plans = b->alloc<QueryPlan>(nq); b->d_items = b->alloc<FuzzyItem>((size_t)nq * MAX_FUZZY); b->d_bc = b->alloc<BatchCounters>(1); b->d_work = b->alloc<int>(8); dev_zero(b->d_work, 8 * sizeof(int));
         size_t K = b->depth_max;
-        b->d_recs = b->alloc<S1Rec>(nq); dev_zero(b->d_recs, sizeof(S1Rec) * (size_t)nq); b->d_light = b->alloc<int32_t>(nq); b->d_heavy = b->alloc<int32_t>(nq);
+        b->d_recs = b->alloc<S1Rec>(nq); dev_zero(b->d_recs, sizeof(S1Rec) * (size_t)nq); b->d_light = b->alloc<int32_t>(nq); b->d_mid = b->alloc<int32_t>(nq); b->d_heavy = b->alloc<int32_t>(nq);
         b->d_s1_key = b->alloc<int64_t>(nq * K); b->d_s1_doc = b->alloc<int32_t>(nq * K); b->d_s1_score = b->alloc<float>(nq * K); b->d_s1_n = b->alloc<int32_t>(nq); b->d_order = b->alloc<int>(nq); b->d_qdbg = b->alloc<long long>((size_t)nq * IFX_QDBG); dev_zero(b->d_qdbg, (size_t)nq * IFX_QDBG * 8);
     } else if (text.size() > b->text_cap) return fail(IFX_ERR_INVALID, "batch text outgrew its buffer");
     h2d(b->d_text, text.data(), text.size() * 2); h2d(b->d_off, off.data(), (nq + 1) * 8); h2d(b->d_par, par.data(), par.size() * 4);

@@ -18,19 +18,20 @@ struct S1TermP { float idf, max_score, suffix_after; int32_t pad; };
 struct S1Rec {
     int64_t off_cand, off_dl, off_tf, off_chunk, off_terms;                    // byte offsets into the batch pool
     int32_t n_cand, n_chunks, n_terms, max_cnt;
-    int32_t state;                                                            // 0 nothing to score, 1 light (score_warp), 3 heavy (score_cta), 2 deferred (pool full), -1 overflow
+    int32_t state;                                                            // 0 nothing to score, 1 light / 4 mid (score_warp), 3 heavy (score_cta), 2 deferred (pool full), -1 overflow
     int32_t K, path, pad;
 };
-struct S1Queues { int32_t* light; int32_t* heavy; };
+struct S1Queues { int32_t* light; int32_t* mid; int32_t* heavy; };
 struct alignas(16) S1Cont { int32_t cstart, cnt, cpad, cfirst; };                // per container: candidates before it, its candidates, padded tf slots before it, chunks before it                           // query ids appended by stage1_lookup (counters in BatchCounters)
 
 IFX_FN int pad16(int x) { return (x + 15) & ~15; }
 constexpr int DEL_BIT = (int)0x80000000;
 
-// warp-scorer limits (a query is "light" when all of these hold)
-constexpr int W_CAP = 256;           // candidates per chunk
-constexpr int W_TF = 6144;           // bytes of one chunk's tf block (terms x pad16(cnt))
-constexpr int W_TERMS = 48;
+// warp-scorer limits: a query is scored by one warp when its largest chunk holds <= W_CAP_MID candidates, it has <= W_TERMS scored terms
+// and its depth fits the per-warp heap; "light" (<= W_CAP candidates per chunk: 8 slots per lane) and "mid" (32 slots per lane)
+constexpr int W_CAP = 256, W_CAP_MID = 1024;
+constexpr int W_TF = 6144;           // bytes of the per-warp tf staging buffer (one tile of term rows of the current chunk)
+constexpr int W_TERMS = 64;
 constexpr int W_K = 512;             // heap capacity kept in shared memory per warp
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -43,12 +44,22 @@ constexpr int W_K = 512;             // heap capacity kept in shared memory per 
 IFX_FN void stage1_lookup(const Ctx& c, const DevIndex& ix, const QueryPlan& p, int path, int q, S1Workspace& ws, S1Shared& sh, S1Rec* recs,
                           unsigned char* spool, unsigned long long spool_cap, S1Queues queues, BatchCounters* bc, Stage1Out out, int fwd_avg_bytes, int force_mode) {
     S1Rec& rec = recs[q]; const int NT = c.nthreads(), NW = c.nwarps(); constexpr int WS = Ctx::WS;
+#if !defined(IFX_EMU) && defined(IFX_S1_TIMERS)
+    long long lmark = 0; if (c.tid() == 0) { asm volatile("mov.u64 %0, %%clock64;" : "=l"(lmark) :: "memory"); if (out.dbg) for (int k = 11; k < 18; k++) out.dbg[k] = 0; }
+#define IFX_LTICK(k) do { c.sync(); if (c.tid() == 0 && out.dbg) { long long now_; asm volatile("mov.u64 %0, %%clock64;" : "=l"(now_) :: "memory"); out.dbg[11 + (k)] += now_ - lmark; lmark = now_; } } while (0)
+#else
+#define IFX_LTICK(k) do { } while (0)
+#endif
     if (path <= 0) { if (c.tid() == 0) { rec.state = path < 0 ? -1 : 0; rec.n_cand = 0; rec.K = p.depth; rec.path = path; } c.sync(); return; }
     const int T = sh.n_terms; const int64_t nwords = ((int64_t)ix.n_docs + 31) >> 5; const int ncont = (ix.n_docs + 65535) >> 16;
     // ---- 1a. count (each warp owns a contiguous span of bitset words; non-dirty containers are skipped)
     const int64_t span = (((nwords + NW - 1) / NW) + 31) / 32 * 32; const int64_t w0 = (int64_t)c.warp() * span, w1 = w0 + span < nwords ? w0 + span : nwords;
     int mycnt = 0;
-    for (int64_t g0 = w0; g0 < w1; g0 += WS) { if (!sh.dirty[g0 >> 11]) continue; const int64_t w = g0 + c.lane(); if (w < w1) mycnt += popc(ws.bits[w]); }
+    for (int64_t g0 = w0; g0 < w1; g0 += 4 * WS) {      // four groups (independent loads) per trip
+        unsigned v[4];
+        for (int u = 0; u < 4; u++) { const int64_t g = g0 + u * WS, w = g + c.lane(); v[u] = (g < w1 && sh.dirty[g >> 11] && w < w1) ? ws.bits[w] : 0u; }
+        for (int u = 0; u < 4; u++) mycnt += popc(v[u]);
+    }
     int n_cand; int ex0 = block_excl_scan(c, mycnt, sh.scan, n_cand); const int wbase = c.shfl(ex0, 0);
     auto clear_bits = [&]() {
         for (int64_t w = c.tid(); w < nwords; w += NT) if (sh.dirty[w >> 11]) ws.bits[w] = 0u;
@@ -69,25 +80,33 @@ IFX_FN void stage1_lookup(const Ctx& c, const DevIndex& ix, const QueryPlan& p, 
     int32_t* cand = reinterpret_cast<int32_t*>(spool + a1); float* dlp = reinterpret_cast<float*>(spool + a1 + (((long long)n_cand * 4 + 31) & ~31LL));
     // ---- 1b. expand + rank directory + candidates before every container
     {   int run = wbase;
-        for (int64_t g0 = w0; g0 < w1; g0 += WS) {
-            if (!sh.dirty[g0 >> 11]) { if ((g0 & 2047) == 0 && c.lane() == 0) ws.cstart[g0 >> 11] = run; continue; }
-            const int64_t w = g0 + c.lane(); unsigned v = w < w1 ? ws.bits[w] : 0u; const int pc = popc(v); int incl = pc;
-            for (int d = 1; d < WS; d <<= 1) { int o = c.shfl(incl, c.lane() >= d ? c.lane() - d : 0); if (c.lane() >= d) incl += o; }
-            int o = run + incl - pc;
-            if (w < w1) { ws.rank[w] = o; if ((w & 2047) == 0) ws.cstart[w >> 11] = o; }
-            while (v) { int b = ffs32(v) - 1; v &= v - 1; cand[o++] = (int32_t)((w << 5) | b); }
-            run += c.shfl(incl, WS - 1);
+        for (int64_t gb = w0; gb < w1; gb += 4 * WS) {          // four groups per trip: their words are loaded together, then scanned one after the other
+            unsigned vv[4];
+            for (int u = 0; u < 4; u++) { const int64_t g = gb + u * WS, w = g + c.lane(); vv[u] = (g < w1 && sh.dirty[g >> 11] && w < w1) ? ws.bits[w] : 0u; }
+            for (int u = 0; u < 4; u++) {
+                const int64_t g0 = gb + u * WS; if (g0 >= w1) break;
+                if (!sh.dirty[g0 >> 11]) { if ((g0 & 2047) == 0 && c.lane() == 0) ws.cstart[g0 >> 11] = run; continue; }
+                const int64_t w = g0 + c.lane(); unsigned v = vv[u]; const int pc = popc(v); int incl = pc;
+                for (int d = 1; d < WS; d <<= 1) { int o = c.shfl(incl, c.lane() >= d ? c.lane() - d : 0); if (c.lane() >= d) incl += o; }
+                int o = run + incl - pc;
+                if (w < w1) { ws.rank[w] = o; if ((w & 2047) == 0) ws.cstart[w >> 11] = o; }
+                while (v) { int b = ffs32(v) - 1; v &= v - 1; cand[o++] = (int32_t)((w << 5) | b); }
+                run += c.shfl(incl, WS - 1);
+            }
         }
         if (c.tid() == 0) ws.cstart[ncont] = n_cand;
     }
     c.sync();
+    IFX_LTICK(0);   // count + expand + rank directory
     // ---- 2. lengths, deleted flags (folded into the id), chunk table
-    for (int i0 = c.tid(); i0 < n_cand; i0 += 4 * NT) {
-        int d[4]; float dl[4]; uint8_t del[4];
-        for (int u = 0; u < 4; u++) { int i = i0 + u * NT; d[u] = i < n_cand ? cand[i] : -1; }
-        for (int u = 0; u < 4; u++) if (d[u] >= 0) { dl[u] = ix.doc_len[d[u]]; del[u] = ix.deleted[d[u]]; }
-        for (int u = 0; u < 4; u++) if (d[u] >= 0) { int i = i0 + u * NT; dlp[i] = dl[u]; if (del[u]) cand[i] = d[u] | DEL_BIT; }
+    const bool any_deleted = ix.n_live != ix.n_docs;
+    for (int i0 = c.tid(); i0 < n_cand; i0 += 8 * NT) {
+        int d[8]; float dl[8]; uint8_t del[8];
+        for (int u = 0; u < 8; u++) { int i = i0 + u * NT; d[u] = i < n_cand ? cand[i] : -1; }
+        for (int u = 0; u < 8; u++) if (d[u] >= 0) { dl[u] = ix.doc_len[d[u]]; del[u] = any_deleted ? ix.deleted[d[u]] : (uint8_t)0; }
+        for (int u = 0; u < 8; u++) if (d[u] >= 0) { int i = i0 + u * NT; dlp[i] = dl[u]; if (del[u]) cand[i] = d[u] | DEL_BIT; }
     }
+    IFX_LTICK(1);   // document lengths + deleted flags
     int Ta = 0;
     if (c.tid() == 0) { for (int t = 0; t < T; t++) sh.order[t] = sh.terms[t].idf > 0.f ? Ta++ : -1; sh.bcast[0] = Ta; sh.bcast[1] = 0; sh.bcast[2] = 0; sh.bcast[3] = 0; }   // sh.order: term -> row of the tf matrix
     c.sync();
@@ -120,10 +139,11 @@ IFX_FN void stage1_lookup(const Ctx& c, const DevIndex& ix, const QueryPlan& p, 
         for (unsigned long long i = c.tid(); i < (tf_bytes + 15ULL) / 16ULL; i += NT) zp[i] = z;
     }
     c.sync();
+    IFX_LTICK(2);   // chunk table + zeroed tf matrix
     // ---- 3. tf lookups
     unsigned long long cost_s = 0; int n_dict = 0;
     for (int t = 0; t < T; t++) if (sh.order[t] >= 0 && sh.terms[t].term_id >= 0) { cost_s += 5ULL * (unsigned long long)sh.terms[t].len; n_dict++; }
-    const bool forward = force_mode == 1 ? true : (force_mode == 2 ? false : (n_dict > 0 && (unsigned long long)n_cand * (unsigned long long)fwd_avg_bytes < cost_s));
+    const bool forward = force_mode == 1 ? true : (force_mode == 2 ? false : (n_dict > 0 && 3ULL * (unsigned long long)n_cand * (unsigned long long)fwd_avg_bytes < cost_s));      // random forward-list reads cost ~3x a streamed byte (measured, profiles/r2)
     const S1Cont* ctab = reinterpret_cast<const S1Cont*>(ws.ctab);
     auto put_hit = [&](int d, unsigned wv, int a, uint8_t tfv) {      // candidate d (bit set in wv) of row a
         const unsigned bit = 1u << (d & 31); const int idx = ws.rank[d >> 5] + popc(wv & (bit - 1)); const S1Cont ct = ctab[d >> 16];
@@ -190,14 +210,17 @@ IFX_FN void stage1_lookup(const Ctx& c, const DevIndex& ix, const QueryPlan& p, 
         for (int t = 0; t < T; t++) if (sh.order[t] >= 0) stream_term(sh.terms[t], sh.order[t]);
     }
     c.sync();
+    IFX_LTICK(3);   // tf lookups
     // ---- 4. bitset back to all-zero; record, queue, roofline accounting
     clear_bits();
+    IFX_LTICK(4);   // bitset cleared
     if (c.tid() == 0) {
         rec.off_cand = a1; rec.off_dl = a1 + (((long long)n_cand * 4 + 31) & ~31LL); rec.off_chunk = a2; rec.off_terms = a2 + (long long)chunk_bytes; rec.off_tf = a2 + (long long)(chunk_bytes + term_bytes);
         rec.n_cand = n_cand; rec.n_chunks = n_chunks; rec.n_terms = Ta; rec.max_cnt = max_cnt; rec.K = p.depth; rec.path = path;
-        const bool light = max_cnt <= W_CAP && Ta <= W_TERMS && Ta * pad16(max_cnt) <= W_TF && p.depth <= W_K;
+        const bool warp_ok = Ta <= W_TERMS && p.depth <= W_K;
         if (Ta == 0) rec.state = 0;
-        else if (light) { rec.state = 1; queues.light[atomic_add(&bc->s1_n_light, 1)] = q; }
+        else if (warp_ok && max_cnt <= W_CAP) { rec.state = 1; queues.light[atomic_add(&bc->s1_n_light, 1)] = q; }
+        else if (warp_ok && max_cnt <= W_CAP_MID) { rec.state = 4; queues.mid[atomic_add(&bc->s1_n_mid, 1)] = q; }
         else { rec.state = 3; queues.heavy[atomic_add(&bc->s1_n_heavy, 1)] = q; }
         unsigned long long algo = path == 1 ? 4ULL * (unsigned long long)n_cand : 2ULL * (unsigned long long)((ix.n_docs + 7) / 8);
         for (int i = 0; i < T; i++) {
@@ -218,13 +241,14 @@ IFX_FN void stage1_lookup(const Ctx& c, const DevIndex& ix, const QueryPlan& p, 
 // block-wide scorer below.
 struct WarpScoreShared {
     alignas(16) float heap_pr[W_K + 8]; int32_t heap_doc[W_K + 8];
-    alignas(16) uint8_t tf[W_TF];                 // the current chunk's tf block; reused for the flush survivors ((doc, score) pairs)
+    alignas(16) uint8_t tf[W_TF];                 // a tile of the current chunk's tf rows; reused for the flush survivors ((doc, score) pairs)
     S1TermP terms[W_TERMS];
 };
-constexpr int W_R = W_CAP / Ctx::WS;              // slots per lane
 
+// CAPW: slot capacity of a chunk (W_CAP or W_CAP_MID); lane l owns slots l, l + 32, ... (CAPW / 32 registers each for score and length)
+template <int CAPW>
 IFX_FN void score_warp(const Ctx& c, float avgdl_in, const S1Rec& rec, const unsigned char* spool, WarpScoreShared& sh, int32_t* out_doc, float* out_score, int32_t* out_n) {
-    constexpr int WS = Ctx::WS; const int lane = c.lane();
+    constexpr int WS = Ctx::WS; constexpr int W_R = CAPW / WS; const int lane = c.lane();
     const int K = rec.K, Ta = rec.n_terms; const float avgdl = avgdl_in > 0.f ? avgdl_in : 1.f;
     const int32_t* cand = reinterpret_cast<const int32_t*>(spool + rec.off_cand); const float* dlp = reinterpret_cast<const float*>(spool + rec.off_dl);
     const S1Chunk* chunks = reinterpret_cast<const S1Chunk*>(spool + rec.off_chunk); const S1TermP* tparams = reinterpret_cast<const S1TermP*>(spool + rec.off_terms);
@@ -234,50 +258,60 @@ IFX_FN void score_warp(const Ctx& c, float avgdl_in, const S1Rec& rec, const uns
     c.syncwarp();
     float thr = 0.f; int hs = 0;
     for (int k = 0; k < rec.n_chunks; k++) {
-        const S1Chunk ch = chunks[k]; const int cnt = ch.cnt, rowlen = pad16(cnt);
-        {   // the chunk's tf block: contiguous, 16-byte aligned
-            struct alignas(16) V16 { unsigned v[4]; }; const V16* src = reinterpret_cast<const V16*>(tfb + ch.tf_off); V16* dst = reinterpret_cast<V16*>(sh.tf); const int n16 = Ta * rowlen / 16;
-            for (int i = lane; i < n16; i += WS) dst[i] = src[i];
-        }
+        const S1Chunk ch = chunks[k]; const int cnt = ch.cnt, rowlen = pad16(cnt); const int rows_per_tile = W_TF / rowlen < Ta ? W_TF / rowlen : Ta;
         float sc[W_R], dl[W_R];
 #pragma unroll
         for (int r = 0; r < W_R; r++) { const int j = r * WS + lane; sc[r] = 0.f; dl[r] = j < cnt ? dlp[ch.start + j] : 0.f; }
-        c.syncwarp();
-        for (int a = 0; a < Ta; a++) {
-            const S1TermP tp = sh.terms[a]; const uint8_t* row = sh.tf + a * rowlen;
-            bool alive[W_R]; int m = 0; int before[W_R];      // (W_R = 8 on the GPU: registers)
-#pragma unroll
-            for (int r = 0; r < W_R; r++) {      // MaxScore test (Bm25Scorer.cs:354) first, then rank among the chunk's matches of this term
-                const int j = r * WS + lane; const unsigned tfv = j < cnt ? row[j] : 0u;
-                const bool al = tfv != 0u && !(sc[r] + tp.max_score + tp.suffix_after <= thr);
-                const unsigned bm = c.ballot(al); before[r] = m + popc(bm & c.lanemask_lt()); m += popc(bm); alive[r] = al;
+        for (int a0 = 0; a0 < Ta; a0 += rows_per_tile) {
+            const int tile = Ta - a0 < rows_per_tile ? Ta - a0 : rows_per_tile;
+            {   // the tile's rows: contiguous in the chunk's block, 16-byte aligned
+                struct alignas(16) V16 { unsigned v[4]; }; const V16* src = reinterpret_cast<const V16*>(tfb + ch.tf_off + (int64_t)a0 * rowlen); V16* dst = reinterpret_cast<V16*>(sh.tf); const int n16 = tile * rowlen / 16;
+                c.syncwarp();
+                for (int i = lane; i < n16; i += WS) dst[i] = src[i];
+                c.syncwarp();
             }
-            if (m == 0) continue;
-            const int vec_end = m - (m & 7);
+            for (int a = a0; a < a0 + tile; a++) {
+                const S1TermP tp = sh.terms[a]; const uint8_t* row = sh.tf + (a - a0) * rowlen;
+                int m = 0;
 #pragma unroll
-            for (int r = 0; r < W_R; r++) if (alive[r]) {
-                const float tf = (float)row[r * WS + lane];
-                const float add = before[r] < vec_end ? bm25_from_norm_vector(tf, bm25_norm_vector(dl[r], avgdl), tp.idf) : bm25_scalar(tf, dl[r], avgdl, tp.idf);
-                sc[r] += add;
+                for (int r = 0; r < W_R; r++) {      // MaxScore test (Bm25Scorer.cs:354): matches of this term in the chunk
+                    const int j = r * WS + lane; const unsigned tfv = j < cnt ? row[j] : 0u;
+                    m += popc(c.ballot(tfv != 0u && !(sc[r] + tp.max_score + tp.suffix_after <= thr)));
+                }
+                if (m == 0) continue;
+                const int vec_end = m - (m & 7); int run = 0;
+#pragma unroll
+                for (int r = 0; r < W_R; r++) {      // rank among them (candidate order = slot order) selects the Vector256 or the scalar form
+                    const int j = r * WS + lane; const unsigned tfv = j < cnt ? row[j] : 0u;
+                    const bool al = tfv != 0u && !(sc[r] + tp.max_score + tp.suffix_after <= thr);
+                    const unsigned bm = c.ballot(al);
+                    if (al) { const int rank = run + popc(bm & c.lanemask_lt()); const float tf = (float)tfv;
+                        sc[r] += rank < vec_end ? bm25_from_norm_vector(tf, bm25_norm_vector(dl[r], avgdl), tp.idf) : bm25_scalar(tf, dl[r], avgdl, tp.idf); }
+                    run += popc(bm);
+                }
             }
         }
         c.syncwarp();
         // flush (Bm25Scorer.cs:316-329): eligibility against the chunk-start threshold, survivors in candidate order, then the exact heap replay
-        unsigned long long* surv = reinterpret_cast<unsigned long long*>(sh.tf); int ns = 0; const bool full = hs >= K;
+        // (the survivor buffer holds W_TF / 8 pairs: larger sets are drained in rounds, order preserved)
+        unsigned long long* surv = reinterpret_cast<unsigned long long*>(sh.tf); const bool full = hs >= K; const float thr0 = thr; constexpr int SCAP = W_TF / 8;
+        for (int r0 = 0; r0 < W_R; r0 += SCAP / WS) {
+            int ns = 0;
 #pragma unroll
-        for (int r = 0; r < W_R; r++) {
-            const int j = r * WS + lane; const bool e0 = j < cnt && sc[r] > 0.f && (!full || sc[r] > thr);
-            int id = e0 ? cand[ch.start + j] : DEL_BIT; const bool e = e0 && id >= 0;      // deleted documents carry bit 31
-            const unsigned bm = c.ballot(e); if (e) surv[ns + popc(bm & c.lanemask_lt())] = kv_pack(id, sc[r]); ns += popc(bm);
+            for (int rr = 0; rr < SCAP / WS; rr++) { const int r = r0 + rr; if (r >= W_R) break;
+                const int j = r * WS + lane; const bool e0 = j < cnt && sc[r] > 0.f && (!full || sc[r] > thr0);
+                int id = e0 ? cand[ch.start + j] : DEL_BIT; const bool e = e0 && id >= 0;      // deleted documents carry bit 31
+                const unsigned bm = c.ballot(e); if (e) surv[ns + popc(bm & c.lanemask_lt())] = kv_pack(id, sc[r]); ns += popc(bm);
+            }
+            c.syncwarp();
+            if (lane == 0) {
+                for (int i = 0; i < ns; i++) { const unsigned long long kv = surv[i]; const float s = kv_score(kv);
+                    if (hs < K) { heap_move_up(sh, (int)(kv >> 32), s, hs); hs++; if (hs == K) thr = sh.heap_pr[3]; }
+                    else if (s > thr) thr = heap_replace_root(sh, (int)(kv >> 32), s, hs); }
+            }
+            thr = c.shfl(thr, 0); hs = c.shfl(hs, 0);
+            c.syncwarp();
         }
-        c.syncwarp();
-        if (lane == 0) {
-            for (int i = 0; i < ns; i++) { const unsigned long long kv = surv[i]; const float s = kv_score(kv);
-                if (hs < K) { heap_move_up(sh, (int)(kv >> 32), s, hs); hs++; if (hs == K) thr = sh.heap_pr[3]; }
-                else if (s > thr) thr = heap_replace_root(sh, (int)(kv >> 32), s, hs); }
-        }
-        thr = c.shfl(thr, 0); hs = c.shfl(hs, 0);
-        c.syncwarp();
     }
     for (int i = lane; i < hs; i += WS) { out_doc[i] = sh.heap_doc[i + 3]; out_score[i] = sh.heap_pr[i + 3]; }
     if (lane == 0) out_n[0] = hs;

@@ -100,7 +100,7 @@ class Stats(C.Structure):
                 ("ms_wordmatch", C.c_float), ("ms_stage2", C.c_float), ("ms_final", C.c_float), ("algo_bytes_stage1", C.c_int64),
                 ("kernel_launches", C.c_int64), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64), ("s1_query_ms_max", C.c_float), ("s1_query_ms_sum", C.c_float),
                 ("ms_s1_select", C.c_float), ("ms_s1_score_warp", C.c_float), ("ms_s1_score_cta", C.c_float), ("ms_s1_finish", C.c_float),
-                ("s1_light", C.c_int32), ("s1_heavy", C.c_int32), ("s1_waves", C.c_int32), ("reserved0", C.c_int32), ("s1_pool_bytes", C.c_int64)]
+                ("s1_light", C.c_int32), ("s1_heavy", C.c_int32), ("s1_waves", C.c_int32), ("s1_mid", C.c_int32), ("s1_pool_bytes", C.c_int64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

@@ -24,3 +24,7 @@ order = np.argsort(-k1)
 for i in order[:8]: print("%-36s cand=%7d T=%3d path=%d mode=%d chunks=%4d maxcnt=%4d sel=%.2f K1=%.2f K2=%.2f ms" % (qs[i][:36], nc[i], ta[i], path[i], mode[i], nch[i], mx[i], dbg[i, 2] / 1e6, k1[i], k2[i]))
 order = np.argsort(-k2)
 for i in order[:5]: print("K2 top: %-30s cand=%7d T=%3d chunks=%4d maxcnt=%4d light=%d K2=%.2f ms" % (qs[i][:30], nc[i], ta[i], nch[i], mx[i], light[i], k2[i]))
+
+if dbg[:, 11:16].sum() > 0:
+    for name, sel in (("forward", mode == 1), ("stream", mode == 2)):
+        if sel.any(): print(name, "lookup phases, mean kcycles [count+expand, lengths, chunk table+zero, tf lookups, clear]:", (dbg[sel, 11:16].mean(0) / 1e3).astype(int), "| selection sticks [sort, tier0/unions, tier1, -]:", (dbg[sel, 20:24].mean(0) / 1e3).astype(int))
