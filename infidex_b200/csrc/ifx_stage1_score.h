@@ -259,9 +259,9 @@ IFX_FN void score_warp(const Ctx& c, float avgdl_in, const S1Rec& rec, const uns
     float thr = 0.f; int hs = 0;
     for (int k = 0; k < rec.n_chunks; k++) {
         const S1Chunk ch = chunks[k]; const int cnt = ch.cnt, rowlen = pad16(cnt); const int rows_per_tile = W_TF / rowlen < Ta ? W_TF / rowlen : Ta;
-        float sc[W_R], dl[W_R];
+        float sc[W_R], nv[W_R];      // score and the length norm of the Vector256 form (one evaluation per slot and chunk; the scalar form re-reads the length)
 #pragma unroll
-        for (int r = 0; r < W_R; r++) { const int j = r * WS + lane; sc[r] = 0.f; dl[r] = j < cnt ? dlp[ch.start + j] : 0.f; }
+        for (int r = 0; r < W_R; r++) { const int j = r * WS + lane; sc[r] = 0.f; nv[r] = j < cnt ? bm25_norm_vector(dlp[ch.start + j], avgdl) : 0.f; }
         for (int a0 = 0; a0 < Ta; a0 += rows_per_tile) {
             const int tile = Ta - a0 < rows_per_tile ? Ta - a0 : rows_per_tile;
             {   // the tile's rows: contiguous in the chunk's block, 16-byte aligned
@@ -272,21 +272,22 @@ IFX_FN void score_warp(const Ctx& c, float avgdl_in, const S1Rec& rec, const uns
             }
             for (int a = a0; a < a0 + tile; a++) {
                 const S1TermP tp = sh.terms[a]; const uint8_t* row = sh.tf + (a - a0) * rowlen;
+                const bool uns = !((0.f + tp.max_score) + tp.suffix_after <= thr);      // the test cannot fire for any score >= 0 (float addition is monotone): every non-zero tf is a match
                 int m = 0;
 #pragma unroll
                 for (int r = 0; r < W_R; r++) {      // MaxScore test (Bm25Scorer.cs:354): matches of this term in the chunk
                     const int j = r * WS + lane; const unsigned tfv = j < cnt ? row[j] : 0u;
-                    m += popc(c.ballot(tfv != 0u && !(sc[r] + tp.max_score + tp.suffix_after <= thr)));
+                    m += popc(c.ballot(tfv != 0u && (uns || !(sc[r] + tp.max_score + tp.suffix_after <= thr))));
                 }
                 if (m == 0) continue;
                 const int vec_end = m - (m & 7); int run = 0;
 #pragma unroll
                 for (int r = 0; r < W_R; r++) {      // rank among them (candidate order = slot order) selects the Vector256 or the scalar form
                     const int j = r * WS + lane; const unsigned tfv = j < cnt ? row[j] : 0u;
-                    const bool al = tfv != 0u && !(sc[r] + tp.max_score + tp.suffix_after <= thr);
+                    const bool al = tfv != 0u && (uns || !(sc[r] + tp.max_score + tp.suffix_after <= thr));
                     const unsigned bm = c.ballot(al);
                     if (al) { const int rank = run + popc(bm & c.lanemask_lt()); const float tf = (float)tfv;
-                        sc[r] += rank < vec_end ? bm25_from_norm_vector(tf, bm25_norm_vector(dl[r], avgdl), tp.idf) : bm25_scalar(tf, dl[r], avgdl, tp.idf); }
+                        sc[r] += rank < vec_end ? bm25_from_norm_vector(tf, nv[r], tp.idf) : bm25_scalar(tf, dlp[ch.start + j], avgdl, tp.idf); }
                     run += popc(bm);
                 }
             }
