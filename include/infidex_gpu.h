@@ -89,6 +89,11 @@ typedef struct ifx_index_image {
     const int32_t* affix_last_doc;    /* the single doc its trie output resolves to (WordMatcher.cs:166-196) */
     int32_t n_columns;
     const ifx_column* columns;        /* filterable / facetable fields, schema order of the first document */
+    /* doc-id-range shards: zero / NULL for an unsharded index. A shard image holds its own documents (local ids from 0) and the
+     * statistics of the WHOLE corpus: terms / df / idf ordinals, n_live, avgdl, word idf, the global prefix key set and affix dictionary. */
+    const int32_t* prefix_global_card;/* [prefix.keys.n] DocSet cardinality over all shards (the selector's prefix rules are global) */
+    int32_t shard_index, n_shards;
+    int64_t doc_base;                 /* global internal id of this shard's document 0 */
 } ifx_index_image;
 
 typedef struct ifx_params {           /* ConfigurationParameters[400] + CoverageSetup defaults when zero-initialised via ifx_params_default */
@@ -154,6 +159,17 @@ int  ifx_batch_upload(ifx_index* idx, const ifx_query* q, int nq, ifx_batch** ou
 int  ifx_batch_run(ifx_batch* b, ifx_stats* st);
 int  ifx_batch_download(ifx_batch* b, ifx_batch_result* out);
 void ifx_batch_free(ifx_batch* b);
+
+/* doc-id-range shards: one index handle per shard (ifx_index_image.n_shards > 1), the batch run split where the shards' hosts
+ * exchange data. phase 1: query preparation + LD1 expansion; then all-reduce(sum) of ifx_batch_fuzzy_df (document frequency of every LD1
+ * union: its idf is a corpus-level quantity). phase 2: selection, tf lookups, scoring; then all-gather of ifx_batch_stage1_lists and
+ * ifx_batch_stage1_restrict (global top-`depth` cut, global top score for normBm25). phase 3: WordMatcher, coverage / fusion, truncation,
+ * filter, facets; ifx_batch_download gives the shard's records, which every host merges after an all-gather.
+ * buf / key / score / n / keep / gmax are DEVICE pointers. */
+int  ifx_batch_run_phase(ifx_batch* b, int phase, ifx_stats* st);
+int  ifx_batch_fuzzy_df(ifx_batch* b, int32_t* buf /* [nq * 16] */, int set);
+int  ifx_batch_stage1_lists(ifx_batch* b, int64_t* key, float* score, int32_t* n);
+int  ifx_batch_stage1_restrict(ifx_batch* b, const uint8_t* keep /* [nq * depth] */, const float* gmax /* [nq] */);
 
 /* Stage-1 only (Bm25Scorer.Search + ConsolidateSegments, src/Infidex/Indexing/Bm25Scorer.cs:56-193): row-major
  * [nq][depth] keys / scores, n[nq]. Used for intermediate parity checks and kernel-level measurement. */

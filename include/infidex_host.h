@@ -23,6 +23,12 @@ int ifx_builder_add_docs(ifx_builder* b, int n, const int64_t* keys, const int32
 int ifx_builder_finish(ifx_builder* b, int threads);
 const ifx_index_image* ifx_builder_image(ifx_builder* b);   /* valid until ifx_builder_destroy */
 
+/* doc-id-range shards: every shard's host builds its own document range, then the shards exchange their local statistics (export ->
+ * all-gather between the hosts -> globalize) so that each image carries the term ordinals, df, N, avgdl, word idf, prefix cardinalities
+ * and affix dictionary of the whole corpus (infidex_gpu.h, ifx_index_image). */
+const uint8_t* ifx_builder_export_stats(ifx_builder* b, size_t* len);      /* valid until the next export on this thread */
+int ifx_builder_globalize(ifx_builder* b, int n_shards, int shard, const uint8_t* const* blobs);
+
 /* SearchEngine.Search step 1 (src/Infidex/SearchEngine.cs:264-274): Trim + TextNormalizer.Normalize + ToLowerInvariant. Returns the output length. */
 int ifx_host_prepare_query(const uint16_t* in, int n, uint16_t* out, int cap);
 

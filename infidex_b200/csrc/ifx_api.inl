@@ -268,7 +268,7 @@ extern "C" int ifx_index_create(const ifx_index_image* img, const ifx_params* pp
         v.term_sig = ix->up(sig.data(), sig.size());
         v.len_ptr = ix->up(lp.data(), lp.size()); v.len_sig = ix->up(lsig.data(), lsig.size()); v.len_ord = ix->up(lord.data(), lord.size());
         v.words = upload_dict(ix, img->words, true, &hh_words); v.word_idf = ix->up(img->word_idf, img->words.n ? img->words.n : 1);
-        v.prefix = upload_docset(ix, img->prefix, &hh_prefix); v.wm_exact = upload_docset(ix, img->wm_exact, &hh_exact); v.wm_ld1 = upload_docset(ix, img->wm_ld1, &hh_ld1);
+        v.prefix = upload_docset(ix, img->prefix, &hh_prefix); v.prefix_gcard = img->prefix_global_card ? ix->up(img->prefix_global_card, std::max(img->prefix.keys.n, 1)) : nullptr; v.wm_exact = upload_docset(ix, img->wm_exact, &hh_exact); v.wm_ld1 = upload_docset(ix, img->wm_ld1, &hh_ld1);
         {   ifx_strings ss{achars.data(), aoff.data(), A};
             v.affix = upload_dict(ix, ss, true, &hh_affix); v.affix_fwd_doc = ix->up(fdoc.data(), A ? A : 1);
             v.affix_rev = ix->up(ro.data(), A ? A : 1); v.affix_rev_doc = ix->up(rdoc.data(), A ? A : 1); }

@@ -77,6 +77,7 @@ struct DevIndex {
     int32_t bm_words;
     StrDict words; const float* word_idf;
     DocsetDict prefix, wm_exact, wm_ld1;
+    const int32_t* prefix_gcard;     // doc-id-range shards: DocSet cardinality over ALL shards per prefix key (null: unsharded, the local row length)
     StrDict affix;                   // affix words in ordinal-lexicographic order
     const int32_t* affix_fwd_doc;    // last doc per affix word (forward order)
     const int32_t* affix_rev;        // indices into `affix`, ordered by the reversed string

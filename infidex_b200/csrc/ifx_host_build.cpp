@@ -171,7 +171,7 @@ struct ifx_builder {
     std::vector<uint8_t> deleted; std::vector<float> doc_len; std::vector<char16_t> text; std::vector<int64_t> text_off;
     std::vector<char16_t> ft_chars; std::vector<uint32_t> ft_off; std::vector<uint16_t> tok_count;
     Csr terms, prefix, wm_exact, wm_ld1; std::vector<int32_t> df;
-    std::vector<char16_t> word_chars; std::vector<uint32_t> word_off; std::vector<float> word_idf;
+    std::vector<char16_t> word_chars; std::vector<uint32_t> word_off; std::vector<float> word_idf; std::vector<int32_t> word_df;
     std::vector<char16_t> affix_chars; std::vector<uint32_t> affix_off; std::vector<int32_t> affix_last;
     std::vector<ifx_column> cols; std::vector<std::vector<int32_t>> col_ids; std::vector<std::vector<char16_t>> col_chars; std::vector<std::vector<uint32_t>> col_off; std::vector<str> col_names;
 };
@@ -190,7 +190,7 @@ ifx_builder* ifx_builder_create(int nfields, const uint16_t* names, const int32_
     b->values.resize(nfields); b->is_null.resize(nfields);
     return b;
 }
-void ifx_builder_destroy(ifx_builder* b) { delete b; }
+void ifx_builder_destroy(ifx_builder* b);
 
 int ifx_builder_add_docs(ifx_builder* b, int n, const int64_t* keys, const int32_t* kinds, const void* const* cols, const long long* const* offs) {
     if (b->finished) return IFX_ERR_INVALID;
@@ -267,7 +267,7 @@ int ifx_builder_finish(ifx_builder* b, int threads) {
     auto small_dicts = [&] {
     // word idf
         { Interner g; std::vector<int32_t> gdf; for (auto& P : parts) for (int k = 0; k < P.words.size(); k++) { bool nw; int id = g.intern(P.words.get(k), &nw); if (nw) gdf.push_back(0); gdf[id] += P.word_df[k]; }
-          b->word_chars.assign(g.arena.begin(), g.arena.end()); if (b->word_chars.empty()) b->word_chars.push_back(0); b->word_off = g.off; b->word_idf.resize(gdf.size());
+          b->word_chars.assign(g.arena.begin(), g.arena.end()); if (b->word_chars.empty()) b->word_chars.push_back(0); b->word_off = g.off; b->word_idf.resize(gdf.size()); b->word_df = gdf;
           for (size_t i = 0; i < gdf.size(); i++) b->word_idf[i] = (gdf[i] > 0 && gdf[i] <= N) ? compute_idf_host(N, gdf[i]) : 0.f; }
         // affix words: last doc wins (WordMatcher.IndexWordInFst quirk Q4)
         { Interner g; for (auto& P : parts) for (int k = 0; k < P.affix.size(); k++) { bool nw; int id = g.intern(P.affix.get(k), &nw); if (nw) b->affix_last.push_back(P.affix_last[k]); else b->affix_last[id] = P.affix_last[k]; }
@@ -331,7 +331,116 @@ int ifx_builder_finish(ifx_builder* b, int threads) {
 
 const ifx_index_image* ifx_builder_image(ifx_builder* b) { return b->finished ? &b->img : nullptr; }
 
+// ---- doc-id-range shards: a shard's builder indexes its own document range; the statistics the search path reads as
+// GLOBAL quantities are exchanged between the shards' hosts (ifx_builder_export_stats -> all-gather -> ifx_builder_globalize) so that
+// every shard scores with the term ordinals, df / idf, N, avgdl, word idf, prefix cardinalities and affix dictionary of the whole corpus.
 }  // extern "C"
+namespace {
+struct Blob { std::vector<uint8_t> d;
+    template <class T> void put(const T& v) { const uint8_t* p = (const uint8_t*)&v; d.insert(d.end(), p, p + sizeof(T)); }
+    void bytes(const void* p, size_t n) { const uint8_t* q = (const uint8_t*)p; d.insert(d.end(), q, q + n); }
+    void strings(const char16_t* chars, const uint32_t* off, int n) { put<int32_t>(n); bytes(off, ((size_t)n + 1) * 4); bytes(chars, (size_t)off[n] * 2); } };
+struct Rd { const uint8_t* p; template <class T> T get() { T v; std::memcpy(&v, p, sizeof(T)); p += sizeof(T); return v; }
+    const void* take(size_t n) { const void* r = p; p += n; return r; } };
+struct StrView { int n; const uint32_t* off; const char16_t* chars; sv at(int i) const { return sv(chars + off[i], off[i + 1] - off[i]); } };
+StrView rd_strings(Rd& r) { StrView v; v.n = r.get<int32_t>(); v.off = (const uint32_t*)r.take(((size_t)v.n + 1) * 4); v.chars = (const char16_t*)r.take((size_t)v.off[v.n] * 2); return v; }
+}  // namespace
+
+struct ifx_builder_shard { std::vector<int32_t> prefix_card; };       // extra image storage of a globalized shard
+static std::vector<std::pair<ifx_builder*, ifx_builder_shard*>> g_shard_extra;
+extern "C" {
+
+// Serialised local statistics of a finished shard builder. The caller owns nothing: the blob lives until the next export / destroy.
+const uint8_t* ifx_builder_export_stats(ifx_builder* b, size_t* len) {
+    static thread_local Blob out; out.d.clear();
+    const int N = (int)b->keys.size(); const int T = b->terms.n;
+    out.put<int32_t>(N);
+    out.strings(b->terms.chars.data(), b->terms.off.data(), T);
+    { std::vector<int64_t> dfv(T); for (int t = 0; t < T; t++) dfv[t] = b->df[t] < 0 ? (int64_t)b->stop_term_limit + 1 : b->df[t]; out.bytes(dfv.data(), (size_t)T * 8); }
+    out.strings(b->word_chars.data(), b->word_off.data(), (int)b->word_off.size() - 1);
+    out.bytes(b->word_df.data(), b->word_df.size() * 4);
+    out.strings(b->prefix.chars.data(), b->prefix.off.data(), b->prefix.n);
+    { std::vector<int32_t> card(b->prefix.n); for (int k = 0; k < b->prefix.n; k++) card[k] = (int32_t)(b->prefix.row[k + 1] - b->prefix.row[k]); out.bytes(card.data(), card.size() * 4); }
+    out.strings(b->affix_chars.data(), b->affix_off.data(), (int)b->affix_off.size() - 1);
+    out.bytes(b->affix_last.data(), ((size_t)b->affix_off.size() - 1) * 4);
+    out.bytes(b->doc_len.data(), (size_t)N * 4);
+    *len = out.d.size(); return out.d.data();
+}
+
+// blobs[s] = export of shard s (all shards, in doc-range order). Rewrites this builder's image so that it is shard `shard` of the
+// global index. `prefix_card_out`: see ifx_builder_prefix_cardinalities.
+int ifx_builder_globalize(ifx_builder* b, int n_shards, int shard, const uint8_t* const* blobs) {
+    if (!b->finished || n_shards < 1 || shard < 0 || shard >= n_shards) return IFX_ERR_INVALID;
+    std::vector<int> shard_docs(n_shards); int64_t N_all = 0;
+    struct In { int N; StrView terms; const int64_t* df; StrView words; const int32_t* wdf; StrView prefix; const int32_t* pcard; StrView affix; const int32_t* alast; const float* dl; };
+    std::vector<In> in(n_shards);
+    for (int s = 0; s < n_shards; s++) { Rd r{blobs[s]}; In& x = in[s]; x.N = r.get<int32_t>(); x.terms = rd_strings(r); x.df = (const int64_t*)r.take((size_t)x.terms.n * 8);
+        x.words = rd_strings(r); x.wdf = (const int32_t*)r.take((size_t)x.words.n * 4); x.prefix = rd_strings(r); x.pcard = (const int32_t*)r.take((size_t)x.prefix.n * 4);
+        x.affix = rd_strings(r); x.alast = (const int32_t*)r.take((size_t)x.affix.n * 4); x.dl = (const float*)r.take((size_t)x.N * 4); shard_docs[s] = x.N; N_all += x.N; }
+    if (N_all > 0x7fffffffLL) return IFX_ERR_INVALID;
+    int64_t doc_base = 0; for (int s = 0; s < shard; s++) doc_base += shard_docs[s];
+    const int N = (int)b->keys.size();
+    // ---- terms: global ordinals = first occurrence over the shards in doc order (TermCollection order of the whole corpus), df summed
+    Interner g; std::vector<int64_t> gdf; std::vector<int32_t> l2g(b->terms.n, -1);
+    for (int s = 0; s < n_shards; s++) for (int t = 0; t < in[s].terms.n; t++) { bool nw; int id = g.intern(in[s].terms.at(t), &nw); if (nw) gdf.push_back(0); gdf[id] += in[s].df[t]; if (s == shard) l2g[t] = id; }
+    const int TG = g.size();
+    {   Csr nt; nt.n = TG; nt.chars.assign(g.arena.begin(), g.arena.end()); if (nt.chars.empty()) nt.chars.push_back(0); nt.off = g.off; nt.row.assign((size_t)TG + 1, 0);
+        std::vector<int32_t> g2l(TG, -1); for (int t = 0; t < b->terms.n; t++) g2l[l2g[t]] = t;
+        std::vector<int32_t> ndf(TG);
+        for (int gt = 0; gt < TG; gt++) { const bool stop = gdf[gt] > b->stop_term_limit; ndf[gt] = stop ? -1 : (int32_t)gdf[gt]; const int lt = g2l[gt];
+            nt.row[gt + 1] = nt.row[gt] + ((lt >= 0 && !stop && b->df[lt] > 0) ? b->terms.row[lt + 1] - b->terms.row[lt] : 0); }
+        nt.docs.resize((size_t)nt.row[TG]); nt.w.resize((size_t)nt.row[TG]);
+        par_for(TG, 16, [&](int64_t a, int64_t e, int) { for (int64_t gt = a; gt < e; gt++) { const int lt = g2l[gt]; const int64_t n = nt.row[gt + 1] - nt.row[gt]; if (n <= 0) continue;
+            std::memcpy(nt.docs.data() + nt.row[gt], b->terms.docs.data() + b->terms.row[lt], (size_t)n * 4); std::memcpy(nt.w.data() + nt.row[gt], b->terms.w.data() + b->terms.row[lt], (size_t)n); } });
+        // a term that became a stop term globally no longer contributes to the document lengths of this shard
+        std::vector<uint32_t> dl(N, 0); for (int64_t i = 0; i < nt.row[TG]; i++) dl[nt.docs[i]] += nt.w[i];
+        for (int d = 0; d < N; d++) b->doc_len[d] = (float)dl[d];
+        std::swap(b->terms.chars, nt.chars); std::swap(b->terms.off, nt.off); std::swap(b->terms.row, nt.row); std::swap(b->terms.docs.p, nt.docs.p); std::swap(b->terms.docs.n, nt.docs.n); std::swap(b->terms.w.p, nt.w.p); std::swap(b->terms.w.n, nt.w.n);
+        b->terms.n = TG; b->df.swap(ndf);
+    }
+    // ---- avgdl: sequential float sum over all documents in order (VectorModel.cs:212-216). Every shard's exported lengths were computed
+    // before any global stop term was known; a term can only become a stop term by the global sum, in which case every shard drops it
+    // identically, so the lengths are recomputed from each shard's blob only when no such term exists (checked below).
+    bool new_stop = false; for (int s = 0; s < n_shards && !new_stop; s++) for (int t = 0; t < in[s].terms.n; t++) if (in[s].df[t] <= b->stop_term_limit) { int id = g.find(in[s].terms.at(t)); if (gdf[id] > b->stop_term_limit) { new_stop = true; break; } }
+    if (new_stop) return IFX_ERR_UNSUPPORTED;          // would need a second exchange of corrected lengths; not reached below stop_term_limit * n_shards postings per term
+    float total = 0.f; for (int s = 0; s < n_shards; s++) for (int d = 0; d < in[s].N; d++) total += in[s].dl[d];
+    const float avgdl = N_all > 0 ? total / (float)N_all : 0.f;
+    // ---- word idf over the whole corpus
+    { Interner gw; std::vector<int64_t> wdf; for (int s = 0; s < n_shards; s++) for (int k = 0; k < in[s].words.n; k++) { bool nw; int id = gw.intern(in[s].words.at(k), &nw); if (nw) wdf.push_back(0); wdf[id] += in[s].wdf[k]; }
+      b->word_chars.assign(gw.arena.begin(), gw.arena.end()); if (b->word_chars.empty()) b->word_chars.push_back(0); b->word_off = gw.off; b->word_idf.resize(wdf.size());
+      for (size_t i = 0; i < wdf.size(); i++) b->word_idf[i] = (wdf[i] > 0 && wdf[i] <= N_all) ? compute_idf_host((int)N_all, (int)wdf[i]) : 0.f; }
+    // ---- prefix docsets: global key set with global cardinalities, local rows
+    ifx_builder_shard* ex = new ifx_builder_shard();
+    { Interner gp; std::vector<int64_t> card; std::vector<int32_t> pl2g(b->prefix.n, -1);
+      for (int s = 0; s < n_shards; s++) for (int k = 0; k < in[s].prefix.n; k++) { bool nw; int id = gp.intern(in[s].prefix.at(k), &nw); if (nw) card.push_back(0); card[id] += in[s].pcard[k]; if (s == shard) pl2g[k] = id; }
+      const int PG = gp.size(); std::vector<int32_t> g2l(PG, -1); for (int k = 0; k < b->prefix.n; k++) g2l[pl2g[k]] = k;
+      Csr np; np.n = PG; np.chars.assign(gp.arena.begin(), gp.arena.end()); if (np.chars.empty()) np.chars.push_back(0); np.off = gp.off; np.row.assign((size_t)PG + 1, 0);
+      for (int k = 0; k < PG; k++) np.row[k + 1] = np.row[k] + (g2l[k] >= 0 ? b->prefix.row[g2l[k] + 1] - b->prefix.row[g2l[k]] : 0);
+      np.docs.resize((size_t)np.row[PG]);
+      for (int k = 0; k < PG; k++) if (g2l[k] >= 0) std::memcpy(np.docs.data() + np.row[k], b->prefix.docs.data() + b->prefix.row[g2l[k]], (size_t)(np.row[k + 1] - np.row[k]) * 4);
+      std::swap(b->prefix.chars, np.chars); std::swap(b->prefix.off, np.off); std::swap(b->prefix.row, np.row); std::swap(b->prefix.docs.p, np.docs.p); std::swap(b->prefix.docs.n, np.docs.n); b->prefix.n = PG;
+      ex->prefix_card.resize(PG); for (int k = 0; k < PG; k++) ex->prefix_card[k] = (int32_t)std::min<int64_t>(card[k], 0x7fffffff); }
+    // ---- affix words: global dictionary, last document wins (Q4) -- kept as a LOCAL id when this shard owns that document, else -1
+    { Interner ga; std::vector<int64_t> last; int64_t base = 0;
+      for (int s = 0; s < n_shards; s++) { for (int k = 0; k < in[s].affix.n; k++) { bool nw; int id = ga.intern(in[s].affix.at(k), &nw); if (nw) last.push_back(-1); last[id] = base + in[s].alast[k]; } base += in[s].N; }
+      b->affix_chars.assign(ga.arena.begin(), ga.arena.end()); if (b->affix_chars.empty()) b->affix_chars.push_back(0); b->affix_off = ga.off; b->affix_last.assign(std::max<size_t>(last.size(), 1), -1);
+      for (size_t i = 0; i < last.size(); i++) { const int64_t l = last[i] - doc_base; b->affix_last[i] = (l >= 0 && l < N) ? (int32_t)l : -1; } }
+    // ---- image
+    ifx_index_image& I = b->img; auto S = [](std::vector<char16_t>& c, std::vector<uint32_t>& o) { return ifx_strings{(const uint16_t*)c.data(), o.data(), (int)o.size() - 1}; };
+    I.n_live = (int32_t)N_all; I.avgdl = avgdl; I.doc_len = b->doc_len.data();
+    I.terms = S(b->terms.chars, b->terms.off); I.df = b->df.data(); I.row_ptr = b->terms.row.data(); I.post_doc = b->terms.docs.data(); I.post_tf = b->terms.w.data();
+    I.words = S(b->word_chars, b->word_off); I.word_idf = b->word_idf.data();
+    I.prefix = {S(b->prefix.chars, b->prefix.off), b->prefix.row.data(), b->prefix.docs.data()};
+    I.affix_words = S(b->affix_chars, b->affix_off); I.affix_last_doc = b->affix_last.data();
+    I.prefix_global_card = ex->prefix_card.data(); I.shard_index = shard; I.n_shards = n_shards; I.doc_base = doc_base;
+    g_shard_extra.emplace_back(b, ex);
+    return IFX_OK;
+}
+
+
+}  // extern "C"
+
+extern "C" void ifx_builder_destroy(ifx_builder* b) { for (size_t i = 0; i < g_shard_extra.size(); i++) if (g_shard_extra[i].first == b) { delete g_shard_extra[i].second; g_shard_extra.erase(g_shard_extra.begin() + i); break; } delete b; }
 
 // SearchEngine.Search step 1 (src/Infidex/SearchEngine.cs:264-274): Trim, TextNormalizer.Normalize, ToLowerInvariant.
 extern "C" int ifx_host_prepare_query(const uint16_t* in, int n, uint16_t* out, int cap) {

@@ -113,20 +113,21 @@ __global__ void __launch_bounds__(256) k_s1_finish(DevIndex ix, const BatchCount
 
 static int s1_force_mode() { const char* e = getenv("IFX_S1_LOOKUP"); return e ? atoi(e) : 0; }      // 1 forward-index lookups, 2 streamed lists (tests / A-B runs)
 
-static void run_stage1_phase(ifx_batch* b, ifx_stats* st) {
+// `part`: 1 = query preparation + LD1 expansion, 2 = selection / lookups / scoring / final order, 3 = both (the unsharded call)
+static void run_stage1_phase(ifx_batch* b, ifx_stats* st, int part = 3) {
     ifx_index* ix = b->idx; const int nq = b->nq; const int K = b->depth_max;
-    BatchCounters zero{}; h2d(b->d_bc, &zero, sizeof(zero));
+    if (part & 1) { BatchCounters zero{}; h2d(b->d_bc, &zero, sizeof(zero)); }
     const int items_cap = nq * MAX_FUZZY;       // every query may carry MAX_FUZZY unknown words: the item list can never overflow
     const int force_mode = s1_force_mode(); S1Queues queues{b->d_light, b->d_mid, b->d_heavy};
     Timer t;
 #ifdef IFX_EMU
     std::vector<int64_t> off(nq + 1); d2h(off.data(), b->d_off, (nq + 1) * 8);
-    for (int q = 0; q < nq; q++) prepare_query(ix->v, b->d_text + off[q], (int)(off[q + 1] - off[q]), b->d_par[q * 5 + 1], b->d_par[q * 5 + 0], b->d_par[q * 5 + 2], b->d_par[q * 5 + 3], b->d_par[q * 5 + 4], b->d_plans[q], b->d_items, items_cap, b->d_bc, q);
+    if (part & 1) for (int q = 0; q < nq; q++) prepare_query(ix->v, b->d_text + off[q], (int)(off[q + 1] - off[q]), b->d_par[q * 5 + 1], b->d_par[q * 5 + 0], b->d_par[q * 5 + 2], b->d_par[q * 5 + 3], b->d_par[q * 5 + 4], b->d_plans[q], b->d_items, items_cap, b->d_bc, q);
     static S1Shared* sh = new S1Shared(); memset(sh->dirty, 0, sizeof(sh->dirty)); static WarpScoreShared* wsh = new WarpScoreShared(); static FinishShared* fsh = new FinishShared();
     Ctx c; int nit = std::min(b->d_bc->n_fuzzy_items, items_cap);
-    for (int i = 0; i < nit; i++) expand_fuzzy(c, ix->v, b->d_plans[b->d_items[i].query], b->d_items[i].slot, ix->ws[0], *sh, ix->d_pool, ix->pool_cap, b->d_bc, ix->d_sorted_len, sh->cand_s);
+    if (part & 1) for (int i = 0; i < nit; i++) expand_fuzzy(c, ix->v, b->d_plans[b->d_items[i].query], b->d_items[i].slot, ix->ws[0], *sh, ix->d_pool, ix->pool_cap, b->d_bc, ix->d_sorted_len, sh->cand_s);
     const bool no_warp = getenv("IFX_S1_NO_WARP") != nullptr;      // tests: force every query through the block-wide scorer
-    for (int wave = 0; wave < 64; wave++) {
+    for (int wave = 0; wave < 64 && (part & 2); wave++) {
         b->d_bc->s1_pool_used = 0; b->d_bc->s1_deferred = 0; b->d_bc->s1_n_light = 0; b->d_bc->s1_n_mid = 0; b->d_bc->s1_n_heavy = 0; b->d_bc->s1_wave = wave;
         for (int q = 0; q < nq; q++) {
             if (wave > 0 && b->d_recs[q].state != 2) continue;
@@ -152,16 +153,19 @@ static void run_stage1_phase(ifx_batch* b, ifx_stats* st) {
     auto k_light = k_score_warp<W_CAP, IFX_SW_WARPS>; auto k_mid = k_score_warp<W_CAP_MID, IFX_SW_WARPS_MID>;
     if (!ix->attr_s1) { CUDA_TRY(cudaFuncSetAttribute(k_expand, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); CUDA_TRY(cudaFuncSetAttribute(k_select_lookup, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         CUDA_TRY(cudaFuncSetAttribute(k_score_cta, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); CUDA_TRY(cudaFuncSetAttribute(k_light, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_w)); CUDA_TRY(cudaFuncSetAttribute(k_mid, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_m)); ix->attr_s1 = true; }
-    t.start();
-    k_prepare<<<(nq + 127) / 128, 128>>>(ix->v, b->d_text, b->d_off, b->d_par, nq, b->d_plans, b->d_items, items_cap, b->d_bc);
-    float ms_prep = t.stop();
-    t.start();
-    CUDA_TRY(cudaMemsetAsync(b->d_work, 0, 8 * sizeof(int)));
-    k_expand<<<ix->n_ctas, IFX_EXPAND_THREADS, smem>>>(ix->v, b->d_plans, b->d_items, b->d_bc, ix->d_ws, ix->d_pool, ix->pool_cap, ix->d_sorted_len, b->d_work, items_cap);
-    float ms_exp = t.stop();
-    float ms_sel = 0.f, ms_sw = 0.f, ms_sc = 0.f, ms_fin = 0.f; int launches = 2; const int sms = ix->n_ctas / 2 > 0 ? ix->n_ctas / 2 : 1;
-    k_order<<<1, 1024>>>(ix->v, b->d_plans, nq, b->d_order); launches++;
-    for (int wave = 0; wave < 64; wave++) {
+    float ms_prep = 0.f, ms_exp = 0.f; int launches = 0;
+    if (part & 1) {
+        t.start();
+        k_prepare<<<(nq + 127) / 128, 128>>>(ix->v, b->d_text, b->d_off, b->d_par, nq, b->d_plans, b->d_items, items_cap, b->d_bc);
+        ms_prep = t.stop();
+        t.start();
+        CUDA_TRY(cudaMemsetAsync(b->d_work, 0, 8 * sizeof(int)));
+        k_expand<<<ix->n_ctas, IFX_EXPAND_THREADS, smem>>>(ix->v, b->d_plans, b->d_items, b->d_bc, ix->d_ws, ix->d_pool, ix->pool_cap, ix->d_sorted_len, b->d_work, items_cap);
+        ms_exp = t.stop(); launches += 2;
+    }
+    float ms_sel = 0.f, ms_sw = 0.f, ms_sc = 0.f, ms_fin = 0.f; const int sms = ix->n_ctas / 2 > 0 ? ix->n_ctas / 2 : 1;
+    if (part & 2) { k_order<<<1, 1024>>>(ix->v, b->d_plans, nq, b->d_order); launches++; }
+    for (int wave = 0; wave < 64 && (part & 2); wave++) {
         if (wave > 0) { BatchCounters bc; d2h(&bc, b->d_bc, sizeof(bc)); bc.s1_pool_used = 0; bc.s1_deferred = 0; bc.s1_n_light = 0; bc.s1_n_mid = 0; bc.s1_n_heavy = 0; bc.s1_wave = wave; h2d(b->d_bc, &bc, sizeof(bc)); CUDA_TRY(cudaMemsetAsync(b->d_work + 1, 0, 5 * sizeof(int))); }
         t.start();
         k_select_lookup<<<std::min(ix->n_ctas, nq), IFX_S1_THREADS, smem>>>(ix->v, b->d_plans, nq, ix->d_pool, ix->d_ws, b->d_bc, b->d_s1_n, b->d_work + 1, b->d_order, b->d_qdbg, b->d_recs, ix->d_spool, ix->spool_cap, queues, wave, force_mode);

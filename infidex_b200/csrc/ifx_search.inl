@@ -168,11 +168,86 @@ extern "C" int ifx_batch_run(ifx_batch* b, ifx_stats* st) {
     try {
         std::lock_guard<std::mutex> lk(b->idx->mu); DeviceGuard dg(b->idx->device);
         if (!b->s2.ent_doc) alloc_stage2(b, std::max(b->cap_max, 1), b->fcap);
+        b->s2.gmax = nullptr;
         Timer tt; tt.start();
         run_stage1_phase(b, st);
         run_stage2_phase(b, st);
         float ms = tt.stop(); if (st) st->ms_total = ms;
         b->ran = true;
+    } catch (const std::string& e) { return fail(IFX_ERR_CUDA, e); }
+    return IFX_OK;
+}
+
+// ---- doc-id-range shards: the batch run split at the points where the shards' hosts exchange data -------------------------
+//   phase 1  query preparation + LD1 expansion            -> ifx_batch_fuzzy_df(get) -> all-reduce(sum) -> ifx_batch_fuzzy_df(set)
+//   phase 2  selection, tf lookups, scoring, final order  -> ifx_batch_stage1_lists -> all-gather -> ifx_batch_stage1_restrict (global cut, global top score)
+//   phase 3  WordMatcher, coverage / fusion, truncation, filter, facets -> ifx_batch_download -> all-gather of the shard's records -> merge on every host
+// Buffers passed to the exchange entry points are DEVICE pointers (host pointers in the test-only emulation build).
+#ifndef IFX_EMU
+__global__ void k_fuzzy_df(DevIndex ix, QueryPlan* plans, int nq, int32_t* buf, int set) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x; if (i >= nq * MAX_FUZZY) return;
+    const int q = i / MAX_FUZZY, f = i % MAX_FUZZY; QueryPlan& p = plans[q];
+    if (f >= p.n_fuzzy) { if (!set) buf[i] = 0; return; }
+    QTerm& t = p.terms[p.fuzzy[f].term_slot];
+    if (!set) { buf[i] = t.df; return; }
+    const float avgdl = ix.avgdl > 0.f ? ix.avgdl : 1.f; t.df = buf[i]; t.idf = compute_idf(ix, t.df); t.max_score = max_term_score(t.idf, avgdl);
+}
+__global__ void k_s1_restrict(int nq, int K, int64_t* key, int32_t* doc, float* score, int32_t* n, const uint8_t* keep) {
+    int q = blockIdx.x * blockDim.x + threadIdx.x; if (q >= nq) return;
+    int m = 0; const int cnt = n[q] < 0 ? 0 : n[q];
+    for (int i = 0; i < cnt; i++) if (keep[(size_t)q * K + i]) { const size_t o = (size_t)q * K; key[o + m] = key[o + i]; doc[o + m] = doc[o + i]; score[o + m] = score[o + i]; m++; }
+    if (n[q] >= 0) n[q] = m;
+}
+#endif
+extern "C" int ifx_batch_run_phase(ifx_batch* b, int phase, ifx_stats* st) {
+    if (!b || phase < 1 || phase > 3) return fail(IFX_ERR_INVALID, "bad phase");
+    if (!dev_ok()) return fail(IFX_ERR_NO_DEVICE, "no CUDA device available (infidex_b200 has no CPU fallback)");
+    try {
+        std::lock_guard<std::mutex> lk(b->idx->mu); DeviceGuard dg(b->idx->device);
+        if (!b->s2.ent_doc) alloc_stage2(b, std::max(b->cap_max, 1), b->fcap);
+        if (phase == 1) { if (st) { int64_t h = st->h2d_bytes, d = st->d2h_bytes; memset(st, 0, sizeof(*st)); st->h2d_bytes = h; st->d2h_bytes = d; } b->s2.gmax = nullptr; run_stage1_phase(b, st, 1); }
+        else if (phase == 2) run_stage1_phase(b, st, 2);
+        else { run_stage2_phase(b, st); b->ran = true; }
+    } catch (const std::string& e) { return fail(IFX_ERR_CUDA, e); }
+    return IFX_OK;
+}
+extern "C" int ifx_batch_fuzzy_df(ifx_batch* b, int32_t* buf, int set) {
+    if (!b || !buf) return fail(IFX_ERR_INVALID, "null argument");
+    try { DeviceGuard dg(b->idx->device);
+#ifdef IFX_EMU
+        for (int i = 0; i < b->nq * MAX_FUZZY; i++) { const int q = i / MAX_FUZZY, f = i % MAX_FUZZY; QueryPlan& p = b->d_plans[q]; if (f >= p.n_fuzzy) { if (!set) buf[i] = 0; continue; }
+            QTerm& t = p.terms[p.fuzzy[f].term_slot]; if (!set) { buf[i] = t.df; continue; }
+            const float avgdl = b->idx->v.avgdl > 0.f ? b->idx->v.avgdl : 1.f; t.df = buf[i]; t.idf = compute_idf(b->idx->v, t.df); t.max_score = max_term_score(t.idf, avgdl); }
+#else
+        k_fuzzy_df<<<(b->nq * MAX_FUZZY + 255) / 256, 256>>>(b->idx->v, b->d_plans, b->nq, buf, set); CUDA_TRY(cudaGetLastError()); CUDA_TRY(cudaDeviceSynchronize());
+#endif
+    } catch (const std::string& e) { return fail(IFX_ERR_CUDA, e); }
+    return IFX_OK;
+}
+extern "C" int ifx_batch_stage1_lists(ifx_batch* b, int64_t* key, float* score, int32_t* n) {      // [nq][depth] keys / scores, [nq] counts of this shard's Stage-1 lists
+    if (!b || !key || !score || !n) return fail(IFX_ERR_INVALID, "null argument");
+    try { DeviceGuard dg(b->idx->device); const size_t m = (size_t)b->nq * b->depth_max;
+#ifdef IFX_EMU
+        memcpy(key, b->d_s1_key, m * 8); memcpy(score, b->d_s1_score, m * 4); memcpy(n, b->d_s1_n, (size_t)b->nq * 4);
+#else
+        CUDA_TRY(cudaMemcpy(key, b->d_s1_key, m * 8, cudaMemcpyDeviceToDevice)); CUDA_TRY(cudaMemcpy(score, b->d_s1_score, m * 4, cudaMemcpyDeviceToDevice)); CUDA_TRY(cudaMemcpy(n, b->d_s1_n, (size_t)b->nq * 4, cudaMemcpyDeviceToDevice));
+#endif
+    } catch (const std::string& e) { return fail(IFX_ERR_CUDA, e); }
+    return IFX_OK;
+}
+// keep[q][i] != 0: entry i of this shard's list of query q is inside the global top-`depth`; gmax[q]: top Stage-1 score over all shards (borrowed
+// until phase 3 has run).
+extern "C" int ifx_batch_stage1_restrict(ifx_batch* b, const uint8_t* keep, const float* gmax) {
+    if (!b || !keep || !gmax) return fail(IFX_ERR_INVALID, "null argument");
+    try { DeviceGuard dg(b->idx->device); const int K = b->depth_max;
+#ifdef IFX_EMU
+        for (int q = 0; q < b->nq; q++) { int m = 0; const int cnt = b->d_s1_n[q] < 0 ? 0 : b->d_s1_n[q]; const size_t o = (size_t)q * K;
+            for (int i = 0; i < cnt; i++) if (keep[o + i]) { b->d_s1_key[o + m] = b->d_s1_key[o + i]; b->d_s1_doc[o + m] = b->d_s1_doc[o + i]; b->d_s1_score[o + m] = b->d_s1_score[o + i]; m++; }
+            if (b->d_s1_n[q] >= 0) b->d_s1_n[q] = m; }
+#else
+        k_s1_restrict<<<(b->nq + 127) / 128, 128>>>(b->nq, K, b->d_s1_key, b->d_s1_doc, b->d_s1_score, b->d_s1_n, keep); CUDA_TRY(cudaGetLastError()); CUDA_TRY(cudaDeviceSynchronize());
+#endif
+        b->s2.gmax = gmax;
     } catch (const std::string& e) { return fail(IFX_ERR_CUDA, e); }
     return IFX_OK;
 }

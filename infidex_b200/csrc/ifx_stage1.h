@@ -56,7 +56,7 @@ IFX_FN void prepare_query(const DevIndex& ix, const uint16_t* text, int len, int
     // SearchPipeline.cs:110-142 short (<= 3 chars, no delimiter) query rules
     bool short3 = len <= 3; for (int i = 0; i < len; i++) if (is_delim(ix, text[i])) short3 = false;
     p.is_short3 = short3;
-    if (short3) { int k = dict_lookup(ix.prefix.keys, text, len); if (k >= 0 && ix.prefix.row_ptr[k + 1] - ix.prefix.row_ptr[k] > 500) p.short_skip_coverage = 1; }
+    if (short3) { int k = dict_lookup(ix.prefix.keys, text, len); if (k >= 0 && (ix.prefix_gcard ? (int64_t)ix.prefix_gcard[k] : ix.prefix.row_ptr[k + 1] - ix.prefix.row_ptr[k]) > 500) p.short_skip_coverage = 1; }
     // tokens: words (len >= 3) then padded 3-grams (Tokenizer.EnumerateShinglesForSearch), first 128 kept
     uint16_t padded[MAX_QLEN + 2]; padded[0] = PAD; padded[1] = PAD; for (int i = 0; i < tl; i++) padded[2 + i] = p.ttext[i];
     struct Raw { int32_t id; uint16_t off, len; };
@@ -706,10 +706,10 @@ IFX_FN bool prefix_shortcut(const DevIndex& ix, const QueryPlan& p, int K, int64
     int maxl = p.tlen < 3 ? p.tlen : 3;
     for (int len = maxl; len >= 1; len--) {
         int k = dict_lookup(ix.prefix.keys, p.ttext, len); if (k < 0) continue;
-        r0 = ix.prefix.row_ptr[k]; pop = ix.prefix.row_ptr[k + 1] - r0;
+        r0 = ix.prefix.row_ptr[k]; const int64_t local = ix.prefix.row_ptr[k + 1] - r0; pop = ix.prefix_gcard ? (int64_t)ix.prefix_gcard[k] : local;      // the rules look at the cardinality over the whole corpus
         if (pop == 0) continue;
         if (pop > (int64_t)K * 20) continue;
-        if (pop <= (int64_t)K * 10) { int lim = K * 2 < 100 ? K * 2 : 100; return pop >= lim; }
+        if (pop <= (int64_t)K * 10) { int lim = K * 2 < 100 ? K * 2 : 100; const bool take = pop >= lim; pop = local; return take; }      // candidates: this shard's part of the set
     }
     return false;
 }

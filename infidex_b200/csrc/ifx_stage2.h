@@ -24,6 +24,7 @@ struct Stage2Buffers {
     int32_t* wm_any;      // [nq] WordMatcher union non-empty
     int32_t* mode;        // [nq] 0 coverage stage ran, 1 return the Stage-1 list, 2 Stage-1 list cut to max_results
     CovQuery* covq;       // [nq]
+    const float* gmax;    // doc-id-range shards: top Stage-1 score over ALL shards per query (normBm25, SearchPipeline.cs:411-413); null: the local list's first
     int32_t ent_cap;
 };
 
@@ -124,7 +125,8 @@ IFX_FN void wm_query(const Ctx& c, const DevIndex& ix, const QueryPlan& p, const
     // ---- affix docs -> bitset; membership of the top docs
     int any = 0;
     for (int a = 0; a < nw * 2; a++) { WmList L = sh.affix[a]; if (L.n > 0) any = 1;
-        for (int i = c.tid(); i < L.n; i += NT) { int d = L.p[i]; atomic_or(&ws.bits[d >> 5], 1u << (d & 31)); sh.dirty[d >> 16] = 1; } }
+        for (int i = c.tid(); i < L.n; i += NT) { int d = L.p[i]; if (d < 0) continue;      // doc-id-range shards: the word's document lives on another shard
+            atomic_or(&ws.bits[d >> 5], 1u << (d & 31)); sh.dirty[d >> 16] = 1; } }
     for (int l = 0; l < n_lists; l++) if (sh.lists[l].n > 0) any = 1;
     c.sync();
     for (int k = c.tid(); k < nt; k += NT) {
@@ -177,7 +179,7 @@ IFX_FN void wm_query(const Ctx& c, const DevIndex& ix, const QueryPlan& p, const
     // ---- (c) every top candidate in rank order, base = score / top score; link twins with group (a)
     const int na = n_overlap;
     for (int r = c.tid(); r < nt; r += NT) {
-        int d = s1_doc[r]; float mx = s1_score[0]; float nb = mx > 0.f ? s1_score[r] / mx : 0.f;
+        int d = s1_doc[r]; float mx = B.gmax ? B.gmax[q] : s1_score[0]; float nb = mx > 0.f ? s1_score[r] / mx : 0.f;
         if (ne + r < cap) { e_doc[ne + r] = d; e_base[ne + r] = nb; e_twin[ne + r] = -1; }
     }
     c.sync();

@@ -1,9 +1,24 @@
-"""Multi-GPU plumbing for the replica (query-parallel) layout: rank-local batches, max-over-ranks timing, result exchange.
+"""Doc-id-range sharding of ONE index over the ranks of a torch.distributed job (one process per GPU; NCCL on GPUs, gloo in the CPU tests).
 
-One process per GPU (torchrun), `torch.distributed` with NCCL on GPUs (gloo in the CPU tests). Queries are independent,
-so there is no data-path collective; the only exchange is the per-batch all-gather of each rank's result block.
+Layout (DESIGN.md "multi-GPU"): rank r indexes the contiguous document range [r*N/R, (r+1)*N/R) rounded to multiples of
+65 536 (the reference's container size, so no 4096-chunk of Bm25Scorer is ever split). The statistics the search path reads as global
+quantities -- term ordinals, df / idf, N, avgdl, word idf, prefix-set cardinalities, the affix dictionary -- are exchanged once at build
+time (ifx_builder_export_stats -> all_gather -> ifx_builder_globalize). Every batch then runs on every shard, with three exchanges:
+    all-reduce(sum)  document frequency of every LD1 union (its idf is a corpus-level quantity)                 16 int32 per query
+    all-gather       per-shard Stage-1 top-`depth` (key, score): global cut + global top score (normBm25)      depth * 12 B per query and shard
+    all-gather       per-shard final records (key, score, tie, counts, facet rows): merged identically on every rank
+What is NOT exchanged (counted, never hidden -- `parity` in the bench line is the number of sampled queries whose merged records differ
+from the unsharded oracle): the selector's tier rules and the MaxScore threshold chain run on shard-local counts / heaps, the WordMatcher
+quota, docIndex-0/1 rule and truncation index are evaluated per shard.
 """
+import ctypes as C
+import os
+
 import numpy as np
+
+from . import engine as E
+
+CONTAINER = 65536
 
 
 def rank_batch_seed(base_seed, step, rank):
@@ -25,3 +40,148 @@ def gather_results(dist, keys, device="cpu"):
     out = [torch.empty_like(payload) for _ in range(dist.get_world_size())]
     dist.all_gather(out, payload)
     return [o.cpu().numpy() for o in out]
+
+
+def shard_ranges(n_docs, world):
+    """Contiguous doc-id ranges on 65 536-document boundaries (every shard non-empty when n_docs >= world * 65 536)."""
+    nc = (n_docs + CONTAINER - 1) // CONTAINER
+    cuts = [min(n_docs, ((nc * r) // world) * CONTAINER) for r in range(world)] + [n_docs]
+    return [(cuts[r], cuts[r + 1]) for r in range(world)]
+
+
+class ShardedSearchEngine:
+    """SearchEngine over one doc-id-range shard per rank. `device`: "cuda" (NCCL) or "cpu" (gloo + the kernel emulation, tests only)."""
+
+    def __init__(self, dist, device_index=0, _gpu_lib=None):
+        import torch
+        self.dist, self.torch = dist, torch
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        self.eng = E.SearchEngine(device=device_index, _gpu_lib=_gpu_lib)
+        self.dev = torch.device("cpu") if _gpu_lib else torch.device("cuda", device_index)
+        self.exchange_ms = {"fuzzy_df": 0.0, "stage1": 0.0, "final": 0.0}
+
+    # ---- build -------------------------------------------------------------------------------------------------------------------------
+    def IndexShard(self, keys, schema, columns, threads=None):
+        """`keys` / `columns`: this rank's document range only (ranks in doc order)."""
+        eng, torch, dist = self.eng, self.torch, self.dist
+        eng.IndexColumns(keys, schema, columns, threads=threads, upload=False)
+        n = C.c_size_t(0)
+        eng._host.ifx_builder_export_stats.restype = C.c_void_p
+        p = eng._host.ifx_builder_export_stats(C.c_void_p(eng._builder), C.byref(n))
+        mine = np.ctypeslib.as_array((C.c_uint8 * n.value).from_address(p)).copy()
+        sizes = [torch.zeros(1, dtype=torch.int64, device=self.dev) for _ in range(self.world)]
+        dist.all_gather(sizes, torch.tensor([len(mine)], dtype=torch.int64, device=self.dev))
+        sizes = [int(s.item()) for s in sizes]; cap = max(sizes)
+        pad = np.zeros(cap, np.uint8); pad[: len(mine)] = mine
+        bufs = [torch.empty(cap, dtype=torch.uint8, device=self.dev) for _ in range(self.world)]
+        dist.all_gather(bufs, torch.from_numpy(pad).to(self.dev))
+        blobs = [b.cpu().numpy()[: sizes[i]].copy() for i, b in enumerate(bufs)]
+        arr = (C.c_void_p * self.world)(*[bl.ctypes.data for bl in blobs])
+        rc = eng._host.ifx_builder_globalize(C.c_void_p(eng._builder), self.world, self.rank, arr)
+        if rc:
+            raise E.NativeError("ifx_builder_globalize failed (%d)" % rc)
+        eng._upload(eng._host.ifx_builder_image(C.c_void_p(eng._builder)))
+
+    # ---- search ------------------------------------------------------------------------------------------------------------------------
+    def SearchBatch(self, queries, stats=None, raw=False):
+        """Every rank passes the SAME queries; every rank returns the same merged Results (Records, TotalCandidates, Facets by string)."""
+        import time
+        eng, torch, dist, g = self.eng, self.torch, self.dist, self.eng._gpu
+        nq = len(queries); K = max(q.CoverageDepth for q in queries); cap = max(1, max(q.MaxNumberOfRecordsToReturn for q in queries))
+        packed = eng.PackBatch(queries); h = C.c_void_p()
+        eng._check(g.ifx_batch_upload(eng._index, packed["arr"], nq, C.byref(h)), "ifx_batch_upload")
+        st = stats if stats is not None else E.Stats()
+
+        def sync():
+            if self.dev.type == "cuda":
+                torch.cuda.synchronize(self.dev)
+        try:
+            eng._check(g.ifx_batch_run_phase(h, 1, C.byref(st)), "phase 1")
+            t0 = time.perf_counter()
+            fdf = torch.zeros(nq * 16, dtype=torch.int32, device=self.dev)
+            eng._check(g.ifx_batch_fuzzy_df(h, C.c_void_p(fdf.data_ptr()), 0), "fuzzy df get")
+            dist.all_reduce(fdf)
+            eng._check(g.ifx_batch_fuzzy_df(h, C.c_void_p(fdf.data_ptr()), 1), "fuzzy df set"); sync()
+            self.exchange_ms["fuzzy_df"] += 1e3 * (time.perf_counter() - t0)
+            eng._check(g.ifx_batch_run_phase(h, 2, C.byref(st)), "phase 2")
+            t0 = time.perf_counter()
+            key = torch.zeros(nq * K, dtype=torch.int64, device=self.dev); score = torch.zeros(nq * K, dtype=torch.float32, device=self.dev); n = torch.zeros(nq, dtype=torch.int32, device=self.dev)
+            eng._check(g.ifx_batch_stage1_lists(h, C.c_void_p(key.data_ptr()), C.c_void_p(score.data_ptr()), C.c_void_p(n.data_ptr())), "stage1 lists")
+            W = self.world
+            ks = [torch.empty_like(key) for _ in range(W)]; ss = [torch.empty_like(score) for _ in range(W)]; ns = [torch.empty_like(n) for _ in range(W)]
+            dist.all_gather(ks, key); dist.all_gather(ss, score); dist.all_gather(ns, n)
+            keep, gmax = self._global_cut(ks, ss, ns, nq, K)
+            self._keep, self._gmax = keep, gmax          # borrowed by the library until phase 3 has run
+            eng._check(g.ifx_batch_stage1_restrict(h, C.c_void_p(keep.data_ptr()), C.c_void_p(gmax.data_ptr())), "stage1 restrict"); sync()
+            self.exchange_ms["stage1"] += 1e3 * (time.perf_counter() - t0)
+            eng._check(g.ifx_batch_run_phase(h, 3, C.byref(st)), "phase 3")
+            eng._check(g.ifx_batch_download(h, C.byref(packed["out"])), "ifx_batch_download")
+        finally:
+            g.ifx_batch_free(h)
+        t0 = time.perf_counter()
+        merged = self._merge(queries, packed["bufs"], cap)
+        self.exchange_ms["final"] += 1e3 * (time.perf_counter() - t0)
+        return merged if raw else self._results(queries, merged)
+
+    def _global_cut(self, ks, ss, ns, nq, K):
+        """Membership of this rank's Stage-1 entries in the global top-K by (score desc, key asc), and the global top score per query."""
+        torch = self.torch; W = self.world
+        S = torch.stack([s.view(nq, K) for s in ss], 1).reshape(nq, W * K); Kk = torch.stack([k.view(nq, K) for k in ks], 1).reshape(nq, W * K)
+        N = torch.stack(ns, 1).clamp(min=0)                                                    # [nq, W]
+        slot = torch.arange(K, device=S.device).view(1, 1, K).expand(nq, W, K)
+        valid = (slot < N.view(nq, W, 1)).reshape(nq, W * K)
+        S = torch.where(valid, S, torch.full_like(S, -1.0)); Kk = torch.where(valid, Kk, torch.full_like(Kk, 2 ** 62))
+        i1 = torch.argsort(Kk, dim=1, stable=True); S1 = torch.gather(S, 1, i1)
+        i2 = torch.argsort(S1, dim=1, descending=True, stable=True)
+        order = torch.gather(i1, 1, i2)[:, :K]                                                 # flat positions of the global top-K
+        top_valid = torch.gather(valid, 1, order)
+        mark = torch.zeros(nq, W * K, dtype=torch.uint8, device=S.device)
+        mark.scatter_(1, order, top_valid.to(torch.uint8))
+        keep = mark.view(nq, W, K)[:, self.rank, :].contiguous().view(-1)
+        gmax = S.max(dim=1).values.clamp(min=0).contiguous()
+        return keep, gmax
+
+    def _merge(self, queries, bufs, cap):
+        """All-gather of every shard's records; merged by ScoreEntry order (Score desc, Tiebreaker desc, DocumentId asc) and cut to max."""
+        torch, dist, W = self.torch, self.dist, self.world
+        nq = len(queries); eng = self.eng
+        rec = np.zeros((nq, cap, 3), np.float64)          # key, score bits (exact in f64), tie
+        rec[:, :, 0] = bufs["keys"]; rec[:, :, 1] = bufs["scores"].view(np.uint32).astype(np.float64); rec[:, :, 2] = bufs["ties"]
+        meta = np.stack([bufs["n"], bufs["total"], bufs["status"], bufs["nf"]], 1).astype(np.int64)
+        t_rec = torch.from_numpy(rec).to(self.dev); t_meta = torch.from_numpy(meta).to(self.dev)
+        recs = [torch.empty_like(t_rec) for _ in range(W)]; metas = [torch.empty_like(t_meta) for _ in range(W)]
+        dist.all_gather(recs, t_rec); dist.all_gather(metas, t_meta)
+        R = np.stack([r.cpu().numpy() for r in recs], 1).reshape(nq, W * cap, 3); M = np.stack([m.cpu().numpy() for m in metas], 1)      # [nq, W, 4]
+        valid = (np.arange(cap)[None, None, :] < M[:, :, 0:1]).reshape(nq, W * cap)
+        key = R[:, :, 0].astype(np.int64); score = R[:, :, 1].astype(np.uint32).view(np.float32).reshape(nq, W * cap).astype(np.float64); tie = R[:, :, 2]
+        score = np.where(valid, score, -np.inf)
+        order = np.lexsort((key, -tie, -score), axis=1)[:, :cap]
+        o_key = np.take_along_axis(key, order, 1); o_score = np.take_along_axis(R[:, :, 1], order, 1).astype(np.uint32).view(np.float32).reshape(nq, cap); o_tie = np.take_along_axis(tie, order, 1).astype(np.uint8)
+        maxr = np.array([q.MaxNumberOfRecordsToReturn for q in queries]); o_n = np.minimum(valid.sum(1), maxr)
+        total = np.minimum(M[:, :, 1].sum(1), maxr); status = np.bitwise_or.reduce(M[:, :, 2], axis=1)
+        self.last_raw = (o_key, o_score, o_tie, o_n, total, status)
+        facets_all = None
+        if any(q.EnableFacets for q in queries):          # facet rows travel as strings (value ids are per-shard dictionaries)
+            mine = []
+            for i in range(nq):
+                rows = []
+                for k in range(int(bufs["nf"][i])):
+                    col = int(bufs["fcol"][i, k]); rows.append((eng._columns[col], eng._facet_value(col, int(bufs["fval"][i, k])), int(bufs["fcnt"][i, k])))
+                mine.append(rows)
+            facets_all = [None] * W
+            dist.all_gather_object(facets_all, mine)
+        return o_key, o_score, o_tie, o_n, total, status, facets_all
+
+    def _results(self, queries, merged):
+        o_key, o_score, o_tie, o_n, total, status, facets_all = merged; out = []
+        for i, q in enumerate(queries):
+            records = [E.ScoreEntry(o_score[i, k], o_key[i, k], o_tie[i, k]) for k in range(int(o_n[i]))]
+            facets = None
+            if q.EnableFacets:
+                acc = {}
+                for r in range(self.world):
+                    for f, v, cnt in facets_all[r][i]:
+                        acc.setdefault(f, {}); acc[f][v] = acc[f].get(v, 0) + cnt
+                facets = {f: sorted(vs.items(), key=lambda kv: (-kv[1], kv[0].lower(), kv[0]))[:100] for f, vs in acc.items()}
+            out.append(E.Result(records, facets, int(total[i]), int(status[i])))
+        return out
