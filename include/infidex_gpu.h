@@ -162,14 +162,19 @@ void ifx_batch_free(ifx_batch* b);
 
 /* doc-id-range shards: one index handle per shard (ifx_index_image.n_shards > 1), the batch run split where the shards' hosts
  * exchange data. phase 1: query preparation + LD1 expansion; then all-reduce(sum) of ifx_batch_fuzzy_df (document frequency of every LD1
- * union: its idf is a corpus-level quantity). phase 2: selection, tf lookups, scoring; then all-gather of ifx_batch_stage1_lists and
+ * union: its idf is a corpus-level quantity). phase 2: count pass of the candidate selection; all-reduce(sum) of ifx_batch_select_counts (the tier
+ * rules compare corpus-level cardinalities). phase 3: selection, tf lookups, scoring; then all-gather of ifx_batch_stage1_lists and
  * ifx_batch_stage1_restrict (global top-`depth` cut, global top score for normBm25). phase 3: WordMatcher, coverage / fusion, truncation,
  * filter, facets; ifx_batch_download gives the shard's records, which every host merges after an all-gather.
  * buf / key / score / n / keep / gmax are DEVICE pointers. */
 int  ifx_batch_run_phase(ifx_batch* b, int phase, ifx_stats* st);
 int  ifx_batch_fuzzy_df(ifx_batch* b, int32_t* buf /* [nq * 16] */, int set);
+int  ifx_batch_select_counts(ifx_batch* b, int32_t* buf /* [nq * 40] */, int set);
 int  ifx_batch_stage1_lists(ifx_batch* b, int64_t* key, float* score, int32_t* n);
-int  ifx_batch_stage1_restrict(ifx_batch* b, const uint8_t* keep /* [nq * depth] */, const float* gmax /* [nq] */);
+int  ifx_batch_stage1_restrict(ifx_batch* b, const uint8_t* keep /* [nq * depth]: 0 drop, 1 keep, 2 / 3 keep = global rank 0 / 1 */, const float* gmax /* [nq] */, const int32_t* n_global /* [nq] entries of the global list */);
+int  ifx_batch_wm_counts(ifx_batch* b, int32_t* buf /* [nq * 4] */);                 /* after phase 4 (WordMatcher lookups) */
+int  ifx_batch_wm_apply(ifx_batch* b, const int32_t* allowed /* [nq] */, const int32_t* any /* [nq] */);   /* then phase 5: coverage, fusion, finalize */
+int  ifx_batch_shard_info(ifx_batch* b, int32_t* info /* [nq * 8], HOST */, int64_t* dkey /* [nq * 2], HOST */);
 
 /* Stage-1 only (Bm25Scorer.Search + ConsolidateSegments, src/Infidex/Indexing/Bm25Scorer.cs:56-193): row-major
  * [nq][depth] keys / scores, n[nq]. Used for intermediate parity checks and kernel-level measurement. */

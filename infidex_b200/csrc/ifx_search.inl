@@ -120,32 +120,37 @@ __global__ void __launch_bounds__(256) k_finalize(DevIndex ix, const QueryPlan* 
 }
 #endif
 
-static void run_stage2_phase(ifx_batch* b, ifx_stats* st) {
+static void run_stage2_phase(ifx_batch* b, ifx_stats* st, int part = 3) {      // part: 1 = WordMatcher lookups, 2 = coverage / fusion / finalize, 3 = both
     ifx_index* ix = b->idx; const int nq = b->nq; const int K = b->depth_max;
     Timer t;
 #ifdef IFX_EMU
     static WmShared* wsh = new WmShared(); static FinShared* fsh = new FinShared(); memset(wsh->dirty, 0, sizeof(wsh->dirty));
     Ctx c;
-    for (int q = 0; q < nq; q++) wm_query(c, ix->v, b->d_plans[q], b->d_s1_doc + (size_t)q * K, b->d_s1_score + (size_t)q * K, b->d_s1_n[q], ix->ws[0], *wsh, b->s2, q);
-    for (int q = 0; q < nq; q++) if (b->s2.mode[q] == 0) { prepare_cov_query(ix->v, b->d_plans[q].qtext, b->d_plans[q].qlen, b->s2.covq[q]); for (int e = 0; e < b->s2.ent_n[q]; e++) cov_eval_entry(ix->v, b->d_plans[q], b->s2, q, e); }
-    for (int q = 0; q < nq; q++) finalize_query(c, ix->v, b->d_plans[q], b->d_s1_doc + (size_t)q * K, b->d_s1_score + (size_t)q * K, b->d_s1_n[q], b->s2, ix->d_filters, (int)ix->h_filters.size(), *fsh, b->fin, q);
+    if (part & 1) for (int q = 0; q < nq; q++) wm_query(c, ix->v, b->d_plans[q], b->d_s1_doc + (size_t)q * K, b->d_s1_score + (size_t)q * K, b->d_s1_n[q], ix->ws[0], *wsh, b->s2, q);
+    if (part & 2) for (int q = 0; q < nq; q++) if (b->s2.mode[q] == 0) { prepare_cov_query(ix->v, b->d_plans[q].qtext, b->d_plans[q].qlen, b->s2.covq[q]); for (int e = 0; e < b->s2.ent_n[q]; e++) cov_eval_entry(ix->v, b->d_plans[q], b->s2, q, e); }
+    if (part & 2) for (int q = 0; q < nq; q++) finalize_query(c, ix->v, b->d_plans[q], b->d_s1_doc + (size_t)q * K, b->d_s1_score + (size_t)q * K, b->d_s1_n[q], b->s2, ix->d_filters, (int)ix->h_filters.size(), *fsh, b->fin, q);
     (void)t; (void)st;
 #else
     if (!ix->attr_s2) { CUDA_TRY(cudaFuncSetAttribute(k_wm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WmShared))); CUDA_TRY(cudaFuncSetAttribute(k_finalize, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FinShared))); ix->attr_s2 = true; }
+    float ms_wm = 0.f, ms_cov = 0.f, ms_fin = 0.f; int launches = 0;
+    if (part & 1) {
     t.start();
     CUDA_TRY(cudaMemsetAsync(b->d_work + 2, 0, sizeof(int)));
     k_wm<<<std::min(ix->n_ctas, nq), 256, sizeof(WmShared)>>>(ix->v, b->d_plans, nq, b->d_s1_doc, b->d_s1_score, b->d_s1_n, K, ix->d_ws, b->s2, b->d_work + 2);
-    float ms_wm = t.stop();
+    ms_wm = t.stop(); launches++;
+    }
+    if (part & 2) {
     t.start();
     k_cov_prepare<<<(nq + 63) / 64, 64>>>(ix->v, b->d_plans, nq, b->s2);
     long long total = (long long)nq * b->s2.ent_cap;
     k_cov_eval<<<(unsigned)((total + IFX_COV_THREADS - 1) / IFX_COV_THREADS), IFX_COV_THREADS>>>(ix->v, b->d_plans, nq, b->s2);
-    float ms_cov = t.stop();
+    ms_cov = t.stop();
     t.start();
     k_finalize<<<nq, 256, sizeof(FinShared)>>>(ix->v, b->d_plans, nq, b->d_s1_doc, b->d_s1_score, b->d_s1_n, K, b->s2, ix->d_filters, (int)ix->h_filters.size(), b->fin);
-    float ms_fin = t.stop();
+    ms_fin = t.stop(); launches += 3;
+    }
     CUDA_TRY(cudaGetLastError());
-    if (st) { st->ms_wordmatch += ms_wm; st->ms_stage2 += ms_cov; st->ms_final += ms_fin; st->kernel_launches += 4; }
+    if (st) { st->ms_wordmatch += ms_wm; st->ms_stage2 += ms_cov; st->ms_final += ms_fin; st->kernel_launches += launches; }
 #endif
 }
 
@@ -154,9 +159,10 @@ static int alloc_stage2(ifx_batch* b, int cap, int fcap) {
     Stage2Buffers& S = b->s2; S.ent_cap = (int)ec;
     S.ent_doc = b->alloc<int32_t>(nq * ec); S.ent_base = b->alloc<float>(nq * ec); S.ent_twin = b->alloc<int32_t>(nq * ec); S.ent_n = b->alloc<int32_t>(nq);
     S.ent_score = b->alloc<float>(nq * ec); S.ent_tie = b->alloc<uint8_t>(nq * ec); S.ent_hits = b->alloc<int32_t>(nq * ec); S.ent_lcs = b->alloc<uint8_t>(nq * ec);
-    S.di_doc = b->alloc<int32_t>(nq * 2); S.wm_any = b->alloc<int32_t>(nq); S.mode = b->alloc<int32_t>(nq); S.covq = b->alloc<CovQuery>(nq);
+    S.di_doc = b->alloc<int32_t>(nq * 2); S.wm_cnt = b->alloc<int32_t>(nq * 4); b->d_g_di = b->alloc<int32_t>(nq * 2); S.g_di = nullptr; S.wm_any = b->alloc<int32_t>(nq); S.mode = b->alloc<int32_t>(nq); S.covq = b->alloc<CovQuery>(nq);
     FinalOut& O = b->fin; O.cap = cap; O.fcap = fcap; size_t fc = std::max(fcap, 1);
     O.key = b->alloc<int64_t>(nq * cap); O.score = b->alloc<float>(nq * cap); O.tie = b->alloc<uint8_t>(nq * cap); O.n = b->alloc<int32_t>(nq); O.total = b->alloc<int32_t>(nq); O.status = b->alloc<int32_t>(nq);
+    b->d_shard_info = b->alloc<int32_t>(nq * 8); b->d_shard_dkey = b->alloc<int64_t>(nq * 2); O.shard_info = nullptr; O.shard_dkey = nullptr;
     O.facet_col = b->alloc<int32_t>(nq * fc); O.facet_val = b->alloc<int32_t>(nq * fc); O.facet_cnt = b->alloc<int32_t>(nq * fc); O.n_facets = b->alloc<int32_t>(nq);
     return IFX_OK;
 }
@@ -192,22 +198,34 @@ __global__ void k_fuzzy_df(DevIndex ix, QueryPlan* plans, int nq, int32_t* buf, 
     if (!set) { buf[i] = t.df; return; }
     const float avgdl = ix.avgdl > 0.f ? ix.avgdl : 1.f; t.df = buf[i]; t.idf = compute_idf(ix, t.df); t.max_score = max_term_score(t.idf, avgdl);
 }
-__global__ void k_s1_restrict(int nq, int K, int64_t* key, int32_t* doc, float* score, int32_t* n, const uint8_t* keep) {
+__global__ void k_s1_restrict(int nq, int K, int64_t* key, int32_t* doc, float* score, int32_t* n, const uint8_t* keep, const int32_t* n_global, int32_t* g_di) {
     int q = blockIdx.x * blockDim.x + threadIdx.x; if (q >= nq) return;
-    int m = 0; const int cnt = n[q] < 0 ? 0 : n[q];
-    for (int i = 0; i < cnt; i++) if (keep[(size_t)q * K + i]) { const size_t o = (size_t)q * K; key[o + m] = key[o + i]; doc[o + m] = doc[o + i]; score[o + m] = score[o + i]; m++; }
+    int m = 0; const int cnt = n[q] < 0 ? 0 : n[q]; int d0 = n_global[q] >= 2 ? -1 : -2, d1 = d0;
+    for (int i = 0; i < cnt; i++) { const uint8_t k = keep[(size_t)q * K + i]; if (!k) continue; const size_t o = (size_t)q * K;
+        if (k == 2 && d0 != -2) d0 = doc[o + i]; if (k == 3 && d1 != -2) d1 = doc[o + i];
+        key[o + m] = key[o + i]; doc[o + m] = doc[o + i]; score[o + m] = score[o + i]; m++; }
     if (n[q] >= 0) n[q] = m;
+    g_di[q * 2] = d0; g_di[q * 2 + 1] = d1;
+}
+__global__ void k_wm_apply(int nq, int cap, Stage2Buffers B, const int32_t* allowed, const int32_t* any) {
+    int q = blockIdx.x * blockDim.x + threadIdx.x; if (q >= nq) return;
+    if (B.mode[q] != 0) return;
+    const int first = B.wm_cnt[q * 4 + 3], taken = B.wm_cnt[q * 4 + 1]; const int a = allowed[q] < taken ? (allowed[q] > 0 ? allowed[q] : 0) : taken;
+    for (int i = first + a; i < first + taken && i < cap; i++) B.ent_twin[(size_t)q * cap + i] = -3;      // beyond this shard's part of the global WordMatcher quota
+    B.wm_any[q] = any[q];
 }
 #endif
 extern "C" int ifx_batch_run_phase(ifx_batch* b, int phase, ifx_stats* st) {
-    if (!b || phase < 1 || phase > 3) return fail(IFX_ERR_INVALID, "bad phase");
+    if (!b || phase < 1 || phase > 5) return fail(IFX_ERR_INVALID, "bad phase");
     if (!dev_ok()) return fail(IFX_ERR_NO_DEVICE, "no CUDA device available (infidex_b200 has no CPU fallback)");
     try {
         std::lock_guard<std::mutex> lk(b->idx->mu); DeviceGuard dg(b->idx->device);
         if (!b->s2.ent_doc) alloc_stage2(b, std::max(b->cap_max, 1), b->fcap);
-        if (phase == 1) { if (st) { int64_t h = st->h2d_bytes, d = st->d2h_bytes; memset(st, 0, sizeof(*st)); st->h2d_bytes = h; st->d2h_bytes = d; } b->s2.gmax = nullptr; run_stage1_phase(b, st, 1); }
-        else if (phase == 2) run_stage1_phase(b, st, 2);
-        else { run_stage2_phase(b, st); b->ran = true; }
+        if (phase == 1) { if (st) { int64_t h = st->h2d_bytes, d = st->d2h_bytes; memset(st, 0, sizeof(*st)); st->h2d_bytes = h; st->d2h_bytes = d; } b->s2.gmax = nullptr; b->s2.g_di = nullptr; b->fin.shard_info = nullptr; b->fin.shard_dkey = nullptr; b->use_gcnt = false; run_stage1_phase(b, st, 1); }
+        else if (phase == 2) run_stage1_phase(b, st, 4);
+        else if (phase == 3) run_stage1_phase(b, st, 2);
+        else if (phase == 4) run_stage2_phase(b, st, 1);
+        else { b->fin.shard_info = b->d_shard_info; b->fin.shard_dkey = b->d_shard_dkey; run_stage2_phase(b, st, 2); b->ran = true; }
     } catch (const std::string& e) { return fail(IFX_ERR_CUDA, e); }
     return IFX_OK;
 }
@@ -237,18 +255,65 @@ extern "C" int ifx_batch_stage1_lists(ifx_batch* b, int64_t* key, float* score, 
 }
 // keep[q][i] != 0: entry i of this shard's list of query q is inside the global top-`depth`; gmax[q]: top Stage-1 score over all shards (borrowed
 // until phase 3 has run).
-extern "C" int ifx_batch_stage1_restrict(ifx_batch* b, const uint8_t* keep, const float* gmax) {
-    if (!b || !keep || !gmax) return fail(IFX_ERR_INVALID, "null argument");
+extern "C" int ifx_batch_stage1_restrict(ifx_batch* b, const uint8_t* keep, const float* gmax, const int32_t* n_global) {
+    if (!b || !keep || !gmax || !n_global) return fail(IFX_ERR_INVALID, "null argument");
     try { DeviceGuard dg(b->idx->device); const int K = b->depth_max;
 #ifdef IFX_EMU
-        for (int q = 0; q < b->nq; q++) { int m = 0; const int cnt = b->d_s1_n[q] < 0 ? 0 : b->d_s1_n[q]; const size_t o = (size_t)q * K;
-            for (int i = 0; i < cnt; i++) if (keep[o + i]) { b->d_s1_key[o + m] = b->d_s1_key[o + i]; b->d_s1_doc[o + m] = b->d_s1_doc[o + i]; b->d_s1_score[o + m] = b->d_s1_score[o + i]; m++; }
-            if (b->d_s1_n[q] >= 0) b->d_s1_n[q] = m; }
+        for (int q = 0; q < b->nq; q++) { int m = 0; const int cnt = b->d_s1_n[q] < 0 ? 0 : b->d_s1_n[q]; const size_t o = (size_t)q * K; int d0 = n_global[q] >= 2 ? -1 : -2, d1 = d0;
+            for (int i = 0; i < cnt; i++) { const uint8_t k = keep[o + i]; if (!k) continue; if (k == 2 && d0 != -2) d0 = b->d_s1_doc[o + i]; if (k == 3 && d1 != -2) d1 = b->d_s1_doc[o + i];
+                b->d_s1_key[o + m] = b->d_s1_key[o + i]; b->d_s1_doc[o + m] = b->d_s1_doc[o + i]; b->d_s1_score[o + m] = b->d_s1_score[o + i]; m++; }
+            if (b->d_s1_n[q] >= 0) b->d_s1_n[q] = m; b->d_g_di[q * 2] = d0; b->d_g_di[q * 2 + 1] = d1; }
 #else
-        k_s1_restrict<<<(b->nq + 127) / 128, 128>>>(b->nq, K, b->d_s1_key, b->d_s1_doc, b->d_s1_score, b->d_s1_n, keep); CUDA_TRY(cudaGetLastError()); CUDA_TRY(cudaDeviceSynchronize());
+        k_s1_restrict<<<(b->nq + 127) / 128, 128>>>(b->nq, K, b->d_s1_key, b->d_s1_doc, b->d_s1_score, b->d_s1_n, keep, n_global, b->d_g_di); CUDA_TRY(cudaGetLastError()); CUDA_TRY(cudaDeviceSynchronize());
 #endif
-        b->s2.gmax = gmax;
+        b->s2.gmax = gmax; b->s2.g_di = b->d_g_di;
     } catch (const std::string& e) { return fail(IFX_ERR_CUDA, e); }
+    return IFX_OK;
+}
+
+// the selector's cardinalities (SEL_CNT int32 per query): get after phase 2, set the sums over all shards before phase 3
+extern "C" int ifx_batch_select_counts(ifx_batch* b, int32_t* buf, int set) {
+    if (!b || !buf) return fail(IFX_ERR_INVALID, "null argument");
+    try { DeviceGuard dg(b->idx->device); const size_t n = (size_t)b->nq * SEL_CNT * 4;
+#ifdef IFX_EMU
+        if (set) memcpy(b->d_sel_cnt, buf, n); else memcpy(buf, b->d_sel_cnt, n);
+#else
+        if (set) CUDA_TRY(cudaMemcpy(b->d_sel_cnt, buf, n, cudaMemcpyDeviceToDevice)); else CUDA_TRY(cudaMemcpy(buf, b->d_sel_cnt, n, cudaMemcpyDeviceToDevice));
+#endif
+        if (set) b->use_gcnt = true;
+    } catch (const std::string& e) { return fail(IFX_ERR_CUDA, e); }
+    return IFX_OK;
+}
+// WordMatcher quota across shards: counts out after phase 4 (k_wm) -- [nq][4]: overlap, WordMatcher-only entries taken, union non-empty, -- ;
+// `allowed`[q] = how many of this shard's WordMatcher-only entries fall inside the global quota, `any`[q] = union non-empty on any shard.
+extern "C" int ifx_batch_wm_counts(ifx_batch* b, int32_t* buf) {
+    if (!b || !buf) return fail(IFX_ERR_INVALID, "null argument");
+    try { DeviceGuard dg(b->idx->device);
+#ifdef IFX_EMU
+        memcpy(buf, b->s2.wm_cnt, (size_t)b->nq * 16);
+#else
+        CUDA_TRY(cudaMemcpy(buf, b->s2.wm_cnt, (size_t)b->nq * 16, cudaMemcpyDeviceToDevice));
+#endif
+    } catch (const std::string& e) { return fail(IFX_ERR_CUDA, e); }
+    return IFX_OK;
+}
+extern "C" int ifx_batch_wm_apply(ifx_batch* b, const int32_t* allowed, const int32_t* any) {
+    if (!b || !allowed || !any) return fail(IFX_ERR_INVALID, "null argument");
+    try { DeviceGuard dg(b->idx->device);
+#ifdef IFX_EMU
+        for (int q = 0; q < b->nq; q++) { if (b->s2.mode[q] != 0) continue; const int first = b->s2.wm_cnt[q * 4 + 3], taken = b->s2.wm_cnt[q * 4 + 1]; const int a = allowed[q] < taken ? (allowed[q] > 0 ? allowed[q] : 0) : taken;
+            for (int i = first + a; i < first + taken && i < b->s2.ent_cap; i++) b->s2.ent_twin[(size_t)q * b->s2.ent_cap + i] = -3; b->s2.wm_any[q] = any[q]; }
+#else
+        k_wm_apply<<<(b->nq + 127) / 128, 128>>>(b->nq, b->s2.ent_cap, b->s2, allowed, any); CUDA_TRY(cudaGetLastError()); CUDA_TRY(cudaDeviceSynchronize());
+#endif
+    } catch (const std::string& e) { return fail(IFX_ERR_CUDA, e); }
+    return IFX_OK;
+}
+// per query [max word hits, records with Score >= 254, word hits / lcs of the docIndex-0 and docIndex-1 documents when this shard owns them (-1 else)]
+// and their keys: what the hosts need to evaluate ResultProcessor.CalculateTruncationIndex over the merged list (valid after phase 4)
+extern "C" int ifx_batch_shard_info(ifx_batch* b, int32_t* info /* [nq][8] */, int64_t* dkey /* [nq][2] */) {
+    if (!b || !info || !dkey) return fail(IFX_ERR_INVALID, "null argument");
+    try { DeviceGuard dg(b->idx->device); d2h(info, b->d_shard_info, (size_t)b->nq * 32); d2h(dkey, b->d_shard_dkey, (size_t)b->nq * 16); } catch (const std::string& e) { return fail(IFX_ERR_CUDA, e); }
     return IFX_OK;
 }
 

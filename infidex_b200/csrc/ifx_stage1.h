@@ -718,7 +718,11 @@ IFX_FN bool prefix_shortcut(const DevIndex& ix, const QueryPlan& p, int K, int64
 // Candidate selection of one query (TieredCandidateSelector.SelectCandidates). Leaves the candidate set as bits in ws.bits (dirty
 // containers flagged in sh.dirty), the scored terms in sh.terms / sh.n_terms; `path`: 0 nothing to score, 1 prefix shortcut, 2 disjunctive,
 // 3 AND tiers, -1 workspace overflow.
-IFX_FN int stage1_select(const Ctx& c, const DevIndex& ix, const QueryPlan& p, const int32_t* pool, S1Workspace& ws, S1Shared& sh, Stage1Out out) {
+// Doc-id-range shards (`smode`): the tier rules compare CORPUS-level cardinalities, so a shard first runs the selection in count mode
+// (smode 1: local cardinality at every decision point into cnt[], following every branch that some shard might need), the hosts sum the
+// counts over the shards, and the real pass (smode 2) takes its decisions from the global values in cnt[]. smode 0: unsharded.
+constexpr int SEL_CNT = 40;          // cnt[0..3]: AND path (tier 0, + tier 1, + first / second high-idf list); cnt[8 + i]: disjunctive path after list i (i < 32)
+IFX_FN int stage1_select(const Ctx& c, const DevIndex& ix, const QueryPlan& p, const int32_t* pool, S1Workspace& ws, S1Shared& sh, Stage1Out out, int smode = 0, int32_t* cnt = nullptr) {
     const int K = p.depth; const int NT = c.nthreads();
     if (c.tid() == 0) {
         int n = 0;
@@ -767,15 +771,19 @@ IFX_FN int stage1_select(const Ctx& c, const DevIndex& ix, const QueryPlan& p, c
         int64_t g = 0;
         IFX_STICK(0);   // prefix shortcut + idf sort
         if (disjunctive) {   // SelectCandidatesDisjunctive
-            bool selective = false;
+            bool selective = false; int li = 0; int64_t df_max = 0;
             for (int oi = 0; oi < T; oi++) {
                 const TermS& t = sh.terms[sh.order[oi]];
                 bool lowq = t.idf < (max_idf * 0.2f);
                 if (T > 1 && lowq && selective) continue;
                 g += or_list_into_bits(c, t.docs, t.len, ws, sh);
                 if (c.tid() == 0) sh.streamed_mask[sh.order[oi] >> 6] |= 1ULL << (sh.order[oi] & 63);
-                if (!lowq && g > 0) selective = true;
-                if (g >= (int64_t)K * 100) break;
+                int64_t gg = g;                                                   // the union's size over the whole corpus decides
+                if (smode == 1 && li < 32) { if (c.tid() == 0) cnt[8 + li] = (int32_t)g; if (t.df > df_max) df_max = t.df; gg = df_max; }      // count pass: go on until the union certainly holds 100 K documents (it contains its largest list)
+                else if (smode == 2 && li < 32) gg = cnt[8 + li];
+                li++;
+                if (!lowq && gg > 0) selective = true;
+                if (gg >= (int64_t)K * 100) break;
             }
         } else {
             if (c.tid() == 0) for (int i = 0; i < T; i++) sh.streamed_mask[i >> 6] |= 1ULL << (i & 63);   // every list of the AND tier
@@ -783,13 +791,18 @@ IFX_FN int stage1_select(const Ctx& c, const DevIndex& ix, const QueryPlan& p, c
             if (n0 < 0) { if (c.tid() == 0) out.n[0] = -1; return -1; }
             g += or_list_into_bits(c, r0, n0, ws, sh);
             IFX_STICK(1);   // AND tier 0
-            if (g < (int64_t)K * 2) {
-                if (T >= 3 && g < (int64_t)K * 3) { const int32_t* r1 = nullptr; int64_t n1 = intersect_terms(c, ix, ws, sh, T - 1, r1); if (n1 > 0) g += or_list_into_bits(c, r1, n1, ws, sh); }
+            // count pass: a shard that alone reaches a limit knows the corpus does; below it every later stage is counted (some shard may need it)
+            int64_t G = smode == 2 ? (int64_t)cnt[0] : g; if (smode == 1 && c.tid() == 0) { cnt[0] = (int32_t)g; cnt[1] = cnt[2] = cnt[3] = (int32_t)g; }
+            if (G < (int64_t)K * 2) {
+                if (T >= 3 && G < (int64_t)K * 3) { const int32_t* r1 = nullptr; int64_t n1 = intersect_terms(c, ix, ws, sh, T - 1, r1); if (n1 > 0) g += or_list_into_bits(c, r1, n1, ws, sh); }
                 IFX_STICK(2);   // AND tier 1
-                if (g < (int64_t)K * 5) {
+                G = smode == 2 ? (int64_t)cnt[1] : g; if (smode == 1 && c.tid() == 0) { cnt[1] = (int32_t)g; cnt[2] = cnt[3] = (int32_t)g; }
+                if (G < (int64_t)K * 5) {
                     int sel[2]; int ns = 0; float cutoff = max_idf * 0.3f; int capn = T < 2 ? T : 2;
                     for (int oi = 0; oi < T && ns < capn; oi++) { const TermS& t = sh.terms[sh.order[oi]]; if (t.idf <= 0.f) continue; if (t.idf < cutoff) continue; sel[ns++] = sh.order[oi]; }
-                    for (int si = 0; si < ns; si++) { const TermS& t = sh.terms[sel[si]]; g += or_list_into_bits(c, t.docs, t.len, ws, sh); if (g >= (int64_t)K * 10) break; }
+                    for (int si = 0; si < ns; si++) { const TermS& t = sh.terms[sel[si]]; g += or_list_into_bits(c, t.docs, t.len, ws, sh);
+                        G = smode == 2 ? (int64_t)cnt[2 + si] : g; if (smode == 1 && c.tid() == 0) { cnt[2 + si] = (int32_t)g; if (si == 0) cnt[3] = (int32_t)g; }
+                        if (G >= (int64_t)K * 10) break; }
                 }
             }
         }
@@ -802,6 +815,16 @@ IFX_FN int stage1_select(const Ctx& c, const DevIndex& ix, const QueryPlan& p, c
 #endif
     }
     return path;
+}
+
+// Candidate bitset back to all-zero (dirty containers only).
+IFX_FN void stage1_clear_bits(const Ctx& c, const DevIndex& ix, S1Workspace& ws, S1Shared& sh) {
+    const int NT = c.nthreads(); const int64_t nwords = ((int64_t)ix.n_docs + 31) >> 5; const int ncont = (ix.n_docs + 65535) >> 16;
+    c.sync();
+    for (int64_t w = c.tid(); w < nwords; w += NT) if (sh.dirty[w >> 11]) ws.bits[w] = 0u;
+    c.sync();
+    for (int k = c.tid(); k < ncont; k += NT) sh.dirty[k] = 0;
+    c.sync();
 }
 
 }  // namespace ifx

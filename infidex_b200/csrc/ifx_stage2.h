@@ -24,11 +24,14 @@ struct Stage2Buffers {
     int32_t* wm_any;      // [nq] WordMatcher union non-empty
     int32_t* mode;        // [nq] 0 coverage stage ran, 1 return the Stage-1 list, 2 Stage-1 list cut to max_results
     CovQuery* covq;       // [nq]
+    int32_t* wm_cnt;      // [nq][4] per shard: top docs that are also WordMatcher docs, WordMatcher-only entries taken, union non-empty, index of the first such entry
+    const int32_t* g_di;  // doc-id-range shards: [nq][2] local id of the document at global Stage-1 rank 0 / 1 (-1: another shard's, -2: fewer than two ranks exist)
     const float* gmax;    // doc-id-range shards: top Stage-1 score over ALL shards per query (normBm25, SearchPipeline.cs:411-413); null: the local list's first
     int32_t ent_cap;
 };
 
-struct FinalOut { int64_t* key; float* score; uint8_t* tie; int32_t* n; int32_t* total; int32_t* status; int32_t* facet_col; int32_t* facet_val; int32_t* facet_cnt; int32_t* n_facets; int32_t cap, fcap; };
+struct FinalOut { int64_t* key; float* score; uint8_t* tie; int32_t* n; int32_t* total; int32_t* status; int32_t* facet_col; int32_t* facet_val; int32_t* facet_cnt; int32_t* n_facets; int32_t cap, fcap;
+                  int32_t* shard_info; int64_t* shard_dkey; };     // doc-id-range shards (non-null): no local truncation, [nq][8] / [nq][2] facts for the hosts' merge
 
 struct WmList { const int32_t* p; int32_t n; };
 
@@ -176,6 +179,7 @@ IFX_FN void wm_query(const Ctx& c, const DevIndex& ix, const QueryPlan& p, const
         }
         c.sync();
     }
+    if (c.tid() == 0 && B.wm_cnt) { B.wm_cnt[q * 4 + 0] = n_overlap; B.wm_cnt[q * 4 + 1] = ne - n_overlap; B.wm_cnt[q * 4 + 2] = any; B.wm_cnt[q * 4 + 3] = n_overlap; }
     // ---- (c) every top candidate in rank order, base = score / top score; link twins with group (a)
     const int na = n_overlap;
     for (int r = c.tid(); r < nt; r += NT) {
@@ -193,9 +197,12 @@ IFX_FN void wm_query(const Ctx& c, const DevIndex& ix, const QueryPlan& p, const
         B.ent_n[q] = ne < cap ? ne : cap; B.wm_any[q] = any;
         // BuildDocumentKeyIndex: keys of the top list in rank order, then live WordMatcher docs ascending
         int d0 = -1, d1 = -1;
-        if (nt >= 1) d0 = s1_doc[0];
-        if (nt >= 2) d1 = s1_doc[1];
-        for (int i = 0; i < 2; i++) { int f = sh.first_live[i]; if (f < 0) continue; if (d0 < 0) d0 = f; else if (d1 < 0 && f != d0) d1 = f; }
+        if (B.g_di && B.g_di[q * 2] != -2) { d0 = B.g_di[q * 2]; d1 = B.g_di[q * 2 + 1]; }      // shards: docIndex 0 / 1 are the documents at GLOBAL rank 0 / 1 (possibly on another shard)
+        else {
+            if (nt >= 1) d0 = s1_doc[0];
+            if (nt >= 2) d1 = s1_doc[1];
+            for (int i = 0; i < 2; i++) { int f = sh.first_live[i]; if (f < 0) continue; if (d0 < 0) d0 = f; else if (d1 < 0 && f != d0) d1 = f; }
+        }
         B.di_doc[q * 2] = d0; B.di_doc[q * 2 + 1] = d1;
     }
     c.sync();
@@ -206,7 +213,7 @@ IFX_FN void wm_query(const Ctx& c, const DevIndex& ix, const QueryPlan& p, const
 IFX_FN void cov_eval_entry(const DevIndex& ix, const QueryPlan& p, const Stage2Buffers& B, int q, int e) {
     const size_t o = (size_t)q * B.ent_cap + e;
     const int doc = B.ent_doc[o];
-    if (ix.deleted[doc]) { B.ent_hits[o] = -1; B.ent_score[o] = -1.f; B.ent_tie[o] = 0; B.ent_lcs[o] = 0; return; }   // ProcessCandidate returns early
+    if (ix.deleted[doc] || B.ent_twin[o] == -3) { B.ent_hits[o] = -1; B.ent_score[o] = -1.f; B.ent_tie[o] = 0; B.ent_lcs[o] = 0; return; }   // ProcessCandidate returns early
     const CovQuery& cq = B.covq[q];
     int lcs = 0;
     if (doc == B.di_doc[q * 2] || doc == B.di_doc[q * 2 + 1]) {
@@ -386,9 +393,16 @@ IFX_FN void finalize_query(const Ctx& c, const DevIndex& ix, const QueryPlan& p,
             if (wh >= min_hits || lb > 0 || sh.keep_score[i] >= 254.f) atomic_max(&sh.bcast[4], i);
         }
         c.sync();
+        if (O.shard_info) {      // shards: the truncation index is a property of the MERGED list -- report the facts, cut only to max_results
+            int ge = 0; for (int i = c.tid(); i < nk; i += NT) if (sh.keep_score[i] >= 254.f) ge++;
+            ge = block_sum(c, ge, sh.scan);
+            if (c.tid() == 0) { int32_t* inf = O.shard_info + (size_t)q * 8; inf[0] = max_hits; inf[1] = ge; inf[2] = d0 >= 0 ? wh0 : -1; inf[3] = d0 >= 0 ? l0 : -1; inf[4] = d1 >= 0 ? wh1 : -1; inf[5] = d1 >= 0 ? l1 : -1; inf[6] = nk; inf[7] = B.wm_any[q];
+                O.shard_dkey[q * 2] = d0 >= 0 ? ix.doc_key[d0] : -1; O.shard_dkey[q * 2 + 1] = d1 >= 0 ? ix.doc_key[d1] : -1; }
+        }
         if (c.tid() == 0) {
             int result = nk;
-            if (max_hits == 0 && !B.wm_any[q]) result = -1;                 // SearchPipeline.cs:418-419 -> coverage returned []
+            if (O.shard_info) { if (result > p.max_results) result = p.max_results; }
+            else if (max_hits == 0 && !B.wm_any[q]) result = -1;                 // SearchPipeline.cs:418-419 -> coverage returned []
             else if (nk > 0) {
                 const int trunc = sh.bcast[4];
                 int count = trunc == -1 ? p.max_results : (trunc + 1 < p.max_results ? trunc + 1 : p.max_results);

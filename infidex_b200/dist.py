@@ -105,17 +105,40 @@ class ShardedSearchEngine:
             self.exchange_ms["fuzzy_df"] += 1e3 * (time.perf_counter() - t0)
             eng._check(g.ifx_batch_run_phase(h, 2, C.byref(st)), "phase 2")
             t0 = time.perf_counter()
+            sc = torch.zeros(nq * 40, dtype=torch.int32, device=self.dev)
+            eng._check(g.ifx_batch_select_counts(h, C.c_void_p(sc.data_ptr()), 0), "select counts get")
+            dist.all_reduce(sc)
+            eng._check(g.ifx_batch_select_counts(h, C.c_void_p(sc.data_ptr()), 1), "select counts set"); sync()
+            self.exchange_ms["select_counts"] = self.exchange_ms.get("select_counts", 0.0) + 1e3 * (time.perf_counter() - t0)
+            eng._check(g.ifx_batch_run_phase(h, 3, C.byref(st)), "phase 3")
+            t0 = time.perf_counter()
             key = torch.zeros(nq * K, dtype=torch.int64, device=self.dev); score = torch.zeros(nq * K, dtype=torch.float32, device=self.dev); n = torch.zeros(nq, dtype=torch.int32, device=self.dev)
             eng._check(g.ifx_batch_stage1_lists(h, C.c_void_p(key.data_ptr()), C.c_void_p(score.data_ptr()), C.c_void_p(n.data_ptr())), "stage1 lists")
             W = self.world
             ks = [torch.empty_like(key) for _ in range(W)]; ss = [torch.empty_like(score) for _ in range(W)]; ns = [torch.empty_like(n) for _ in range(W)]
             dist.all_gather(ks, key); dist.all_gather(ss, score); dist.all_gather(ns, n)
-            keep, gmax = self._global_cut(ks, ss, ns, nq, K)
-            self._keep, self._gmax = keep, gmax          # borrowed by the library until phase 3 has run
-            eng._check(g.ifx_batch_stage1_restrict(h, C.c_void_p(keep.data_ptr()), C.c_void_p(gmax.data_ptr())), "stage1 restrict"); sync()
+            keep, gmax, nglob = self._global_cut(ks, ss, ns, nq, K)
+            self._keep, self._gmax = keep, gmax          # borrowed by the library until the last phase has run
+            eng._check(g.ifx_batch_stage1_restrict(h, C.c_void_p(keep.data_ptr()), C.c_void_p(gmax.data_ptr()), C.c_void_p(nglob.data_ptr())), "stage1 restrict"); sync()
             self.exchange_ms["stage1"] += 1e3 * (time.perf_counter() - t0)
-            eng._check(g.ifx_batch_run_phase(h, 3, C.byref(st)), "phase 3")
+            eng._check(g.ifx_batch_run_phase(h, 4, C.byref(st)), "phase 4")
+            t0 = time.perf_counter()
+            wc = torch.zeros(nq * 4, dtype=torch.int32, device=self.dev)
+            eng._check(g.ifx_batch_wm_counts(h, C.c_void_p(wc.data_ptr())), "wm counts")
+            wcs = [torch.empty_like(wc) for _ in range(W)]; dist.all_gather(wcs, wc)
+            WC = torch.stack([x.view(nq, 4) for x in wcs], 1)                                # [nq, W, 4]
+            depth = torch.tensor([q.CoverageDepth for q in queries], dtype=torch.int32, device=self.dev)
+            limit = (depth - WC[:, :, 0].sum(1)).clamp(min=0)                                 # wmLimit = coverageDepth - overlap over all shards
+            before = torch.cumsum(WC[:, :, 1], 1) - WC[:, :, 1]                               # WordMatcher-only documents of the lower shards come first (ascending ids)
+            allowed = (limit.view(nq, 1) - before).clamp(min=0)[:, self.rank].to(torch.int32).contiguous()
+            anyg = (WC[:, :, 2].sum(1) > 0).to(torch.int32).contiguous()
+            eng._check(g.ifx_batch_wm_apply(h, C.c_void_p(allowed.data_ptr()), C.c_void_p(anyg.data_ptr())), "wm apply"); sync()
+            self.exchange_ms["wm"] = self.exchange_ms.get("wm", 0.0) + 1e3 * (time.perf_counter() - t0)
+            eng._check(g.ifx_batch_run_phase(h, 5, C.byref(st)), "phase 5")
             eng._check(g.ifx_batch_download(h, C.byref(packed["out"])), "ifx_batch_download")
+            info = np.zeros((nq, 8), np.int32); dkey = np.zeros((nq, 2), np.int64)
+            eng._check(g.ifx_batch_shard_info(h, E._p(info), E._p(dkey)), "shard info")
+            packed["bufs"]["info"], packed["bufs"]["dkey"] = info, dkey
         finally:
             g.ifx_batch_free(h)
         t0 = time.perf_counter()
@@ -136,10 +159,14 @@ class ShardedSearchEngine:
         order = torch.gather(i1, 1, i2)[:, :K]                                                 # flat positions of the global top-K
         top_valid = torch.gather(valid, 1, order)
         mark = torch.zeros(nq, W * K, dtype=torch.uint8, device=S.device)
-        mark.scatter_(1, order, top_valid.to(torch.uint8))
+        flag = top_valid.to(torch.uint8); flag[:, 0] *= 2                                     # 2: global rank 0, 3: global rank 1 (docIndex 0 / 1)
+        if K > 1:
+            flag[:, 1] *= 3
+        mark.scatter_(1, order, flag)
         keep = mark.view(nq, W, K)[:, self.rank, :].contiguous().view(-1)
         gmax = S.max(dim=1).values.clamp(min=0).contiguous()
-        return keep, gmax
+        nglob = valid.sum(1).clamp(max=K).to(torch.int32).contiguous()
+        return keep, gmax, nglob
 
     def _merge(self, queries, bufs, cap):
         """All-gather of every shard's records; merged by ScoreEntry order (Score desc, Tiebreaker desc, DocumentId asc) and cut to max."""
@@ -147,7 +174,7 @@ class ShardedSearchEngine:
         nq = len(queries); eng = self.eng
         rec = np.zeros((nq, cap, 3), np.float64)          # key, score bits (exact in f64), tie
         rec[:, :, 0] = bufs["keys"]; rec[:, :, 1] = bufs["scores"].view(np.uint32).astype(np.float64); rec[:, :, 2] = bufs["ties"]
-        meta = np.stack([bufs["n"], bufs["total"], bufs["status"], bufs["nf"]], 1).astype(np.int64)
+        meta = np.concatenate([np.stack([bufs["n"], bufs["total"], bufs["status"], bufs["nf"]], 1).astype(np.int64), bufs["info"].astype(np.int64), bufs["dkey"]], 1)      # [nq, 4 + 8 + 2]
         t_rec = torch.from_numpy(rec).to(self.dev); t_meta = torch.from_numpy(meta).to(self.dev)
         recs = [torch.empty_like(t_rec) for _ in range(W)]; metas = [torch.empty_like(t_meta) for _ in range(W)]
         dist.all_gather(recs, t_rec); dist.all_gather(metas, t_meta)
@@ -157,8 +184,20 @@ class ShardedSearchEngine:
         score = np.where(valid, score, -np.inf)
         order = np.lexsort((key, -tie, -score), axis=1)[:, :cap]
         o_key = np.take_along_axis(key, order, 1); o_score = np.take_along_axis(R[:, :, 1], order, 1).astype(np.uint32).view(np.float32).reshape(nq, cap); o_tie = np.take_along_axis(tie, order, 1).astype(np.uint8)
-        maxr = np.array([q.MaxNumberOfRecordsToReturn for q in queries]); o_n = np.minimum(valid.sum(1), maxr)
-        total = np.minimum(M[:, :, 1].sum(1), maxr); status = np.bitwise_or.reduce(M[:, :, 2], axis=1)
+        maxr = np.array([q.MaxNumberOfRecordsToReturn for q in queries])
+        # ResultProcessor.CalculateTruncationIndex over the merged list: the last record with Score >= 254 (records are sorted: the first n_ge),
+        # or a docIndex-0/1 document whose word hits reach max(1, max word hits over all shards) or whose lcs is non-zero
+        info = M[:, :, 4:12]; dk = M[:, :, 12:14]
+        min_hits = np.maximum(info[:, :, 0].max(1), 1); trunc = info[:, :, 1].sum(1) - 1
+        for j in range(2):
+            wh = info[:, :, 2 + 2 * j].max(1); lc = info[:, :, 3 + 2 * j].max(1); dkj = dk[:, :, j].max(1)      # the owner reports >= 0, the others -1
+            qual = (wh >= 0) & ((wh >= min_hits) | (lc > 0))
+            hit = (o_key == dkj[:, None]) & (np.arange(cap)[None, :] < np.minimum(valid.sum(1), cap)[:, None])
+            pos = np.where(hit.any(1), hit.argmax(1), cap)                                    # beyond the merged top: at least `cap`
+            trunc = np.where(qual, np.maximum(trunc, pos), trunc)
+        count = np.where(trunc < 0, maxr, np.minimum(trunc + 1, maxr))
+        o_n = np.minimum(np.minimum(valid.sum(1), count), maxr)
+        total = o_n.copy(); status = np.bitwise_or.reduce(M[:, :, 2], axis=1)
         self.last_raw = (o_key, o_score, o_tie, o_n, total, status)
         facets_all = None
         if any(q.EnableFacets for q in queries):          # facet rows travel as strings (value ids are per-shard dictionaries)
