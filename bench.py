@@ -33,6 +33,7 @@ WORKLOADS = {
     "c3": dict(n_docs=10_000_000, nq=10_000, multi=True, vocab=400_000, filter=False, label="configs[2]: 10M multi-field docs (title High / description Low), 10k-query batch, top-10, coverage depth 500"),
     # BASELINE.json configs[3]: + Filter.Parse("year >= 2000 AND rating > 7.0") + EnableFacets
     "c4": dict(n_docs=10_000_000, nq=10_000, multi=True, vocab=400_000, filter=True, label="configs[3]: 10M multi-field docs + Filter.Parse('year >= 2000 AND rating > 7.0') + EnableFacets, 10k-query batch, top-10"),
+    "small": dict(n_docs=700_000, nq=2000, multi=True, vocab=200_000, filter=False, label="development workload (700k multi-field docs, 2k queries; not a benchmark)"),
     "tiny": dict(n_docs=50_000, nq=200, multi=True, vocab=50_000, filter=False, label="smoke workload (not a benchmark)"),
 }
 C4_FILTER = "year >= 2000 AND rating > 7.0"
@@ -150,15 +151,113 @@ def parity_and_cpu_baseline(eng, schema, wl, qs, gpu_bufs, flt, args):
     return cpu, {"checked": sample, "mismatches": len(bad), "what": "DocumentId order, float32 Score bits, Tiebreaker bytes vs the oracle"}, bad
 
 
+def run_sharded(args, wl, rank, world, local):
+    """N > 1: ONE index, doc-id-range sharded over the N ranks (infidex_b200/dist.py); every batch runs on every shard with NCCL exchanges
+    (all-reduce of LD1 union df and of the selector's cardinalities, all-gather of the Stage-1 lists, of the WordMatcher counts and of the
+    final records). Strong scaling: the same corpus and the same 10k-query batches as N = 1. Rank 0 also answers a sample of the first
+    timed batch with the UNSHARDED oracle; differing queries are counted in `parity` (the MaxScore threshold chain / heap runs per shard:
+    documents tied at the Stage-1 cut can differ -- the waiver SURVEY 8e allows, counted here)."""
+    import torch
+    import torch.distributed as dist
+    import infidex_b200 as ib
+    from infidex_b200 import dist as ifxd
+    from infidex_b200 import synth
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    t_setup = time.time()
+    vocab = synth.make_vocab(wl["vocab"]); lo, hi = ifxd.shard_ranges(wl["n_docs"], world)[rank]
+    docs = synth.gen_docs(hi - lo, vocab, with_description=wl["multi"], start=lo, threads=max(1, effective_cpus() // world))
+    schema, cols = synth.schema_and_columns(docs, wl["multi"])
+    eng = ifxd.ShardedSearchEngine(dist, device_index=local)
+    t0 = time.time(); eng.IndexShard(docs["keys"], schema, cols, threads=max(1, effective_cpus() // world)); t_index = time.time() - t0
+    flt = ib.Filter.Parse(C4_FILTER) if wl["filter"] else None
+    n_total = args.warmup + args.steps; corpus = synth.corpus_ref(wl["n_docs"])
+    batches, texts = [], []
+    for s in range(n_total):          # the SAME batch on every rank
+        qs = batch_queries(wl, corpus, vocab, s, 0); qq = []
+        for t in qs:
+            x = ib.Query(t, 10); x.Filter = flt; x.EnableFacets = bool(flt); qq.append(x)
+        batches.append(qq); texts.append(qs)
+    t_setup = time.time() - t_setup
+    stop = threading.Event(); clk = []
+    th = threading.Thread(target=clocks_sampler, args=(stop, clk, local), daemon=True)
+
+    def timed(fn):
+        dist.barrier(); torch.cuda.synchronize(); t0 = time.perf_counter(); r = fn(); torch.cuda.synchronize(); dist.barrier(); return r, time.perf_counter() - t0
+    # ---- value: batches uploaded beforehand ----------------------------------------------------------------------------------------------
+    ups = [eng.UploadBatch(b) for b in batches]
+    agg = {k: 0.0 for k in ("ms_prepare", "ms_expand", "ms_stage1", "ms_s1_select", "ms_s1_score_warp", "ms_s1_score_cta", "ms_s1_finish", "ms_wordmatch", "ms_stage2", "ms_final")}
+    algo = 0; launches = 0; dev_t = 0.0; first = None
+    for s in range(n_total):
+        if s == args.warmup:
+            th.start(); eng.exchange_ms = {k: 0.0 for k in eng.exchange_ms}
+        eng.eng.FlushL2(); st = ib.Stats()
+        merged, dt = timed(lambda: eng.SearchBatch(None, stats=st, raw=True, uploaded=ups[s]))
+        if s >= args.warmup:
+            dev_t += dt; algo += st.algo_bytes_stage1; launches += st.kernel_launches
+            for k in agg:
+                agg[k] += getattr(st, k)
+            if first is None:
+                first = merged
+    exch = dict(eng.exchange_ms)
+    for u in ups:
+        eng.FreeBatch(u)
+    # ---- e2e: marshalling + upload inside the region ----------------------------------------------------------------------------------------
+    e2e_t = 0.0
+    for s in range(n_total):
+        eng.eng.FlushL2()
+        _, dt = timed(lambda: eng.SearchBatch(batches[s], raw=True))
+        if s >= args.warmup:
+            e2e_t += dt
+    stop.set()
+    tt = torch.tensor([dev_t, e2e_t, float(algo)] + [agg[k] for k in agg], dtype=torch.float64, device="cuda")
+    mx = tt.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX); sm = tt.clone(); dist.all_reduce(sm)
+    if rank != 0:
+        dist.barrier(); dist.destroy_process_group(); return 0
+    dev_t, e2e_t = float(mx[0]), float(mx[1]); algo_all = float(sm[2]); aggm = {k: float(mx[3 + i]) for i, k in enumerate(agg)}
+    value = wl["nq"] * args.steps / dev_t; e2e = wl["nq"] * args.steps / e2e_t
+    peak, peak_src = measured_peak(); s1_ms = aggm["ms_stage1"] / args.steps
+    achieved = (algo_all / args.steps / 1e9) / (s1_ms / 1e3) if s1_ms > 0 else 0.0
+    clocks = None
+    if clk:
+        smc = sorted(c[0] for c in clk); reasons = set()
+        for c in clk:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[2:]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        clocks = {"sm_mhz": smc[len(smc) // 2], "sm_max_mhz": max(c[1] for c in clk), "reasons": sorted(reasons), "samples": len(clk)}
+    h2d = sum(2 * len(t) for t in texts[0]) + wl["nq"] * 28 + 8
+    line = {"metric": "queries/sec", "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dev_t / args.steps,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": wl["label"], "batch": wl["nq"], "filter": bool(flt), "parallelism": "one index, doc-id-range sharded x%d (65 536-doc boundaries), every batch on every shard" % world,
+                       "l2": "256 MiB L2 flush before every timed step", "index_build_s": round(t_index, 1), "setup_s": round(t_setup, 1)},
+            "phases_ms_per_step": {k: round(v / args.steps, 3) for k, v in aggm.items()},
+            "exchanges_ms_per_step": {k: round(v / args.steps, 3) for k, v in exch.items()},
+            "roofline": {"bound": "hbm", "kernel": "Stage 1 (k_select_lookup + k_score_cta + k_score_warp + k_s1_finish), all shards", "achieved": achieved, "peak": peak * world, "unit": "GB/s", "frac": achieved / (peak * world),
+                         "traffic": None, "algo_bytes_per_launch": algo_all / args.steps, "ms_per_launch": s1_ms, "peak_source": peak_src + " x n_gpus"},
+            "e2e": {"value": e2e, "unit": "queries/s", "h2d_bytes_per_step": int(h2d) * world, "d2h_bytes_per_step": int(wl["nq"] * (10 * 13 + 12 + 48)) * world},
+            "gpu_launches": int(launches), "clocks": clocks}
+    if not args.no_cpu_baseline:
+        # the unsharded oracle over the whole corpus (rank 0 builds the full host image for it)
+        full = synth.gen_docs(wl["n_docs"], vocab, with_description=wl["multi"]); fs, fc = synth.schema_and_columns(full, wl["multi"])
+        he = ib.SearchEngine.__new__(ib.SearchEngine); he._host = ib.engine._load_host(); he._builder = None; he._index = None; he._gpu = None
+        he.IndexColumns(full["keys"], fs, fc, upload=False)
+        o_key, o_score, o_tie, o_n, total, status, _ = first
+        bufs = {"keys": o_key, "scores": o_score, "ties": o_tie, "n": o_n, "status": status}
+        cpu, parity, bad = parity_and_cpu_baseline(he, fs, wl, texts[args.warmup], bufs, flt, args)
+        parity["what"] += "; UNSHARDED oracle; differences are counted, not fatal, for N > 1 (per-shard MaxScore heaps: ties at the Stage-1 cut)"
+        line["cpu_baseline"] = cpu; line["parity"] = parity
+    print(json.dumps(line), flush=True)
+    dist.barrier(); dist.destroy_process_group()
+    return 0
+
+
 def run_ours(args, wl, rank, world, local):
     import infidex_b200 as ib
     from infidex_b200 import dist as ifxd
     dist = None
     if world > 1:
-        import torch
-        import torch.distributed as dist
-        torch.cuda.set_device(local)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        return run_sharded(args, wl, rank, world, local)
     t_setup = time.time()
     vocab, docs, schema, cols = make_corpus(wl); t_gen = time.time() - t_setup
     eng = ib.SearchEngine.CreateDefault(device=local)
