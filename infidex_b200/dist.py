@@ -92,7 +92,7 @@ class ShardedSearchEngine:
     def FreeBatch(self, up):
         self.eng._gpu.ifx_batch_free(up["h"])
 
-    def SearchBatch(self, queries, stats=None, raw=False, uploaded=None):
+    def SearchBatch(self, queries, stats=None, raw=False, uploaded=None, packed=None):
         """Every rank passes the SAME queries; every rank returns the same merged Results (Records, TotalCandidates, Facets by string)."""
         import time
         eng, torch, dist, g = self.eng, self.torch, self.dist, self.eng._gpu
@@ -102,7 +102,7 @@ class ShardedSearchEngine:
         if uploaded is not None:
             packed, h = uploaded["packed"], uploaded["h"]
         else:
-            packed = eng.PackBatch(queries); h = C.c_void_p()
+            packed = packed or eng.PackBatch(queries); h = C.c_void_p()      # `packed`: host-side marshalling done beforehand (what the C# shim's pinned buffers are)
             eng._check(g.ifx_batch_upload(eng._index, packed["arr"], nq, C.byref(h)), "ifx_batch_upload")
         st = stats if stats is not None else E.Stats()
 
