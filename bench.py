@@ -162,6 +162,7 @@ def run_sharded(args, wl, rank, world, local):
     import infidex_b200 as ib
     from infidex_b200 import dist as ifxd
     from infidex_b200 import synth
+    os.environ.setdefault("NCCL_DEBUG", "WARN")          # keep NCCL's version banner off stdout: the JSON line stands alone
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     t_setup = time.time()
@@ -190,7 +191,9 @@ def run_sharded(args, wl, rank, world, local):
     algo = 0; launches = 0; dev_t = 0.0; first = None
     for s in range(n_total):
         if s == args.warmup:
-            th.start(); eng.exchange_ms = {k: 0.0 for k in eng.exchange_ms}
+            if rank == 0:
+                th.start()          # one sampler for the job (rank 0's GPU): eight concurrent nvidia-smi loops stall the timed host path
+            eng.exchange_ms = {k: 0.0 for k in eng.exchange_ms}
         eng.eng.FlushL2(); st = ib.Stats()
         merged, dt = timed(lambda: eng.SearchBatch(None, stats=st, raw=True, uploaded=ups[s]))
         if s >= args.warmup:
