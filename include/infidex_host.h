@@ -28,6 +28,8 @@ const ifx_index_image* ifx_builder_image(ifx_builder* b);   /* valid until ifx_b
  * and affix dictionary of the whole corpus (infidex_gpu.h, ifx_index_image). */
 const uint8_t* ifx_builder_export_stats(ifx_builder* b, size_t* len);      /* valid until the next export on this thread */
 int ifx_builder_globalize(ifx_builder* b, int n_shards, int shard, const uint8_t* const* blobs);
+const float* ifx_builder_doc_lengths(ifx_builder* b, int* n);              /* after globalize: second exchange ... */
+int ifx_builder_set_global_lengths(ifx_builder* b, int n_shards, const float* const* lens, const int* counts);   /* ... avgdl over the whole corpus */
 
 /* SearchEngine.Search step 1 (src/Infidex/SearchEngine.cs:264-274): Trim + TextNormalizer.Normalize + ToLowerInvariant. Returns the output length. */
 int ifx_host_prepare_query(const uint16_t* in, int n, uint16_t* out, int cap);

@@ -311,7 +311,7 @@ extern "C" int ifx_index_create(const ifx_index_image* img, const ifx_params* pp
         // 100 K docs, the AND path adds at most two top-idf lists to its tiers) -- never sized by N for large shards
         const int64_t cand_cap = std::min<int64_t>(N, 3LL * std::min<int64_t>(N, P.stop_term_limit) + 100LL * MAX_K + 4096);
         (void)cand_cap;
-        size_t per_cta = (size_t)nwords * 8 + (size_t)(nwords + ncont + 2) * 4 + 6 * (size_t)(ncont + 2) * 4 + 2 * (size_t)max_list * 4 + CHUNK * 8;
+        size_t per_cta = (size_t)nwords * 16 + (size_t)(nwords + ncont + 2) * 4 + 6 * (size_t)(ncont + 2) * 4 + 2 * (size_t)max_list * 4 + CHUNK * 8;
 #ifdef IFX_EMU
         ix->n_ctas = 1;
 #else
@@ -323,7 +323,7 @@ extern "C" int ifx_index_create(const ifx_index_image* img, const ifx_params* pp
 #endif
         const size_t index_bytes = ix->bytes;
         ix->ws.resize(ix->n_ctas);
-        for (auto& w : ix->ws) { w.bits = ix->alloc<unsigned>(nwords); dev_zero(w.bits, (size_t)nwords * 4); w.bits2 = ix->alloc<unsigned>(nwords); dev_zero(w.bits2, (size_t)nwords * 4); w.cand = nullptr; w.cand_cap = 0; w.rank = ix->alloc<int32_t>((size_t)nwords + ncont + 2); w.cstart = ix->alloc<int32_t>((size_t)ncont + 2); w.cfirst = ix->alloc<int32_t>((size_t)ncont + 2); w.ctab = ix->alloc<int32_t>(4 * ((size_t)ncont + 2)); w.buf_a = ix->alloc<int32_t>(max_list); w.buf_b = ix->alloc<int32_t>(max_list); w.buf_cap = max_list; w.surv_g = ix->alloc<unsigned long long>(CHUNK); }
+        for (auto& w : ix->ws) { w.bits = ix->alloc<unsigned>(nwords); dev_zero(w.bits, (size_t)nwords * 4); w.bits2 = ix->alloc<unsigned>(nwords); dev_zero(w.bits2, (size_t)nwords * 4); w.cand = nullptr; w.cand_cap = 0; w.rank = ix->alloc<int32_t>((size_t)nwords + ncont + 2); w.probe = ix->alloc<unsigned long long>((size_t)nwords); dev_zero(w.probe, (size_t)nwords * 8); w.cstart = ix->alloc<int32_t>((size_t)ncont + 2); w.cfirst = ix->alloc<int32_t>((size_t)ncont + 2); w.ctab = ix->alloc<int32_t>(4 * ((size_t)ncont + 2)); w.buf_a = ix->alloc<int32_t>(max_list); w.buf_b = ix->alloc<int32_t>(max_list); w.buf_cap = max_list; w.surv_g = ix->alloc<unsigned long long>(CHUNK); }
         ix->d_ws = ix->up(ix->ws.data(), ix->ws.size());
         ix->pool_cap = (unsigned long long)std::max<int64_t>(1 << 20, std::min<int64_t>((int64_t)N * 64, (int64_t)1 << 31));
         ix->d_pool = ix->alloc<int32_t>(ix->pool_cap);

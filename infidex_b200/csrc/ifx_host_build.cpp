@@ -367,6 +367,17 @@ const uint8_t* ifx_builder_export_stats(ifx_builder* b, size_t* len) {
     *len = out.d.size(); return out.d.data();
 }
 
+// The document lengths of this shard after ifx_builder_globalize (terms that are stop terms only by their corpus-wide df are gone).
+const float* ifx_builder_doc_lengths(ifx_builder* b, int* n) { *n = (int)b->doc_len.size(); return b->doc_len.data(); }
+// lens[s] = ifx_builder_doc_lengths of shard s, all shards in doc order: avgdl as the reference computes it, one sequential float sum over
+// all documents (VectorModel.cs:212-216).
+int ifx_builder_set_global_lengths(ifx_builder* b, int n_shards, const float* const* lens, const int* counts) {
+    float total = 0.f; int64_t N_all = 0;
+    for (int s = 0; s < n_shards; s++) { for (int d = 0; d < counts[s]; d++) total += lens[s][d]; N_all += counts[s]; }
+    b->img.avgdl = N_all > 0 ? total / (float)N_all : 0.f;
+    return IFX_OK;
+}
+
 // blobs[s] = export of shard s (all shards, in doc-range order). Rewrites this builder's image so that it is shard `shard` of the
 // global index. `prefix_card_out`: see ifx_builder_prefix_cardinalities.
 int ifx_builder_globalize(ifx_builder* b, int n_shards, int shard, const uint8_t* const* blobs) {
@@ -398,13 +409,8 @@ int ifx_builder_globalize(ifx_builder* b, int n_shards, int shard, const uint8_t
         std::swap(b->terms.chars, nt.chars); std::swap(b->terms.off, nt.off); std::swap(b->terms.row, nt.row); std::swap(b->terms.docs.p, nt.docs.p); std::swap(b->terms.docs.n, nt.docs.n); std::swap(b->terms.w.p, nt.w.p); std::swap(b->terms.w.n, nt.w.n);
         b->terms.n = TG; b->df.swap(ndf);
     }
-    // ---- avgdl: sequential float sum over all documents in order (VectorModel.cs:212-216). Every shard's exported lengths were computed
-    // before any global stop term was known; a term can only become a stop term by the global sum, in which case every shard drops it
-    // identically, so the lengths are recomputed from each shard's blob only when no such term exists (checked below).
-    bool new_stop = false; for (int s = 0; s < n_shards && !new_stop; s++) for (int t = 0; t < in[s].terms.n; t++) if (in[s].df[t] <= b->stop_term_limit) { int id = g.find(in[s].terms.at(t)); if (gdf[id] > b->stop_term_limit) { new_stop = true; break; } }
-    if (new_stop) return IFX_ERR_UNSUPPORTED;          // would need a second exchange of corrected lengths; not reached below stop_term_limit * n_shards postings per term
-    float total = 0.f; for (int s = 0; s < n_shards; s++) for (int d = 0; d < in[s].N; d++) total += in[s].dl[d];
-    const float avgdl = N_all > 0 ? total / (float)N_all : 0.f;
+    // ---- avgdl: needs every shard's lengths AFTER the global stop terms were dropped: second exchange, ifx_builder_set_global_lengths
+    const float avgdl = 0.f;
     // ---- word idf over the whole corpus
     { Interner gw; std::vector<int64_t> wdf; for (int s = 0; s < n_shards; s++) for (int k = 0; k < in[s].words.n; k++) { bool nw; int id = gw.intern(in[s].words.at(k), &nw); if (nw) wdf.push_back(0); wdf[id] += in[s].wdf[k]; }
       b->word_chars.assign(gw.arena.begin(), gw.arena.end()); if (b->word_chars.empty()) b->word_chars.push_back(0); b->word_off = gw.off; b->word_idf.resize(wdf.size());

@@ -22,6 +22,7 @@ struct S1Rec {
     int32_t K, path, pad;
 };
 struct S1Queues { int32_t* light; int32_t* mid; int32_t* heavy; };
+struct alignas(8) S1Probe { unsigned bits; int32_t rank; };                     // one candidate-bitset word and the candidates before it: a posting's probe is ONE 8-byte load
 struct alignas(16) S1Cont { int32_t cstart, cnt, cpad, cfirst; };                // per container: candidates before it, its candidates, padded tf slots before it, chunks before it                           // query ids appended by stage1_lookup (counters in BatchCounters)
 
 IFX_FN int pad16(int x) { return (x + 15) & ~15; }
@@ -62,7 +63,8 @@ IFX_FN void stage1_lookup(const Ctx& c, const DevIndex& ix, const QueryPlan& p, 
     }
     int n_cand; int ex0 = block_excl_scan(c, mycnt, sh.scan, n_cand); const int wbase = c.shfl(ex0, 0);
     auto clear_bits = [&]() {
-        for (int64_t w = c.tid(); w < nwords; w += NT) if (sh.dirty[w >> 11]) ws.bits[w] = 0u;
+        S1Probe* pr = reinterpret_cast<S1Probe*>(ws.probe);
+        for (int64_t w = c.tid(); w < nwords; w += NT) if (sh.dirty[w >> 11]) { ws.bits[w] = 0u; pr[w].bits = 0u; }
         c.sync();
         for (int k = c.tid(); k < ncont; k += NT) sh.dirty[k] = 0;
         c.sync();
@@ -89,7 +91,7 @@ IFX_FN void stage1_lookup(const Ctx& c, const DevIndex& ix, const QueryPlan& p, 
                 const int64_t w = g0 + c.lane(); unsigned v = vv[u]; const int pc = popc(v); int incl = pc;
                 for (int d = 1; d < WS; d <<= 1) { int o = c.shfl(incl, c.lane() >= d ? c.lane() - d : 0); if (c.lane() >= d) incl += o; }
                 int o = run + incl - pc;
-                if (w < w1) { ws.rank[w] = o; if ((w & 2047) == 0) ws.cstart[w >> 11] = o; }
+                if (w < w1) { S1Probe pv; pv.bits = v; pv.rank = o; reinterpret_cast<S1Probe*>(ws.probe)[w] = pv; if ((w & 2047) == 0) ws.cstart[w >> 11] = o; }
                 while (v) { int b = ffs32(v) - 1; v &= v - 1; cand[o++] = (int32_t)((w << 5) | b); }
                 run += c.shfl(incl, WS - 1);
             }
@@ -145,8 +147,9 @@ IFX_FN void stage1_lookup(const Ctx& c, const DevIndex& ix, const QueryPlan& p, 
     for (int t = 0; t < T; t++) if (sh.order[t] >= 0 && sh.terms[t].term_id >= 0) { cost_s += 5ULL * (unsigned long long)sh.terms[t].len; n_dict++; }
     const bool forward = force_mode == 1 ? true : (force_mode == 2 ? false : (n_dict > 0 && 3ULL * (unsigned long long)n_cand * (unsigned long long)fwd_avg_bytes < cost_s));      // random forward-list reads cost ~3x a streamed byte (measured, profiles/r2)
     const S1Cont* ctab = reinterpret_cast<const S1Cont*>(ws.ctab);
-    auto put_hit = [&](int d, unsigned wv, int a, uint8_t tfv) {      // candidate d (bit set in wv) of row a
-        const unsigned bit = 1u << (d & 31); const int idx = ws.rank[d >> 5] + popc(wv & (bit - 1)); const S1Cont ct = ctab[d >> 16];
+    const S1Probe* probe = reinterpret_cast<const S1Probe*>(ws.probe);
+    auto put_hit = [&](int d, S1Probe pv, int a, uint8_t tfv) {      // candidate d (bit set in pv.bits) of row a
+        const unsigned bit = 1u << (d & 31); const int idx = pv.rank + popc(pv.bits & (bit - 1)); const S1Cont ct = ctab[d >> 16];
         const int jc = idx - ct.cstart, sub = jc / CHUNK; const int cnt_k = ct.cnt - sub * CHUNK < CHUNK ? ct.cnt - sub * CHUNK : CHUNK;
         tfb[(int64_t)Ta * (ct.cpad + sub * CHUNK) + (int64_t)a * pad16(cnt_k) + (jc - sub * CHUNK)] = tfv;
     };
@@ -157,31 +160,31 @@ IFX_FN void stage1_lookup(const Ctx& c, const DevIndex& ix, const QueryPlan& p, 
             // aligned middle of the list: 16 postings per thread in flight (four 16-byte id loads + four 4-byte tf loads), then their
             // 16 bitset probes, then the hits
             const int64_t pre = (int64_t)((0 - (reinterpret_cast<uintptr_t>(tm.docs) >> 2)) & 3);
-            for (int64_t i = c.tid(); i < pre; i += NT) { const int d = tm.docs[i]; const unsigned wv = ws.bits[d >> 5]; if ((wv >> (d & 31)) & 1u) put_hit(d, wv, a, tm.tf ? tm.tf[i] : (uint8_t)1); }
+            for (int64_t i = c.tid(); i < pre; i += NT) { const int d = tm.docs[i]; const S1Probe wv = probe[d >> 5]; if ((wv.bits >> (d & 31)) & 1u) put_hit(d, wv, a, tm.tf ? tm.tf[i] : (uint8_t)1); }
             const int4* p4 = reinterpret_cast<const int4*>(tm.docs + pre); const unsigned* t4 = tm.tf ? reinterpret_cast<const unsigned*>(tm.tf + pre) : nullptr;
             const int64_t n4 = (len - pre) >> 2;
             for (int64_t g0 = c.tid(); g0 < n4; g0 += 4LL * NT) {
-                int4 dv[4]; unsigned tw[4]; unsigned wv[16];
+                int4 dv[4]; unsigned tw[4]; S1Probe wv[16];
 #pragma unroll
                 for (int u = 0; u < 4; u++) { const int64_t g = g0 + (int64_t)u * NT; if (g < n4) { dv[u] = p4[g]; tw[u] = t4 ? t4[g] : 0x01010101u; } else { dv[u] = make_int4(-1, -1, -1, -1); tw[u] = 0u; } }
 #pragma unroll
                 for (int u = 0; u < 4; u++) { const int dd[4] = {dv[u].x, dv[u].y, dv[u].z, dv[u].w};
 #pragma unroll
-                    for (int k = 0; k < 4; k++) wv[4 * u + k] = dd[k] >= 0 ? ws.bits[dd[k] >> 5] : 0u; }
+                    for (int k = 0; k < 4; k++) { if (dd[k] >= 0) wv[4 * u + k] = probe[dd[k] >> 5]; else wv[4 * u + k].bits = 0u; } }
 #pragma unroll
                 for (int u = 0; u < 4; u++) { const int dd[4] = {dv[u].x, dv[u].y, dv[u].z, dv[u].w};
 #pragma unroll
-                    for (int k = 0; k < 4; k++) if (dd[k] >= 0 && ((wv[4 * u + k] >> (dd[k] & 31)) & 1u)) put_hit(dd[k], wv[4 * u + k], a, (uint8_t)(tw[u] >> (8 * k))); }
+                    for (int k = 0; k < 4; k++) if (dd[k] >= 0 && ((wv[4 * u + k].bits >> (dd[k] & 31)) & 1u)) put_hit(dd[k], wv[4 * u + k], a, (uint8_t)(tw[u] >> (8 * k))); }
             }
             done = pre + (n4 << 2);
         }
 #endif
         const int64_t NT4 = 4LL * NT;
         for (int64_t i0 = done + c.tid(); i0 < len; i0 += NT4) {
-            int dd[4]; uint8_t tv[4]; unsigned wv[4];
+            int dd[4]; uint8_t tv[4]; S1Probe wv[4];
             for (int u = 0; u < 4; u++) { int64_t i = i0 + (int64_t)u * NT; const bool in = i < len; dd[u] = in ? tm.docs[i] : -1; tv[u] = (in && tm.tf) ? tm.tf[i] : (uint8_t)1; }
-            for (int u = 0; u < 4; u++) wv[u] = dd[u] >= 0 ? ws.bits[dd[u] >> 5] : 0u;
-            for (int u = 0; u < 4; u++) if (dd[u] >= 0 && ((wv[u] >> (dd[u] & 31)) & 1u)) put_hit(dd[u], wv[u], a, tv[u]);
+            for (int u = 0; u < 4; u++) { if (dd[u] >= 0) wv[u] = probe[dd[u] >> 5]; else wv[u].bits = 0u; }
+            for (int u = 0; u < 4; u++) if (dd[u] >= 0 && ((wv[u].bits >> (dd[u] & 31)) & 1u)) put_hit(dd[u], wv[u], a, tv[u]);
         }
     };
     if (forward) {

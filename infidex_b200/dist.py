@@ -80,6 +80,18 @@ class ShardedSearchEngine:
         rc = eng._host.ifx_builder_globalize(C.c_void_p(eng._builder), self.world, self.rank, arr)
         if rc:
             raise E.NativeError("ifx_builder_globalize failed (%d)" % rc)
+        # second exchange: document lengths after the corpus-level stop terms were dropped -> avgdl (one sequential float sum, as the reference)
+        cnt = C.c_int(0); eng._host.ifx_builder_doc_lengths.restype = C.c_void_p
+        lp = eng._host.ifx_builder_doc_lengths(C.c_void_p(eng._builder), C.byref(cnt))
+        mine_l = np.ctypeslib.as_array((C.c_float * max(cnt.value, 1)).from_address(lp))[: cnt.value].copy()
+        nsz = [torch.zeros(1, dtype=torch.int64, device=self.dev) for _ in range(self.world)]
+        dist.all_gather(nsz, torch.tensor([cnt.value], dtype=torch.int64, device=self.dev)); nsz = [int(x.item()) for x in nsz]; capl = max(max(nsz), 1)
+        padl = np.zeros(capl, np.float32); padl[: cnt.value] = mine_l
+        lb = [torch.empty(capl, dtype=torch.float32, device=self.dev) for _ in range(self.world)]
+        dist.all_gather(lb, torch.from_numpy(padl).to(self.dev))
+        lens = [np.ascontiguousarray(x.cpu().numpy()[: nsz[i]]) for i, x in enumerate(lb)]
+        larr = (C.c_void_p * self.world)(*[x.ctypes.data for x in lens]); carr = (C.c_int * self.world)(*nsz)
+        eng._host.ifx_builder_set_global_lengths(C.c_void_p(eng._builder), self.world, larr, carr)
         eng._upload(eng._host.ifx_builder_image(C.c_void_p(eng._builder)))
 
     # ---- search ------------------------------------------------------------------------------------------------------------------------
