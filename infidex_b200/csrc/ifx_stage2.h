@@ -420,10 +420,30 @@ IFX_FN void finalize_query(const Ctx& c, const DevIndex& ix, const QueryPlan& p,
         for (int i = c.tid(); i < n_rec; i += NT) { sh.keep_doc[i] = s1_doc[i]; sh.keep_score[i] = s1_score[i]; sh.keep_tie[i] = 0; }
         c.sync();
     }
+    // ---- SearchEngine.HandleEmptyQueryWithFacets (SearchEngine.cs:321-346): a blank query with EnableFacets browses the corpus -- every live
+    // document in id order with score ushort.MaxValue, the filter, Take(max), facets over what was taken
+    const bool browse = p.status == 8 && p.enable_facets && p.filter_id < n_filters;
+    if (browse) {
+        int have = 0; const int want = p.max_results < MAX_K ? p.max_results : MAX_K; bool unsup = false;
+        if (c.tid() == 0) sh.bcast[5] = 0;
+        c.sync();
+        for (int base = 0; base < ix.n_docs && have < want; base += NT) {
+            const int d = base + c.tid(); bool pass = d < ix.n_docs && !ix.deleted[d];
+            if (pass && p.filter_id >= 0) pass = filter_exec(ix, filters[p.filter_id], d, unsup);
+            int tot; const int off = block_excl_scan(c, pass ? 1 : 0, sh.scan, tot);
+            if (pass && have + off < want) { sh.keep_doc[have + off] = d; sh.keep_score[have + off] = 65535.f; sh.keep_tie[have + off] = 0; }
+            have += tot;
+        }
+        if (unsup) sh.bcast[5] = 1;
+        c.sync();
+        if (sh.bcast[5]) status |= 2;
+        n_rec = have < want ? have : want;
+    }
     // ---- ApplyFilter (ResultProcessor.cs:56-69), facets over the filtered records, Take(max)
     if (c.tid() == 0) {
         int nk = n_rec; bool unsupported = false;
-        if (p.filter_id >= 0 && p.filter_id < n_filters) {
+        if (browse) { /* filtered above */ }
+        else if (p.filter_id >= 0 && p.filter_id < n_filters) {
             const FilterProg fp = filters[p.filter_id]; int w = 0;
             for (int i = 0; i < nk; i++) if (filter_exec(ix, fp, sh.keep_doc[i], unsupported)) { sh.keep_doc[w] = sh.keep_doc[i]; sh.keep_score[w] = sh.keep_score[i]; sh.keep_tie[w] = sh.keep_tie[i]; w++; }
             nk = w;
@@ -448,7 +468,7 @@ IFX_FN void finalize_query(const Ctx& c, const DevIndex& ix, const QueryPlan& p,
                 for (int u = 0; u < lim; u++) { if (nf < O.fcap) { size_t fo = (size_t)q * O.fcap + nf; O.facet_col[fo] = col; O.facet_val[fo] = sh.fv[u]; O.facet_cnt[fo] = sh.fc[u]; nf++; } else status |= 4; }
             }
         }
-        O.n_facets[q] = nf; O.total[q] = nk;
+        O.n_facets[q] = nf; O.total[q] = browse ? 0 : nk;       // (TotalCandidates is not set on the browse path)
         int nout = nk < p.max_results ? nk : p.max_results; if (nout > O.cap) nout = O.cap;
         for (int i = 0; i < nout; i++) { size_t oo = (size_t)q * O.cap + i; O.key[oo] = ix.doc_key[sh.keep_doc[i]]; O.score[oo] = sh.keep_score[i]; O.tie[oo] = sh.keep_tie[i]; }
         O.n[q] = nout; O.status[q] = status;

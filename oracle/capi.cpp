@@ -24,7 +24,16 @@ static SearchResult do_search(const Engine& e, sv raw, int max_results, int dept
     SearchResult r;
     if (!e.ix.built) return r;
     str q = to_lower(normalize(trim(raw)));
-    if (is_blank(q)) return r;   // (empty query + facets over all docs: SURVEY 8(f) "next")
+    if (is_blank(q)) {
+        if (!facets) return r;                      // SearchEngine.cs:295-296 Result.MakeEmptyResult()
+        // SearchEngine.HandleEmptyQueryWithFacets (SearchEngine.cs:321-346): every live document with score ushort.MaxValue in id order, the
+        // filter, Take(max), facets over what was taken; TotalCandidates is not set on this path
+        std::vector<ScoreEntry> all; FilterVM vm;
+        for (size_t id = 0; id < e.ix.docs.size(); id++) { const Doc& d = e.ix.docs[id]; if (d.deleted) continue; if (filt && !vm.execute(*filt, e.ix, (int)id)) continue; all.push_back({65535.f, d.key, 0}); if ((int)all.size() >= max_results) break; }
+        if (vm.unsupported) r.status = 1;
+        r.facets = build_facets(e.ix, all); r.total = 0; r.recs = std::move(all);
+        return r;
+    }
     SearchOut o = e.pipe->execute(q, enable_cov, depth, max_results, stage1, st);
     if (o.unsupported) { r.status = 1; return r; }
     std::vector<ScoreEntry> res = std::move(o.records);

@@ -64,3 +64,17 @@ def test_emu_matches_oracle_on_the_book_library(oracle_books):
                 F.Or(F.Value("author", "J.K. Rowling"), F.Value("author", "Stephen King")), F.Not(F.Value("genre", "Fantasy")),
                 F.In("genre", ["Horror", "Mystery"]), F.String("author", "CONTAINS", "king")):
         assert not compare_search(eng, oracle_books, qs, max_results=30, flt=flt, facets=True), flt
+
+
+def test_emu_blank_query_with_facets_browses_the_corpus(oracle_books):
+    """SearchEngine.HandleEmptyQueryWithFacets (SearchEngine.cs:321-346): a blank query with EnableFacets returns the first live documents
+    (id order, score 65535) that pass the filter, cut to max, and the facets over them; without EnableFacets the result stays empty."""
+    eng = ib.SearchEngine(_gpu_lib=emu_lib())
+    eng.IndexColumns(np.array([b[0] for b in BOOKS], np.int64), _schema(), _columns())
+    for mx in (5, 10, 50):
+        assert not compare_search(eng, oracle_books, ["", "   "], max_results=mx, facets=True)
+        for flt in (F.Range("year", "2000", None), F.Value("genre", "Fantasy"), F.Not(F.Value("genre", "Fantasy"))):
+            assert not compare_search(eng, oracle_books, ["", " "], max_results=mx, flt=flt, facets=True), (mx, flt)
+    r = eng.Search(ib.Query("", 10)); assert r.Records == [] and not r.Facets
+    q = ib.Query("  ", 7); q.EnableFacets = True
+    r = eng.Search(q); assert len(r.Records) == 7 and all(e.Score == 65535.0 for e in r.Records) and r.Facets and r.TotalCandidates == 0
