@@ -64,7 +64,7 @@ struct ifx_index {
     DevIndex v{};                       // device pointers
     std::vector<void*> allocs;
     uint8_t* d_sorted_len = nullptr;
-    int n_ctas = 1;
+    int n_ctas = 1, n_ctas_sel = 1;       // resident CTAs of the 512-thread persistent kernels / of the selection + lookup kernel (one workspace each)
     std::vector<S1Workspace> ws; S1Workspace* d_ws = nullptr;
     int32_t* d_pool = nullptr; unsigned long long pool_cap = 0;
     unsigned char* d_spool = nullptr; unsigned long long spool_cap = 0;   // Stage-1 staging pool of a batch (candidates, lengths, chunk tables, tf matrices)
@@ -313,16 +313,17 @@ extern "C" int ifx_index_create(const ifx_index_image* img, const ifx_params* pp
         (void)cand_cap;
         size_t per_cta = (size_t)nwords * 16 + (size_t)(nwords + ncont + 2) * 4 + 6 * (size_t)(ncont + 2) * 4 + 2 * (size_t)max_list * 4 + CHUNK * 8;
 #ifdef IFX_EMU
-        ix->n_ctas = 1;
+        ix->n_ctas = 1; ix->n_ctas_sel = 1;
 #else
         { cudaDeviceProp prop; CUDA_TRY(cudaGetDeviceProperties(&prop, P.device));
           size_t free_b = 0, total_b = 0; CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
           int want = prop.multiProcessorCount * 2;          // = resident CTAs of the persistent kernels (__launch_bounds__(.., 2)): one workspace each
           size_t budget = free_b / 2;
-          ix->n_ctas = (int)std::max<size_t>(1, std::min<size_t>((size_t)want, budget / std::max<size_t>(per_cta, 1))); }
+          ix->n_ctas_sel = (int)std::max<size_t>(1, std::min<size_t>((size_t)prop.multiProcessorCount * 4, budget / std::max<size_t>(per_cta, 1)));
+          ix->n_ctas = std::min(want, ix->n_ctas_sel); }
 #endif
         const size_t index_bytes = ix->bytes;
-        ix->ws.resize(ix->n_ctas);
+        ix->ws.resize(std::max(ix->n_ctas, ix->n_ctas_sel));
         for (auto& w : ix->ws) { w.bits = ix->alloc<unsigned>(nwords); dev_zero(w.bits, (size_t)nwords * 4); w.bits2 = ix->alloc<unsigned>(nwords); dev_zero(w.bits2, (size_t)nwords * 4); w.cand = nullptr; w.cand_cap = 0; w.rank = ix->alloc<int32_t>((size_t)nwords + ncont + 2); w.probe = ix->alloc<unsigned long long>((size_t)nwords); dev_zero(w.probe, (size_t)nwords * 8); w.cstart = ix->alloc<int32_t>((size_t)ncont + 2); w.cfirst = ix->alloc<int32_t>((size_t)ncont + 2); w.ctab = ix->alloc<int32_t>(4 * ((size_t)ncont + 2)); w.buf_a = ix->alloc<int32_t>(max_list); w.buf_b = ix->alloc<int32_t>(max_list); w.buf_cap = max_list; w.surv_g = ix->alloc<unsigned long long>(CHUNK); }
         ix->d_ws = ix->up(ix->ws.data(), ix->ws.size());
         ix->pool_cap = (unsigned long long)std::max<int64_t>(1 << 20, std::min<int64_t>((int64_t)N * 64, (int64_t)1 << 31));
@@ -336,8 +337,8 @@ extern "C" int ifx_index_create(const ifx_index_image* img, const ifx_params* pp
             ix->spool_cap = want; ix->d_spool = ix->alloc<unsigned char>(want); }
         ix->max_batch = P.max_batch > 0 ? P.max_batch : 16384;
         stage("workspaces");
-        if (timing) fprintf(stderr, "[ifx_index_create] device memory: index %.1f MB, workspaces %d x %.1f MB, fuzzy pool %.1f MB\n", index_bytes / 1e6, ix->n_ctas,
-                            (ix->bytes - index_bytes - (size_t)ix->pool_cap * 4) / 1e6 / ix->n_ctas, ix->pool_cap * 4 / 1e6);
+        if (timing) fprintf(stderr, "[ifx_index_create] device memory: index %.1f MB, workspaces %d x %.1f MB, fuzzy pool %.1f MB\n", index_bytes / 1e6, (int)ix->ws.size(),
+                            (ix->bytes - index_bytes - (size_t)ix->pool_cap * 4) / 1e6 / ix->ws.size(), ix->pool_cap * 4 / 1e6);
     } catch (const std::string& e) { delete ix; return fail(IFX_ERR_CUDA, e); }
     catch (const std::bad_alloc&) { delete ix; return fail(IFX_ERR_OOM, "host allocation failed"); }
     *out = ix; return IFX_OK;

@@ -41,11 +41,17 @@ __global__ void __launch_bounds__(IFX_EXPAND_THREADS, 2) k_expand(DevIndex ix, Q
 }
 // Stage 1, kernel 1: candidate selection + tf lookups of one query per CTA (persistent, LPT order). `wave` > 0: only the queries an earlier
 // wave deferred because the staging pool was full.
-__global__ void __launch_bounds__(IFX_S1_THREADS, 2) k_select_lookup(DevIndex ix, const QueryPlan* plans, int nq, const int32_t* pool, S1Workspace* wss, BatchCounters* bc,
+#ifndef IFX_SEL_THREADS
+#define IFX_SEL_THREADS 256
+#endif
+#ifndef IFX_SEL_CTAS
+#define IFX_SEL_CTAS 4
+#endif
+__global__ void __launch_bounds__(IFX_SEL_THREADS, IFX_SEL_CTAS) k_select_lookup(DevIndex ix, const QueryPlan* plans, int nq, const int32_t* pool, S1Workspace* wss, BatchCounters* bc,
                                                 int32_t* s1_n, int* work, const int* order, long long* qdbg, S1Rec* recs, unsigned char* spool, unsigned long long spool_cap,
                                                 S1Queues queues, int wave, int force_mode, int smode, int32_t* sel_cnt) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    S1Shared& sh = *reinterpret_cast<S1Shared*>(smem_raw); Ctx c; S1Workspace ws = wss[blockIdx.x];
+    S1SelShared& sh = *reinterpret_cast<S1SelShared*>(smem_raw); Ctx c; S1Workspace ws = wss[blockIdx.x];
     for (int i = threadIdx.x; i < MAX_CONTAINERS; i += blockDim.x) sh.dirty[i] = 0;
     __syncthreads();
     for (;;) {
@@ -154,9 +160,9 @@ static void run_stage1_phase(ifx_batch* b, ifx_stats* st, int part = 3) {
     }
     (void)t;
 #else
-    const size_t smem = sizeof(S1Shared), smem_w = sizeof(WarpScoreShared) * IFX_SW_WARPS, smem_m = sizeof(WarpScoreShared) * IFX_SW_WARPS_MID;
+    const size_t smem = sizeof(S1Shared), smem_sel = sizeof(S1SelShared), smem_w = sizeof(WarpScoreShared) * IFX_SW_WARPS, smem_m = sizeof(WarpScoreShared) * IFX_SW_WARPS_MID;
     auto k_light = k_score_warp<W_CAP, IFX_SW_WARPS>; auto k_mid = k_score_warp<W_CAP_MID, IFX_SW_WARPS_MID>;
-    if (!ix->attr_s1) { CUDA_TRY(cudaFuncSetAttribute(k_expand, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); CUDA_TRY(cudaFuncSetAttribute(k_select_lookup, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (!ix->attr_s1) { CUDA_TRY(cudaFuncSetAttribute(k_expand, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); CUDA_TRY(cudaFuncSetAttribute(k_select_lookup, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_sel));
         CUDA_TRY(cudaFuncSetAttribute(k_score_cta, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); CUDA_TRY(cudaFuncSetAttribute(k_light, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_w)); CUDA_TRY(cudaFuncSetAttribute(k_mid, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_m)); ix->attr_s1 = true; }
     float ms_prep = 0.f, ms_exp = 0.f; int launches = 0;
     if (part & 1) {
@@ -173,14 +179,14 @@ static void run_stage1_phase(ifx_batch* b, ifx_stats* st, int part = 3) {
     if (part & 4) {      // count pass of the selection
         t.start();
         CUDA_TRY(cudaMemsetAsync(b->d_sel_cnt, 0, (size_t)nq * SEL_CNT * 4)); CUDA_TRY(cudaMemsetAsync(b->d_work + 1, 0, sizeof(int)));
-        k_select_lookup<<<std::min(ix->n_ctas, nq), IFX_S1_THREADS, smem>>>(ix->v, b->d_plans, nq, ix->d_pool, ix->d_ws, b->d_bc, b->d_s1_n, b->d_work + 1, b->d_order, b->d_qdbg, b->d_recs, ix->d_spool, ix->spool_cap, queues, 0, force_mode, 1, b->d_sel_cnt);
+        k_select_lookup<<<std::min(ix->n_ctas_sel, nq), IFX_SEL_THREADS, smem_sel>>>(ix->v, b->d_plans, nq, ix->d_pool, ix->d_ws, b->d_bc, b->d_s1_n, b->d_work + 1, b->d_order, b->d_qdbg, b->d_recs, ix->d_spool, ix->spool_cap, queues, 0, force_mode, 1, b->d_sel_cnt);
         ms_sel += t.stop(); launches++;
         CUDA_TRY(cudaMemsetAsync(b->d_work + 1, 0, sizeof(int)));
     }
     for (int wave = 0; wave < 64 && (part & 2); wave++) {
         if (wave > 0) { BatchCounters bc; d2h(&bc, b->d_bc, sizeof(bc)); bc.s1_pool_used = 0; bc.s1_deferred = 0; bc.s1_n_light = 0; bc.s1_n_mid = 0; bc.s1_n_heavy = 0; bc.s1_wave = wave; h2d(b->d_bc, &bc, sizeof(bc)); CUDA_TRY(cudaMemsetAsync(b->d_work + 1, 0, 5 * sizeof(int))); }
         t.start();
-        k_select_lookup<<<std::min(ix->n_ctas, nq), IFX_S1_THREADS, smem>>>(ix->v, b->d_plans, nq, ix->d_pool, ix->d_ws, b->d_bc, b->d_s1_n, b->d_work + 1, b->d_order, b->d_qdbg, b->d_recs, ix->d_spool, ix->spool_cap, queues, wave, force_mode, smode, b->d_sel_cnt);
+        k_select_lookup<<<std::min(ix->n_ctas_sel, nq), IFX_SEL_THREADS, smem_sel>>>(ix->v, b->d_plans, nq, ix->d_pool, ix->d_ws, b->d_bc, b->d_s1_n, b->d_work + 1, b->d_order, b->d_qdbg, b->d_recs, ix->d_spool, ix->spool_cap, queues, wave, force_mode, smode, b->d_sel_cnt);
         ms_sel += t.stop(); t.start();
         k_score_cta<<<std::min(ix->n_ctas, nq), IFX_S1_THREADS, smem>>>(ix->v, b->d_recs, ix->d_spool, b->d_heavy, b->d_bc, b->d_work + 2, ix->d_ws, b->d_s1_doc, b->d_s1_score, b->d_s1_n, K, b->d_qdbg);
         ms_sc += t.stop(); t.start();

@@ -193,28 +193,29 @@ constexpr int QH_SIZE = 256;
 constexpr int SMALL_CHUNK = 512;                               // chunks up to this size are scored by a single warp, without block barriers
 constexpr int SMALL_TERMS = S1_TILE * CHUNK / SMALL_CHUNK;      // ... when all their terms fit the tile buffer re-cut as [term][SMALL_CHUNK]
 IFX_FN unsigned qh_hash(int32_t term_id) { return ((unsigned)term_id * 2654435761u) >> 24; }     // 8 bits = QH_SIZE
-struct S1Shared {
+// shared memory of the selection / tf-lookup kernel (small: four 256-thread CTAs per SM)
+struct S1SelShared {
     TermS terms[MAX_TERMS];
     int order[MAX_TERMS];
     int n_terms;
-    alignas(16) float score[CHUNK];
-    alignas(16) uint8_t tfm[S1_TILE][CHUNK];   // per-tile tf of (term, candidate slot); 0 = no match
-    int32_t cand_s[CHUNK]; alignas(16) float nv_s[CHUNK];   // per-slot length norm of the vector form (the scalar form is needed for < 8 matches per term and chunk: recomputed)
-    uint16_t cpref[2048];                // rank directory of `cbits`
-    unsigned ballots[2][CHUNK / Ctx::WS + 8]; int bprefix[CHUNK / Ctx::WS + 8];
-    int heap_size; float thr;
-    // .NET PriorityQueue nodes packed as (doc << 32 | float bits of the priority), stored with a +3 shift so the four children of
-    // node i (4i+1..4i+4) form one aligned 32-byte group; slots beyond the current size hold +huge sentinels
-    alignas(16) float heap_pr[MAX_K + 8]; int32_t heap_doc[MAX_K + 8];   // split so that one 16-byte load fetches the four child priorities
     int32_t qh_key[QH_SIZE]; uint8_t qh_slot[QH_SIZE];   // term id -> slot in `terms` (open addressing; terms with idf > 0 only), for the forward-index lookups
-    unsigned long long surv[SURV_CAP];     // (doc, score) of the last chunk's flush survivors, drained into the heap while the next chunk is staged
-    union {                               // never live at the same time: selection/compaction vs. chunk scoring
-        uint8_t dirty[MAX_CONTAINERS];    // containers of the global bitset touched by the current set operation (all zero between uses)
-        unsigned cbits[2048];             // container-local bitmap of the current chunk's candidates (stream mode)
-    };
-    ScanTmp scan; ScanTmp scan2[2]; alignas(16) unsigned scan3[32][4];   // scan3: packed per-warp totals of the batched rank scan
+    uint8_t dirty[MAX_CONTAINERS];          // containers of the global bitset touched by the current set operation (all zero between uses)
+    ScanTmp scan; ScanTmp scan2[2];
     int bcast[8]; long long bcast64[4];
     unsigned long long streamed_mask[2];   // terms whose list the selector streamed in full (roofline accounting)
+};
+// ... plus what the block-wide scorer and the LD1 expansion need
+struct S1Shared : S1SelShared {
+    alignas(16) float score[CHUNK];
+    alignas(16) uint8_t tfm[S1_TILE][CHUNK];   // one tile of term rows of the current chunk
+    int32_t cand_s[CHUNK]; alignas(16) float nv_s[CHUNK];   // per-slot length norm of the vector form (the scalar form is needed for < 8 matches per term and chunk: recomputed)
+    unsigned ballots[2][CHUNK / Ctx::WS + 8]; int bprefix[CHUNK / Ctx::WS + 8];
+    int heap_size; float thr;
+    // .NET PriorityQueue nodes, stored with a +3 shift so the four children of node i (4i+1..4i+4) form one aligned 16-byte group; slots beyond
+    // the current size hold +huge sentinels
+    alignas(16) float heap_pr[MAX_K + 8]; int32_t heap_doc[MAX_K + 8];   // split so that one 16-byte load fetches the four child priorities
+    unsigned long long surv[SURV_CAP];     // (doc, score) of the last chunk's flush survivors, drained into the heap while the next chunk is staged
+    alignas(16) unsigned scan3[32][4];   // packed per-warp totals of the batched rank scan
     unsigned long long peq[128];           // Myers pattern masks of the word being expanded (ASCII fast path)
 };
 
@@ -249,7 +250,7 @@ IFX_FN void stream_list_words(const Ctx& c, const int32_t* list, int64_t n, Put 
 }
 
 // OR a sorted id list into the CTA's bitset; returns the number of newly set docs (block-wide).
-IFX_FN int or_list_into_bits(const Ctx& c, const int32_t* list, int64_t n, S1Workspace& ws, S1Shared& sh) {
+IFX_FN int or_list_into_bits(const Ctx& c, const int32_t* list, int64_t n, S1Workspace& ws, S1SelShared& sh) {
     int fresh = 0;
     stream_list_words(c, list, n, [&](int word, unsigned mask) { unsigned old = atomic_or(&ws.bits[word], mask); fresh += popc(mask & ~old); sh.dirty[word >> 11] = 1; });
     c.sync();
@@ -269,7 +270,7 @@ IFX_FN void warp_append(const Ctx& c, bool pred, int32_t value, int32_t* arr, in
 // unordered id array (ping-pong ws.buf_a / ws.buf_b) and as the membership bitset ws.bits2. Each further list either streams
 // past the bitset (coalesced, when it is not much longer than the running set) or is probed per surviving id (binary search).
 // Returns the size (-1: buffer overflow); `res` points at the surviving ids; ws.bits2 is left all-zero.
-IFX_FN int64_t intersect_terms(const Ctx& c, const DevIndex& ix, S1Workspace& ws, S1Shared& sh, int cnt, const int32_t*& res) {
+IFX_FN int64_t intersect_terms(const Ctx& c, const DevIndex& ix, S1Workspace& ws, S1SelShared& sh, int cnt, const int32_t*& res) {
     const int NT = c.nthreads();
     int by_len[MAX_TERMS];
     for (int i = 0; i < cnt; i++) by_len[i] = sh.order[i];
@@ -364,7 +365,7 @@ IFX_FN int64_t intersect_terms(const Ctx& c, const DevIndex& ix, S1Workspace& ws
 }
 
 // Expand the dirty containers of the bitset into ws.cand (ascending) and clear them. Returns the count.
-IFX_FN int64_t compact_bits(const Ctx& c, const DevIndex& ix, S1Workspace& ws, S1Shared& sh, int32_t* out, int64_t out_cap, bool& overflow) {
+IFX_FN int64_t compact_bits(const Ctx& c, const DevIndex& ix, S1Workspace& ws, S1SelShared& sh, int32_t* out, int64_t out_cap, bool& overflow) {
     int ncont = (ix.n_docs + 65535) >> 16; int64_t total = 0; int64_t nwords = ((int64_t)ix.n_docs + 31) >> 5;
     overflow = false;
     for (int k = 0; k < ncont; k++) {
@@ -470,67 +471,6 @@ template <class H> IFX_FN float heap_replace_root(H& sh, int doc, float pr, int 
     }
     sh.IFX_HP(idx) = pr; sh.IFX_HD(idx) = doc;
     return root;
-}
-
-// Exclusive scan over the worker threads [hw, nthreads) only (named barrier 1); every worker must call it.
-IFX_FN int worker_excl_scan(const Ctx& c, int v, ScanTmp& tmp, int hw, int ntw) {
-#ifdef IFX_EMU
-    (void)c; (void)v; (void)tmp; (void)hw; (void)ntw; return 0;
-#else
-    int incl = v;
-    for (int d = 1; d < 32; d <<= 1) { int o = __shfl_up_sync(0xffffffffu, incl, d); if (c.lane() >= d) incl += o; }
-    if (c.lane() == 31) tmp.w[c.warp()] = incl;
-    c.sync_workers(ntw);
-    int base = 0; const int w0 = hw >> 5;
-    for (int i = w0; i < c.warp(); i++) base += tmp.w[i];
-    c.sync_workers(ntw);
-    return base + incl - v;
-#endif
-}
-
-// tf of ONE term for every candidate slot of the chunk into tfb[0..cnt) (slots without a match are left untouched, i.e. 0),
-// executed by the `ntw` threads numbered wt. `may_stream`: the chunk's container-local bitmap (sh.cbits / sh.cpref) exists.
-IFX_FN void stage1_lookup_term(S1Shared& sh, const TermS& tm, uint8_t* tfb, int cnt, int wt, int ntw, bool may_stream) {
-    const int64_t sublen = tm.s1 - tm.s0;
-    if (tm.bm && sublen > 2LL * cnt) {          // dense term, sparse chunk: O(1) bitmap probe per candidate (doc -> posting index -> tf)
-        for (int jb = wt; jb < cnt; jb += 4 * ntw) {
-            unsigned wv[4]; int rk[4]; int dd[4];
-            for (int u = 0; u < 4; u++) { int j = jb + u * ntw; dd[u] = j < cnt ? sh.cand_s[j] : -1; if (dd[u] >= 0) { wv[u] = tm.bm[dd[u] >> 5]; rk[u] = tm.bmr[dd[u] >> 5]; } }
-            for (int u = 0; u < 4; u++) if (dd[u] >= 0) { unsigned bit = 1u << (dd[u] & 31); if (wv[u] & bit) tfb[jb + u * ntw] = tm.tf[rk[u] + popc(wv[u] & (bit - 1))]; }
-        }
-    } else if (may_stream && sublen <= 16LL * cnt) {   // stream the posting sub-range (coalesced), O(1) slot lookup per posting
-        for (int64_t i0 = tm.s0 + wt; i0 < tm.s1; i0 += 4LL * ntw) {      // four independent loads in flight per thread
-            int dd[4]; uint8_t tv[4];                                          // tf fetched alongside the id (one latency, not two)
-            for (int u = 0; u < 4; u++) { int64_t i = i0 + (int64_t)u * ntw; bool in = i < tm.s1; dd[u] = in ? tm.docs[i] : -1; tv[u] = (in && tm.tf) ? tm.tf[i] : (uint8_t)1; }
-            for (int u = 0; u < 4; u++) if (dd[u] >= 0) {
-                int d = dd[u] & 0xFFFF; unsigned wv = sh.cbits[d >> 5], bit = 1u << (d & 31);
-                if (wv & bit) tfb[sh.cpref[d >> 5] + popc(wv & (bit - 1))] = tv[u];
-            }
-        }
-    } else {                                    // sparse candidates: level-synchronous binary searches, four per thread at a time
-        for (int jb = wt; jb < cnt; jb += 4 * ntw) {
-            int64_t lo[4], hi[4]; int32_t d[4];
-            for (int u = 0; u < 4; u++) { int j = jb + u * ntw; d[u] = j < cnt ? sh.cand_s[j] : 0x7fffffff; lo[u] = tm.s0; hi[u] = j < cnt ? tm.s1 : tm.s0; }
-            for (int64_t span = sublen; span > 0; span >>= 1) {
-                int32_t v[4]; int64_t mid[4];
-                for (int u = 0; u < 4; u++) { mid[u] = lo[u] + ((hi[u] - lo[u]) >> 1); v[u] = lo[u] < hi[u] ? tm.docs[mid[u]] : 0; }
-                for (int u = 0; u < 4; u++) if (lo[u] < hi[u]) { if (v[u] < d[u]) lo[u] = mid[u] + 1; else hi[u] = mid[u]; }
-            }
-            for (int u = 0; u < 4; u++) { int j = jb + u * ntw; if (j < cnt && lo[u] < tm.s1 && tm.docs[lo[u]] == d[u]) tfb[j] = tm.tf ? tm.tf[lo[u]] : (uint8_t)1; }
-        }
-    }
-}
-
-// Phase A of one term tile: tf of every (term, candidate slot) pair of the chunk into sh.tfm (0 = no match). Independent of the
-// scores and of the threshold, so it runs on the worker threads (wt of ntw) while the heap warp is still draining the last chunk.
-IFX_FN void stage1_phase_a(const Ctx& c, S1Shared& sh, int t0, int T, int cnt, int wt, int ntw) {
-    (void)c;
-    const int tile = T - t0 < S1_TILE ? T - t0 : S1_TILE; const bool use_bitmap = sh.bcast[5] != 0;
-    for (int tt = 0; tt < tile; tt++) {
-        const TermS& tm = sh.terms[t0 + tt];
-        if (tm.idf <= 0.f || tm.s1 == tm.s0) continue;   // uniform
-        stage1_lookup_term(sh, tm, sh.tfm[tt], cnt, wt, ntw, use_bitmap);
-    }
 }
 
 // Bm25Scorer.cs:395-433 (Vector256 lanes) and :643-652 (scalar remainder); must not be contracted into FMAs.
@@ -647,60 +587,6 @@ IFX_FN void expand_fuzzy(const Ctx& c, const DevIndex& ix, QueryPlan& p, int fsl
     c.sync();
 }
 
-// Scoring + flush of a small chunk (cnt <= SMALL_CHUNK) by a team of SMALL_TEAM warps: team thread i owns the consecutive slots
-// [i*PER, (i+1)*PER), ranks come from a warp scan plus the team's per-warp totals (named barrier 2), nothing synchronises with the
-// rest of the block. Same arithmetic and the same order as the tiled path below (MaxScore test, rank -> Vector256 / scalar form,
-// accumulation, eligibility, survivors in candidate order); tf bytes are read from the tile buffer re-cut as [term][SMALL_CHUNK]
-// (filled by the workers) and zeroed again after use. `tw0`: first warp of the team.
-#ifdef IFX_EMU
-constexpr int SMALL_TEAM = 1;
-#else
-#ifndef IFX_SMALL_TEAM
-#define IFX_SMALL_TEAM 8
-#endif
-constexpr int SMALL_TEAM = IFX_SMALL_TEAM;
-#endif
-IFX_FN void stage1_small_chunk(const Ctx& c, const DevIndex& ix, S1Shared& sh, int T, int cnt, int K, float avgdl, int tw0) {
-    constexpr int PER = SMALL_CHUNK / (SMALL_TEAM * Ctx::WS);     // 4 slots per thread on the GPU
-    const int wi = c.warp() - tw0, ti = wi * Ctx::WS + c.lane();
-    const int j0 = ti * PER < cnt ? ti * PER : cnt, j1 = j0 + PER < cnt ? j0 + PER : cnt, nj = j1 - j0;
-    const float thr = sh.thr; uint8_t* tfs = &sh.tfm[0][0]; int nscan = 0;
-    auto team_excl = [&](int mine, int& total) -> int {           // exclusive prefix over the team's threads + team total
-        int incl = mine;
-        for (int d = 1; d < Ctx::WS; d <<= 1) { int o = c.shfl(incl, c.lane() >= d ? c.lane() - d : 0); if (c.lane() >= d) incl += o; }
-        const int buf = nscan & 1; nscan++;
-        if (c.lane() == Ctx::WS - 1) sh.scan3[wi][buf] = (unsigned)incl;
-        c.sync_team(SMALL_TEAM * Ctx::WS);
-        int base = 0, tot = 0;
-        for (int i = 0; i < SMALL_TEAM; i++) { int x = (int)sh.scan3[i][buf]; if (i < wi) base += x; tot += x; }
-        total = tot;
-        return base + incl - mine;
-    };
-    for (int t = 0; t < T; t++) {
-        const TermS& tm = sh.terms[t];
-        if (tm.idf <= 0.f || (tm.term_id < 0 && tm.s1 == tm.s0)) continue;          // uniform (dictionary terms came through the forward index: no sub-range)
-        uint8_t* tfb = tfs + t * SMALL_CHUNK; const float tbound = tm.max_score, tsuffix = tm.suffix_after;
-        uint8_t tfv[PER]; bool alive[PER]; int mine = 0;
-        for (int k = 0; k < PER; k++) { tfv[k] = k < nj ? tfb[j0 + k] : (uint8_t)0; alive[k] = tfv[k] != 0 && !(sh.score[j0 + k] + tbound + tsuffix <= thr); mine += alive[k] ? 1 : 0; }
-        int m; int rank = team_excl(mine, m);
-        const int vec_end = m - (m & 7);
-        for (int k = 0; k < PER; k++) {
-            if (alive[k]) {
-                const float tf = (float)tfv[k];
-                const float add = rank < vec_end ? bm25_from_norm_vector(tf, sh.nv_s[j0 + k], tm.idf) : bm25_scalar(tf, ix.doc_len[sh.cand_s[j0 + k]], avgdl, tm.idf);
-                sh.score[j0 + k] += add; rank++;
-            }
-            if (tfv[k] != 0) tfb[j0 + k] = 0;
-        }
-    }
-    // flush, part 1 (see the tiled path): eligibility against the chunk-start threshold, survivors compacted in candidate order
-    const bool full = sh.heap_size >= K; int mine = 0; bool el[PER];
-    for (int k = 0; k < PER; k++) { el[k] = k < nj && sh.score[j0 + k] > 0.f && (!full || sh.score[j0 + k] > thr) && !ix.deleted[sh.cand_s[j0 + k]]; mine += el[k] ? 1 : 0; }
-    int total; int off = team_excl(mine, total);
-    for (int k = 0; k < PER; k++) if (el[k]) sh.surv[off++] = kv_pack(sh.cand_s[j0 + k], sh.score[j0 + k]);
-    if (ti == 0) sh.bcast[6] = total;
-}
-
 // Prefix precedence (TieredCandidateSelector.TrySelectPrefixCandidates): the candidates are the doc set of the query's first 1-3
 // characters when that set is small enough. Returns its range in ix.prefix.doc_id.
 IFX_FN bool prefix_shortcut(const DevIndex& ix, const QueryPlan& p, int K, int64_t& r0, int64_t& pop) {
@@ -723,7 +609,7 @@ IFX_FN bool prefix_shortcut(const DevIndex& ix, const QueryPlan& p, int K, int64
 // (smode 1: local cardinality at every decision point into cnt[], following every branch that some shard might need), the hosts sum the
 // counts over the shards, and the real pass (smode 2) takes its decisions from the global values in cnt[]. smode 0: unsharded.
 constexpr int SEL_CNT = 40;          // cnt[0..3]: AND path (tier 0, + tier 1, + first / second high-idf list); cnt[8 + i]: disjunctive path after list i (i < 32)
-IFX_FN int stage1_select(const Ctx& c, const DevIndex& ix, const QueryPlan& p, const int32_t* pool, S1Workspace& ws, S1Shared& sh, Stage1Out out, int smode = 0, int32_t* cnt = nullptr) {
+IFX_FN int stage1_select(const Ctx& c, const DevIndex& ix, const QueryPlan& p, const int32_t* pool, S1Workspace& ws, S1SelShared& sh, Stage1Out out, int smode = 0, int32_t* cnt = nullptr) {
     const int K = p.depth; const int NT = c.nthreads();
     if (c.tid() == 0) {
         int n = 0;
@@ -740,14 +626,12 @@ IFX_FN int stage1_select(const Ctx& c, const DevIndex& ix, const QueryPlan& p, c
         for (int i = 0; i < QH_SIZE; i++) sh.qh_key[i] = -1;
         for (int i = 0; i < n; i++) { const TermS& t = sh.terms[i]; if (t.term_id < 0 || t.idf <= 0.f) continue;      // (ids are unique within a query)
             unsigned h = qh_hash(t.term_id); while (sh.qh_key[h] >= 0) h = (h + 1) & (QH_SIZE - 1); sh.qh_key[h] = t.term_id; sh.qh_slot[h] = (uint8_t)i; }
-        sh.n_terms = n; sh.heap_size = 0; sh.thr = 0.f; sh.streamed_mask[0] = sh.streamed_mask[1] = 0;
-        for (int i = 0; i < MAX_K + 8; i++) { sh.heap_pr[i] = 3.0e38f; sh.heap_doc[i] = 0; }    // sentinels (any real BM25 score is far smaller)
+        sh.n_terms = n; sh.streamed_mask[0] = sh.streamed_mask[1] = 0;
         out.n[0] = 0;
     }
     c.sync();
     const int T = sh.n_terms;
     if (T == 0 || ix.n_live == 0 || p.status != 0) return 0;
-    const float avgdl = ix.avgdl > 0.f ? ix.avgdl : 1.f;
 
     // ---- candidate selection (TieredCandidateSelector.SelectCandidates)
 #if !defined(IFX_EMU) && defined(IFX_S1_TIMERS)
@@ -819,7 +703,7 @@ IFX_FN int stage1_select(const Ctx& c, const DevIndex& ix, const QueryPlan& p, c
 }
 
 // Candidate bitset back to all-zero (dirty containers only).
-IFX_FN void stage1_clear_bits(const Ctx& c, const DevIndex& ix, S1Workspace& ws, S1Shared& sh) {
+IFX_FN void stage1_clear_bits(const Ctx& c, const DevIndex& ix, S1Workspace& ws, S1SelShared& sh) {
     const int NT = c.nthreads(); const int64_t nwords = ((int64_t)ix.n_docs + 31) >> 5; const int ncont = (ix.n_docs + 65535) >> 16;
     c.sync();
     for (int64_t w = c.tid(); w < nwords; w += NT) if (sh.dirty[w >> 11]) ws.bits[w] = 0u;

@@ -42,7 +42,7 @@ constexpr int W_K = 512;             // heap capacity kept in shared memory per 
 //   3. tf of every (term, candidate): either every posting list streamed once against the candidate bitset (coalesced; the byte
 //      volume SURVEY 8d calls algorithmic), or -- few candidates relative to the lists -- one forward-index read per candidate
 //   4. bitset cleared again
-IFX_FN void stage1_lookup(const Ctx& c, const DevIndex& ix, const QueryPlan& p, int path, int q, S1Workspace& ws, S1Shared& sh, S1Rec* recs,
+IFX_FN void stage1_lookup(const Ctx& c, const DevIndex& ix, const QueryPlan& p, int path, int q, S1Workspace& ws, S1SelShared& sh, S1Rec* recs,
                           unsigned char* spool, unsigned long long spool_cap, S1Queues queues, BatchCounters* bc, Stage1Out out, int fwd_avg_bytes, int force_mode) {
     S1Rec& rec = recs[q]; const int NT = c.nthreads(), NW = c.nwarps(); constexpr int WS = Ctx::WS;
 #if !defined(IFX_EMU) && defined(IFX_S1_TIMERS)
