@@ -75,7 +75,7 @@ __global__ void __launch_bounds__(IFX_SEL_THREADS, IFX_SEL_CTAS) k_select_lookup
 #define IFX_SW_WARPS 16
 #endif
 #ifndef IFX_SW_WARPS_MID
-#define IFX_SW_WARPS_MID 12
+#define IFX_SW_WARPS_MID 16
 #endif
 template <int CAPW, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32, 1) k_score_warp(DevIndex ix, const S1Rec* recs, const unsigned char* spool, const int32_t* queue, const int32_t* n_queue, int* work,

@@ -29,8 +29,8 @@ IFX_FN int pad16(int x) { return (x + 15) & ~15; }
 constexpr int DEL_BIT = (int)0x80000000;
 
 // warp-scorer limits: a query is scored by one warp when its largest chunk holds <= W_CAP_MID candidates, it has <= W_TERMS scored terms
-// and its depth fits the per-warp heap; "light" (<= W_CAP candidates per chunk: 8 slots per lane) and "mid" (32 slots per lane)
-constexpr int W_CAP = 256, W_CAP_MID = 1024;
+// and its depth fits the per-warp heap; "light" (<= W_CAP candidates per chunk: 8 slots per lane) and "mid" (16 slots per lane)
+constexpr int W_CAP = 256, W_CAP_MID = 512;
 constexpr int W_TF = 6144;           // bytes of the per-warp tf staging buffer (one tile of term rows of the current chunk)
 constexpr int W_TERMS = 64;
 constexpr int W_K = 512;             // heap capacity kept in shared memory per warp
@@ -288,13 +288,10 @@ IFX_FN void score_warp(const Ctx& c, float avgdl_in, const S1Rec& rec, const uns
                 for (int r = 0; r < W_R; r++) {      // rank among them (candidate order = slot order) selects the Vector256 or the scalar form
                     const int j = r * WS + lane; const unsigned tfv = j < cnt ? row[j] : 0u;
                     const bool al = tfv != 0u && (uns || !(sc[r] + tp.max_score + tp.suffix_after <= thr));
-                    const unsigned bm = c.ballot(al); const int rank = run + popc(bm & c.lanemask_lt()); run += popc(bm);
-                    // branch-free in the common case (the Vector256 form is evaluated for every lane and selected): the iterations stay
-                    // independent, which is what lets one warp keep its pipes busy; only the last (m mod 8) matches take the scalar form
-                    const float tf = (float)tfv; float add = bm25_from_norm_vector(tf, nv[r], tp.idf);
-                    const bool sca = al && rank >= vec_end;
-                    if (c.ballot(sca)) { if (sca) add = bm25_scalar(tf, dlp[ch.start + j], avgdl, tp.idf); }
-                    sc[r] = al ? sc[r] + add : sc[r];
+                    const unsigned bm = c.ballot(al);
+                    if (al) { const int rank = run + popc(bm & c.lanemask_lt()); const float tf = (float)tfv;
+                        sc[r] += rank < vec_end ? bm25_from_norm_vector(tf, nv[r], tp.idf) : bm25_scalar(tf, dlp[ch.start + j], avgdl, tp.idf); }
+                    run += popc(bm);
                 }
             }
         }
