@@ -84,7 +84,7 @@ struct ifx_batch {
     std::vector<void*> allocs;
     uint16_t* d_text = nullptr; int64_t* d_off = nullptr; int32_t* d_par = nullptr;   // par: [nq][5] max_results, depth, enable_cov, filter_id, enable_facets
     QueryPlan* d_plans = nullptr; FuzzyItem* d_items = nullptr; BatchCounters* d_bc = nullptr; int* d_work = nullptr;
-    bool use_gcnt = false; int32_t* d_sel_cnt = nullptr; S1Rec* d_recs = nullptr; int32_t* d_light = nullptr; int32_t* d_mid = nullptr; int32_t* d_heavy = nullptr;
+    bool use_gcnt = false; int32_t* d_sel_cnt = nullptr; int32_t* d_sel_done = nullptr; S1Rec* d_recs = nullptr; int32_t* d_light = nullptr; int32_t* d_mid = nullptr; int32_t* d_heavy = nullptr;
     int* d_order = nullptr; long long* d_qdbg = nullptr;
     int64_t* d_s1_key = nullptr; int32_t* d_s1_doc = nullptr; float* d_s1_score = nullptr; int32_t* d_s1_n = nullptr;
     Stage2Buffers s2{};                 // WordMatcher + coverage outputs

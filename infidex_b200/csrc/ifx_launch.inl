@@ -49,7 +49,7 @@ __global__ void __launch_bounds__(IFX_EXPAND_THREADS, 2) k_expand(DevIndex ix, Q
 #endif
 __global__ void __launch_bounds__(IFX_SEL_THREADS, IFX_SEL_CTAS) k_select_lookup(DevIndex ix, const QueryPlan* plans, int nq, const int32_t* pool, S1Workspace* wss, BatchCounters* bc,
                                                 int32_t* s1_n, int* work, const int* order, long long* qdbg, S1Rec* recs, unsigned char* spool, unsigned long long spool_cap,
-                                                S1Queues queues, int wave, int force_mode, int smode, int32_t* sel_cnt) {
+                                                S1Queues queues, int wave, int force_mode, int smode, int32_t* sel_cnt, int32_t* sel_done) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     S1SelShared& sh = *reinterpret_cast<S1SelShared*>(smem_raw); Ctx c; S1Workspace ws = wss[blockIdx.x];
     for (int i = threadIdx.x; i < MAX_CONTAINERS; i += blockDim.x) sh.dirty[i] = 0;
@@ -63,8 +63,14 @@ __global__ void __launch_bounds__(IFX_SEL_THREADS, IFX_SEL_CTAS) k_select_lookup
         if (wave > 0 && recs[q].state != 2) continue;
         Stage1Out o{nullptr, nullptr, nullptr, s1_n + q, qdbg + (size_t)q * IFX_QDBG};
         unsigned long long t0 = 0; if (threadIdx.x == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-        const int path = stage1_select(c, ix, plans[q], pool, ws, sh, o, smode, sel_cnt ? sel_cnt + (size_t)q * SEL_CNT : nullptr);
-        if (smode == 1) { stage1_clear_bits(c, ix, ws, sh); continue; }      // count pass (doc-id-range shards): only the cardinalities leave
+        int32_t* cq = sel_cnt ? sel_cnt + (size_t)q * SEL_CNT : nullptr;
+        if (smode == 2 && sel_done[q] == 1 && recs[q].state != 2) continue;   // its candidate set was already final in the count pass
+        const int path = stage1_select(c, ix, plans[q], pool, ws, sh, o, smode, cq);
+        if (smode == 1) {      // count pass (doc-id-range shards): the cardinalities leave; a query whose decisions this shard could take alone is finished now
+            __syncthreads();
+            if (path > 0 && cq[4] != 1) { stage1_clear_bits(c, ix, ws, sh); continue; }
+            if (threadIdx.x == 0) sel_done[q] = 1;
+        }
         stage1_lookup(c, ix, plans[q], path, q, ws, sh, recs, spool, spool_cap, queues, bc, o, ix.fwd_avg_bytes, force_mode);
         __syncthreads();
         if (threadIdx.x == 0) { unsigned long long t1; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1)); atomicAdd(&bc->s1_ns_sum, t1 - t0); atomicMax(&bc->s1_ns_max, t1 - t0); qdbg[(size_t)q * IFX_QDBG + 4] = (long long)(t1 - t0); qdbg[(size_t)q * IFX_QDBG + 2] -= (long long)t0; qdbg[(size_t)q * IFX_QDBG + 5] = blockIdx.x; }
@@ -135,13 +141,18 @@ static void run_stage1_phase(ifx_batch* b, ifx_stats* st, int part = 3) {
     Ctx c; int nit = std::min(b->d_bc->n_fuzzy_items, items_cap);
     if (part & 1) for (int i = 0; i < nit; i++) expand_fuzzy(c, ix->v, b->d_plans[b->d_items[i].query], b->d_items[i].slot, ix->ws[0], *sh, ix->d_pool, ix->pool_cap, b->d_bc, ix->d_sorted_len, sh->cand_s);
     const int smode = b->use_gcnt ? 2 : 0;
-    if (part & 4) for (int q = 0; q < nq; q++) { Stage1Out o{nullptr, nullptr, nullptr, b->d_s1_n + q, nullptr}; for (int k = 0; k < SEL_CNT; k++) b->d_sel_cnt[(size_t)q * SEL_CNT + k] = 0;
-        stage1_select(c, ix->v, b->d_plans[q], ix->d_pool, ix->ws[0], *sh, o, 1, b->d_sel_cnt + (size_t)q * SEL_CNT); stage1_clear_bits(c, ix->v, ix->ws[0], *sh); }
+    if (part & 4) for (int q = 0; q < nq; q++) { Stage1Out o{nullptr, nullptr, nullptr, b->d_s1_n + q, nullptr}; for (int k = 0; k < SEL_CNT; k++) b->d_sel_cnt[(size_t)q * SEL_CNT + k] = 0; b->d_sel_done[q] = 0;
+        int32_t* cq = b->d_sel_cnt + (size_t)q * SEL_CNT;
+        const int path = stage1_select(c, ix->v, b->d_plans[q], ix->d_pool, ix->ws[0], *sh, o, 1, cq);
+        if (path > 0 && cq[4] != 1) { stage1_clear_bits(c, ix->v, ix->ws[0], *sh); continue; }
+        b->d_sel_done[q] = 1; stage1_lookup(c, ix->v, b->d_plans[q], path, q, ix->ws[0], *sh, b->d_recs, ix->d_spool, ix->spool_cap, queues, b->d_bc, o, ix->v.fwd_avg_bytes, force_mode); }
     const bool no_warp = getenv("IFX_S1_NO_WARP") != nullptr;      // tests: force every query through the block-wide scorer
     for (int wave = 0; wave < 64 && (part & 2); wave++) {
-        b->d_bc->s1_pool_used = 0; b->d_bc->s1_deferred = 0; b->d_bc->s1_n_light = 0; b->d_bc->s1_n_mid = 0; b->d_bc->s1_n_heavy = 0; b->d_bc->s1_wave = wave;
+        if (wave > 0 || smode == 0) { b->d_bc->s1_pool_used = 0; b->d_bc->s1_deferred = 0; b->d_bc->s1_n_light = 0; b->d_bc->s1_n_mid = 0; b->d_bc->s1_n_heavy = 0; }      // (shards: the count pass already queued the queries it could finish)
+        b->d_bc->s1_wave = wave;
         for (int q = 0; q < nq; q++) {
             if (wave > 0 && b->d_recs[q].state != 2) continue;
+            if (smode == 2 && b->d_sel_done[q] == 1 && b->d_recs[q].state != 2) continue;
             Stage1Out o{nullptr, nullptr, nullptr, b->d_s1_n + q, nullptr};
             const int path = stage1_select(c, ix->v, b->d_plans[q], ix->d_pool, ix->ws[0], *sh, o, smode, b->d_sel_cnt + (size_t)q * SEL_CNT);
             stage1_lookup(c, ix->v, b->d_plans[q], path, q, ix->ws[0], *sh, b->d_recs, ix->d_spool, ix->spool_cap, queues, b->d_bc, o, ix->v.fwd_avg_bytes, force_mode);
@@ -178,15 +189,15 @@ static void run_stage1_phase(ifx_batch* b, ifx_stats* st, int part = 3) {
     if (part & 6) { k_order<<<1, 1024>>>(ix->v, b->d_plans, nq, b->d_order); launches++; }
     if (part & 4) {      // count pass of the selection
         t.start();
-        CUDA_TRY(cudaMemsetAsync(b->d_sel_cnt, 0, (size_t)nq * SEL_CNT * 4)); CUDA_TRY(cudaMemsetAsync(b->d_work + 1, 0, sizeof(int)));
-        k_select_lookup<<<std::min(ix->n_ctas_sel, nq), IFX_SEL_THREADS, smem_sel>>>(ix->v, b->d_plans, nq, ix->d_pool, ix->d_ws, b->d_bc, b->d_s1_n, b->d_work + 1, b->d_order, b->d_qdbg, b->d_recs, ix->d_spool, ix->spool_cap, queues, 0, force_mode, 1, b->d_sel_cnt);
+        CUDA_TRY(cudaMemsetAsync(b->d_sel_cnt, 0, (size_t)nq * SEL_CNT * 4)); CUDA_TRY(cudaMemsetAsync(b->d_sel_done, 0, (size_t)nq * 4)); CUDA_TRY(cudaMemsetAsync(b->d_work + 1, 0, sizeof(int)));
+        k_select_lookup<<<std::min(ix->n_ctas_sel, nq), IFX_SEL_THREADS, smem_sel>>>(ix->v, b->d_plans, nq, ix->d_pool, ix->d_ws, b->d_bc, b->d_s1_n, b->d_work + 1, b->d_order, b->d_qdbg, b->d_recs, ix->d_spool, ix->spool_cap, queues, 0, force_mode, 1, b->d_sel_cnt, b->d_sel_done);
         ms_sel += t.stop(); launches++;
         CUDA_TRY(cudaMemsetAsync(b->d_work + 1, 0, sizeof(int)));
     }
     for (int wave = 0; wave < 64 && (part & 2); wave++) {
         if (wave > 0) { BatchCounters bc; d2h(&bc, b->d_bc, sizeof(bc)); bc.s1_pool_used = 0; bc.s1_deferred = 0; bc.s1_n_light = 0; bc.s1_n_mid = 0; bc.s1_n_heavy = 0; bc.s1_wave = wave; h2d(b->d_bc, &bc, sizeof(bc)); CUDA_TRY(cudaMemsetAsync(b->d_work + 1, 0, 5 * sizeof(int))); }
         t.start();
-        k_select_lookup<<<std::min(ix->n_ctas_sel, nq), IFX_SEL_THREADS, smem_sel>>>(ix->v, b->d_plans, nq, ix->d_pool, ix->d_ws, b->d_bc, b->d_s1_n, b->d_work + 1, b->d_order, b->d_qdbg, b->d_recs, ix->d_spool, ix->spool_cap, queues, wave, force_mode, smode, b->d_sel_cnt);
+        k_select_lookup<<<std::min(ix->n_ctas_sel, nq), IFX_SEL_THREADS, smem_sel>>>(ix->v, b->d_plans, nq, ix->d_pool, ix->d_ws, b->d_bc, b->d_s1_n, b->d_work + 1, b->d_order, b->d_qdbg, b->d_recs, ix->d_spool, ix->spool_cap, queues, wave, force_mode, smode, b->d_sel_cnt, b->d_sel_done);
         ms_sel += t.stop(); t.start();
         k_score_cta<<<std::min(ix->n_ctas, nq), IFX_S1_THREADS, smem>>>(ix->v, b->d_recs, ix->d_spool, b->d_heavy, b->d_bc, b->d_work + 2, ix->d_ws, b->d_s1_doc, b->d_s1_score, b->d_s1_n, K, b->d_qdbg);
         ms_sc += t.stop(); t.start();
@@ -221,7 +232,7 @@ static int fill_batch(ifx_batch* b, const ifx_query* q, int nq) {
         b->d_text = b->alloc<uint16_t>(b->text_cap); b->d_off = b->alloc<int64_t>(nq + 1); b->d_par = b->alloc<int32_t>(par.size());
         b->d_plans = b->alloc<QueryPlan>(nq); b->d_items = b->alloc<FuzzyItem>((size_t)nq * MAX_FUZZY); b->d_bc = b->alloc<BatchCounters>(1); b->d_work = b->alloc<int>(8); dev_zero(b->d_work, 8 * sizeof(int));
         size_t K = b->depth_max;
-        b->d_recs = b->alloc<S1Rec>(nq); dev_zero(b->d_recs, sizeof(S1Rec) * (size_t)nq); b->d_sel_cnt = b->alloc<int32_t>((size_t)nq * SEL_CNT); b->d_light = b->alloc<int32_t>(nq); b->d_mid = b->alloc<int32_t>(nq); b->d_heavy = b->alloc<int32_t>(nq);
+        b->d_recs = b->alloc<S1Rec>(nq); dev_zero(b->d_recs, sizeof(S1Rec) * (size_t)nq); b->d_sel_cnt = b->alloc<int32_t>((size_t)nq * SEL_CNT); b->d_sel_done = b->alloc<int32_t>(nq); dev_zero(b->d_sel_done, (size_t)nq * 4); b->d_light = b->alloc<int32_t>(nq); b->d_mid = b->alloc<int32_t>(nq); b->d_heavy = b->alloc<int32_t>(nq);
         b->d_s1_key = b->alloc<int64_t>(nq * K); b->d_s1_doc = b->alloc<int32_t>(nq * K); b->d_s1_score = b->alloc<float>(nq * K); b->d_s1_n = b->alloc<int32_t>(nq); b->d_order = b->alloc<int>(nq); b->d_qdbg = b->alloc<long long>((size_t)nq * IFX_QDBG); dev_zero(b->d_qdbg, (size_t)nq * IFX_QDBG * 8);
     } else if (text.size() > b->text_cap) return fail(IFX_ERR_INVALID, "batch text outgrew its buffer");
     h2d(b->d_text, text.data(), text.size() * 2); h2d(b->d_off, off.data(), (nq + 1) * 8); h2d(b->d_par, par.data(), par.size() * 4);

@@ -609,6 +609,8 @@ IFX_FN bool prefix_shortcut(const DevIndex& ix, const QueryPlan& p, int K, int64
 // (smode 1: local cardinality at every decision point into cnt[], following every branch that some shard might need), the hosts sum the
 // counts over the shards, and the real pass (smode 2) takes its decisions from the global values in cnt[]. smode 0: unsharded.
 constexpr int SEL_CNT = 40;          // cnt[0..3]: AND path (tier 0, + tier 1, + first / second high-idf list); cnt[8 + i]: disjunctive path after list i (i < 32)
+                                     // cnt[4]: count pass only -- 1 when every decision was forced by this shard's own count (local >= limit implies corpus >= limit): the
+                                     // candidate set is already final and the shard goes straight on to the lookups; (kept per shard in a separate flag array, not summed)
 IFX_FN int stage1_select(const Ctx& c, const DevIndex& ix, const QueryPlan& p, const int32_t* pool, S1Workspace& ws, S1SelShared& sh, Stage1Out out, int smode = 0, int32_t* cnt = nullptr) {
     const int K = p.depth; const int NT = c.nthreads();
     if (c.tid() == 0) {
@@ -640,10 +642,10 @@ IFX_FN int stage1_select(const Ctx& c, const DevIndex& ix, const QueryPlan& p, c
 #else
 #define IFX_STICK(k) do { } while (0)
 #endif
-    int path = 0;
+    int path = 0; bool certain = false;
     if (c.tid() == 0) { sh.bcast64[0] = -1; sh.bcast64[1] = 0; int64_t r0, pop; if (prefix_shortcut(ix, p, K, r0, pop)) { sh.bcast64[0] = r0; sh.bcast64[1] = pop; } }
     c.sync();
-    if (sh.bcast64[0] >= 0) { path = 1; or_list_into_bits(c, ix.prefix.doc_id + sh.bcast64[0], sh.bcast64[1], ws, sh); }
+    if (sh.bcast64[0] >= 0) { path = 1; certain = true; or_list_into_bits(c, ix.prefix.doc_id + sh.bcast64[0], sh.bcast64[1], ws, sh); }      // (the prefix rules read replicated corpus-level cardinalities)
     else {
         if (c.tid() == 0) {
             bool typo = false; float max_idf = 0.f;
@@ -656,7 +658,7 @@ IFX_FN int stage1_select(const Ctx& c, const DevIndex& ix, const QueryPlan& p, c
         int64_t g = 0;
         IFX_STICK(0);   // prefix shortcut + idf sort
         if (disjunctive) {   // SelectCandidatesDisjunctive
-            bool selective = false; int li = 0; int64_t df_max = 0;
+            bool selective = false; int li = 0; int64_t df_max = 0; if (smode == 1 && T == 1) certain = true;      // a single list: nothing to decide
             for (int oi = 0; oi < T; oi++) {
                 const TermS& t = sh.terms[sh.order[oi]];
                 bool lowq = t.idf < (max_idf * 0.2f);
@@ -664,7 +666,8 @@ IFX_FN int stage1_select(const Ctx& c, const DevIndex& ix, const QueryPlan& p, c
                 g += or_list_into_bits(c, t.docs, t.len, ws, sh);
                 if (c.tid() == 0) sh.streamed_mask[sh.order[oi] >> 6] |= 1ULL << (sh.order[oi] & 63);
                 int64_t gg = g;                                                   // the union's size over the whole corpus decides
-                if (smode == 1 && li < 32) { if (c.tid() == 0) cnt[8 + li] = (int32_t)g; if (t.df > df_max) df_max = t.df; gg = df_max; }      // count pass: go on until the union certainly holds 100 K documents (it contains its largest list)
+                if (smode == 1 && li < 32) { if (c.tid() == 0) cnt[8 + li] = (int32_t)g; if (t.df > df_max) df_max = t.df; gg = df_max;      // count pass: go on until the union certainly holds 100 K documents (it contains its largest list)
+                    if (g >= (int64_t)K * 100 && li == 0) { certain = true; gg = g; } }                                                      // ... or, at the very first list, stop for good: this shard alone has them
                 else if (smode == 2 && li < 32) gg = cnt[8 + li];
                 li++;
                 if (!lowq && gg > 0) selective = true;
@@ -678,6 +681,7 @@ IFX_FN int stage1_select(const Ctx& c, const DevIndex& ix, const QueryPlan& p, c
             IFX_STICK(1);   // AND tier 0
             // count pass: a shard that alone reaches a limit knows the corpus does; below it every later stage is counted (some shard may need it)
             int64_t G = smode == 2 ? (int64_t)cnt[0] : g; if (smode == 1 && c.tid() == 0) { cnt[0] = (int32_t)g; cnt[1] = cnt[2] = cnt[3] = (int32_t)g; }
+            if (smode == 1 && g >= (int64_t)K * 2) certain = true;          // tier 0 alone is enough on this shard, hence in the corpus
             if (G < (int64_t)K * 2) {
                 if (T >= 3 && G < (int64_t)K * 3) { const int32_t* r1 = nullptr; int64_t n1 = intersect_terms(c, ix, ws, sh, T - 1, r1); if (n1 > 0) g += or_list_into_bits(c, r1, n1, ws, sh); }
                 IFX_STICK(2);   // AND tier 1
@@ -694,6 +698,7 @@ IFX_FN int stage1_select(const Ctx& c, const DevIndex& ix, const QueryPlan& p, c
         IFX_STICK(1);   // list unions (disjunctive: everything; AND path: the top-idf lists after the tiers)
         path = disjunctive ? 2 : 3;
     }
+    if (smode == 1 && c.tid() == 0) cnt[4] = certain ? 1 : 0;
     if (c.tid() == 0 && out.dbg) { out.dbg[1] = T; out.dbg[3] = path;
 #ifndef IFX_EMU
         unsigned long long tn; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tn)); out.dbg[2] = (long long)tn;
