@@ -35,8 +35,7 @@ enum {
 /* per-query status bits in ifx_batch_result.status */
 enum {
     IFX_Q_OK = 0,
-    IFX_Q_SHORT_QUERY = 1,    /* no word >= 3 chars: ShortQueryProcessor path (not built) */
-    IFX_Q_UNSUPPORTED_OP = 2, /* MATCHES (regex) opcode */
+    IFX_Q_UNSUPPORTED_OP = 2, /* MATCHES (regex) opcode; a query without a word of >= 3 characters on a doc-id-range SHARD (that path is built for the unsharded index) */
     IFX_Q_OVERFLOW = 4,       /* a fixed device buffer was too small for this query */
     IFX_Q_EMPTY = 8           /* blank query -> empty result (SearchEngine.cs:295-296) */
 };
@@ -89,6 +88,16 @@ typedef struct ifx_index_image {
     const int32_t* affix_last_doc;    /* the single doc its trie output resolves to (WordMatcher.cs:166-196) */
     int32_t n_columns;
     const ifx_column* columns;        /* filterable / facetable fields, schema order of the first document */
+    /* short-query path (queries without a word of >= 3 characters; Scoring/ShortQueryProcessor.cs, Indexing/ShortQuery/ShortQueryResolver.cs) */
+    int32_t n_champ_chars;            /* ShortQueryResolver champion lists of the 1-character prefixes: */
+    const uint16_t* champ_chars;      /*   the character, */
+    const int32_t* champ_off;         /*   [n_champ_chars + 1] */
+    const int32_t* champ_doc;         /*   internal doc ids, in the order BuildChampionLists leaves them (List.Sort by score descending, first 64) */
+    const float* champ_score;         /*   (precedence << 8) | base */
+    int32_t n_raw;                    /* documents whose IndexedText differs from its normalised form (the short-query scorers read ToLowerInvariant(IndexedText)): */
+    const int32_t* raw_doc;           /*   ascending internal ids, */
+    const int64_t* raw_off;           /*   [n_raw + 1] */
+    const uint16_t* raw_chars;        /*   raw IndexedText, original case */
     /* doc-id-range shards: zero / NULL for an unsharded index. A shard image holds its own documents (local ids from 0) and the
      * statistics of the WHOLE corpus: terms / df / idf ordinals, n_live, avgdl, word idf, the global prefix key set and affix dictionary. */
     const int32_t* prefix_global_card;/* [prefix.keys.n] DocSet cardinality over all shards (the selector's prefix rules are global) */

@@ -2,6 +2,7 @@
 // Included by ifx_api.cu (CUDA product) and by tests/emu/emu_api.cpp (IFX_EMU host emulation of the kernels, tests only).
 #include "../../include/infidex_gpu.h"
 #include "ifx_stage1_score.h"
+#include "ifx_short.h"
 #include "ifx_stage2.h"
 #include "ifx_build.h"
 #include <thread>
@@ -69,6 +70,7 @@ struct ifx_index {
     int32_t* d_pool = nullptr; unsigned long long pool_cap = 0;
     unsigned char* d_spool = nullptr; unsigned long long spool_cap = 0;   // Stage-1 staging pool of a batch (candidates, lengths, chunk tables, tf matrices)
     int max_batch = 16384;
+    SqScratch sq{}; std::vector<uint16_t> h_champ_chars; std::vector<int32_t> h_champ_off; bool attr_sq = false;     // short-query path: lazily allocated scratch, host copy of the champion directory
     int device = 0; uint8_t* d_flush = nullptr; bool attr_s1 = false, attr_s2 = false;   // kernel attributes are per device: tracked per index (guarded by mu)
     std::vector<FilterProg> h_filters; FilterProg* d_filters = nullptr;
     std::vector<Column> h_columns; std::vector<std::u16string> column_names;
@@ -81,10 +83,11 @@ struct ifx_index {
 
 struct ifx_batch {
     ifx_index* idx = nullptr; int nq = 0; int depth_max = 0; int cap_max = 0; size_t text_cap = 0;
+    int s1_stride = 0;                  // row length of the Stage-1 list arrays: max(depth, max_results) -- the single-character short-query path returns max_results entries whatever the depth
     std::vector<void*> allocs;
     uint16_t* d_text = nullptr; int64_t* d_off = nullptr; int32_t* d_par = nullptr;   // par: [nq][5] max_results, depth, enable_cov, filter_id, enable_facets
     QueryPlan* d_plans = nullptr; FuzzyItem* d_items = nullptr; BatchCounters* d_bc = nullptr; int* d_work = nullptr;
-    bool use_gcnt = false; int32_t* d_sel_cnt = nullptr; int32_t* d_sel_done = nullptr; S1Rec* d_recs = nullptr; int32_t* d_light = nullptr; int32_t* d_mid = nullptr; int32_t* d_heavy = nullptr;
+    int32_t* d_short_kind = nullptr; int32_t* d_s1_total = nullptr; bool use_gcnt = false; int32_t* d_sel_cnt = nullptr; int32_t* d_sel_done = nullptr; S1Rec* d_recs = nullptr; int32_t* d_light = nullptr; int32_t* d_mid = nullptr; int32_t* d_heavy = nullptr;
     int* d_order = nullptr; long long* d_qdbg = nullptr;
     int64_t* d_s1_key = nullptr; int32_t* d_s1_doc = nullptr; float* d_s1_score = nullptr; int32_t* d_s1_n = nullptr;
     Stage2Buffers s2{};                 // WordMatcher + coverage outputs
@@ -273,6 +276,14 @@ extern "C" int ifx_index_create(const ifx_index_image* img, const ifx_params* pp
             v.affix = upload_dict(ix, ss, true, &hh_affix); v.affix_fwd_doc = ix->up(fdoc.data(), A ? A : 1);
             v.affix_rev = ix->up(ro.data(), A ? A : 1); v.affix_rev_doc = ix->up(rdoc.data(), A ? A : 1); }
         stage("dictionaries");
+        {   // short-query structures
+            const int nc = img->n_champ_chars; v.n_champ = nc; static const uint16_t z16 = 0; static const int32_t z32[2] = {0, 0}; static const float zf = 0.f; static const int64_t z64[2] = {0, 0}; static const int32_t m1 = -1;
+            v.champ_chars = ix->up(nc ? img->champ_chars : &z16, std::max(nc, 1)); v.champ_off = ix->up(nc ? img->champ_off : z32, (size_t)nc + 1);
+            const size_t ne = nc ? (size_t)img->champ_off[nc] : 0; v.champ_doc = ix->up(ne ? img->champ_doc : z32, std::max<size_t>(ne, 1)); v.champ_score = ix->up(ne ? img->champ_score : &zf, std::max<size_t>(ne, 1));
+            if (nc) { ix->h_champ_chars.assign(img->champ_chars, img->champ_chars + nc); ix->h_champ_off.assign(img->champ_off, img->champ_off + nc + 1); }
+            const int nr = img->n_raw; v.n_raw = nr; v.raw_doc = ix->up(nr ? img->raw_doc : &m1, std::max(nr, 1)); v.raw_off = ix->up(nr ? img->raw_off : z64, (size_t)nr + 1);
+            const size_t rc = nr ? (size_t)img->raw_off[nr] : 0; v.raw_chars = ix->up(rc ? img->raw_chars : &z16, std::max<size_t>(rc, 1));
+        }
         {   // character tables (tools/gen_chartables.py) + host-evaluated MathF.Log2(len + 1)
             std::vector<uint16_t> lo(65536), upv(65536); std::vector<uint8_t> fl(65536, 0);
             for (int i = 0; i < 65536; i++) lo[i] = upv[i] = (uint16_t)i;

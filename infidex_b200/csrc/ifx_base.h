@@ -89,6 +89,9 @@ struct DevIndex {
     const float* idf_table;          // Bm25Scorer.ComputeIdf(n_live, df) for df in [0, idf_table_n): evaluated on the host with the
     int32_t idf_table_n;             // C runtime's logf (what MathF.Log calls), so device scores cannot drift from the reference by an ulp
     int32_t n_columns; const Column* columns;
+    // short-query path (ifx_short.h): champion lists of the 1-character prefixes, raw IndexedText of the documents that normalisation changed
+    int32_t n_champ; const uint16_t* champ_chars; const int32_t* champ_off; const int32_t* champ_doc; const float* champ_score;
+    int32_t n_raw; const int32_t* raw_doc; const int64_t* raw_off; const uint16_t* raw_chars;
 };
 
 IFX_FN uint64_t hash64(const uint16_t* s, int n) {
@@ -198,6 +201,8 @@ struct QueryPlan {
     int32_t depth, max_results, enable_coverage, filter_id, enable_facets;
     int32_t short_skip_coverage;           // SearchPipeline.cs:139-142 (3-char query whose prefix docset > 500)
     int32_t is_short3;                     // SearchPipeline.cs:110-112
+    int32_t short_kind;                    // 0: n-gram path; 1 / 2: no word of >= 3 characters -- one character / ShortQueryProcessor.SearchShortQuery (ifx_short.h)
+    int32_t short_no_cov;                  // short-query path and the coverage stage is not allowed (SearchPipeline.cs:133-170)
     uint16_t qtext[MAX_QLEN];
     uint16_t ttext[MAX_QLEN];
     QTerm terms[MAX_TERMS];
@@ -205,7 +210,7 @@ struct QueryPlan {
 };
 
 struct BatchCounters { int32_t n_fuzzy_items; int32_t overflow; unsigned long long fuzzy_pool_used; unsigned long long algo_bytes; unsigned long long s1_ns_sum; unsigned long long s1_ns_max; unsigned long long s1_cand_sum;
-                       unsigned long long s1_pool_used; int32_t s1_deferred, s1_n_light, s1_n_heavy, s1_wave, s1_n_mid, s1_pad; };
+                       unsigned long long s1_pool_used; int32_t s1_deferred, s1_n_light, s1_n_heavy, s1_wave, s1_n_mid, n_short; };
 
 struct FuzzyItem { int32_t query; int32_t slot; };
 

@@ -56,6 +56,34 @@ inline uint64_t hash64(const char16_t* s, size_t n) {
     h ^= h >> 29; h *= 0xbf58476d1ce4e5b9ULL; h ^= h >> 32; return h | 1ULL;
 }
 
+// .NET ArraySortHelper<T>.IntrospectiveSort (List<T>.Sort(Comparison)): unstable, and the tie order is observable in the champion lists
+// (ShortQueryResolver.BuildChampionLists keeps the first 64 after the sort) -- the same rules as the device's IdfSorter.
+template <class T, class Cmp> struct DotnetIntroSort {
+    Cmp cmp;
+    void swap_if_greater(T* k, int i, int j) { if (cmp(k[i], k[j]) > 0) std::swap(k[i], k[j]); }
+    void insertion(T* k, int n) { for (int i = 0; i < n - 1; i++) { T t = k[i + 1]; int j = i; while (j >= 0 && cmp(t, k[j]) < 0) { k[j + 1] = k[j]; j--; } k[j + 1] = t; } }
+    void down_heap(T* k, int i, int n) { T d = k[i - 1]; while (i <= n / 2) { int ch = 2 * i; if (ch < n && cmp(k[ch - 1], k[ch]) < 0) ch++; if (!(cmp(d, k[ch - 1]) < 0)) break; k[i - 1] = k[ch - 1]; i = ch; } k[i - 1] = d; }
+    void heap_sort(T* k, int n) { for (int i = n >> 1; i >= 1; i--) down_heap(k, i, n); for (int i = n; i > 1; i--) { std::swap(k[0], k[i - 1]); down_heap(k, 1, i - 1); } }
+    int partition(T* k, int n) {
+        int hi = n - 1, mid = hi >> 1;
+        swap_if_greater(k, 0, mid); swap_if_greater(k, 0, hi); swap_if_greater(k, mid, hi);
+        T pivot = k[mid]; std::swap(k[mid], k[hi - 1]);
+        int left = 0, right = hi - 1;
+        while (left < right) { while (cmp(k[++left], pivot) < 0) {} while (cmp(pivot, k[--right]) < 0) {} if (left >= right) break; std::swap(k[left], k[right]); }
+        if (left != hi - 1) std::swap(k[left], k[hi - 1]);
+        return left;
+    }
+    void intro(T* k, int n, int depth) {
+        while (n > 1) {
+            if (n <= 16) { if (n == 2) swap_if_greater(k, 0, 1); else if (n == 3) { swap_if_greater(k, 0, 1); swap_if_greater(k, 0, 2); swap_if_greater(k, 1, 2); } else insertion(k, n); return; }
+            if (depth == 0) { heap_sort(k, n); return; }
+            depth--; int p = partition(k, n); intro(k + p + 1, n - (p + 1), depth); n = p;
+        }
+    }
+    void sort(T* k, int n) { if (n < 2) return; int lg = 0; for (unsigned v = (unsigned)n; v >>= 1;) lg++; intro(k, n, 2 * (lg + 1)); }
+};
+inline bool is_ws(char16_t c) { static std::vector<uint8_t> ws = [] { std::vector<uint8_t> w(65536, 0); for (int i = 0; i < IFX_SPACE_LIST_N; i++) w[IFX_SPACE_LIST[i]] = 1; return w; }(); return ws[c] != 0; }
+
 // string interner: open addressing over a char arena; ids in first-insertion order
 struct Interner {
     std::vector<char16_t> arena; std::vector<uint32_t> off{0}; std::vector<uint64_t> hk; std::vector<int32_t> hv; size_t mask = 0;
@@ -173,6 +201,8 @@ struct ifx_builder {
     Csr terms, prefix, wm_exact, wm_ld1; std::vector<int32_t> df;
     std::vector<char16_t> word_chars; std::vector<uint32_t> word_off; std::vector<float> word_idf; std::vector<int32_t> word_df;
     std::vector<char16_t> affix_chars; std::vector<uint32_t> affix_off; std::vector<int32_t> affix_last;
+    std::vector<uint16_t> champ_chars; std::vector<int32_t> champ_off, champ_doc; std::vector<float> champ_score;
+    std::vector<int32_t> raw_doc; std::vector<char16_t> raw_chars; std::vector<int64_t> raw_off;
     std::vector<ifx_column> cols; std::vector<std::vector<int32_t>> col_ids; std::vector<std::vector<char16_t>> col_chars; std::vector<std::vector<uint32_t>> col_off; std::vector<str> col_names;
 };
 
@@ -213,12 +243,14 @@ int ifx_builder_finish(ifx_builder* b, int threads) {
     struct Part {
         std::unique_ptr<KeyedRecords> terms, prefix, exact, ld1; Interner words; std::vector<int32_t> word_df; Interner affix; std::vector<int32_t> affix_last;
         std::vector<char16_t> text; std::vector<int64_t> text_len; std::vector<char16_t> ft; std::vector<uint32_t> ft_len; std::vector<uint16_t> tokc;
+        struct Champ { char16_t ch; uint16_t score; int32_t doc; }; std::vector<Champ> champs;      // ShortQueryResolver: one record per (first character of a word, document)
+        std::vector<int32_t> raw_doc; std::vector<char16_t> raw_chars; std::vector<int64_t> raw_len;   // documents whose raw IndexedText differs from its normalised form
     };
     std::vector<Part> parts(threads);
     auto work = [&](int t) {
         Part& P = parts[t]; P.terms.reset(new KeyedRecords(true)); P.prefix.reset(new KeyedRecords(false)); P.exact.reset(new KeyedRecords(false)); P.ld1.reset(new KeyedRecords(false));
         int d0 = (int)((int64_t)N * t / threads), d1 = (int)((int64_t)N * (t + 1) / threads);
-        str raw, nrm, idx, padded, wm, tmp; std::vector<std::pair<int, int>> bounds; std::vector<int> seen_words;
+        str raw, nrm, idx, padded, wm, tmp; std::vector<std::pair<int, int>> bounds; std::vector<int> seen_words; std::vector<sv> tok_scratch;
         for (int d = d0; d < d1; d++) {
             raw.clear(); bounds.clear();
             for (size_t k = 0; k < order.size(); k++) { bounds.emplace_back((int)(uint16_t)raw.size(), b->schema[order[k]].weight); raw += b->values[order[k]][d]; if (k + 1 < order.size()) raw.push_back(u'§'); }
@@ -234,6 +266,28 @@ int ifx_builder_finish(ifx_builder* b, int threads) {
             // prefix docsets (PositionalPrefixIndex over the index text)
             for (size_t i = 0; i < idx.size();) { while (i < idx.size() && is_delim(idx[i])) i++; if (i >= idx.size()) break; size_t s = i; while (i < idx.size() && !is_delim(idx[i])) i++;
                 size_t ml = std::min<size_t>(3, i - s); for (size_t l = 1; l <= ml; l++) P.prefix->add_doc(P.prefix->key(sv(idx.data() + s, l)), d); }
+            // short-query structures (Indexing/ShortQuery/ShortQueryResolver.cs:83-160,268-311): per first character of a word of the index text,
+            // (first token index, number of such word starts) -> precedence / base score against the document's lower-cased RAW title
+            {   tmp = raw; lower_inplace(tmp);                                // ToLowerInvariant(IndexedText), not normalised
+                if (nrm != raw) { P.raw_doc.push_back(d); P.raw_chars.insert(P.raw_chars.end(), raw.begin(), raw.end()); P.raw_len.push_back((int64_t)raw.size()); }
+                // title tokens (split on the delimiters, empty entries removed) and trim
+                int n_tok = 0; sv first_tok; std::vector<sv>& toks = tok_scratch; toks.clear();
+                for (size_t i = 0; i < tmp.size();) { while (i < tmp.size() && is_delim(tmp[i])) i++; if (i >= tmp.size()) break; size_t s0 = i; while (i < tmp.size() && !is_delim(tmp[i])) i++; toks.emplace_back(tmp.data() + s0, i - s0); }
+                n_tok = (int)toks.size(); if (n_tok) first_tok = toks[0];
+                size_t tb = 0, te = tmp.size(); while (tb < te && is_ws(tmp[tb])) tb++; while (te > tb && is_ws(tmp[te - 1])) te--;
+                struct Acc { char16_t ch; int first_pos, n; }; Acc acc[64]; int na = 0; int ti = 0;
+                for (size_t i = 0; i < idx.size();) { while (i < idx.size() && is_delim(idx[i])) i++; if (i >= idx.size()) break; size_t s0 = i; while (i < idx.size() && !is_delim(idx[i])) i++;
+                    const char16_t ch = idx[s0]; int a = 0; for (; a < na; a++) if (acc[a].ch == ch) break;
+                    if (a == na) { if (na < 64) { acc[na].ch = ch; acc[na].first_pos = ti; acc[na].n = 1; na++; } } else acc[a].n++;
+                    ti++; }
+                for (int a = 0; a < na; a++) {
+                    const char16_t ch = acc[a].ch; int prec = 128; if (acc[a].first_pos == 0) prec |= 64;
+                    bool any = false, first = false; for (int i = 0; i < n_tok; i++) if (toks[i].size() == 1 && toks[i][0] == ch) { any = true; if (i == 0) first = true; break; }
+                    if (any) prec |= 32; if (first) prec |= 16; if (te - tb == 1 && tmp[tb] == ch) prec |= 8; if (n_tok <= 3) prec |= 32;
+                    const int pos_c = 255 - std::min(acc[a].first_pos * 16, 240), dens = std::min(acc[a].n * 8, 32); const int base = std::max(0, std::min(255, pos_c + dens));
+                    P.champs.push_back({ch, (uint16_t)((prec << 8) | base), d});
+                }
+            }
             // WordMatcher.Load / word-idf / metadata work on normalize(lower(IndexedText))
             tmp = raw; lower_inplace(tmp); normalize_into(tmp, wm);
             int ntok = 0; bool first = true; seen_words.clear();
@@ -265,6 +319,19 @@ int ifx_builder_finish(ifx_builder* b, int threads) {
     }
     stage("text concat");
     auto small_dicts = [&] {
+        {   // champion lists: per first character the documents in ascending id order, List.Sort by score descending (unstable, reproduced), first 64
+            std::vector<std::vector<std::pair<uint16_t, int32_t>>> by_ch(65536);
+            for (auto& P : parts) for (auto& cr : P.champs) by_ch[cr.ch].emplace_back(cr.score, cr.doc);
+            b->champ_off.assign(1, 0);
+            for (int ch = 0; ch < 65536; ch++) { auto& v = by_ch[ch]; if (v.empty()) continue;
+                auto cmpf = [](const std::pair<uint16_t, int32_t>& x, const std::pair<uint16_t, int32_t>& y) { return y.first < x.first ? -1 : (y.first > x.first ? 1 : 0); };
+                DotnetIntroSort<std::pair<uint16_t, int32_t>, decltype(cmpf)> srt{cmpf}; srt.sort(v.data(), (int)v.size());
+                const size_t keep = std::min<size_t>(v.size(), 64);
+                b->champ_chars.push_back((uint16_t)ch); for (size_t i = 0; i < keep; i++) { b->champ_doc.push_back(v[i].second); b->champ_score.push_back((float)v[i].first); } b->champ_off.push_back((int32_t)b->champ_doc.size()); }
+            if (b->champ_chars.empty()) b->champ_chars.push_back(0); if (b->champ_doc.empty()) { b->champ_doc.push_back(0); b->champ_score.push_back(0.f); }
+            b->raw_off.assign(1, 0); for (auto& P : parts) { b->raw_doc.insert(b->raw_doc.end(), P.raw_doc.begin(), P.raw_doc.end()); b->raw_chars.insert(b->raw_chars.end(), P.raw_chars.begin(), P.raw_chars.end()); for (auto l : P.raw_len) b->raw_off.push_back(b->raw_off.back() + l); }
+            if (b->raw_doc.empty()) b->raw_doc.push_back(-1); if (b->raw_chars.empty()) b->raw_chars.push_back(0);
+        }
     // word idf
         { Interner g; std::vector<int32_t> gdf; for (auto& P : parts) for (int k = 0; k < P.words.size(); k++) { bool nw; int id = g.intern(P.words.get(k), &nw); if (nw) gdf.push_back(0); gdf[id] += P.word_df[k]; }
           b->word_chars.assign(g.arena.begin(), g.arena.end()); if (b->word_chars.empty()) b->word_chars.push_back(0); b->word_off = g.off; b->word_idf.resize(gdf.size()); b->word_df = gdf;
@@ -324,6 +391,8 @@ int ifx_builder_finish(ifx_builder* b, int threads) {
     I.wm_ld1 = {S(b->wm_ld1.chars, b->wm_ld1.off), b->wm_ld1.row.data(), b->wm_ld1.docs.data()};
     I.affix_words = S(b->affix_chars, b->affix_off); I.affix_last_doc = b->affix_last.data();
     I.n_columns = (int)b->cols.size(); I.columns = b->cols.data();
+    I.n_champ_chars = (int)b->champ_off.size() - 1; I.champ_chars = b->champ_chars.data(); I.champ_off = b->champ_off.data(); I.champ_doc = b->champ_doc.data(); I.champ_score = b->champ_score.data();
+    I.n_raw = (int)b->raw_off.size() - 1; I.raw_doc = b->raw_doc.data(); I.raw_off = b->raw_off.data(); I.raw_chars = (const uint16_t*)b->raw_chars.data();
     // free the raw documents
     b->values.clear(); b->values.shrink_to_fit(); b->is_null.clear();
     b->finished = true; return IFX_OK;

@@ -2,10 +2,35 @@
 
 #ifndef IFX_EMU
 __global__ void k_prepare(DevIndex ix, const uint16_t* text, const int64_t* off, const int32_t* par, int nq, QueryPlan* plans,
-                          FuzzyItem* items, int items_cap, BatchCounters* bc) {
+                          FuzzyItem* items, int items_cap, BatchCounters* bc, int32_t* short_kind) {
     int q = blockIdx.x * blockDim.x + threadIdx.x; if (q >= nq) return;
     prepare_query(ix, text + off[q], (int)(off[q + 1] - off[q]), par[q * 5 + 1], par[q * 5 + 0], par[q * 5 + 2], par[q * 5 + 3], par[q * 5 + 4], plans[q], items, items_cap, bc, q);
+    short_kind[q] = plans[q].short_kind; if (plans[q].short_kind) atomicAdd(&bc->n_short, 1);
 }
+// ---- short-query path (ifx_short.h): grid-wide launches per query ---------------------------------------------------------------------------
+__global__ void k_sq_char(DevIndex ix, SqScratch S, uint16_t ch) {
+    for (int64_t d = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; d < ix.n_docs; d += (int64_t)gridDim.x * blockDim.x) S.vf[d] = ix.deleted[d] ? 0.f : sq_single_char_score(ix, (int)d, ch);
+}
+__global__ void k_sq_terms(DevIndex ix, const QueryPlan* plan, SqScratch S) { if (threadIdx.x == 0) { SqPatterns P; sq_build_patterns(plan->qtext, plan->qlen, P); sq_collect_pattern_terms(ix, P, S); } }
+__global__ void k_sq_accum(DevIndex ix, SqScratch S) {
+    Ctx c; const int n = S.counters[1]; const int64_t w0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t t = w0; t < n; t += nw) sq_process_term(c, ix, S.terms[t], S.tmult[t], S);
+}
+__global__ void k_sq_fuzzy(DevIndex ix, const QueryPlan* plan, SqScratch S) {
+    __shared__ SqPatterns P; Ctx c; if (threadIdx.x == 0) sq_build_patterns(plan->qtext, plan->qlen, P); __syncthreads();
+    const int64_t w0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t t = w0; t < ix.terms.n; t += nw) { int w = 0; if (c.lane() == 0) w = ix.df[t] > 0 ? sq_fuzzy_weight(ix, (int)t, P, plan->qtext, plan->qlen) : 0; w = __shfl_sync(0xffffffffu, w, 0); if (w) sq_process_term(c, ix, (int)t, w, S); }
+}
+__global__ void k_sq_max(DevIndex ix, SqScratch S) { int m = 0; for (int64_t d = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; d < ix.n_docs; d += (int64_t)gridDim.x * blockDim.x) m = S.vi[d] > m ? S.vi[d] : m; if (m > 0) atomicMax(&S.counters[2], m); }
+__global__ void k_sq_final(DevIndex ix, const QueryPlan* plan, SqScratch S) {
+    const int vmax = S.counters[2];
+    for (int64_t d = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; d < ix.n_docs; d += (int64_t)gridDim.x * blockDim.x) { const int v = S.vi[d]; S.vf[d] = (v > 0 && !ix.deleted[d]) ? sq_final_score(ix, (int)d, v, vmax, plan->qtext, plan->qlen) : 0.f; }
+}
+__global__ void __launch_bounds__(256) k_sq_top1(DevIndex ix, SqScratch S) { extern __shared__ __align__(16) unsigned char smem_raw[]; Ctx c; sq_topk_stage1(c, ix, S, *reinterpret_cast<SqTopShared*>(smem_raw), blockIdx.x, gridDim.x); }
+__global__ void __launch_bounds__(256) k_sq_top2(SqScratch S, int nblk, int keep, int64_t* key, int32_t* doc, float* score, int32_t* n, int32_t* total) {
+    extern __shared__ __align__(16) unsigned char smem_raw[]; Ctx c; sq_topk_stage2(c, S, *reinterpret_cast<SqTopShared*>(smem_raw), nblk, keep, key, doc, score, n, total); }
+__global__ void __launch_bounds__(256) k_sq_champ(DevIndex ix, int ci, int m, int64_t* key, int32_t* doc, float* score, int32_t* n, int32_t* total) {
+    extern __shared__ __align__(16) unsigned char smem_raw[]; Ctx c; sq_champions(c, ix, *reinterpret_cast<SqTopShared*>(smem_raw), ci, m, key, doc, score, n, total); }
 // Longest-processing-time-first order: queries bucketed by their estimated work (posting volume, or the candidate count when the
 // prefix shortcut will apply; log2 scale, eight steps per octave), heaviest
 // bucket first, so the long sequential chunk chains of heavy queries start at once instead of forming the tail of the launch.
@@ -124,19 +149,93 @@ __global__ void __launch_bounds__(256) k_s1_finish(DevIndex ix, const BatchCount
 }
 #endif
 
+// Stage 1 of the queries without a word of >= 3 characters (ifx_short.h): a handful of grid-wide launches per such query. Returns how many ran.
+static int run_short_queries(ifx_batch* b, ifx_stats* st) {
+    ifx_index* ix = b->idx; const int nq = b->nq; const int K = b->s1_stride;
+    dev_zero(b->d_s1_total, (size_t)nq * 4);
+    BatchCounters bc; d2h(&bc, b->d_bc, sizeof(bc)); if (bc.n_short == 0) return 0;
+    std::vector<int32_t> kinds(nq); d2h(kinds.data(), b->d_short_kind, (size_t)nq * 4);
+    const int N = ix->v.n_docs; const int nblk = std::max(1, std::min(ix->n_ctas, (N + 4095) / 4096));
+    if (!ix->sq.vi) { SqScratch& S = ix->sq; S.vi = ix->alloc<int32_t>((size_t)N + 1); S.vf = ix->alloc<float>((size_t)N + 1); S.terms = ix->alloc<int32_t>(SQ_PATTERNS * SQ_TERMS); S.tmult = ix->alloc<int32_t>(SQ_PATTERNS * SQ_TERMS); S.counters = ix->alloc<int32_t>(8);
+        const size_t nb = (size_t)std::max(ix->n_ctas, 1) * SQ_KB; S.cand_score = ix->alloc<float>(nb); S.cand_key = ix->alloc<int64_t>(nb); S.cand_doc = ix->alloc<int32_t>(nb); S.cand_n = ix->alloc<int32_t>(std::max(ix->n_ctas, 1)); }
+    SqScratch S = ix->sq; int ran = 0; QueryPlan plan;
+#ifdef IFX_EMU
+    static SqTopShared* tsh = new SqTopShared(); Ctx c;
+#else
+    if (!ix->attr_sq) { CUDA_TRY(cudaFuncSetAttribute(k_sq_top1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SqTopShared))); CUDA_TRY(cudaFuncSetAttribute(k_sq_top2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SqTopShared))); CUDA_TRY(cudaFuncSetAttribute(k_sq_champ, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SqTopShared))); ix->attr_sq = true; }
+    const int grid = ix->n_ctas * 2;
+#endif
+    for (int q = 0; q < nq; q++) {
+        if (!kinds[q]) continue;
+        d2h(&plan, b->d_plans + q, sizeof(QueryPlan)); if (plan.status != 0) continue;
+        int64_t* o_key = b->d_s1_key + (size_t)q * K; int32_t* o_doc = b->d_s1_doc + (size_t)q * K; float* o_score = b->d_s1_score + (size_t)q * K; int32_t* o_n = b->d_s1_n + q; int32_t* o_tot = b->d_s1_total + q;
+        const int keep = std::min(K, SQ_KB); ran++;       // K = row length of the list arrays (>= depth and >= max_results up to 1024)
+        if (plan.short_kind == 1) {
+            const uint16_t ch = plan.qtext[0]; int ci = -1; int have = 0;      // (the host normalised and lower-cased the query)
+            for (int i = 0; i < ix->h_champ_chars.size(); i++) if (ix->h_champ_chars[i] == ch) { ci = i; have = ix->h_champ_off[i + 1] - ix->h_champ_off[i]; }
+            const int m = plan.max_results;
+            if (ci >= 0 && m > 0 && have >= m && m <= keep) {      // ShortQueryResolver.TryGetChampions
+#ifdef IFX_EMU
+                sq_champions(c, ix->v, *tsh, ci, m, o_key, o_doc, o_score, o_n, o_tot);
+#else
+                k_sq_champ<<<1, 256, sizeof(SqTopShared)>>>(ix->v, ci, m, o_key, o_doc, o_score, o_n, o_tot);
+#endif
+                continue;
+            }
+#ifdef IFX_EMU
+            for (int d = 0; d < N; d++) S.vf[d] = ix->v.deleted[d] ? 0.f : sq_single_char_score(ix->v, d, ch);
+#else
+            k_sq_char<<<grid, 256>>>(ix->v, S, ch);
+#endif
+        } else {
+            dev_zero(S.vi, (size_t)N * 4); dev_zero(S.counters, 32);
+#ifdef IFX_EMU
+            { SqPatterns P; sq_build_patterns(plan.qtext, plan.qlen, P); sq_collect_pattern_terms(ix->v, P, S);
+              for (int t = 0; t < S.counters[1]; t++) sq_process_term(c, ix->v, S.terms[t], S.tmult[t], S);
+              if (S.counters[0] < 100) for (int t = 0; t < ix->v.terms.n; t++) { int w = ix->v.df[t] > 0 ? sq_fuzzy_weight(ix->v, t, P, plan.qtext, plan.qlen) : 0; if (w) sq_process_term(c, ix->v, t, w, S); }
+              int vmax = 0; for (int d = 0; d < N; d++) vmax = std::max(vmax, S.vi[d]); S.counters[2] = vmax;
+              for (int d = 0; d < N; d++) { const int v = S.vi[d]; S.vf[d] = (v > 0 && !ix->v.deleted[d]) ? sq_final_score(ix->v, d, v, vmax, plan.qtext, plan.qlen) : 0.f; } }
+#else
+            k_sq_terms<<<1, 32>>>(ix->v, b->d_plans + q, S);
+            k_sq_accum<<<grid, 256>>>(ix->v, S);
+            int32_t cnt[4]; d2h(cnt, S.counters, 16);
+            if (cnt[0] < 100) k_sq_fuzzy<<<grid, 256>>>(ix->v, b->d_plans + q, S);      // ProcessFuzzyFallback: every term of the dictionary
+            k_sq_max<<<grid, 256>>>(ix->v, S);
+            k_sq_final<<<grid, 256>>>(ix->v, b->d_plans + q, S);
+#endif
+        }
+        // the query's Stage-1 list: exact top-`keep` by (score descending, key ascending) + the number of matched documents
+#ifdef IFX_EMU
+        S.counters[3] = 0; for (int bl = 0; bl < nblk; bl++) sq_topk_stage1(c, ix->v, S, *tsh, bl, nblk);
+        int keep_q = plan.short_kind == 1 ? std::min(keep, plan.max_results) : keep;
+        sq_topk_stage2(c, S, *tsh, nblk, keep_q, o_key, o_doc, o_score, o_n, o_tot);
+        if (plan.short_kind == 1) *o_tot = *o_n;
+#else
+        CUDA_TRY(cudaMemsetAsync(S.counters + 3, 0, 4));
+        k_sq_top1<<<nblk, 256, sizeof(SqTopShared)>>>(ix->v, S);
+        const int keep_q = plan.short_kind == 1 ? std::min(keep, plan.max_results) : keep;
+        k_sq_top2<<<1, 256, sizeof(SqTopShared)>>>(S, nblk, keep_q, o_key, o_doc, o_score, o_n, o_tot);
+        if (plan.short_kind == 1) CUDA_TRY(cudaMemcpyAsync(o_tot, o_n, 4, cudaMemcpyDeviceToDevice));      // SearchSingleCharacter cuts its list to max_results before anything counts it
+        CUDA_TRY(cudaGetLastError());
+#endif
+    }
+    if (st) st->kernel_launches += 6 * ran;
+    return ran;
+}
+
 static int s1_force_mode() { const char* e = getenv("IFX_S1_LOOKUP"); return e ? atoi(e) : 0; }      // 1 forward-index lookups, 2 streamed lists (tests / A-B runs)
 
 // `part`: 1 = query preparation + LD1 expansion, 2 = selection / lookups / scoring / final order, 3 = both (the unsharded call)
 //         4 = selection count pass only (doc-id-range shards; the hosts sum b->d_sel_cnt over the shards before part 2 runs with smode 2)
 static void run_stage1_phase(ifx_batch* b, ifx_stats* st, int part = 3) {
-    ifx_index* ix = b->idx; const int nq = b->nq; const int K = b->depth_max;
+    ifx_index* ix = b->idx; const int nq = b->nq; const int K = b->s1_stride;
     if (part & 1) { BatchCounters zero{}; h2d(b->d_bc, &zero, sizeof(zero)); }
     const int items_cap = nq * MAX_FUZZY;       // every query may carry MAX_FUZZY unknown words: the item list can never overflow
     const int force_mode = s1_force_mode(); S1Queues queues{b->d_light, b->d_mid, b->d_heavy};
     Timer t;
 #ifdef IFX_EMU
     std::vector<int64_t> off(nq + 1); d2h(off.data(), b->d_off, (nq + 1) * 8);
-    if (part & 1) for (int q = 0; q < nq; q++) prepare_query(ix->v, b->d_text + off[q], (int)(off[q + 1] - off[q]), b->d_par[q * 5 + 1], b->d_par[q * 5 + 0], b->d_par[q * 5 + 2], b->d_par[q * 5 + 3], b->d_par[q * 5 + 4], b->d_plans[q], b->d_items, items_cap, b->d_bc, q);
+    if (part & 1) for (int q = 0; q < nq; q++) { prepare_query(ix->v, b->d_text + off[q], (int)(off[q + 1] - off[q]), b->d_par[q * 5 + 1], b->d_par[q * 5 + 0], b->d_par[q * 5 + 2], b->d_par[q * 5 + 3], b->d_par[q * 5 + 4], b->d_plans[q], b->d_items, items_cap, b->d_bc, q); b->d_short_kind[q] = b->d_plans[q].short_kind; if (b->d_plans[q].short_kind) b->d_bc->n_short++; }
     static S1Shared* sh = new S1Shared(); memset(sh->dirty, 0, sizeof(sh->dirty)); static WarpScoreShared* wsh = new WarpScoreShared(); static FinishShared* fsh = new FinishShared();
     Ctx c; int nit = std::min(b->d_bc->n_fuzzy_items, items_cap);
     if (part & 1) for (int i = 0; i < nit; i++) expand_fuzzy(c, ix->v, b->d_plans[b->d_items[i].query], b->d_items[i].slot, ix->ws[0], *sh, ix->d_pool, ix->pool_cap, b->d_bc, ix->d_sorted_len, sh->cand_s);
@@ -178,7 +277,7 @@ static void run_stage1_phase(ifx_batch* b, ifx_stats* st, int part = 3) {
     float ms_prep = 0.f, ms_exp = 0.f; int launches = 0;
     if (part & 1) {
         t.start();
-        k_prepare<<<(nq + 127) / 128, 128>>>(ix->v, b->d_text, b->d_off, b->d_par, nq, b->d_plans, b->d_items, items_cap, b->d_bc);
+        k_prepare<<<(nq + 127) / 128, 128>>>(ix->v, b->d_text, b->d_off, b->d_par, nq, b->d_plans, b->d_items, items_cap, b->d_bc, b->d_short_kind);
         ms_prep = t.stop();
         t.start();
         CUDA_TRY(cudaMemsetAsync(b->d_work, 0, 8 * sizeof(int)));
@@ -231,8 +330,8 @@ static int fill_batch(ifx_batch* b, const ifx_query* q, int nq) {
         b->nq = nq; b->depth_max = depth_max; b->cap_max = cap_max; b->text_cap = std::max<size_t>(text.size(), (size_t)nq * 64);
         b->d_text = b->alloc<uint16_t>(b->text_cap); b->d_off = b->alloc<int64_t>(nq + 1); b->d_par = b->alloc<int32_t>(par.size());
         b->d_plans = b->alloc<QueryPlan>(nq); b->d_items = b->alloc<FuzzyItem>((size_t)nq * MAX_FUZZY); b->d_bc = b->alloc<BatchCounters>(1); b->d_work = b->alloc<int>(8); dev_zero(b->d_work, 8 * sizeof(int));
-        size_t K = b->depth_max;
-        b->d_recs = b->alloc<S1Rec>(nq); dev_zero(b->d_recs, sizeof(S1Rec) * (size_t)nq); b->d_sel_cnt = b->alloc<int32_t>((size_t)nq * SEL_CNT); b->d_sel_done = b->alloc<int32_t>(nq); dev_zero(b->d_sel_done, (size_t)nq * 4); b->d_light = b->alloc<int32_t>(nq); b->d_mid = b->alloc<int32_t>(nq); b->d_heavy = b->alloc<int32_t>(nq);
+        b->s1_stride = std::max(depth_max, std::min(cap_max, (int)MAX_K)); size_t K = b->s1_stride;
+        b->d_recs = b->alloc<S1Rec>(nq); dev_zero(b->d_recs, sizeof(S1Rec) * (size_t)nq); b->d_short_kind = b->alloc<int32_t>(nq); b->d_s1_total = b->alloc<int32_t>(nq); dev_zero(b->d_s1_total, (size_t)nq * 4); b->d_sel_cnt = b->alloc<int32_t>((size_t)nq * SEL_CNT); b->d_sel_done = b->alloc<int32_t>(nq); dev_zero(b->d_sel_done, (size_t)nq * 4); b->d_light = b->alloc<int32_t>(nq); b->d_mid = b->alloc<int32_t>(nq); b->d_heavy = b->alloc<int32_t>(nq);
         b->d_s1_key = b->alloc<int64_t>(nq * K); b->d_s1_doc = b->alloc<int32_t>(nq * K); b->d_s1_score = b->alloc<float>(nq * K); b->d_s1_n = b->alloc<int32_t>(nq); b->d_order = b->alloc<int>(nq); b->d_qdbg = b->alloc<long long>((size_t)nq * IFX_QDBG); dev_zero(b->d_qdbg, (size_t)nq * IFX_QDBG * 8);
     } else if (text.size() > b->text_cap) return fail(IFX_ERR_INVALID, "batch text outgrew its buffer");
     h2d(b->d_text, text.data(), text.size() * 2); h2d(b->d_off, off.data(), (nq + 1) * 8); h2d(b->d_par, par.data(), par.size() * 4);
@@ -256,8 +355,11 @@ extern "C" int ifx_stage1_batch(ifx_index* idx, const ifx_query* q, int nq, int 
     if (st) memset(st, 0, sizeof(*st));
     try {
         std::lock_guard<std::mutex> lk(idx->mu); DeviceGuard dg(idx->device);
-        run_stage1_phase(b, st);
-        d2h(doc_key, b->d_s1_key, (size_t)nq * depth * 8); d2h(score, b->d_s1_score, (size_t)nq * depth * 4); d2h(n, b->d_s1_n, (size_t)nq * 4);
+        run_stage1_phase(b, st); run_short_queries(b, st);
+        d2h(n, b->d_s1_n, (size_t)nq * 4);
+        if (b->s1_stride == depth) { d2h(doc_key, b->d_s1_key, (size_t)nq * depth * 8); d2h(score, b->d_s1_score, (size_t)nq * depth * 4); }
+        else { std::vector<int64_t> k((size_t)nq * b->s1_stride); std::vector<float> sc((size_t)nq * b->s1_stride); d2h(k.data(), b->d_s1_key, k.size() * 8); d2h(sc.data(), b->d_s1_score, sc.size() * 4);
+            for (int i = 0; i < nq; i++) { memcpy(doc_key + (size_t)i * depth, k.data() + (size_t)i * b->s1_stride, (size_t)depth * 8); memcpy(score + (size_t)i * depth, sc.data() + (size_t)i * b->s1_stride, (size_t)depth * 4); if (n[i] > depth) n[i] = depth; } }
         if (status) { std::vector<QueryPlan> pl(nq); d2h(pl.data(), b->d_plans, sizeof(QueryPlan) * (size_t)nq); for (int i = 0; i < nq; i++) { status[i] = pl[i].status; if (n[i] < 0) { status[i] |= IFX_Q_OVERFLOW; n[i] = 0; } } }
     } catch (const std::string& e) { delete b; return fail(IFX_ERR_CUDA, e); }
     delete b; return IFX_OK;

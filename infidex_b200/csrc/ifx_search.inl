@@ -121,7 +121,7 @@ __global__ void __launch_bounds__(256) k_finalize(DevIndex ix, const QueryPlan* 
 #endif
 
 static void run_stage2_phase(ifx_batch* b, ifx_stats* st, int part = 3) {      // part: 1 = WordMatcher lookups, 2 = coverage / fusion / finalize, 3 = both
-    ifx_index* ix = b->idx; const int nq = b->nq; const int K = b->depth_max;
+    ifx_index* ix = b->idx; const int nq = b->nq; const int K = b->s1_stride;
     Timer t;
 #ifdef IFX_EMU
     static WmShared* wsh = new WmShared(); static FinShared* fsh = new FinShared(); memset(wsh->dirty, 0, sizeof(wsh->dirty));
@@ -177,6 +177,7 @@ extern "C" int ifx_batch_run(ifx_batch* b, ifx_stats* st) {
         b->s2.gmax = nullptr;
         Timer tt; tt.start();
         run_stage1_phase(b, st);
+        run_short_queries(b, st); b->s2.s1_total = b->d_s1_total;
         run_stage2_phase(b, st);
         float ms = tt.stop(); if (st) st->ms_total = ms;
         b->ran = true;
@@ -223,7 +224,7 @@ extern "C" int ifx_batch_run_phase(ifx_batch* b, int phase, ifx_stats* st) {
         if (!b->s2.ent_doc) alloc_stage2(b, std::max(b->cap_max, 1), b->fcap);
         if (phase == 1) { if (st) { int64_t h = st->h2d_bytes, d = st->d2h_bytes; memset(st, 0, sizeof(*st)); st->h2d_bytes = h; st->d2h_bytes = d; } b->s2.gmax = nullptr; b->s2.g_di = nullptr; b->fin.shard_info = nullptr; b->fin.shard_dkey = nullptr; b->use_gcnt = false; run_stage1_phase(b, st, 1); }
         else if (phase == 2) run_stage1_phase(b, st, 4);
-        else if (phase == 3) run_stage1_phase(b, st, 2);
+        else if (phase == 3) { run_stage1_phase(b, st, 2); b->s2.s1_total = nullptr; }      // (short queries are not run on shards: they keep an empty list and IFX_Q_UNSUPPORTED_OP)
         else if (phase == 4) run_stage2_phase(b, st, 1);
         else { b->fin.shard_info = b->d_shard_info; b->fin.shard_dkey = b->d_shard_dkey; run_stage2_phase(b, st, 2); b->ran = true; }
     } catch (const std::string& e) { return fail(IFX_ERR_CUDA, e); }
@@ -244,7 +245,7 @@ extern "C" int ifx_batch_fuzzy_df(ifx_batch* b, int32_t* buf, int set) {
 }
 extern "C" int ifx_batch_stage1_lists(ifx_batch* b, int64_t* key, float* score, int32_t* n) {      // [nq][depth] keys / scores, [nq] counts of this shard's Stage-1 lists
     if (!b || !key || !score || !n) return fail(IFX_ERR_INVALID, "null argument");
-    try { DeviceGuard dg(b->idx->device); const size_t m = (size_t)b->nq * b->depth_max;
+    try { DeviceGuard dg(b->idx->device); const size_t m = (size_t)b->nq * b->s1_stride;
 #ifdef IFX_EMU
         memcpy(key, b->d_s1_key, m * 8); memcpy(score, b->d_s1_score, m * 4); memcpy(n, b->d_s1_n, (size_t)b->nq * 4);
 #else
@@ -257,7 +258,7 @@ extern "C" int ifx_batch_stage1_lists(ifx_batch* b, int64_t* key, float* score, 
 // until phase 3 has run).
 extern "C" int ifx_batch_stage1_restrict(ifx_batch* b, const uint8_t* keep, const float* gmax, const int32_t* n_global) {
     if (!b || !keep || !gmax || !n_global) return fail(IFX_ERR_INVALID, "null argument");
-    try { DeviceGuard dg(b->idx->device); const int K = b->depth_max;
+    try { DeviceGuard dg(b->idx->device); const int K = b->s1_stride;
 #ifdef IFX_EMU
         for (int q = 0; q < b->nq; q++) { int m = 0; const int cnt = b->d_s1_n[q] < 0 ? 0 : b->d_s1_n[q]; const size_t o = (size_t)q * K; int d0 = n_global[q] >= 2 ? -1 : -2, d1 = d0;
             for (int i = 0; i < cnt; i++) { const uint8_t k = keep[o + i]; if (!k) continue; if (k == 2 && d0 != -2) d0 = b->d_s1_doc[o + i]; if (k == 3 && d1 != -2) d1 = b->d_s1_doc[o + i];

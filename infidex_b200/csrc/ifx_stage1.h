@@ -32,7 +32,7 @@ IFX_FN float max_term_score(float idf, float avgdl) {   // VectorModel.cs:523-53
 IFX_FN void prepare_query(const DevIndex& ix, const uint16_t* text, int len, int depth, int max_results, int enable_cov,
                           int filter_id, int enable_facets, QueryPlan& p, FuzzyItem* items, int items_cap, BatchCounters* bc, int qi) {
     p.status = 0; p.n_terms = 0; p.n_fuzzy = 0; p.qlen = 0; p.tlen = 0; p.depth = depth; p.max_results = max_results;
-    p.enable_coverage = enable_cov; p.filter_id = filter_id; p.enable_facets = enable_facets; p.short_skip_coverage = 0; p.is_short3 = 0;
+    p.enable_coverage = enable_cov; p.filter_id = filter_id; p.enable_facets = enable_facets; p.short_skip_coverage = 0; p.is_short3 = 0; p.short_kind = 0; p.short_no_cov = 0;
     if (len > MAX_QLEN || depth > MAX_K || depth < 1) { p.status = 4; return; }
     bool blank = true;
     for (int i = 0; i < len; i++) { p.qtext[i] = text[i]; if (!is_space(ix, text[i])) blank = false; }
@@ -49,7 +49,15 @@ IFX_FN void prepare_query(const DevIndex& ix, const uint16_t* text, int len, int
         if (i - b >= 3) { if (n_long > 0) p.ttext[tl++] = u' '; for (int k = b; k < i; k++) p.ttext[tl++] = text[k]; n_long++; } else n_short++;
     }
     bool can_ngrams = n_words == 0 ? len >= 3 : n_long > 0;
-    if (!can_ngrams) { p.status |= 1; return; }
+    if (!can_ngrams) {      // no word of >= 3 characters: ShortQueryProcessor / ShortQueryResolver (SearchPipeline.cs:222-262), scored by the launches of ifx_short.h
+        if (ix.prefix_gcard) { p.status |= 2; return; }      // a doc-id-range shard: the short-query path is not distributed -- flagged (IFX_Q_UNSUPPORTED_OP), never answered partially
+        p.short_kind = len == 1 ? 1 : 2; p.tlen = 0;
+        bool short3 = len <= 3; for (int i = 0; i < len; i++) if (is_delim(ix, text[i])) short3 = false;
+        p.is_short3 = short3; int64_t pc = -1;
+        if (short3) { int k = dict_lookup(ix.prefix.keys, text, len); pc = k < 0 ? 0 : (ix.prefix_gcard ? (int64_t)ix.prefix_gcard[k] : ix.prefix.row_ptr[k + 1] - ix.prefix.row_ptr[k]); if (pc > 500) p.short_skip_coverage = 1; }
+        p.short_no_cov = !(short3 && pc > 0 && pc <= 500);      // allowShortQueryCoverage (SearchPipeline.cs:133-137)
+        return;
+    }
     bool mixed = n_short > 0 && n_long > 0;
     if (!mixed) { tl = len; for (int i = 0; i < len; i++) p.ttext[i] = text[i]; }
     p.tlen = tl;

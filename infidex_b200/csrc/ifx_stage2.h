@@ -26,6 +26,7 @@ struct Stage2Buffers {
     CovQuery* covq;       // [nq]
     int32_t* wm_cnt;      // [nq][4] per shard: top docs that are also WordMatcher docs, WordMatcher-only entries taken, union non-empty, index of the first such entry
     const int32_t* g_di;  // doc-id-range shards: [nq][2] local id of the document at global Stage-1 rank 0 / 1 (-1: another shard's, -2: fewer than two ranks exist)
+    const int32_t* s1_total;   // [nq] short-query path: documents matched by Stage 1 (the list itself is cut to the depth); null / 0 otherwise
     const float* gmax;    // doc-id-range shards: top Stage-1 score over ALL shards per query (normBm25, SearchPipeline.cs:411-413); null: the local list's first
     int32_t ent_cap;
 };
@@ -67,7 +68,7 @@ IFX_FN void wm_query(const Ctx& c, const DevIndex& ix, const QueryPlan& p, const
         int mode = 0; int n1 = n1_in < 0 ? 0 : n1_in;
         if (p.status != 0) mode = 1;
         else if (p.is_short3 && n1 >= p.max_results) mode = 2;                       // SearchPipeline.cs:114-120
-        else if (!p.enable_coverage || p.short_skip_coverage) mode = 1;              // SearchPipeline.cs:157-170
+        else if (!p.enable_coverage || p.short_skip_coverage || p.short_no_cov) mode = 1;              // SearchPipeline.cs:157-170
         B.mode[q] = mode; B.ent_n[q] = 0; B.wm_any[q] = 0; B.di_doc[q * 2] = -1; B.di_doc[q * 2 + 1] = -1;
         sh.bcast[0] = mode;
     }
@@ -468,8 +469,9 @@ IFX_FN void finalize_query(const Ctx& c, const DevIndex& ix, const QueryPlan& p,
                 for (int u = 0; u < lim; u++) { if (nf < O.fcap) { size_t fo = (size_t)q * O.fcap + nf; O.facet_col[fo] = col; O.facet_val[fo] = sh.fv[u]; O.facet_cnt[fo] = sh.fc[u]; nf++; } else status |= 4; }
             }
         }
+        if (mode == 1 && p.short_kind != 0 && p.filter_id < 0 && B.s1_total && B.s1_total[q] > nk) nk = B.s1_total[q];      // the reference returns the WHOLE short-query list: TotalCandidates counts it
         O.n_facets[q] = nf; O.total[q] = browse ? 0 : nk;       // (TotalCandidates is not set on the browse path)
-        int nout = nk < p.max_results ? nk : p.max_results; if (nout > O.cap) nout = O.cap;
+        int nout = nk < p.max_results ? nk : p.max_results; if (nout > O.cap) nout = O.cap; if (nout > n_rec && !browse && p.filter_id < 0) nout = n_rec;
         for (int i = 0; i < nout; i++) { size_t oo = (size_t)q * O.cap + i; O.key[oo] = ix.doc_key[sh.keep_doc[i]]; O.score[oo] = sh.keep_score[i]; O.tie[oo] = sh.keep_tie[i]; }
         O.n[q] = nout; O.status[q] = status;
     }

@@ -110,7 +110,7 @@ class ShardedSearchEngine:
         eng, torch, dist, g = self.eng, self.torch, self.dist, self.eng._gpu
         if uploaded is not None:
             queries = uploaded["queries"]
-        nq = len(queries); K = max(q.CoverageDepth for q in queries); cap = max(1, max(q.MaxNumberOfRecordsToReturn for q in queries))
+        cap = max(1, max(q.MaxNumberOfRecordsToReturn for q in queries)); nq = len(queries); K = max(max(q.CoverageDepth for q in queries), min(cap, 1024))      # row length of the Stage-1 lists
         if uploaded is not None:
             packed, h = uploaded["packed"], uploaded["h"]
         else:

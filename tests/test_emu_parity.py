@@ -151,3 +151,19 @@ def test_emu_degenerate_corpora(emu):
     orc = OracleEngine(); orc.index_texts(texts, keys=np.arange(len(texts)))
     qs = ["hello", "hel", "a", "ab", "---", "x y z", "hellp", "hello hello"]
     assert not compare_search(eng, orc, qs) and not compare_stage1(eng, orc, qs)
+
+
+def test_emu_short_queries(emu, movie_titles, oracle_movies):
+    """Queries without a word of >= 3 characters: champion lists, single-character scan, SearchShortQuery with its fuzzy
+    fallback -- ids, Score bits and TotalCandidates against the oracle (which the reference's own short-query tests pin)."""
+    eng = ib.SearchEngine(_gpu_lib=emu)
+    eng.IndexColumns(np.arange(len(movie_titles)), [ib.Field("content")], [movie_titles])
+    qs = ["a", "x", "th", "io", "as am", "a b", "é", "of", "I", "to be", "x y z", "q", "zz", "9"]
+    for mx in (10, 100):
+        bad = compare_search(eng, oracle_movies, qs, max_results=mx)
+        assert not bad, (mx, bad[:3])
+    for texts in (["a", "b", "ab", "a b", "b a", "c"], ["x", "xx", "x x", "The X", "y"]):       # the reference's tiny short-query corpora in spirit
+        from oracle.oracle import OracleEngine
+        orc = OracleEngine(); orc.index_texts(texts); e2 = ib.SearchEngine(_gpu_lib=emu); e2.IndexColumns(np.arange(len(texts)), [ib.Field("content")], [texts])
+        bad = compare_search(e2, orc, ["a", "b", "x", "ab", "a b", "xx", "y z"], max_results=10)
+        assert not bad, bad[:3]

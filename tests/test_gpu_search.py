@@ -44,14 +44,23 @@ MOVIE_CASES = json.load(open(os.path.join(HERE, "golden", "movie_known_answers.j
 def test_movie_known_answer(case, movie_engine, movie_titles):
     """One test per case of MovieSearchParityTests.cs (tests/golden/movie_known_answers.json)."""
     r = movie_engine.Search(ib.Query(case["query"], case["max"]))
-    if r.Status & 1:        # IFX_Q_SHORT_QUERY: reported, tied to SURVEY 8f-1 -- never silently skipped, never fatal for the cases behind it
-        pytest.xfail("SURVEY 8f-1: the short-query path (no word of >= 3 characters) is answered by the host, not by the device")
+    assert r.Status & ~8 == 0
     check_movie_case(case, [x.DocumentId for x in r.Records], [x.Score for x in r.Records], movie_titles)
+
+
+SHORT_QUERIES = ["a", "x", "th", "io", "as am", "a b", "é", "of", "I", "to be", "x y z", "q", "zz", "it", "9"]      # no word of >= 3 characters (SURVEY 8f-1)
+
+
+def test_short_queries_vs_oracle(movie_engine, oracle_movies):
+    """ShortQueryResolver champion lists (max 10), the single-character scan (max 100), SearchShortQuery incl. its fuzzy fallback."""
+    for mx in (10, 100):
+        bad = compare_search(movie_engine, oracle_movies, SHORT_QUERIES, max_results=mx)
+        assert not bad, (mx, bad[:3])
 
 
 def test_movies_vs_oracle(movie_engine, oracle_movies):
     eng = movie_engine
-    bad = compare_search(eng, oracle_movies, MOVIE_QUERIES + ["sap", "two fo", "two f", "shawsh"])
+    bad = compare_search(eng, oracle_movies, MOVIE_QUERIES + ["sap", "two fo", "two f", "shawsh"] + SHORT_QUERIES)
     assert not bad, bad[:5]
     bad = compare_search(eng, oracle_movies, ["star", "sap", "the"], max_results=500)
     assert not bad, bad[:5]
