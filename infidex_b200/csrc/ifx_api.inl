@@ -17,6 +17,7 @@
 #include <chrono>
 #include <cmath>
 #include <mutex>
+#include <unordered_map>
 
 namespace {
 #include "chartables.inc"
@@ -196,6 +197,12 @@ extern "C" int ifx_index_create(const ifx_index_image* img, const ifx_params* pp
 
         v.n_docs = N; v.n_live = img->n_live; v.avgdl = img->avgdl; v.stop_term_limit = P.stop_term_limit;
         v.doc_key = ix->up(img->doc_key, N); v.deleted = ix->up(img->deleted, N); v.doc_len = ix->up(img->doc_len, N);
+        {   // duplicate DocumentKeys (segments of one document): first live document per key
+            std::vector<int64_t> ks(img->doc_key, img->doc_key + N); std::sort(ks.begin(), ks.end()); const bool dup = std::adjacent_find(ks.begin(), ks.end()) != ks.end(); v.key_first = nullptr;
+            if (dup) { std::unordered_map<int64_t, int32_t> first; first.reserve((size_t)N * 2); std::vector<int32_t> kf(N);
+                for (int d = 0; d < N; d++) if (!img->deleted[d]) first.emplace(img->doc_key[d], d);
+                for (int d = 0; d < N; d++) { auto it = first.find(img->doc_key[d]); kf[d] = it == first.end() ? d : it->second; }
+                v.key_first = ix->up(kf.data(), N); } }
         size_t ntext = N ? (size_t)img->text_off[N] : 0;
         v.text = ix->up(img->text_chars, ntext ? ntext : 1); v.text_off = ix->up(img->text_off, (size_t)N + 1);
         v.first_token = upload_dict(ix, img->first_token, false); v.token_count = ix->up(img->token_count, N);

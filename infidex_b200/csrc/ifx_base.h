@@ -57,6 +57,8 @@ struct Column { const int32_t* value_id; StrDict dict; const double* dict_num; c
 struct DevIndex {
     int32_t n_docs, n_live; float avgdl; int32_t stop_term_limit;
     const int64_t* doc_key; const uint8_t* deleted; const float* doc_len;
+    const int32_t* key_first;        // null when every DocumentKey is unique; else per doc the first live document with the same key (DocumentCollection.GetDocumentByPublicKey,
+                                     // Core/DocumentCollection.cs:60-82): segments of one document share a key and are consolidated per key (SegmentProcessor.cs:15-37)
     const uint16_t* text; const int64_t* text_off;
     StrDict first_token; const uint16_t* token_count;
     StrDict terms; const int32_t* df; const int64_t* row_ptr; const int32_t* post_doc; const uint8_t* post_tf;

@@ -50,7 +50,7 @@ IFX_FN void prepare_query(const DevIndex& ix, const uint16_t* text, int len, int
     }
     bool can_ngrams = n_words == 0 ? len >= 3 : n_long > 0;
     if (!can_ngrams) {      // no word of >= 3 characters: ShortQueryProcessor / ShortQueryResolver (SearchPipeline.cs:222-262), scored by the launches of ifx_short.h
-        if (ix.prefix_gcard) { p.status |= 2; return; }      // a doc-id-range shard: the short-query path is not distributed -- flagged (IFX_Q_UNSUPPORTED_OP), never answered partially
+        if (ix.prefix_gcard || ix.key_first) { p.status |= 2; return; }      // a doc-id-range shard, or documents sharing a DocumentKey (the reference accumulates short-query scores per KEY): that combination is not built -- flagged (IFX_Q_UNSUPPORTED_OP), never answered partially
         p.short_kind = len == 1 ? 1 : 2; p.tlen = 0;
         bool short3 = len <= 3; for (int i = 0; i < len; i++) if (is_delim(ix, text[i])) short3 = false;
         p.is_short3 = short3; int64_t pc = -1;

@@ -511,6 +511,15 @@ IFX_FN void s1_finish(const Ctx& c, const DevIndex& ix, FinishShared& sh, int64_
         for (int i = c.tid(); i < n2; i += NT) { int l = i ^ j; if (l > i) { bool up = (i & k) == 0; bool sw = up ? before(l, i) : before(i, l); if (sw) { float x = ks[i]; ks[i] = ks[l]; ks[l] = x; int y = kd[i]; kd[i] = kd[l]; kd[l] = y; } } }
         c.sync();
     }
+    if (ix.key_first) {      // ConsolidateSegments (SegmentProcessor.cs:15-37): the best entry per DocumentKey; the coverage stage then reads the first live document of the key
+        if (c.tid() == 0) { int m = 0;
+            for (int i = 0; i < n; i++) { const int64_t k = ix.doc_key[kd[i]]; bool seen = false; for (int j = 0; j < m && !seen; j++) seen = ix.doc_key[kd[j]] == k; if (!seen) { kd[m] = kd[i]; ks[m] = ks[i]; m++; } }
+            n_io[0] = m; }
+        c.sync();
+        const int m = n_io[0];
+        for (int i = c.tid(); i < m; i += NT) { const int d = ix.key_first[kd[i]]; doc[i] = d; score[i] = ks[i]; key[i] = ix.doc_key[d]; }
+        c.sync(); return;
+    }
     for (int i = c.tid(); i < n; i += NT) { doc[i] = kd[i]; score[i] = ks[i]; key[i] = ix.doc_key[kd[i]]; }
     c.sync();
 }

@@ -368,7 +368,8 @@ IFX_FN void finalize_query(const Ctx& c, const DevIndex& ix, const QueryPlan& p,
         const int lim = n2 < K ? n2 : K; int nk = 0;
         for (int base = 0; base < lim; base += NT) {
             const int i = base + c.tid(); int e = -1; bool keep = false;
-            if (i < lim) { e = sh.idx[i]; if (e >= 0) { int tw = B.ent_twin[eo + e]; keep = !(tw >= 0 && sh.pos[tw] < i); } }
+            if (i < lim) { e = sh.idx[i]; if (e >= 0) { int tw = B.ent_twin[eo + e]; keep = !(tw >= 0 && sh.pos[tw] < i);
+                if (keep && ix.key_first) { const int64_t k = sh.ekey[e]; for (int j = 0; j < i && keep; j++) { const int ej = sh.idx[j]; if (ej >= 0 && sh.ekey[ej] == k) keep = false; } } } }      // duplicate keys: the better entry of a key wins
             int tot; int off = block_excl_scan(c, keep ? 1 : 0, sh.scan, tot);
             if (keep) { sh.keep_doc[nk + off] = B.ent_doc[eo + e]; sh.keep_score[nk + off] = sh.score[i]; sh.keep_tie[nk + off] = sh.etie[e]; }
             nk += tot;
