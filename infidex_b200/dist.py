@@ -181,9 +181,14 @@ class ShardedSearchEngine:
         slot = torch.arange(K, device=S.device).view(1, 1, K).expand(nq, W, K)
         valid = (slot < N.view(nq, W, 1)).reshape(nq, W * K)
         S = torch.where(valid, S, torch.full_like(S, -1.0)); Kk = torch.where(valid, Kk, torch.full_like(Kk, 2 ** 62))
-        i1 = torch.argsort(Kk, dim=1, stable=True); S1 = torch.gather(S, 1, i1)
-        i2 = torch.argsort(S1, dim=1, descending=True, stable=True)
-        order = torch.gather(i1, 1, i2)[:, :K]                                                 # flat positions of the global top-K
+        if bool(((Kk >= 0) & (Kk < 2 ** 32) | ~valid).all()):
+            # keys fit 32 bits: (score bits, inverted key) pack into one int64 whose order IS the list order -> one top-K instead of two full sorts
+            comp = torch.where(valid, (S.view(torch.int32).to(torch.int64) << 32) | (0xFFFFFFFF - Kk), torch.full_like(Kk, -1))
+            order = torch.topk(comp, min(K, W * K), dim=1, sorted=True).indices
+        else:
+            i1 = torch.argsort(Kk, dim=1, stable=True); S1 = torch.gather(S, 1, i1)
+            i2 = torch.argsort(S1, dim=1, descending=True, stable=True)
+            order = torch.gather(i1, 1, i2)[:, :K]                                             # flat positions of the global top-K
         top_valid = torch.gather(valid, 1, order)
         mark = torch.zeros(nq, W * K, dtype=torch.uint8, device=S.device)
         flag = top_valid.to(torch.uint8); flag[:, 0] *= 2                                     # 2: global rank 0, 3: global rank 1 (docIndex 0 / 1)
@@ -205,26 +210,34 @@ class ShardedSearchEngine:
         t_rec = torch.from_numpy(rec).to(self.dev); t_meta = torch.from_numpy(meta).to(self.dev)
         recs = [torch.empty_like(t_rec) for _ in range(W)]; metas = [torch.empty_like(t_meta) for _ in range(W)]
         dist.all_gather(recs, t_rec); dist.all_gather(metas, t_meta)
-        R = np.stack([r.cpu().numpy() for r in recs], 1).reshape(nq, W * cap, 3); M = np.stack([m.cpu().numpy() for m in metas], 1)      # [nq, W, 4]
-        valid = (np.arange(cap)[None, None, :] < M[:, :, 0:1]).reshape(nq, W * cap)
-        key = R[:, :, 0].astype(np.int64); score = R[:, :, 1].astype(np.uint32).view(np.float32).reshape(nq, W * cap).astype(np.float64); tie = R[:, :, 2]
-        score = np.where(valid, score, -np.inf)
-        order = np.lexsort((key, -tie, -score), axis=1)[:, :cap]
-        o_key = np.take_along_axis(key, order, 1); o_score = np.take_along_axis(R[:, :, 1], order, 1).astype(np.uint32).view(np.float32).reshape(nq, cap); o_tie = np.take_along_axis(tie, order, 1).astype(np.uint8)
-        maxr = np.array([q.MaxNumberOfRecordsToReturn for q in queries])
+        # merge on the device: ScoreEntry order (Score desc, Tiebreaker desc, DocumentId asc) = three stable sorts, least significant key first
+        R = torch.stack(recs, 1).reshape(nq, W * cap, 3); M = torch.stack(metas, 1)                                                   # [nq, W*cap, 3], [nq, W, 14]
+        valid = (torch.arange(cap, device=self.dev).view(1, 1, cap) < M[:, :, 0:1]).reshape(nq, W * cap)
+        key = R[:, :, 0].to(torch.int64); sbits = R[:, :, 1].to(torch.int64); tie = R[:, :, 2].to(torch.int64)
+        score = torch.where(valid, sbits.to(torch.int32).view(torch.float32).to(torch.float64), torch.full((), float("-inf"), dtype=torch.float64, device=self.dev))
+        o1 = torch.argsort(key, dim=1, stable=True)
+        o2 = torch.gather(o1, 1, torch.argsort(torch.gather(-tie, 1, o1), dim=1, stable=True))
+        order = torch.gather(o2, 1, torch.argsort(torch.gather(-score, 1, o2), dim=1, stable=True))[:, :cap]
+        t_key = torch.gather(key, 1, order); t_sbits = torch.gather(sbits, 1, order); t_tie = torch.gather(tie, 1, order); nvalid = valid.sum(1)
+        maxr = torch.tensor([q.MaxNumberOfRecordsToReturn for q in queries], dtype=torch.int64, device=self.dev)
         # ResultProcessor.CalculateTruncationIndex over the merged list: the last record with Score >= 254 (records are sorted: the first n_ge),
         # or a docIndex-0/1 document whose word hits reach max(1, max word hits over all shards) or whose lcs is non-zero
         info = M[:, :, 4:12]; dk = M[:, :, 12:14]
-        min_hits = np.maximum(info[:, :, 0].max(1), 1); trunc = info[:, :, 1].sum(1) - 1
+        min_hits = info[:, :, 0].max(1).values.clamp(min=1); trunc = info[:, :, 1].sum(1) - 1
+        pos_idx = torch.arange(cap, device=self.dev).view(1, cap)
         for j in range(2):
-            wh = info[:, :, 2 + 2 * j].max(1); lc = info[:, :, 3 + 2 * j].max(1); dkj = dk[:, :, j].max(1)      # the owner reports >= 0, the others -1
+            wh = info[:, :, 2 + 2 * j].max(1).values; lc = info[:, :, 3 + 2 * j].max(1).values; dkj = dk[:, :, j].max(1).values      # the owner reports >= 0, the others -1
             qual = (wh >= 0) & ((wh >= min_hits) | (lc > 0))
-            hit = (o_key == dkj[:, None]) & (np.arange(cap)[None, :] < np.minimum(valid.sum(1), cap)[:, None])
-            pos = np.where(hit.any(1), hit.argmax(1), cap)                                    # beyond the merged top: at least `cap`
-            trunc = np.where(qual, np.maximum(trunc, pos), trunc)
-        count = np.where(trunc < 0, maxr, np.minimum(trunc + 1, maxr))
-        o_n = np.minimum(np.minimum(valid.sum(1), count), maxr)
-        total = o_n.copy(); status = np.bitwise_or.reduce(M[:, :, 2], axis=1)
+            hit = (t_key == dkj.view(nq, 1)) & (pos_idx < nvalid.clamp(max=cap).view(nq, 1))
+            pos = torch.where(hit.any(1), hit.to(torch.int64).argmax(1), torch.full((), cap, dtype=torch.int64, device=self.dev))      # beyond the merged top: at least `cap`
+            trunc = torch.where(qual, torch.maximum(trunc, pos), trunc)
+        count = torch.where(trunc < 0, maxr, torch.minimum(trunc + 1, maxr))
+        t_n = torch.minimum(torch.minimum(nvalid, count), maxr)
+        status_t = M[:, 0, 2].clone()
+        for r in range(1, W):
+            status_t |= M[:, r, 2]
+        o_key = t_key.cpu().numpy(); o_score = t_sbits.to(torch.int32).cpu().numpy().view(np.float32); o_tie = t_tie.to(torch.uint8).cpu().numpy(); o_n = t_n.cpu().numpy()
+        total = o_n.copy(); status = status_t.cpu().numpy()
         self.last_raw = (o_key, o_score, o_tie, o_n, total, status)
         facets_all = None
         if any(q.EnableFacets for q in queries):          # facet rows travel as strings (value ids are per-shard dictionaries)
