@@ -148,6 +148,12 @@ extern "C" int ifx_device_count(void) {
 #endif
 }
 
+#ifndef IFX_EMU
+// document token table (ifx_cov.h): one thread per document, count pass then fill pass
+__global__ void __launch_bounds__(256) k_tok_count(DevIndex ix, unsigned* cnt) { const int d = blockIdx.x * blockDim.x + threadIdx.x; if (d < ix.n_docs) cnt[d] = (unsigned)doc_tokens_emit(ix, d, nullptr); }
+__global__ void __launch_bounds__(256) k_tok_fill(DevIndex ix, const int64_t* ptr, uint32_t* tab) { const int d = blockIdx.x * blockDim.x + threadIdx.x; if (d < ix.n_docs) doc_tokens_emit(ix, d, tab + ptr[d]); }
+#endif
+
 extern "C" int ifx_index_create(const ifx_index_image* img, const ifx_params* pp, ifx_index** out) {
     if (!img || !out) return fail(IFX_ERR_INVALID, "null argument");
     if (!dev_ok()) return fail(IFX_ERR_NO_DEVICE, "no CUDA device available (infidex_b200 has no CPU fallback)");
@@ -307,6 +313,28 @@ extern "C" int ifx_index_create(const ifx_index_image* img, const ifx_params* pp
             int tn = std::max(1, std::min(img->n_live, P.stop_term_limit)) + 1; std::vector<float> idf(tn, 0.f);
             for (int df = 1; df < tn; df++) { float d = (float)df, Nf = (float)img->n_live; float ratio = (Nf - d + 0.5f) / (d + 0.5f); idf[df] = ratio <= 0.f ? 0.f : std::log(ratio + 1.f); }
             v.idf_table = ix->up(idf.data(), tn); v.idf_table_n = tn;
+        }
+        {   // document token table: needs the text and the character tables above
+#ifdef IFX_EMU
+            std::vector<int64_t> tp((size_t)N + 1, 0); for (int d = 0; d < N; d++) tp[(size_t)d + 1] = tp[d] + doc_tokens_emit(v, d, nullptr);
+            std::vector<uint32_t> tab((size_t)std::max<int64_t>(tp[N], 1)); for (int d = 0; d < N; d++) doc_tokens_emit(v, d, tab.data() + tp[d]);
+            v.tok_ptr = ix->up(tp.data(), tp.size()); v.tok_tab = ix->up(tab.data(), tab.size());
+#else
+            unsigned* cnt = (unsigned*)dev_alloc(((size_t)N + 1) * 4); const unsigned g = (unsigned)((N + 255) / 256);
+            if (N > 0) k_tok_count<<<g, 256>>>(v, cnt);
+            const int64_t n_tiles = ((int64_t)N + SCAN_TILE - 1) / SCAN_TILE;
+            unsigned long long* tile = (unsigned long long*)dev_alloc((size_t)std::max<int64_t>(n_tiles, 1) * 8);
+            int64_t* tok_ptr = ix->alloc<int64_t>((size_t)N + 1);
+            if (N > 0) { k_scan_tile_sums<<<(unsigned)n_tiles, SCAN_THREADS>>>(cnt, N, tile); k_scan_tiles<<<1, 1024>>>(tile, n_tiles); k_scan_final<<<(unsigned)n_tiles, SCAN_THREADS>>>(cnt, N, tile, tok_ptr); }
+            else dev_zero(tok_ptr, 8);
+            int64_t TW = 0; d2h(&TW, tok_ptr + N, 8);
+            uint32_t* tab = ix->alloc<uint32_t>((size_t)std::max<int64_t>(TW, 1));
+            if (N > 0) k_tok_fill<<<g, 256>>>(v, tok_ptr, tab);
+            CUDA_TRY(cudaGetLastError()); CUDA_TRY(cudaDeviceSynchronize());
+            dev_free(cnt); dev_free(tile);
+            v.tok_ptr = tok_ptr; v.tok_tab = tab;
+#endif
+            stage("document token table");
         }
         {   // filter / facet columns: ToString() dictionary + parsed numeric view of every dictionary entry
             ix->h_columns.resize(img->n_columns);

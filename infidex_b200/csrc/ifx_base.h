@@ -60,6 +60,7 @@ struct DevIndex {
     const int32_t* key_first;        // null when every DocumentKey is unique; else per doc the first live document with the same key (DocumentCollection.GetDocumentByPublicKey,
                                      // Core/DocumentCollection.cs:60-82): segments of one document share a key and are consolidated per key (SegmentProcessor.cs:15-37)
     const uint16_t* text; const int64_t* text_off;
+    const int64_t* tok_ptr; const uint32_t* tok_tab;   // per document: its tokens as the coverage stage needs them (ifx_cov.h doc_tokens_emit), derived at index creation
     StrDict first_token; const uint16_t* token_count;
     StrDict terms; const int32_t* df; const int64_t* row_ptr; const int32_t* post_doc; const uint8_t* post_tf;
     const int32_t* term_sorted;      // term ordinals in ordinal-lexicographic order (trie DFS order)

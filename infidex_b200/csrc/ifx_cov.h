@@ -84,6 +84,34 @@ IFX_FN_OUTLINED int damerau(const DevIndex& ix, Str s, Str t, int maxd, bool ic)
     }
     return dist;
 }
+// ---- exact shortcuts around the Levenshtein row (same results as damerau(), far fewer instructions on the ~99 % of token pairs that do not match)
+// ASCII fold-equality (both units < 128): same letter in either case
+IFX_FN bool eq_fold_ascii(unsigned x, unsigned y) { if (x == y) return true; const unsigned l = x | 0x20u; return (x ^ y) == 0x20u && l >= 'a' && l <= 'z'; }
+// damerau(s, t, 1, ic = true) for strings whose units are all < 128 (there ToUpperInvariant and ToLowerInvariant induce the same
+// equivalence, so the two folds the reference mixes agree): the value when it is <= 1, else 2. Distance <= 1 means: equal; one
+// substitution; one adjacent transposition at the first mismatch with equal rests (CalculateDamerau's only transposition site,
+// LevenshteinDistance.cs:300-341); or, lengths one apart, one deletion. Linear time, no DP row.
+IFX_FN int damerau1_ascii(Str s, Str t) {
+    int d = s.n - t.n; if (d > 1 || d < -1) return 2;
+    if (d < 0) { Str x = s; s = t; t = x; }            // s is the longer one
+    int p = 0; while (p < t.n && eq_fold_ascii(s.p[p], t.p[p])) p++;
+    if (d == 0) {
+        if (p == s.n) return 0;
+        int k = p + 1; while (k < s.n && eq_fold_ascii(s.p[k], t.p[k])) k++;
+        if (k == s.n) return 1;
+        if (k == p + 1 && eq_fold_ascii(s.p[p], t.p[p + 1]) && eq_fold_ascii(s.p[p + 1], t.p[p])) { k = p + 2; while (k < s.n && eq_fold_ascii(s.p[k], t.p[k])) k++; if (k == s.n) return 1; }
+        return 2;
+    }
+    int k = p; while (k < t.n && eq_fold_ascii(s.p[k + 1], t.p[k])) k++;
+    return k == t.n ? 1 : 2;
+}
+// character-set signature of the case-folded token (one bit per hashed unit). damerau(s, t, maxd) <= maxd implies a Levenshtein
+// distance <= maxd + 1 under the ToUpperInvariant fold (<= maxd when every unit is ASCII: the transposition branch then keeps the
+// character multiset), and k edits change at most k characters of either set -- so more than k one-sided signature bits is a proof
+// of "no match" and the row is never started.
+IFX_FN unsigned fold_sig(const DevIndex& ix, Str s) { unsigned g = 0; for (int i = 0; i < s.n; i++) g |= 1u << ((up_c(ix, s.p[i]) * 0x9E37u >> 4) & 31); return g; }
+IFX_FN bool sig_far(unsigned a, unsigned b, int k) { return popc(a & ~b) > k || popc(b & ~a) > k; }
+
 // SegmentProcessor.CalculateLcs -> StringMetrics.Lcs on lower-cased inputs (query is already lower case)
 IFX_FN int lcs_metric(const DevIndex& ix, Str q, Str r, int tol) {
     if (q.n == 0 || r.n == 0) return 0;
@@ -104,6 +132,8 @@ struct CovQuery {
     Tok tok[MAX_QTOK]; float term_idf[MAX_QTOK]; float word_idf[MAX_QTOK];
     Tok ftok[MAX_QTOK * 2];
     int overflow;
+    int ascii;                                 // every unit of the query < 128 (enables the exact ASCII shortcuts)
+    unsigned tsig[MAX_QTOK];                   // fold_sig of tok[i]
 };
 
 IFX_FN int tokenize(const DevIndex& ix, Str s, int min_size, Tok* out, int cap, bool& overflow) {   // CoverageTokenizer.TokenizeToSpan
@@ -137,7 +167,41 @@ IFX_FN void prepare_cov_query(const DevIndex& ix, const uint16_t* q, int qlen, C
         c.word_idf[i] = w >= 0 ? ix.word_idf[w] : 0.f;
     }
     c.n_ftok = tokenize(ix, qs, 0, c.ftok, MAX_QTOK * 2, ovf);
+    { unsigned o = 0; for (int i = 0; i < qlen; i++) o |= q[i]; c.ascii = o < 128u ? 1 : 0; }
+    for (int i = 0; i < nu; i++) c.tsig[i] = fold_sig(ix, sub(qs, c.tok[i].off, c.tok[i].len));
     c.overflow = ovf ? 1 : 0;
+}
+
+// ---- document token table (derived once per index, ifx_index_create): what CalculateCoverageInternal / ComputeSignals tokenise
+// again for every (query, candidate) pair is a pure function of the document text, so it is stored. Per document, 32-bit words:
+//   [0] unfiltered tokens fd | deduplicated tokens dc << 16      [1] raw count of tokens of >= 2 units (24 bits) | ascii << 30 | overflow << 31
+//   [2 .. 2 + fd)            every token (CoverageTokenizer.TokenizeToSpan with minWordSize 0), Tok = off | len << 16
+//   [2 + fd .. 2 + fd + dc)  tokens of >= 2 units, first occurrence only (case-insensitive), in document order
+// Returns the number of words; `out` may be null (count pass).
+IFX_FN int doc_tokens_emit(const DevIndex& ix, int doc, uint32_t* out) {
+    const int64_t t0 = ix.text_off[doc]; const Str d{ix.text + t0, (int)(ix.text_off[doc + 1] - t0)};
+    Tok dt[MAX_DTOK]; bool ovf = false; int draw = 0, dc = 0, fd = 0; unsigned tok_or = 0;
+    int i = 0; const int maxtok = d.n / 2 + 1;
+    while (i < d.n) {
+        while (i < d.n && delim_c(ix, d.p[i])) i++;
+        if (i >= d.n) break;
+        const int b = i; while (i < d.n && !delim_c(ix, d.p[i])) { tok_or |= d.p[i]; i++; }
+        const int len = i - b;
+        if (fd < maxtok) { if (fd < MAX_DTOK && b < 65536) { if (out) out[2 + fd] = (uint32_t)b | ((uint32_t)(uint16_t)len << 16); fd++; } else ovf = true; }
+        if (len >= 2 && draw < maxtok) {
+            draw++;
+            bool dup = false;
+            for (int j = 0; j < dc; j++) if (dt[j].len == len && eq_ic(ix, sub(d, dt[j].off, dt[j].len), sub(d, b, len))) { dup = true; break; }
+            if (!dup) { if (dc < MAX_DTOK && b < 65536 && len < 65536) { dt[dc].off = (uint16_t)b; dt[dc].len = (uint16_t)len; dc++; } else ovf = true; }
+        }
+    }
+    if (draw > 0xFFFFFF) { draw = 0xFFFFFF; ovf = true; }
+    if (out) {
+        for (int j = 0; j < dc; j++) out[2 + fd + j] = (uint32_t)dt[j].off | ((uint32_t)dt[j].len << 16);
+        out[0] = (uint32_t)fd | ((uint32_t)dc << 16);
+        out[1] = (uint32_t)draw | (tok_or < 128u ? 1u << 30 : 0u) | (ovf ? 1u << 31 : 0u);
+    }
+    return 2 + fd + dc;
 }
 
 struct CovResult { float score; uint8_t tie; int word_hits; int overflow; };
@@ -148,24 +212,14 @@ IFX_FN CovResult coverage_fusion(const DevIndex& ix, const CovQuery& c, const ui
     const Str q{qtext, c.qlen};
     const int64_t t0 = ix.text_off[doc]; const Str d{ix.text + t0, (int)(ix.text_off[doc + 1] - t0)};
     const int qc = c.n_tok;
-    // ---- doc tokens (len >= 2), raw count and dedupe
-    Tok dt[MAX_DTOK]; bool ovf = false;
-    int draw = 0, dc = 0;
-    {
-        int i = 0; int maxtok = d.n / 2 + 1;
-        while (i < d.n) {
-            while (i < d.n && delim_c(ix, d.p[i])) i++;
-            if (i >= d.n) break;
-            int b = i; while (i < d.n && !delim_c(ix, d.p[i])) i++;
-            if (i - b >= 2 && draw < maxtok) {
-                draw++;
-                bool dup = false;
-                for (int j = 0; j < dc; j++) if (dt[j].len == i - b && eq_ic(ix, sub(d, dt[j].off, dt[j].len), sub(d, b, i - b))) { dup = true; break; }
-                if (!dup) { if (dc < MAX_DTOK && b < 65536 && i - b < 65536) { dt[dc].off = (uint16_t)b; dt[dc].len = (uint16_t)(i - b); dc++; } else ovf = true; }
-            }
-        }
-    }
-    const int doc_tokens = draw;
+    // ---- doc tokens from the index's token table: every token (fdt), and the deduplicated tokens of >= 2 units (dt)
+    const uint32_t* tt = ix.tok_tab + ix.tok_ptr[doc];
+    const uint32_t h0 = tt[0], h1 = tt[1];
+    const int fd = (int)(h0 & 0xFFFFu), dc = (int)(h0 >> 16);
+    const Tok* fdt = (const Tok*)(tt + 2); const Tok* dt = fdt + fd;
+    const bool ovf = (h1 >> 31) != 0;
+    const int doc_tokens = (int)(h1 & 0xFFFFFFu);
+    const bool ascii = c.ascii && ((h1 >> 30) & 1u);   // query and every document token are ASCII
     int word_hits = 0; double num_whole = 0, num_joined = 0, num_fuzzy = 0, num_ps = 0; int penalty = 0;
     float matched[MAX_QTOK]; int first_pos[MAX_QTOK]; uint8_t qa[MAX_QTOK], hw[MAX_QTOK], hj[MAX_QTOK], hp[MAX_QTOK]; uint8_t da[MAX_DTOK];
     for (int i = 0; i < qc; i++) { matched[i] = 0.f; first_pos[i] = -1; qa[i] = 1; hw[i] = hj[i] = hp[i] = 0; }
@@ -235,12 +289,12 @@ IFX_FN CovResult coverage_fusion(const DevIndex& ix, const CovQuery& c, const ui
                     int j = di[b]; if (!da[j]) continue;
                     int dl = dt[j].len; if (ql >= dl) continue;
                     Str dtx = DT(j); bool m = false; double sc = 0;
-                    int dist = damerau(ix, qt, sub(dtx, 0, ql), 1, true);
+                    int dist = ascii ? damerau1_ascii(qt, sub(dtx, 0, ql)) : damerau(ix, qt, sub(dtx, 0, ql), 1, true);
                     if (dist <= 1) { sc = ql - dist; if (sc < 0.1) sc = 0.1; m = true; }
                     else if (dl > ql) {
-                        dist = damerau(ix, qt, sub(dtx, 0, ql + 1), 1, true);
+                        dist = ascii ? damerau1_ascii(qt, sub(dtx, 0, ql + 1)) : damerau(ix, qt, sub(dtx, 0, ql + 1), 1, true);
                         if (dist <= 1) { sc = ql - dist; if (sc < 0.1) sc = 0.1; m = true; }
-                        else if (ql > 1) { dist = damerau(ix, qt, sub(dtx, 0, ql - 1), 1, true); if (dist <= 1) { sc = ql - 1 - dist; if (sc < 0.1) sc = 0.1; m = true; } }
+                        else if (ql > 1) { dist = ascii ? damerau1_ascii(qt, sub(dtx, 0, ql - 1)) : damerau(ix, qt, sub(dtx, 0, ql - 1), 1, true); if (dist <= 1) { sc = ql - 1 - dist; if (sc < 0.1) sc = 0.1; m = true; } }
                     }
                     if (m) { num_ps += sc; word_hits++; matched[i] += (float)sc; POSMIN(i, (int)dt[j].off); qa[i] = 0; da[j] = 0; break; }
                 }
@@ -268,7 +322,9 @@ IFX_FN CovResult coverage_fusion(const DevIndex& ix, const CovQuery& c, const ui
                             int dl = dt[j].len; if (dl > maxl || dl < minl) continue;
                             Str dtx = DT(j);
                             if (special && (dtx.n == 0 || lo_c(ix, dtx.p[0]) != lo_c(ix, qt.p[0]))) continue;
-                            int dist = damerau(ix, qt, dtx, e, true);
+                            int dist;
+                            if (e == 1 && ascii) dist = damerau1_ascii(qt, dtx);
+                            else { if (sig_far(c.tsig[i], fold_sig(ix, dtx), ascii ? e : e + 1)) continue; dist = damerau(ix, qt, dtx, e, true); }
                             if (dist <= e) { word_hits++; num_fuzzy += (ql - dist); matched[i] += (float)(ql - dist); POSMIN(i, (int)dt[j].off); qa[i] = 0; da[j] = 0; break; }
                         }
                     }
@@ -308,10 +364,6 @@ IFX_FN CovResult coverage_fusion(const DevIndex& ix, const CovQuery& c, const ui
     (void)fully;
     // ---- FusionSignalComputer.ComputeSignals: unfiltered tokens (len >= 1), no dedupe; minStemLength = MinWordSize (2)
     const int fq = c.n_ftok;
-    int fd = 0; Tok fdt[MAX_DTOK];
-    { int i = 0; int maxtok = d.n / 2 + 1;
-      while (i < d.n) { while (i < d.n && delim_c(ix, d.p[i])) i++; if (i >= d.n) break; int b = i; while (i < d.n && !delim_c(ix, d.p[i])) i++;
-          if (fd < maxtok) { if (fd < MAX_DTOK && b < 65536) { fdt[fd].off = (uint16_t)b; fdt[fd].len = (uint16_t)(i - b); fd++; } else ovf = true; } } }
     bool lex_prefix_last = false, perfect_doc = false, stem_evidence = false, anchor_stem = false; int trailing_density = 0, single_sim = 0, single_char_boost = 0;
 #define FQ(i) sub(q, c.ftok[i].off, c.ftok[i].len)
 #define FD(j) sub(d, fdt[j].off, fdt[j].len)
@@ -354,7 +406,7 @@ IFX_FN CovResult coverage_fusion(const DevIndex& ix, const CovQuery& c, const ui
             if (cnt > 0) { float dens = (float)cnt / (float)fd; float v = dens * 255.f; v = v < 0.f ? 0.f : (v > 255.f ? 255.f : v); trailing_density = (int)(uint8_t)v; }
         }
         if (fq == 1) {   // ComputeSingleTermLexicalSimilarity (query already lower case)
-            Str qt = FQ(0); int ql = qt.n; float best = 0.f;
+            Str qt = FQ(0); int ql = qt.n; float best = 0.f; const unsigned qsig = fold_sig(ix, qt);
             if (ql >= 3) {
                 for (int t = 0; t < fd; t++) {
                     Str tk = FD(t); if (tk.n < 2) continue;
@@ -364,7 +416,7 @@ IFX_FN CovResult coverage_fusion(const DevIndex& ix, const CovQuery& c, const ui
                     int maxk = ql < tk.n ? ql : tk.n, bestk = 0;
                     for (int len = maxk; len >= 2; len--) { bool e = true; for (int k = 0; k < len; k++) if (qt.p[ql - len + k] != lo_c(ix, tk.p[k])) { e = false; break; } if (e) { bestk = len; break; } }
                     float ps = bestk > 0 ? (float)bestk / (float)ql : 0.f, fz = 0.f;
-                    if (tk.n <= 32) { int dist = damerau(ix, qt, tk, 2, true); if (dist <= 2) fz = (float)(ql - dist) / (float)ql; }   // both sides lower-cased in the reference; case-folded compare is identical
+                    if (tk.n <= 32 && !sig_far(qsig, fold_sig(ix, tk), ascii ? 2 : 3)) { int dist = damerau(ix, qt, tk, 2, true); if (dist <= 2) fz = (float)(ql - dist) / (float)ql; }   // both sides lower-cased in the reference; case-folded compare is identical
                     float comb = ps > fz ? ps : fz; if (comb > best) best = comb;
                 }
                 if (ql >= 6) {

@@ -130,7 +130,7 @@ IFX_FN void wm_query(const Ctx& c, const DevIndex& ix, const QueryPlan& p, const
     int any = 0;
     for (int a = 0; a < nw * 2; a++) { WmList L = sh.affix[a]; if (L.n > 0) any = 1;
         for (int i = c.tid(); i < L.n; i += NT) { int d = L.p[i]; if (d < 0) continue;      // doc-id-range shards: the word's document lives on another shard
-            atomic_or(&ws.bits[d >> 5], 1u << (d & 31)); sh.dirty[d >> 16] = 1; } }
+            atomic_or(&ws.bits[d >> 5], 1u << (d & 31)); atomic_or(&ws.bits2[d >> 10], 1u << ((d >> 5) & 31)); sh.dirty[d >> 16] = 1; } }
     for (int l = 0; l < n_lists; l++) if (sh.lists[l].n > 0) any = 1;
     c.sync();
     for (int k = c.tid(); k < nt; k += NT) {
@@ -145,7 +145,7 @@ IFX_FN void wm_query(const Ctx& c, const DevIndex& ix, const QueryPlan& p, const
     // ---- leading elements of every list -> bitset (the first M elements of the union lie within the first M of each list)
     const int M = K + nt + 2;
     for (int l = 0; l < n_lists; l++) { WmList L = sh.lists[l]; int m = L.n < M ? L.n : M;
-        for (int i = c.tid(); i < m; i += NT) { int d = L.p[i]; atomic_or(&ws.bits[d >> 5], 1u << (d & 31)); sh.dirty[d >> 16] = 1; } }
+        for (int i = c.tid(); i < m; i += NT) { int d = L.p[i]; atomic_or(&ws.bits[d >> 5], 1u << (d & 31)); atomic_or(&ws.bits2[d >> 10], 1u << ((d >> 5) & 31)); sh.dirty[d >> 16] = 1; } }
     c.sync();
     // ---- entries: (a) WM ∩ top ascending, base 0
     int ne = 0;
@@ -154,30 +154,43 @@ IFX_FN void wm_query(const Ctx& c, const DevIndex& ix, const QueryPlan& p, const
             if (f && ne + off < cap) { e_doc[ne + off] = sh.top_sorted[k]; e_base[ne + off] = 0.f; e_twin[ne + off] = -2; } ne += tot; flag_cnt += tot; }
         (void)flag_cnt;
     }
-    // ---- (b) WM \ top ascending, first wm_limit; also the first two live WM docs overall (docIndex assignment)
+    // ---- (b) WM \ top ascending, first wm_limit; also the first two live WM docs overall (docIndex assignment).
+    //      The union is sparse (a few thousand documents over the whole shard), so every bitset word that was touched is also recorded in a
+    //      summary bitset (ws.bits2: one bit per word, one word per 1024 documents). The ascending walk reads the summary, visits touched
+    //      words only, runs its block scans once per 4 * NT summary words (4 M documents at 256 threads... per iteration NT * 4096 documents),
+    //      and once the quota and the two live documents are found the remaining words are only cleared.
     {
-        int ncont = (ix.n_docs + 65535) >> 16; int64_t nwords = ((int64_t)ix.n_docs + 31) >> 5; int taken = 0; int seen_live = 0;
-        for (int k = 0; k < ncont; k++) {
-            if (!sh.dirty[k]) continue;
-            int64_t w0 = (int64_t)k * 2048, w1 = w0 + 2048; if (w1 > nwords) w1 = nwords;
-            int per = (int)((w1 - w0 + NT - 1) / NT); int64_t my0 = w0 + (int64_t)c.tid() * per, my1 = my0 + per; if (my1 > w1) my1 = w1;
-            bool need = taken < wm_limit || seen_live < 2;      // uniform
+        const int64_t nwords = ((int64_t)ix.n_docs + 31) >> 5; const int64_t nsum = (nwords + 31) >> 5; int taken = 0; int seen_live = 0;
+        constexpr int SPT = 4;                                   // summary words per thread and iteration
+        const int64_t step = (int64_t)NT * SPT;
+        for (int64_t s0 = 0; s0 < nsum; s0 += step) {
+            {   // containers of this iteration: summary word s covers documents [s << 10, (s + 1) << 10) -> container s >> 6
+                int64_t c0 = s0 >> 6, c1 = ((s0 + step < nsum ? s0 + step : nsum) + 63) >> 6; bool dirty = false;
+                for (int64_t k = c0; k < c1 && !dirty; k++) dirty = sh.dirty[k] != 0;      // uniform (shared flags, written before the last sync)
+                if (!dirty) continue;
+            }
+            const int64_t my0 = s0 + (int64_t)c.tid() * SPT; int64_t my1 = my0 + SPT; if (my1 > nsum) my1 = nsum;
+            const bool need = taken < wm_limit || seen_live < 2;      // uniform
             if (need) {
                 int cnt = 0, live = 0;
-                for (int64_t w = my0; w < my1; w++) { unsigned v = ws.bits[w]; while (v) { int b = ffs32(v) - 1; v &= v - 1; int d = (int)((w << 5) | b); if (!ix.deleted[d]) live++; if (!sorted_contains(sh.top_sorted, nt, d)) cnt++; } }
+                for (int64_t sw = my0; sw < my1; sw++) { unsigned m = ws.bits2[sw]; while (m) { const int64_t w = (sw << 5) | (ffs32(m) - 1); m &= m - 1;
+                    unsigned v = ws.bits[w]; while (v) { int b = ffs32(v) - 1; v &= v - 1; int d = (int)((w << 5) | b); if (!ix.deleted[d]) live++; if (!sorted_contains(sh.top_sorted, nt, d)) cnt++; } } }
                 int tot; int off = block_excl_scan(c, cnt, sh.scan, tot);
                 int ltot; int loff = block_excl_scan(c, live, sh.scan, ltot);
-                int o = off, lo2 = loff;
-                for (int64_t w = my0; w < my1; w++) { unsigned v = ws.bits[w]; while (v) { int b = ffs32(v) - 1; v &= v - 1; int d = (int)((w << 5) | b);
-                    if (!ix.deleted[d]) { if (seen_live + lo2 < 2) sh.first_live[seen_live + lo2] = d; lo2++; }
-                    if (!sorted_contains(sh.top_sorted, nt, d)) { if (taken + o < wm_limit && ne + o < cap) { e_doc[ne + o] = d; e_base[ne + o] = 0.f; e_twin[ne + o] = -1; } o++; } } }
+                if (tot > 0 || ltot > 0) {
+                    int o = off, lo2 = loff;
+                    for (int64_t sw = my0; sw < my1; sw++) { unsigned m = ws.bits2[sw]; while (m) { const int64_t w = (sw << 5) | (ffs32(m) - 1); m &= m - 1;
+                        unsigned v = ws.bits[w]; while (v) { int b = ffs32(v) - 1; v &= v - 1; int d = (int)((w << 5) | b);
+                            if (!ix.deleted[d]) { if (seen_live + lo2 < 2) sh.first_live[seen_live + lo2] = d; lo2++; }
+                            if (!sorted_contains(sh.top_sorted, nt, d)) { if (taken + o < wm_limit && ne + o < cap) { e_doc[ne + o] = d; e_base[ne + o] = 0.f; e_twin[ne + o] = -1; } o++; } } } }
+                }
                 int add = tot; if (taken + add > wm_limit) add = wm_limit - taken;
                 taken += add; ne += add; seen_live += ltot;
             }
-            for (int64_t w = my0; w < my1; w++) ws.bits[w] = 0;
-            c.sync();
-            if (c.tid() == 0) sh.dirty[k] = 0;
+            for (int64_t sw = my0; sw < my1; sw++) { unsigned m = ws.bits2[sw]; if (!m) continue; ws.bits2[sw] = 0; while (m) { ws.bits[(sw << 5) | (ffs32(m) - 1)] = 0; m &= m - 1; } }
         }
+        c.sync();
+        { const int ncont = (ix.n_docs + 65535) >> 16; for (int k = c.tid(); k < ncont; k += NT) sh.dirty[k] = 0; }
         c.sync();
     }
     if (c.tid() == 0 && B.wm_cnt) { B.wm_cnt[q * 4 + 0] = n_overlap; B.wm_cnt[q * 4 + 1] = ne - n_overlap; B.wm_cnt[q * 4 + 2] = any; B.wm_cnt[q * 4 + 3] = n_overlap; }
