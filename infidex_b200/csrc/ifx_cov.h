@@ -204,11 +204,11 @@ IFX_FN int doc_tokens_emit(const DevIndex& ix, int doc, uint32_t* out) {
     return 2 + fd + dc;
 }
 
-struct CovResult { float score; uint8_t tie; int word_hits; int overflow; };
+struct CovResult { float score; float score0; uint8_t tie; int word_hits; int overflow; };   // score0: the same evaluation with a Stage-1 base of 0 (the WordMatcher twin of a top candidate)
 
 // One (query, document) evaluation: coverage features -> fusion score. `lcs` as cached by the pipeline (0 unless docIndex < 2).
 IFX_FN CovResult coverage_fusion(const DevIndex& ix, const CovQuery& c, const uint16_t* qtext, int doc, int lcs, float bm25) {
-    CovResult R; R.score = 0.f; R.tie = 0; R.word_hits = 0; R.overflow = 0;
+    CovResult R; R.score = 0.f; R.score0 = 0.f; R.tie = 0; R.word_hits = 0; R.overflow = 0;
     const Str q{qtext, c.qlen};
     const int64_t t0 = ix.text_off[doc]; const Str d{ix.text + t0, (int)(ix.text_off[doc + 1] - t0)};
     const int qc = c.n_tok;
@@ -511,11 +511,13 @@ IFX_FN CovResult coverage_fusion(const DevIndex& ix, const CovQuery& c, const ui
         if (terms >= 2) { float md = (float)trailing_density / 255.f; if (md > 0.f) { float head = 1.f - sem; sem += head * md; } }
     }
     float gap = 1.f - ratio;
+    float sem0 = sem;                                      // base 0: `partial` means gap > 0, so the mix below never applies
     if (partial && bm25 >= gap) sem = ratio * sem + gap * bm25;
     sem = sem < 0.f ? 0.f : (sem > 0.999f ? 0.999f : sem);
+    sem0 = sem0 < 0.f ? 0.f : (sem0 > 0.999f ? 0.999f : sem0);
     uint8_t tie = 0;
     if (n >= 2 && d.n > 0) { float focus = (float)c.qlen / (float)d.n; if (focus > 1.f) focus = 1.f; tie = (uint8_t)(focus * 255.f); }
-    R.score = (float)prec + sem; R.tie = tie; R.word_hits = word_hits; R.overflow = ovf ? 1 : 0;
+    R.score = (float)prec + sem; R.score0 = (float)prec + sem0; R.tie = tie; R.word_hits = word_hits; R.overflow = ovf ? 1 : 0;
 #undef QT
 #undef DT
 #undef FQ

@@ -40,7 +40,8 @@ struct WmShared {
     WmList lists[MAX_WM_WORDS * 18];
     WmList affix[MAX_WM_WORDS * 2];
     Tok words[MAX_WM_WORDS]; int n_words;
-    int32_t top_sorted[MAX_K]; uint8_t in_wm[MAX_K];
+    int32_t top_sorted[MAX_K]; uint16_t top_rank[MAX_K]; uint8_t in_wm[MAX_K];     // Stage-1 docs ascending, their Stage-1 rank, WordMatcher membership
+    uint16_t nz[MAX_WM_WORDS * 18]; int n_nz;                                      // the non-empty dictionary lists
     uint8_t dirty[MAX_CONTAINERS];
     ScanTmp scan; int bcast[8]; int first_live[2];
 };
@@ -118,79 +119,73 @@ IFX_FN void wm_query(const Ctx& c, const DevIndex& ix, const QueryPlan& p, const
         sh.affix[w * 2].p = ix.affix_fwd_doc + p0; sh.affix[w * 2].n = tp;
         sh.affix[w * 2 + 1].p = ix.affix_rev_doc + s0; sh.affix[w * 2 + 1].n = ts;
     }
-    // ---- top docs ascending
+    // ---- top docs ascending (with their Stage-1 rank)
     int n2 = 1; while (n2 < nt) n2 <<= 1;
-    for (int i = c.tid(); i < n2; i += NT) { sh.top_sorted[i] = i < nt ? s1_doc[i] : 0x7fffffff; if (i < MAX_K) sh.in_wm[i] = 0; }
+    for (int i = c.tid(); i < n2; i += NT) { sh.top_sorted[i] = i < nt ? s1_doc[i] : 0x7fffffff; sh.top_rank[i] = (uint16_t)i; if (i < MAX_K) sh.in_wm[i] = 0; }
     c.sync();
     for (int k = 2; k <= n2; k <<= 1) for (int j = k >> 1; j > 0; j >>= 1) {
-        for (int i = c.tid(); i < n2; i += NT) { int l = i ^ j; if (l > i) { bool up = (i & k) == 0; int a = sh.top_sorted[i], b = sh.top_sorted[l]; if (up ? a > b : a < b) { sh.top_sorted[i] = b; sh.top_sorted[l] = a; } } }
+        for (int i = c.tid(); i < n2; i += NT) { int l = i ^ j; if (l > i) { bool up = (i & k) == 0; int a = sh.top_sorted[i], b = sh.top_sorted[l];
+            if (up ? a > b : a < b) { sh.top_sorted[i] = b; sh.top_sorted[l] = a; uint16_t ra = sh.top_rank[i]; sh.top_rank[i] = sh.top_rank[l]; sh.top_rank[l] = ra; } } }
         c.sync();
     }
-    // ---- affix docs -> bitset; membership of the top docs
+    // ---- affix docs -> bitset (every touched word also in the summary bitset ws.bits2: one bit per word); membership of the top docs
     int any = 0;
     for (int a = 0; a < nw * 2; a++) { WmList L = sh.affix[a]; if (L.n > 0) any = 1;
         for (int i = c.tid(); i < L.n; i += NT) { int d = L.p[i]; if (d < 0) continue;      // doc-id-range shards: the word's document lives on another shard
-            atomic_or(&ws.bits[d >> 5], 1u << (d & 31)); atomic_or(&ws.bits2[d >> 10], 1u << ((d >> 5) & 31)); sh.dirty[d >> 16] = 1; } }
-    for (int l = 0; l < n_lists; l++) if (sh.lists[l].n > 0) any = 1;
+            atomic_or(&ws.bits[d >> 5], 1u << (d & 31)); if (!((ws.bits2[d >> 10] >> ((d >> 5) & 31)) & 1u)) atomic_or(&ws.bits2[d >> 10], 1u << ((d >> 5) & 31)); sh.dirty[d >> 16] = 1; } }
+    if (c.tid() == 0) { int n = 0; for (int l = 0; l < n_lists; l++) if (sh.lists[l].n > 0) sh.nz[n++] = (uint16_t)l; sh.n_nz = n; }
     c.sync();
-    for (int k = c.tid(); k < nt; k += NT) {
-        int d = sh.top_sorted[k]; bool in = (ws.bits[d >> 5] >> (d & 31)) & 1u;
-        for (int l = 0; l < n_lists && !in; l++) { WmList L = sh.lists[l]; if (L.n > 0 && sorted_contains(L.p, L.n, d)) in = true; }
-        sh.in_wm[k] = in ? 1 : 0;
-    }
+    const int nnz = sh.n_nz; if (nnz > 0) any = 1;
+    for (int k = c.tid(); k < nt; k += NT) { int d = sh.top_sorted[k]; sh.in_wm[k] = (uint8_t)((ws.bits[d >> 5] >> (d & 31)) & 1u); }
+    c.sync();
+    // one (list, top doc) probe per thread and step: consecutive threads search the same list for consecutive (ascending) documents
+    for (int it = c.tid(); it < nnz * nt; it += NT) { const int k = it % nt; if (sh.in_wm[k]) continue;
+        const WmList L = sh.lists[sh.nz[it / nt]]; const int d = sh.top_sorted[k];
+        if (d >= L.p[0] && d <= L.p[L.n - 1] && sorted_contains(L.p, L.n, d)) sh.in_wm[k] = 1; }
     c.sync();
     int my = 0; for (int k = c.tid(); k < nt; k += NT) my += sh.in_wm[k];
     const int n_overlap = block_sum(c, my, sh.scan);
     const int wm_limit = K - n_overlap > 0 ? K - n_overlap : 0;
     // ---- leading elements of every list -> bitset (the first M elements of the union lie within the first M of each list)
     const int M = K + nt + 2;
-    for (int l = 0; l < n_lists; l++) { WmList L = sh.lists[l]; int m = L.n < M ? L.n : M;
-        for (int i = c.tid(); i < m; i += NT) { int d = L.p[i]; atomic_or(&ws.bits[d >> 5], 1u << (d & 31)); atomic_or(&ws.bits2[d >> 10], 1u << ((d >> 5) & 31)); sh.dirty[d >> 16] = 1; } }
+    for (int z = 0; z < nnz; z++) { WmList L = sh.lists[sh.nz[z]]; int m = L.n < M ? L.n : M;
+        for (int i = c.tid(); i < m; i += NT) { int d = L.p[i]; atomic_or(&ws.bits[d >> 5], 1u << (d & 31)); if (!((ws.bits2[d >> 10] >> ((d >> 5) & 31)) & 1u)) atomic_or(&ws.bits2[d >> 10], 1u << ((d >> 5) & 31)); sh.dirty[d >> 16] = 1; } }
     c.sync();
-    // ---- entries: (a) WM ∩ top ascending, base 0
+    // ---- entries: (a) WM ∩ top ascending, base 0; the twin field holds the Stage-1 rank until group (c) is placed
     int ne = 0;
+    for (int k0 = 0; k0 < nt; k0 += NT) { int k = k0 + c.tid(); int f = (k < nt && sh.in_wm[k]) ? 1 : 0; int tot; int off = block_excl_scan(c, f, sh.scan, tot);
+        if (f && ne + off < cap) { e_doc[ne + off] = sh.top_sorted[k]; e_base[ne + off] = 0.f; e_twin[ne + off] = (int)sh.top_rank[k]; } ne += tot; }
+    // ---- (b) WM \ top ascending, first wm_limit; also the first two live WM docs overall (docIndex assignment). Containers are walked in
+    //      order while the quota or the two live documents are still open -- the summary bits say which words of the container to read at
+    //      all -- and whatever is left afterwards is only cleared, through the summary, strided over the block.
     {
-        int flag_cnt = 0; for (int k0 = 0; k0 < nt; k0 += NT) { int k = k0 + c.tid(); int f = (k < nt && sh.in_wm[k]) ? 1 : 0; int tot; int off = block_excl_scan(c, f, sh.scan, tot);
-            if (f && ne + off < cap) { e_doc[ne + off] = sh.top_sorted[k]; e_base[ne + off] = 0.f; e_twin[ne + off] = -2; } ne += tot; flag_cnt += tot; }
-        (void)flag_cnt;
-    }
-    // ---- (b) WM \ top ascending, first wm_limit; also the first two live WM docs overall (docIndex assignment).
-    //      The union is sparse (a few thousand documents over the whole shard), so every bitset word that was touched is also recorded in a
-    //      summary bitset (ws.bits2: one bit per word, one word per 1024 documents). The ascending walk reads the summary, visits touched
-    //      words only, runs its block scans once per 4 * NT summary words (4 M documents at 256 threads... per iteration NT * 4096 documents),
-    //      and once the quota and the two live documents are found the remaining words are only cleared.
-    {
-        const int64_t nwords = ((int64_t)ix.n_docs + 31) >> 5; const int64_t nsum = (nwords + 31) >> 5; int taken = 0; int seen_live = 0;
-        constexpr int SPT = 4;                                   // summary words per thread and iteration
-        const int64_t step = (int64_t)NT * SPT;
-        for (int64_t s0 = 0; s0 < nsum; s0 += step) {
-            {   // containers of this iteration: summary word s covers documents [s << 10, (s + 1) << 10) -> container s >> 6
-                int64_t c0 = s0 >> 6, c1 = ((s0 + step < nsum ? s0 + step : nsum) + 63) >> 6; bool dirty = false;
-                for (int64_t k = c0; k < c1 && !dirty; k++) dirty = sh.dirty[k] != 0;      // uniform (shared flags, written before the last sync)
-                if (!dirty) continue;
-            }
-            const int64_t my0 = s0 + (int64_t)c.tid() * SPT; int64_t my1 = my0 + SPT; if (my1 > nsum) my1 = nsum;
-            const bool need = taken < wm_limit || seen_live < 2;      // uniform
-            if (need) {
-                int cnt = 0, live = 0;
-                for (int64_t sw = my0; sw < my1; sw++) { unsigned m = ws.bits2[sw]; while (m) { const int64_t w = (sw << 5) | (ffs32(m) - 1); m &= m - 1;
-                    unsigned v = ws.bits[w]; while (v) { int b = ffs32(v) - 1; v &= v - 1; int d = (int)((w << 5) | b); if (!ix.deleted[d]) live++; if (!sorted_contains(sh.top_sorted, nt, d)) cnt++; } } }
-                int tot; int off = block_excl_scan(c, cnt, sh.scan, tot);
-                int ltot; int loff = block_excl_scan(c, live, sh.scan, ltot);
-                if (tot > 0 || ltot > 0) {
-                    int o = off, lo2 = loff;
-                    for (int64_t sw = my0; sw < my1; sw++) { unsigned m = ws.bits2[sw]; while (m) { const int64_t w = (sw << 5) | (ffs32(m) - 1); m &= m - 1;
-                        unsigned v = ws.bits[w]; while (v) { int b = ffs32(v) - 1; v &= v - 1; int d = (int)((w << 5) | b);
-                            if (!ix.deleted[d]) { if (seen_live + lo2 < 2) sh.first_live[seen_live + lo2] = d; lo2++; }
-                            if (!sorted_contains(sh.top_sorted, nt, d)) { if (taken + o < wm_limit && ne + o < cap) { e_doc[ne + o] = d; e_base[ne + o] = 0.f; e_twin[ne + o] = -1; } o++; } } } }
-                }
-                int add = tot; if (taken + add > wm_limit) add = wm_limit - taken;
-                taken += add; ne += add; seen_live += ltot;
-            }
-            for (int64_t sw = my0; sw < my1; sw++) { unsigned m = ws.bits2[sw]; if (!m) continue; ws.bits2[sw] = 0; while (m) { ws.bits[(sw << 5) | (ffs32(m) - 1)] = 0; m &= m - 1; } }
+        const int ncont = (ix.n_docs + 65535) >> 16; const int64_t nwords = ((int64_t)ix.n_docs + 31) >> 5; const int64_t nsum = (nwords + 31) >> 5;
+        int taken = 0, seen_live = 0, kdone = 0;
+        for (int k = 0; k < ncont; k++) {
+            if (!(taken < wm_limit || seen_live < 2)) break;      // uniform
+            kdone = k + 1;
+            if (!sh.dirty[k]) continue;
+            int64_t w0 = (int64_t)k * 2048, w1 = w0 + 2048; if (w1 > nwords) w1 = nwords;
+            int per = (int)((w1 - w0 + NT - 1) / NT); int64_t my0 = w0 + (int64_t)c.tid() * per, my1 = my0 + per; if (my1 > w1) my1 = w1;
+            int cnt = 0, live = 0;
+            for (int64_t w = my0; w < my1; w++) { if (!((ws.bits2[w >> 5] >> (w & 31)) & 1u)) continue;
+                unsigned v = ws.bits[w]; while (v) { int b = ffs32(v) - 1; v &= v - 1; int d = (int)((w << 5) | b); if (!ix.deleted[d]) live++; if (!sorted_contains(sh.top_sorted, nt, d)) cnt++; } }
+            int tot; int off = block_excl_scan(c, cnt, sh.scan, tot);
+            int ltot; int loff = block_excl_scan(c, live, sh.scan, ltot);
+            int o = off, lo2 = loff;
+            for (int64_t w = my0; w < my1; w++) { if (!((ws.bits2[w >> 5] >> (w & 31)) & 1u)) continue;
+                unsigned v = ws.bits[w]; ws.bits[w] = 0;
+                while (v) { int b = ffs32(v) - 1; v &= v - 1; int d = (int)((w << 5) | b);
+                    if (!ix.deleted[d]) { if (seen_live + lo2 < 2) sh.first_live[seen_live + lo2] = d; lo2++; }
+                    if (!sorted_contains(sh.top_sorted, nt, d)) { if (taken + o < wm_limit && ne + o < cap) { e_doc[ne + o] = d; e_base[ne + o] = 0.f; e_twin[ne + o] = -1; } o++; } } }
+            int add = tot; if (taken + add > wm_limit) add = wm_limit - taken;
+            taken += add; ne += add; seen_live += ltot;
+            c.sync();                                              // every thread has read this container's summary words
+            for (int64_t sw = (w0 >> 5) + c.tid(); sw < ((w1 + 31) >> 5); sw += NT) ws.bits2[sw] = 0;
         }
+        for (int64_t sw = (((int64_t)kdone * 2048) >> 5) + c.tid(); sw < nsum; sw += NT) { unsigned m = ws.bits2[sw]; if (!m) continue; ws.bits2[sw] = 0; while (m) { ws.bits[(sw << 5) | (ffs32(m) - 1)] = 0; m &= m - 1; } }
         c.sync();
-        { const int ncont = (ix.n_docs + 65535) >> 16; for (int k = c.tid(); k < ncont; k += NT) sh.dirty[k] = 0; }
+        for (int k = c.tid(); k < ncont; k += NT) sh.dirty[k] = 0;
         c.sync();
     }
     if (c.tid() == 0 && B.wm_cnt) { B.wm_cnt[q * 4 + 0] = n_overlap; B.wm_cnt[q * 4 + 1] = ne - n_overlap; B.wm_cnt[q * 4 + 2] = any; B.wm_cnt[q * 4 + 3] = n_overlap; }
@@ -201,9 +196,9 @@ IFX_FN void wm_query(const Ctx& c, const DevIndex& ix, const QueryPlan& p, const
         if (ne + r < cap) { e_doc[ne + r] = d; e_base[ne + r] = nb; e_twin[ne + r] = -1; }
     }
     c.sync();
-    for (int a = c.tid(); a < na; a += NT) {           // group (a) entry a <-> its rank-order twin
-        int d = e_doc[a];
-        for (int r = 0; r < nt; r++) if (s1_doc[r] == d) { if (ne + r < cap) { e_twin[a] = ne + r; e_twin[ne + r] = a; } break; }
+    for (int a = c.tid(); a < na && a < cap; a += NT) {           // group (a) entry a <-> its rank-order twin
+        const int r = e_twin[a];
+        if (ne + r < cap) { e_twin[a] = ne + r; e_twin[ne + r] = a; } else e_twin[a] = -2;
     }
     ne += nt;
     c.sync();
@@ -227,7 +222,14 @@ IFX_FN void wm_query(const Ctx& c, const DevIndex& ix, const QueryPlan& p, const
 IFX_FN void cov_eval_entry(const DevIndex& ix, const QueryPlan& p, const Stage2Buffers& B, int q, int e) {
     const size_t o = (size_t)q * B.ent_cap + e;
     const int doc = B.ent_doc[o];
-    if (ix.deleted[doc] || B.ent_twin[o] == -3) { B.ent_hits[o] = -1; B.ent_score[o] = -1.f; B.ent_tie[o] = 0; B.ent_lcs[o] = 0; return; }   // ProcessCandidate returns early
+    // A top candidate that is also a WordMatcher document appears twice (group (a) with base 0 and in rank order with its normalised
+    // Stage-1 score): the evaluation differs in the last mix only, so the rank-order entry computes both and the group-(a) entry --
+    // those are the leading entries of a query, whole warps of them -- does nothing.
+    const int tw = B.ent_twin[o];
+    if (tw > e) return;
+    const size_t o2 = tw >= 0 ? (size_t)q * B.ent_cap + tw : o;
+    if (ix.deleted[doc] || tw == -3) { B.ent_hits[o] = -1; B.ent_score[o] = -1.f; B.ent_tie[o] = 0; B.ent_lcs[o] = 0;      // ProcessCandidate returns early
+        if (tw >= 0) { B.ent_hits[o2] = -1; B.ent_score[o2] = -1.f; B.ent_tie[o2] = 0; B.ent_lcs[o2] = 0; } return; }
     const CovQuery& cq = B.covq[q];
     int lcs = 0;
     if (doc == B.di_doc[q * 2] || doc == B.di_doc[q * 2 + 1]) {
@@ -236,7 +238,9 @@ IFX_FN void cov_eval_entry(const DevIndex& ix, const QueryPlan& p, const Stage2B
         lcs = lcs_metric(ix, Str{p.qtext, cq.qlen}, d, tol); if (lcs > 255) lcs = 255;
     }
     CovResult r = coverage_fusion(ix, cq, p.qtext, doc, lcs, B.ent_base[o]);
-    B.ent_score[o] = r.score; B.ent_tie[o] = r.tie; B.ent_hits[o] = r.word_hits | (r.overflow ? 0x40000000 : 0); B.ent_lcs[o] = (uint8_t)lcs;
+    const int hits = r.word_hits | (r.overflow ? 0x40000000 : 0);
+    B.ent_score[o] = r.score; B.ent_tie[o] = r.tie; B.ent_hits[o] = hits; B.ent_lcs[o] = (uint8_t)lcs;
+    if (tw >= 0) { B.ent_score[o2] = r.score0; B.ent_tie[o2] = r.tie; B.ent_hits[o2] = hits; B.ent_lcs[o2] = (uint8_t)lcs; }
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
