@@ -193,7 +193,7 @@ def run_sharded(args, wl, rank, world, local):
         if s == args.warmup:
             if rank == 0:
                 th.start()          # one sampler for the job (rank 0's GPU): eight concurrent nvidia-smi loops stall the timed host path
-            eng.exchange_ms = {k: 0.0 for k in eng.exchange_ms}
+            eng.exchange_ms = {k: 0.0 for k in eng.exchange_ms}; eng.host_ms = {}
         eng.eng.FlushL2(); st = ib.Stats()
         merged, dt = timed(lambda: eng.SearchBatch(None, stats=st, raw=True, uploaded=ups[s]))
         if s >= args.warmup:
@@ -202,7 +202,7 @@ def run_sharded(args, wl, rank, world, local):
                 agg[k] += getattr(st, k)
             if first is None:
                 first = merged
-    exch = dict(eng.exchange_ms)
+    exch = dict(eng.exchange_ms); host = dict(eng.host_ms)
     for u in ups:
         eng.FreeBatch(u)
     # ---- e2e: marshalling + upload inside the region ----------------------------------------------------------------------------------------
@@ -236,6 +236,7 @@ def run_sharded(args, wl, rank, world, local):
                        "l2": "256 MiB L2 flush before every timed step", "index_build_s": round(t_index, 1), "setup_s": round(t_setup, 1)},
             "phases_ms_per_step": {k: round(v / args.steps, 3) for k, v in aggm.items()},
             "exchanges_ms_per_step": {k: round(v / args.steps, 3) for k, v in exch.items()},
+            "host_wall_ms_per_step_rank0": {k: round(v / args.steps, 3) for k, v in host.items()},
             "roofline": {"bound": "hbm", "kernel": "Stage 1 (k_select_lookup + k_score_cta + k_score_warp + k_s1_finish), all shards", "achieved": achieved, "peak": peak * world, "unit": "GB/s", "frac": achieved / (peak * world),
                          "traffic": None, "algo_bytes_per_launch": algo_all / args.steps, "ms_per_launch": s1_ms, "peak_source": peak_src + " x n_gpus"},
             "e2e": {"value": e2e, "unit": "queries/s", "h2d_bytes_per_step": int(h2d) * world, "d2h_bytes_per_step": int(wl["nq"] * (10 * 13 + 12 + 48)) * world},

@@ -59,6 +59,7 @@ class ShardedSearchEngine:
         self.eng = E.SearchEngine(device=device_index, _gpu_lib=_gpu_lib)
         self.dev = torch.device("cpu") if _gpu_lib else torch.device("cuda", device_index)
         self.exchange_ms = {"fuzzy_df": 0.0, "stage1": 0.0, "final": 0.0}
+        self.host_ms = {}          # wall time of the phased C-ABI calls of this rank (kernels + their host side), download, merge pieces
 
     # ---- build -------------------------------------------------------------------------------------------------------------------------
     def IndexShard(self, keys, schema, columns, threads=None):
@@ -122,21 +123,21 @@ class ShardedSearchEngine:
             if self.dev.type == "cuda":
                 torch.cuda.synchronize(self.dev)
         try:
-            eng._check(g.ifx_batch_run_phase(h, 1, C.byref(st)), "phase 1")
+            tp = time.perf_counter(); eng._check(g.ifx_batch_run_phase(h, 1, C.byref(st)), "phase 1"); self._acc("phase1", tp)
             t0 = time.perf_counter()
             fdf = torch.zeros(nq * 16, dtype=torch.int32, device=self.dev)
             eng._check(g.ifx_batch_fuzzy_df(h, C.c_void_p(fdf.data_ptr()), 0), "fuzzy df get")
             dist.all_reduce(fdf)
             eng._check(g.ifx_batch_fuzzy_df(h, C.c_void_p(fdf.data_ptr()), 1), "fuzzy df set"); sync()
             self.exchange_ms["fuzzy_df"] += 1e3 * (time.perf_counter() - t0)
-            eng._check(g.ifx_batch_run_phase(h, 2, C.byref(st)), "phase 2")
+            tp = time.perf_counter(); eng._check(g.ifx_batch_run_phase(h, 2, C.byref(st)), "phase 2"); self._acc("phase2", tp)
             t0 = time.perf_counter()
             sc = torch.zeros(nq * 40, dtype=torch.int32, device=self.dev)
             eng._check(g.ifx_batch_select_counts(h, C.c_void_p(sc.data_ptr()), 0), "select counts get")
             dist.all_reduce(sc)
             eng._check(g.ifx_batch_select_counts(h, C.c_void_p(sc.data_ptr()), 1), "select counts set"); sync()
             self.exchange_ms["select_counts"] = self.exchange_ms.get("select_counts", 0.0) + 1e3 * (time.perf_counter() - t0)
-            eng._check(g.ifx_batch_run_phase(h, 3, C.byref(st)), "phase 3")
+            tp = time.perf_counter(); eng._check(g.ifx_batch_run_phase(h, 3, C.byref(st)), "phase 3"); self._acc("phase3", tp)
             t0 = time.perf_counter()
             key = torch.zeros(nq * K, dtype=torch.int64, device=self.dev); score = torch.zeros(nq * K, dtype=torch.float32, device=self.dev); n = torch.zeros(nq, dtype=torch.int32, device=self.dev)
             eng._check(g.ifx_batch_stage1_lists(h, C.c_void_p(key.data_ptr()), C.c_void_p(score.data_ptr()), C.c_void_p(n.data_ptr())), "stage1 lists")
@@ -147,7 +148,7 @@ class ShardedSearchEngine:
             self._keep, self._gmax = keep, gmax          # borrowed by the library until the last phase has run
             eng._check(g.ifx_batch_stage1_restrict(h, C.c_void_p(keep.data_ptr()), C.c_void_p(gmax.data_ptr()), C.c_void_p(nglob.data_ptr())), "stage1 restrict"); sync()
             self.exchange_ms["stage1"] += 1e3 * (time.perf_counter() - t0)
-            eng._check(g.ifx_batch_run_phase(h, 4, C.byref(st)), "phase 4")
+            tp = time.perf_counter(); eng._check(g.ifx_batch_run_phase(h, 4, C.byref(st)), "phase 4"); self._acc("phase4", tp)
             t0 = time.perf_counter()
             wc = torch.zeros(nq * 4, dtype=torch.int32, device=self.dev)
             eng._check(g.ifx_batch_wm_counts(h, C.c_void_p(wc.data_ptr())), "wm counts")
@@ -160,11 +161,11 @@ class ShardedSearchEngine:
             anyg = (WC[:, :, 2].sum(1) > 0).to(torch.int32).contiguous()
             eng._check(g.ifx_batch_wm_apply(h, C.c_void_p(allowed.data_ptr()), C.c_void_p(anyg.data_ptr())), "wm apply"); sync()
             self.exchange_ms["wm"] = self.exchange_ms.get("wm", 0.0) + 1e3 * (time.perf_counter() - t0)
-            eng._check(g.ifx_batch_run_phase(h, 5, C.byref(st)), "phase 5")
-            eng._check(g.ifx_batch_download(h, C.byref(packed["out"])), "ifx_batch_download")
+            tp = time.perf_counter(); eng._check(g.ifx_batch_run_phase(h, 5, C.byref(st)), "phase 5"); self._acc("phase5", tp)
+            tp = time.perf_counter(); eng._check(g.ifx_batch_download(h, C.byref(packed["out"])), "ifx_batch_download")
             info = np.zeros((nq, 8), np.int32); dkey = np.zeros((nq, 2), np.int64)
             eng._check(g.ifx_batch_shard_info(h, E._p(info), E._p(dkey)), "shard info")
-            packed["bufs"]["info"], packed["bufs"]["dkey"] = info, dkey
+            packed["bufs"]["info"], packed["bufs"]["dkey"] = info, dkey; self._acc("download", tp)
         finally:
             if uploaded is None:
                 g.ifx_batch_free(h)
@@ -172,6 +173,10 @@ class ShardedSearchEngine:
         merged = self._merge(queries, packed["bufs"], cap)
         self.exchange_ms["final"] += 1e3 * (time.perf_counter() - t0)
         return merged if raw else self._results(queries, merged)
+
+    def _acc(self, name, t0):
+        import time
+        self.host_ms[name] = self.host_ms.get(name, 0.0) + 1e3 * (time.perf_counter() - t0)
 
     def _global_cut(self, ks, ss, ns, nq, K):
         """Membership of this rank's Stage-1 entries in the global top-K by (score desc, key asc), and the global top score per query."""
@@ -203,13 +208,18 @@ class ShardedSearchEngine:
     def _merge(self, queries, bufs, cap):
         """All-gather of every shard's records; merged by ScoreEntry order (Score desc, Tiebreaker desc, DocumentId asc) and cut to max."""
         torch, dist, W = self.torch, self.dist, self.world
-        nq = len(queries); eng = self.eng
+        import time
+        nq = len(queries); eng = self.eng; tp = time.perf_counter()
         rec = np.zeros((nq, cap, 3), np.float64)          # key, score bits (exact in f64), tie
         rec[:, :, 0] = bufs["keys"]; rec[:, :, 1] = bufs["scores"].view(np.uint32).astype(np.float64); rec[:, :, 2] = bufs["ties"]
         meta = np.concatenate([np.stack([bufs["n"], bufs["total"], bufs["status"], bufs["nf"]], 1).astype(np.int64), bufs["info"].astype(np.int64), bufs["dkey"]], 1)      # [nq, 4 + 8 + 2]
         t_rec = torch.from_numpy(rec).to(self.dev); t_meta = torch.from_numpy(meta).to(self.dev)
         recs = [torch.empty_like(t_rec) for _ in range(W)]; metas = [torch.empty_like(t_meta) for _ in range(W)]
+        self._acc("merge_pack", tp); tp = time.perf_counter()
         dist.all_gather(recs, t_rec); dist.all_gather(metas, t_meta)
+        if self.dev.type == "cuda":
+            torch.cuda.synchronize(self.dev)
+        self._acc("merge_gather", tp); tp = time.perf_counter()
         # merge on the device: ScoreEntry order (Score desc, Tiebreaker desc, DocumentId asc) = three stable sorts, least significant key first
         R = torch.stack(recs, 1).reshape(nq, W * cap, 3); M = torch.stack(metas, 1)                                                   # [nq, W*cap, 3], [nq, W, 14]
         valid = (torch.arange(cap, device=self.dev).view(1, 1, cap) < M[:, :, 0:1]).reshape(nq, W * cap)
@@ -237,7 +247,7 @@ class ShardedSearchEngine:
         for r in range(1, W):
             status_t |= M[:, r, 2]
         o_key = t_key.cpu().numpy(); o_score = t_sbits.to(torch.int32).cpu().numpy().view(np.float32); o_tie = t_tie.to(torch.uint8).cpu().numpy(); o_n = t_n.cpu().numpy()
-        total = o_n.copy(); status = status_t.cpu().numpy()
+        total = o_n.copy(); status = status_t.cpu().numpy(); self._acc("merge_sort_cut", tp)
         self.last_raw = (o_key, o_score, o_tie, o_n, total, status)
         facets_all = None
         if any(q.EnableFacets for q in queries):          # facet rows travel as strings (value ids are per-shard dictionaries)
