@@ -52,16 +52,36 @@ def effective_cpus():
 
 
 def clocks_sampler(stop, out, gpu_index):
+    """ONE long-lived `nvidia-smi -lms 200` process for the timed region (the profiling recipe's clocks line), read line by line: a
+    process per sample re-initialises NVML over every GPU of the box each time, which stalls the CUDA calls of all ranks on an 8-GPU node."""
+    import shutil
     q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
-    while not stop.is_set():
+    cmd = ["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "200"]
+    if shutil.which("stdbuf"):
+        cmd = ["stdbuf", "-oL"] + cmd          # line-buffered stdout into the pipe
+    try:
+        pr = subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, bufsize=1)
+    except Exception:
+        return
+    try:
+        while not stop.is_set():
+            line = pr.stdout.readline()
+            if not line:
+                break
+            f = [x.strip() for x in line.split(",")]
+            try:
+                if len(f) >= 6:
+                    out.append((float(f[0]), float(f[1]), f[2], f[3], f[4], f[5]))
+            except ValueError:
+                pass
+    finally:
         try:
-            r = subprocess.run(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + q, "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5)
-            f = [x.strip() for x in r.stdout.strip().split(",")]
-            if len(f) >= 6:
-                out.append((float(f[0]), float(f[1]), f[2], f[3], f[4], f[5]))
+            pr.terminate(); pr.wait(timeout=5)
         except Exception:
-            pass
-        stop.wait(0.2)
+            try:
+                pr.kill()
+            except Exception:
+                pass
 
 
 def measured_peak():
@@ -212,7 +232,9 @@ def run_sharded(args, wl, rank, world, local):
         _, dt = timed(lambda: eng.SearchBatch(batches[s], raw=True, packed=prepacked[s]))
         if s >= args.warmup:
             e2e_t += dt
-    stop.set()
+    stop.set(); eng.Close()
+    if th.is_alive():
+        th.join(timeout=10)
     tt = torch.tensor([dev_t, e2e_t, float(algo)] + [agg[k] for k in agg], dtype=torch.float64, device="cuda")
     mx = tt.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX); sm = tt.clone(); dist.all_reduce(sm)
     if rank != 0:
@@ -310,6 +332,8 @@ def run_ours(args, wl, rank, world, local):
         if s >= args.warmup:
             e2e_t += dt; h2d, d2h = st.h2d_bytes, st.d2h_bytes
     stop.set()
+    if th.is_alive():
+        th.join(timeout=10)
     bad_status = int(sum(((p["bufs"]["status"] & ~8) != 0).sum() for p in packed[args.warmup:]))
     dev_ms = agg["ms_total"]
     if dist is not None:

@@ -165,6 +165,7 @@ int  ifx_search_batch(ifx_index* idx, const ifx_query* q, int nq, ifx_batch_resu
 
 /* split form: upload once, run on device (timed), read back */
 int  ifx_batch_upload(ifx_index* idx, const ifx_query* q, int nq, ifx_batch** out);
+int  ifx_batch_refill(ifx_batch* b, const ifx_query* q, int nq);      /* the same handle for the next batch: device buffers are kept while they fit */
 int  ifx_batch_run(ifx_batch* b, ifx_stats* st);
 int  ifx_batch_download(ifx_batch* b, ifx_batch_result* out);
 void ifx_batch_free(ifx_batch* b);

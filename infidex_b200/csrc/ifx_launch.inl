@@ -346,6 +346,10 @@ extern "C" int ifx_batch_upload(ifx_index* idx, const ifx_query* q, int nq, ifx_
     catch (const std::string& e) { delete b; return fail(IFX_ERR_CUDA, e); }
     *out = b; return IFX_OK;
 }
+extern "C" int ifx_batch_refill(ifx_batch* b, const ifx_query* q, int nq) {
+    if (!b || !q || nq <= 0) return fail(IFX_ERR_INVALID, "bad batch arguments");
+    try { DeviceGuard dg(b->idx->device); return fill_batch(b, q, nq); } catch (const std::string& e) { return fail(IFX_ERR_CUDA, e); }
+}
 extern "C" void ifx_batch_free(ifx_batch* b) { if (!b) return; try { DeviceGuard dg(b->idx->device); delete b; } catch (...) { } }
 
 extern "C" int ifx_stage1_batch(ifx_index* idx, const ifx_query* q, int nq, int depth, int64_t* doc_key, float* score, int32_t* n, int32_t* status, ifx_stats* st) {

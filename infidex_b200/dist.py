@@ -105,6 +105,12 @@ class ShardedSearchEngine:
     def FreeBatch(self, up):
         self.eng._gpu.ifx_batch_free(up["h"])
 
+    def Close(self):
+        """Release the batch handle SearchBatch keeps between calls (must happen before the index is destroyed)."""
+        h = getattr(self, "_cached_h", None)
+        if h is not None:
+            self.eng._gpu.ifx_batch_free(h); self._cached_h = None
+
     def SearchBatch(self, queries, stats=None, raw=False, uploaded=None, packed=None):
         """Every rank passes the SAME queries; every rank returns the same merged Results (Records, TotalCandidates, Facets by string)."""
         import time
@@ -115,8 +121,12 @@ class ShardedSearchEngine:
         if uploaded is not None:
             packed, h = uploaded["packed"], uploaded["h"]
         else:
-            packed = packed or eng.PackBatch(queries); h = C.c_void_p()      # `packed`: host-side marshalling done beforehand (what the C# shim's pinned buffers are)
-            eng._check(g.ifx_batch_upload(eng._index, packed["arr"], nq, C.byref(h)), "ifx_batch_upload")
+            packed = packed or eng.PackBatch(queries); h = getattr(self, "_cached_h", None)      # `packed`: host-side marshalling done beforehand (what the C# shim's pinned buffers are)
+            if h is not None and g.ifx_batch_refill(h, packed["arr"], nq) != 0:      # the handle of the previous call is reused (no device allocation per batch), like ifx_search_batch does
+                g.ifx_batch_free(h); h = None
+            if h is None:
+                h = C.c_void_p(); eng._check(g.ifx_batch_upload(eng._index, packed["arr"], nq, C.byref(h)), "ifx_batch_upload")
+            self._cached_h = h
         st = stats if stats is not None else E.Stats()
 
         def sync():
@@ -166,9 +176,10 @@ class ShardedSearchEngine:
             info = np.zeros((nq, 8), np.int32); dkey = np.zeros((nq, 2), np.int64)
             eng._check(g.ifx_batch_shard_info(h, E._p(info), E._p(dkey)), "shard info")
             packed["bufs"]["info"], packed["bufs"]["dkey"] = info, dkey; self._acc("download", tp)
-        finally:
+        except Exception:
             if uploaded is None:
-                g.ifx_batch_free(h)
+                g.ifx_batch_free(h); self._cached_h = None
+            raise
         t0 = time.perf_counter()
         merged = self._merge(queries, packed["bufs"], cap)
         self.exchange_ms["final"] += 1e3 * (time.perf_counter() - t0)
