@@ -190,21 +190,45 @@ class ShardedSearchEngine:
         self.host_ms[name] = self.host_ms.get(name, 0.0) + 1e3 * (time.perf_counter() - t0)
 
     def _global_cut(self, ks, ss, ns, nq, K):
-        """Membership of this rank's Stage-1 entries in the global top-K by (score desc, key asc), and the global top score per query."""
+        """Membership of this rank's Stage-1 entries in the global top-K by (score desc, key asc), and the global top score per query.
+        Every shard's list is already in that order, so an entry's global rank is its local rank plus, per other shard, the number of
+        entries ahead of it -- W - 1 binary searches over packed (score bits, inverted key) words instead of a sort of all W * K entries."""
+        torch = self.torch; W = self.world; dev = ss[0].device
+        N = torch.stack(ns, 1).clamp(min=0, max=K)                                             # [nq, W]
+        slot = torch.arange(K, device=dev).view(1, K)
+        big = torch.iinfo(torch.int64).max
+        negc = []
+        fits = True
+        for r in range(W):
+            k = ks[r].view(nq, K); v = slot < N[:, r].view(nq, 1)
+            if not bool((((k >= 0) & (k < 2 ** 32)) | ~v).all()):
+                fits = False; break
+            comp = (ss[r].view(nq, K).view(torch.int32).to(torch.int64) << 32) | (0xFFFFFFFF - k)      # larger = earlier in the list order
+            negc.append(torch.where(v, -comp, torch.full_like(comp, big)).contiguous())           # ascending along the list; invalid slots last
+        if not fits:
+            return self._global_cut_sort(ks, ss, ns, nq, K)
+        mine = negc[self.rank]; grank = slot.expand(nq, K).clone()
+        for o in range(W):
+            if o != self.rank:
+                grank += torch.searchsorted(negc[o], mine, right=False)
+        valid = slot < N[:, self.rank].view(nq, 1)
+        keep = torch.where(valid & (grank < K), torch.where(grank == 0, 2, torch.where(grank == 1, 3, 1)), 0).to(torch.uint8).contiguous().view(-1)      # 2 / 3: global rank 0 / 1 (docIndex 0 / 1)
+        first = torch.stack([torch.where(N[:, r] > 0, ss[r].view(nq, K)[:, 0], torch.zeros((), dtype=ss[r].dtype, device=dev)) for r in range(W)], 1)
+        gmax = first.max(dim=1).values.clamp(min=0).contiguous()
+        nglob = N.sum(1).clamp(max=K).to(torch.int32).contiguous()
+        return keep, gmax, nglob
+
+    def _global_cut_sort(self, ks, ss, ns, nq, K):
+        """General form (keys beyond 32 bits): two stable sorts over all W * K entries."""
         torch = self.torch; W = self.world
         S = torch.stack([s.view(nq, K) for s in ss], 1).reshape(nq, W * K); Kk = torch.stack([k.view(nq, K) for k in ks], 1).reshape(nq, W * K)
         N = torch.stack(ns, 1).clamp(min=0)                                                    # [nq, W]
         slot = torch.arange(K, device=S.device).view(1, 1, K).expand(nq, W, K)
         valid = (slot < N.view(nq, W, 1)).reshape(nq, W * K)
         S = torch.where(valid, S, torch.full_like(S, -1.0)); Kk = torch.where(valid, Kk, torch.full_like(Kk, 2 ** 62))
-        if bool(((Kk >= 0) & (Kk < 2 ** 32) | ~valid).all()):
-            # keys fit 32 bits: (score bits, inverted key) pack into one int64 whose order IS the list order -> one top-K instead of two full sorts
-            comp = torch.where(valid, (S.view(torch.int32).to(torch.int64) << 32) | (0xFFFFFFFF - Kk), torch.full_like(Kk, -1))
-            order = torch.topk(comp, min(K, W * K), dim=1, sorted=True).indices
-        else:
-            i1 = torch.argsort(Kk, dim=1, stable=True); S1 = torch.gather(S, 1, i1)
-            i2 = torch.argsort(S1, dim=1, descending=True, stable=True)
-            order = torch.gather(i1, 1, i2)[:, :K]                                             # flat positions of the global top-K
+        i1 = torch.argsort(Kk, dim=1, stable=True); S1 = torch.gather(S, 1, i1)
+        i2 = torch.argsort(S1, dim=1, descending=True, stable=True)
+        order = torch.gather(i1, 1, i2)[:, :K]                                                 # flat positions of the global top-K
         top_valid = torch.gather(valid, 1, order)
         mark = torch.zeros(nq, W * K, dtype=torch.uint8, device=S.device)
         flag = top_valid.to(torch.uint8); flag[:, 0] *= 2                                     # 2: global rank 0, 3: global rank 1 (docIndex 0 / 1)
