@@ -85,7 +85,7 @@ extern "C" int ifx_filter_register(ifx_index* idx, const uint8_t* data, size_t l
 
 // ---- kernels ---------------------------------------------------------------------------------------------------------------
 #ifndef IFX_EMU
-__global__ void __launch_bounds__(256) k_wm(DevIndex ix, const QueryPlan* plans, int nq, const int32_t* s1_doc, const float* s1_score, const int32_t* s1_n, int K,
+__global__ void __launch_bounds__(256, 4) k_wm(DevIndex ix, const QueryPlan* plans, int nq, const int32_t* s1_doc, const float* s1_score, const int32_t* s1_n, int K,
                                             S1Workspace* wss, Stage2Buffers B, int* work) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     WmShared& sh = *reinterpret_cast<WmShared*>(smem_raw); Ctx c; S1Workspace ws = wss[blockIdx.x];
@@ -136,7 +136,7 @@ static void run_stage2_phase(ifx_batch* b, ifx_stats* st, int part = 3) {      /
     if (part & 1) {
     t.start();
     CUDA_TRY(cudaMemsetAsync(b->d_work + 2, 0, sizeof(int)));
-    k_wm<<<std::min(ix->n_ctas, nq), 256, sizeof(WmShared)>>>(ix->v, b->d_plans, nq, b->d_s1_doc, b->d_s1_score, b->d_s1_n, K, ix->d_ws, b->s2, b->d_work + 2);
+    k_wm<<<std::min(ix->n_ctas_sel, nq), 256, sizeof(WmShared)>>>(ix->v, b->d_plans, nq, b->d_s1_doc, b->d_s1_score, b->d_s1_n, K, ix->d_ws, b->s2, b->d_work + 2);
     ms_wm = t.stop(); launches++;
     }
     if (part & 2) {
