@@ -40,7 +40,7 @@ struct WmShared {
     WmList lists[MAX_WM_WORDS * 18];
     WmList affix[MAX_WM_WORDS * 2];
     Tok words[MAX_WM_WORDS]; int n_words;
-    int32_t top_sorted[MAX_K]; uint16_t top_rank[MAX_K]; uint8_t in_wm[MAX_K];     // Stage-1 docs ascending, their Stage-1 rank, WordMatcher membership
+    int32_t top_sorted[MAX_K]; uint16_t top_rank[MAX_K]; alignas(4) uint8_t in_wm[MAX_K];     // Stage-1 docs ascending, their Stage-1 rank, WordMatcher membership
     uint16_t nz[MAX_WM_WORDS * 18]; int n_nz;                                      // the non-empty dictionary lists
     uint8_t dirty[MAX_CONTAINERS];
     ScanTmp scan; int bcast[8]; int first_live[2];
@@ -139,9 +139,9 @@ IFX_FN void wm_query(const Ctx& c, const DevIndex& ix, const QueryPlan& p, const
     for (int k = c.tid(); k < nt; k += NT) { int d = sh.top_sorted[k]; sh.in_wm[k] = (uint8_t)((ws.bits[d >> 5] >> (d & 31)) & 1u); }
     c.sync();
     // one (list, top doc) probe per thread and step: consecutive threads search the same list for consecutive (ascending) documents
-    for (int it = c.tid(); it < nnz * nt; it += NT) { const int k = it % nt; if (sh.in_wm[k]) continue;
+    for (int it = c.tid(); it < nnz * nt; it += NT) { const int k = it % nt;
         const WmList L = sh.lists[sh.nz[it / nt]]; const int d = sh.top_sorted[k];
-        if (d >= L.p[0] && d <= L.p[L.n - 1] && sorted_contains(L.p, L.n, d)) sh.in_wm[k] = 1; }
+        if (d >= L.p[0] && d <= L.p[L.n - 1] && sorted_contains(L.p, L.n, d)) atomic_or(reinterpret_cast<unsigned*>(sh.in_wm) + (k >> 2), 1u << ((k & 3) * 8)); }      // several lists may hold the same document
     c.sync();
     int my = 0; for (int k = c.tid(); k < nt; k += NT) my += sh.in_wm[k];
     const int n_overlap = block_sum(c, my, sh.scan);

@@ -1,8 +1,9 @@
 #!/usr/bin/env python3
 """Markdown summary of (a) an ncu launch list (--metrics gpu__time_duration.sum --csv) and (b) an ncu --set full raw-page export.
-usage: ncu_summary.py <tag> <launches.csv> <raw_page.csv>"""
+usage: ncu_summary.py <tag> <launches.csv> <raw_page.csv> [workload text] [bench flags of the launch list]"""
 import csv, sys, collections
 tag, lpath, rpath = sys.argv[1:4]
+wl = sys.argv[4] if len(sys.argv) > 4 else 'configs[1]'; flags = sys.argv[5] if len(sys.argv) > 5 else '--steps 3 --warmup 1 --no-cpu-baseline'
 rows = [r for r in csv.reader(l for l in open(lpath) if l.startswith('"'))]
 hdr = rows[0]; kn = hdr.index("Kernel Name"); mv = hdr.index("Metric Value"); mn = hdr.index("Metric Name")
 agg = collections.OrderedDict()
@@ -10,7 +11,7 @@ for r in rows[1:]:
     if r[mn] != "gpu__time_duration.sum": continue
     name = r[kn].split("(")[0]; e = agg.setdefault(name, [0, 0.0]); e[0] += 1; e[1] += float(r[mv].replace(",", "")) / 1e6
 tot = sum(v[1] for v in agg.values())
-print("# %s launch list (ncu --metrics gpu__time_duration.sum --clock-control none; `python bench.py --steps 3 --warmup 1 --no-cpu-baseline`, configs[1])\n" % tag)
+print("# %s launch list (ncu --metrics gpu__time_duration.sum --clock-control none; `python bench.py %s`, %s)\n" % (tag, flags, wl))
 print("Cold-cache, serialised per-launch times: compare SHARES, not absolutes (the raw CSV is `%s`).\n" % lpath.split("/")[-1])
 print("| kernel | launches | total ms | share | avg ms |\n|---|---|---|---|---|")
 for k, (n, ms) in sorted(agg.items(), key=lambda x: -x[1][1]):
