@@ -72,8 +72,6 @@ __global__ void __launch_bounds__(IFX_EXPAND_THREADS, 2) k_expand(DevIndex ix, Q
 #ifndef IFX_SEL_CTAS
 #define IFX_SEL_CTAS 4
 #endif
-// dynamic shared memory of k_select_lookup: the selection struct, then the SUM_WORDS-word candidate summary of the lookup pass (16-byte aligned)
-static constexpr size_t S1_SEL_SMEM = (sizeof(S1SelShared) + 15) & ~(size_t)15;
 __global__ void __launch_bounds__(IFX_SEL_THREADS, IFX_SEL_CTAS) k_select_lookup(DevIndex ix, const QueryPlan* plans, int nq, const int32_t* pool, S1Workspace* wss, BatchCounters* bc,
                                                 int32_t* s1_n, int* work, const int* order, long long* qdbg, S1Rec* recs, unsigned char* spool, unsigned long long spool_cap,
                                                 S1Queues queues, int wave, int force_mode, int smode, int32_t* sel_cnt, int32_t* sel_done) {
@@ -98,7 +96,7 @@ __global__ void __launch_bounds__(IFX_SEL_THREADS, IFX_SEL_CTAS) k_select_lookup
             if (path > 0 && cq[4] != 1) { stage1_clear_bits(c, ix, ws, sh); continue; }
             if (threadIdx.x == 0) sel_done[q] = 1;
         }
-        stage1_lookup(c, ix, plans[q], path, q, ws, sh, recs, spool, spool_cap, queues, bc, o, ix.fwd_avg_bytes, force_mode, reinterpret_cast<unsigned*>(smem_raw + S1_SEL_SMEM));
+        stage1_lookup(c, ix, plans[q], path, q, ws, sh, recs, spool, spool_cap, queues, bc, o, ix.fwd_avg_bytes, force_mode);
         __syncthreads();
         if (threadIdx.x == 0) { unsigned long long t1; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1)); atomicAdd(&bc->s1_ns_sum, t1 - t0); atomicMax(&bc->s1_ns_max, t1 - t0); qdbg[(size_t)q * IFX_QDBG + 4] = (long long)(t1 - t0); qdbg[(size_t)q * IFX_QDBG + 2] -= (long long)t0; qdbg[(size_t)q * IFX_QDBG + 5] = blockIdx.x; }
     }
@@ -238,7 +236,6 @@ static void run_stage1_phase(ifx_batch* b, ifx_stats* st, int part = 3) {
 #ifdef IFX_EMU
     std::vector<int64_t> off(nq + 1); d2h(off.data(), b->d_off, (nq + 1) * 8);
     if (part & 1) for (int q = 0; q < nq; q++) { prepare_query(ix->v, b->d_text + off[q], (int)(off[q + 1] - off[q]), b->d_par[q * 5 + 1], b->d_par[q * 5 + 0], b->d_par[q * 5 + 2], b->d_par[q * 5 + 3], b->d_par[q * 5 + 4], b->d_plans[q], b->d_items, items_cap, b->d_bc, q); b->d_short_kind[q] = b->d_plans[q].short_kind; if (b->d_plans[q].short_kind) b->d_bc->n_short++; }
-    static std::vector<unsigned> emu_sum(SUM_WORDS);
     static S1Shared* sh = new S1Shared(); memset(sh->dirty, 0, sizeof(sh->dirty)); static WarpScoreShared* wsh = new WarpScoreShared(); static FinishShared* fsh = new FinishShared();
     Ctx c; int nit = std::min(b->d_bc->n_fuzzy_items, items_cap);
     if (part & 1) for (int i = 0; i < nit; i++) expand_fuzzy(c, ix->v, b->d_plans[b->d_items[i].query], b->d_items[i].slot, ix->ws[0], *sh, ix->d_pool, ix->pool_cap, b->d_bc, ix->d_sorted_len, sh->cand_s);
@@ -247,7 +244,7 @@ static void run_stage1_phase(ifx_batch* b, ifx_stats* st, int part = 3) {
         int32_t* cq = b->d_sel_cnt + (size_t)q * SEL_CNT;
         const int path = stage1_select(c, ix->v, b->d_plans[q], ix->d_pool, ix->ws[0], *sh, o, 1, cq);
         if (path > 0 && cq[4] != 1) { stage1_clear_bits(c, ix->v, ix->ws[0], *sh); continue; }
-        b->d_sel_done[q] = 1; stage1_lookup(c, ix->v, b->d_plans[q], path, q, ix->ws[0], *sh, b->d_recs, ix->d_spool, ix->spool_cap, queues, b->d_bc, o, ix->v.fwd_avg_bytes, force_mode, emu_sum.data()); }
+        b->d_sel_done[q] = 1; stage1_lookup(c, ix->v, b->d_plans[q], path, q, ix->ws[0], *sh, b->d_recs, ix->d_spool, ix->spool_cap, queues, b->d_bc, o, ix->v.fwd_avg_bytes, force_mode); }
     const bool no_warp = getenv("IFX_S1_NO_WARP") != nullptr;      // tests: force every query through the block-wide scorer
     for (int wave = 0; wave < 64 && (part & 2); wave++) {
         if (wave > 0 || smode == 0) { b->d_bc->s1_pool_used = 0; b->d_bc->s1_deferred = 0; b->d_bc->s1_n_light = 0; b->d_bc->s1_n_mid = 0; b->d_bc->s1_n_heavy = 0; }      // (shards: the count pass already queued the queries it could finish)
@@ -257,7 +254,7 @@ static void run_stage1_phase(ifx_batch* b, ifx_stats* st, int part = 3) {
             if (smode == 2 && b->d_sel_done[q] == 1 && b->d_recs[q].state != 2) continue;
             Stage1Out o{nullptr, nullptr, nullptr, b->d_s1_n + q, nullptr};
             const int path = stage1_select(c, ix->v, b->d_plans[q], ix->d_pool, ix->ws[0], *sh, o, smode, b->d_sel_cnt + (size_t)q * SEL_CNT);
-            stage1_lookup(c, ix->v, b->d_plans[q], path, q, ix->ws[0], *sh, b->d_recs, ix->d_spool, ix->spool_cap, queues, b->d_bc, o, ix->v.fwd_avg_bytes, force_mode, emu_sum.data());
+            stage1_lookup(c, ix->v, b->d_plans[q], path, q, ix->ws[0], *sh, b->d_recs, ix->d_spool, ix->spool_cap, queues, b->d_bc, o, ix->v.fwd_avg_bytes, force_mode);
         }
         for (int i = 0; i < b->d_bc->s1_n_light; i++) { const int q = b->d_light[i];
             if (no_warp) score_cta(c, ix->v.avgdl, b->d_recs[q], ix->d_spool, ix->ws[0], *sh, b->d_s1_doc + (size_t)q * K, b->d_s1_score + (size_t)q * K, b->d_s1_n + q);
@@ -273,7 +270,7 @@ static void run_stage1_phase(ifx_batch* b, ifx_stats* st, int part = 3) {
     }
     (void)t;
 #else
-    const size_t smem = sizeof(S1Shared), smem_sel = S1_SEL_SMEM + SUM_WORDS * sizeof(unsigned), smem_w = sizeof(WarpScoreShared) * IFX_SW_WARPS, smem_m = sizeof(WarpScoreShared) * IFX_SW_WARPS_MID;
+    const size_t smem = sizeof(S1Shared), smem_sel = sizeof(S1SelShared), smem_w = sizeof(WarpScoreShared) * IFX_SW_WARPS, smem_m = sizeof(WarpScoreShared) * IFX_SW_WARPS_MID;
     auto k_light = k_score_warp<W_CAP, IFX_SW_WARPS>; auto k_mid = k_score_warp<W_CAP_MID, IFX_SW_WARPS_MID>;
     if (!ix->attr_s1) { CUDA_TRY(cudaFuncSetAttribute(k_expand, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); CUDA_TRY(cudaFuncSetAttribute(k_select_lookup, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_sel));
         CUDA_TRY(cudaFuncSetAttribute(k_score_cta, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); CUDA_TRY(cudaFuncSetAttribute(k_light, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_w)); CUDA_TRY(cudaFuncSetAttribute(k_mid, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_m)); ix->attr_s1 = true; }

@@ -42,18 +42,8 @@ constexpr int W_K = 512;             // heap capacity kept in shared memory per 
 //   3. tf of every (term, candidate): either every posting list streamed once against the candidate bitset (coalesced; the byte
 //      volume SURVEY 8d calls algorithmic), or -- few candidates relative to the lists -- one forward-index read per candidate
 //   4. bitset cleared again
-// On-chip summary of the candidate bitset for the streamed lookups: one bit per 2^sum_shift documents, set when any candidate lies in the
-// block. A streamed posting first tests its block in shared memory; only postings whose block holds a candidate go on to the probe table
-// in HBM (most postings of a long list fall between the candidates: ncu showed the probe loads as 1/3 of the kernel's stall samples and the
-// kernel at 3x its algorithmic traffic). SUM_WORDS * 32 blocks; the shift grows with the shard so the table always fits.
-#ifndef IFX_SUM_WORDS
-#define IFX_SUM_WORDS 5120
-#endif
-constexpr int SUM_WORDS = IFX_SUM_WORDS;      // 20 KB of shared memory per CTA of k_select_lookup (tests shrink it to exercise large shifts)
-IFX_FN int sum_shift_for(int n_docs) { int sh = 5; while (((int64_t)n_docs >> sh) >= (int64_t)SUM_WORDS * 32) sh++; return sh; }
-
 IFX_FN void stage1_lookup(const Ctx& c, const DevIndex& ix, const QueryPlan& p, int path, int q, S1Workspace& ws, S1SelShared& sh, S1Rec* recs,
-                          unsigned char* spool, unsigned long long spool_cap, S1Queues queues, BatchCounters* bc, Stage1Out out, int fwd_avg_bytes, int force_mode, unsigned* sum = nullptr) {
+                          unsigned char* spool, unsigned long long spool_cap, S1Queues queues, BatchCounters* bc, Stage1Out out, int fwd_avg_bytes, int force_mode) {
     S1Rec& rec = recs[q]; const int NT = c.nthreads(), NW = c.nwarps(); constexpr int WS = Ctx::WS;
 #if !defined(IFX_EMU) && defined(IFX_S1_TIMERS)
     long long lmark = 0; if (c.tid() == 0) { asm volatile("mov.u64 %0, %%clock64;" : "=l"(lmark) :: "memory"); if (out.dbg) for (int k = 11; k < 18; k++) out.dbg[k] = 0; }
@@ -90,9 +80,7 @@ IFX_FN void stage1_lookup(const Ctx& c, const DevIndex& ix, const QueryPlan& p, 
     const long long a1 = pool_alloc(8ULL * (unsigned long long)n_cand + 64);
     if (a1 < 0) { give_up(a1); return; }
     int32_t* cand = reinterpret_cast<int32_t*>(spool + a1); float* dlp = reinterpret_cast<float*>(spool + a1 + (((long long)n_cand * 4 + 31) & ~31LL));
-    const int sshift = sum_shift_for(ix.n_docs);
-    if (sum) { for (int i = c.tid(); i < SUM_WORDS; i += NT) sum[i] = 0u; c.sync(); }
-    // ---- 1b. expand + rank directory + candidates before every container (+ the on-chip summary)
+    // ---- 1b. expand + rank directory + candidates before every container
     {   int run = wbase;
         for (int64_t gb = w0; gb < w1; gb += 4 * WS) {          // four groups per trip: their words are loaded together, then scanned one after the other
             unsigned vv[4];
@@ -103,8 +91,7 @@ IFX_FN void stage1_lookup(const Ctx& c, const DevIndex& ix, const QueryPlan& p, 
                 const int64_t w = g0 + c.lane(); unsigned v = vv[u]; const int pc = popc(v); int incl = pc;
                 for (int d = 1; d < WS; d <<= 1) { int o = c.shfl(incl, c.lane() >= d ? c.lane() - d : 0); if (c.lane() >= d) incl += o; }
                 int o = run + incl - pc;
-                if (w < w1) { S1Probe pv; pv.bits = v; pv.rank = o; reinterpret_cast<S1Probe*>(ws.probe)[w] = pv; if ((w & 2047) == 0) ws.cstart[w >> 11] = o;
-                              if (sum && v) { const unsigned sb = (unsigned)((w << 5) >> sshift); atomic_or(&sum[sb >> 5], 1u << (sb & 31)); } }
+                if (w < w1) { S1Probe pv; pv.bits = v; pv.rank = o; reinterpret_cast<S1Probe*>(ws.probe)[w] = pv; if ((w & 2047) == 0) ws.cstart[w >> 11] = o; }
                 while (v) { int b = ffs32(v) - 1; v &= v - 1; cand[o++] = (int32_t)((w << 5) | b); }
                 run += c.shfl(incl, WS - 1);
             }
@@ -161,9 +148,6 @@ IFX_FN void stage1_lookup(const Ctx& c, const DevIndex& ix, const QueryPlan& p, 
     const bool forward = force_mode == 1 ? true : (force_mode == 2 ? false : (n_dict > 0 && 3ULL * (unsigned long long)n_cand * (unsigned long long)fwd_avg_bytes < cost_s));      // random forward-list reads cost ~3x a streamed byte (measured, profiles/r2)
     const S1Cont* ctab = reinterpret_cast<const S1Cont*>(ws.ctab);
     const S1Probe* probe = reinterpret_cast<const S1Probe*>(ws.probe);
-    auto probe_at = [&](int d) -> S1Probe {      // the probe-table word of document d, or an empty one when the summary says its block holds no candidate
-        if (sum) { const unsigned sb = (unsigned)d >> sshift; if (!((sum[sb >> 5] >> (sb & 31)) & 1u)) { S1Probe z; z.bits = 0u; z.rank = 0; return z; } }
-        return probe[d >> 5]; };
     auto put_hit = [&](int d, S1Probe pv, int a, uint8_t tfv) {      // candidate d (bit set in pv.bits) of row a
         const unsigned bit = 1u << (d & 31); const int idx = pv.rank + popc(pv.bits & (bit - 1)); const S1Cont ct = ctab[d >> 16];
         const int jc = idx - ct.cstart, sub = jc / CHUNK; const int cnt_k = ct.cnt - sub * CHUNK < CHUNK ? ct.cnt - sub * CHUNK : CHUNK;
@@ -176,7 +160,7 @@ IFX_FN void stage1_lookup(const Ctx& c, const DevIndex& ix, const QueryPlan& p, 
             // aligned middle of the list: 16 postings per thread in flight (four 16-byte id loads + four 4-byte tf loads), then their
             // 16 bitset probes, then the hits
             const int64_t pre = (int64_t)((0 - (reinterpret_cast<uintptr_t>(tm.docs) >> 2)) & 3);
-            for (int64_t i = c.tid(); i < pre; i += NT) { const int d = tm.docs[i]; const S1Probe wv = probe_at(d); if ((wv.bits >> (d & 31)) & 1u) put_hit(d, wv, a, tm.tf ? tm.tf[i] : (uint8_t)1); }
+            for (int64_t i = c.tid(); i < pre; i += NT) { const int d = tm.docs[i]; const S1Probe wv = probe[d >> 5]; if ((wv.bits >> (d & 31)) & 1u) put_hit(d, wv, a, tm.tf ? tm.tf[i] : (uint8_t)1); }
             const int4* p4 = reinterpret_cast<const int4*>(tm.docs + pre); const unsigned* t4 = tm.tf ? reinterpret_cast<const unsigned*>(tm.tf + pre) : nullptr;
             const int64_t n4 = (len - pre) >> 2;
             for (int64_t g0 = c.tid(); g0 < n4; g0 += 4LL * NT) {
@@ -186,7 +170,7 @@ IFX_FN void stage1_lookup(const Ctx& c, const DevIndex& ix, const QueryPlan& p, 
 #pragma unroll
                 for (int u = 0; u < 4; u++) { const int dd[4] = {dv[u].x, dv[u].y, dv[u].z, dv[u].w};
 #pragma unroll
-                    for (int k = 0; k < 4; k++) { if (dd[k] >= 0) wv[4 * u + k] = probe_at(dd[k]); else wv[4 * u + k].bits = 0u; } }
+                    for (int k = 0; k < 4; k++) { if (dd[k] >= 0) wv[4 * u + k] = probe[dd[k] >> 5]; else wv[4 * u + k].bits = 0u; } }
 #pragma unroll
                 for (int u = 0; u < 4; u++) { const int dd[4] = {dv[u].x, dv[u].y, dv[u].z, dv[u].w};
 #pragma unroll
@@ -199,7 +183,7 @@ IFX_FN void stage1_lookup(const Ctx& c, const DevIndex& ix, const QueryPlan& p, 
         for (int64_t i0 = done + c.tid(); i0 < len; i0 += NT4) {
             int dd[4]; uint8_t tv[4]; S1Probe wv[4];
             for (int u = 0; u < 4; u++) { int64_t i = i0 + (int64_t)u * NT; const bool in = i < len; dd[u] = in ? tm.docs[i] : -1; tv[u] = (in && tm.tf) ? tm.tf[i] : (uint8_t)1; }
-            for (int u = 0; u < 4; u++) { if (dd[u] >= 0) wv[u] = probe_at(dd[u]); else wv[u].bits = 0u; }
+            for (int u = 0; u < 4; u++) { if (dd[u] >= 0) wv[u] = probe[dd[u] >> 5]; else wv[u].bits = 0u; }
             for (int u = 0; u < 4; u++) if (dd[u] >= 0 && ((wv[u].bits >> (dd[u] & 31)) & 1u)) put_hit(dd[u], wv[u], a, tv[u]);
         }
     };
