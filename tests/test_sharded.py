@@ -28,6 +28,11 @@ def _worker(rank, world, port, emu, outdir, multi):
     eng = ifxd.ShardedSearchEngine(dist, _gpu_lib=emu); eng.IndexShard(docs["keys"], schema, cols, threads=2)
     qs = synth.gen_queries(160, synth.corpus_ref(N), vocab)
     res = eng.SearchBatch([ib.Query(q, 10) for q in qs])
+    # the engine keeps its batch handle between calls (ifx_batch_refill): a smaller batch, then the full one again, must reproduce the first answer
+    sig = lambda rr: [[(e.DocumentId, np.float32(e.Score).view(np.uint32).item(), e.Tiebreaker) for e in r.Records] for r in rr]
+    part = eng.SearchBatch([ib.Query(q, 10) for q in qs[:50]]); again = eng.SearchBatch([ib.Query(q, 10) for q in qs])
+    assert sig(part) == sig(res)[:50] and sig(again) == sig(res)
+    eng.Close()
     if rank == 0:
         import pickle
         pickle.dump([[(e.DocumentId, np.float32(e.Score).view(np.uint32).item(), e.Tiebreaker) for e in r.Records] for r in res], open(os.path.join(outdir, "merged.pkl"), "wb"))
